@@ -1,0 +1,189 @@
+/*
+ * arrowspace_b200.h -- C ABI of the B200-native (sm_100a) lambda-tau build + lambda-aware
+ * search path of ArrowSpace.
+ *
+ * The reference (arrowspace-rs v0.18.1, pure Rust, CPU only) has no FFI; its seam is the
+ * public `EigenMaps` trait (src/eigenmaps.rs:93-172) plus `ArrowSpace::prepare_query_item`
+ * / `search_lambda_aware` (src/core.rs:533,760) and `ArrowSpaceBuilder::build`
+ * (src/builder.rs:249).  Each entry point below replaces the body of one of those
+ * methods; a Rust `-sys` crate binds exactly these symbols.
+ *
+ * Conventions
+ *  - every matrix is contiguous ROW-MAJOR f64; CSR uses int64 indptr/indices (Rust usize).
+ *  - every data pointer may be a HOST pointer or a DEVICE pointer on the context's GPU;
+ *    the library classifies it (cudaPointerGetAttributes).  Host inputs are copied to the
+ *    device inside the call, host outputs are copied back before the call returns; device
+ *    pointers are used in place (zero copy).
+ *  - calls are synchronous on return; one context per host thread; no global state.
+ *  - return value: 0 = ASB_OK, otherwise one of the ASB_ERR_* codes; asb_last_error(ctx)
+ *    gives the text.  The library never aborts and has NO CPU fallback.
+ */
+#ifndef ARROWSPACE_B200_H
+#define ARROWSPACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASB_OK 0
+#define ASB_ERR_INVALID 1         /* bad argument                                         */
+#define ASB_ERR_CUDA 2            /* CUDA runtime error / no device                        */
+#define ASB_ERR_NCCL 3            /* reserved                                              */
+#define ASB_ERR_NONFINITE_QUERY 4 /* src/core.rs:534-537 assert                            */
+#define ASB_ERR_ZERO_LAMBDA 5     /* src/core.rs:773-776 assert_ne!(query.lambda, 0.0)     */
+#define ASB_ERR_SHAPE 6           /* src/laplacian.rs:129-134 (needs >= 2x2)               */
+#define ASB_ERR_TOO_SPARSE 7      /* src/graph.rs:185-193 (sparsity_check)                 */
+#define ASB_ERR_NO_CLUSTERS 8     /* src/clustering.rs:869-874                             */
+#define ASB_ERR_NAN_SCORE 9       /* src/core.rs:785 partial_cmp().unwrap() on NaN         */
+#define ASB_ERR_ZERO_NORM 10      /* zero-magnitude feature column in the cosine kNN       */
+#define ASB_ERR_EMPTY 11          /* src/core.rs:416-420 (items empty / single row)        */
+#define ASB_ERR_DIM 12            /* src/core.rs:510-516 query dimension mismatch          */
+#define ASB_ERR_CAPACITY 13       /* caller buffer too small                               */
+#define ASB_ERR_UNSUPPORTED 14    /* valid in the reference, not built here (documented)   */
+
+/* TauMode, src/taumode.rs:75-82 */
+#define ASB_TAU_FIXED 0
+#define ASB_TAU_MEDIAN 1
+#define ASB_TAU_MEAN 2
+#define ASB_TAU_PERCENTILE 3
+
+typedef struct asb_ctx asb_ctx;
+typedef struct asb_index asb_index;
+
+/* GraphParams, src/graph.rs:94-102, as passed by with_lambda_graph (src/builder.rs:109-137) */
+typedef struct {
+    double eps;
+    int64_t k;
+    int64_t topk;
+    double p;
+    int32_t has_sigma; /* sigma: Option<f64>; None -> 1.0 (src/laplacian.rs:254) */
+    double sigma;
+    int32_t normalise;      /* must be 0 (StandardScaler path is host-side, unsupported) */
+    int32_t sparsity_check; /* src/graph.rs:185-193 */
+    int32_t self_included;  /* smartcore kNN switch, default 0 (see DESIGN.md "unpinned") */
+    int32_t rectified;      /* 0: 1-cos (default) ; 1: 1-max(0,cos) */
+} asb_graph_params;
+
+/* Everything ArrowSpaceBuilder::build needs once (max_clusters, radius) are known
+ * (src/builder.rs:20-57; compute_optimal_k stays on the host, src/clustering.rs:36-72). */
+typedef struct {
+    asb_graph_params graph;
+    int32_t tau_mode; /* with_synthesis, src/builder.rs:142-146 */
+    double tau_value;
+    int64_t max_clusters; /* builder.cluster_max_clusters, src/eigenmaps.rs:216 */
+    double radius;        /* builder.cluster_radius (a SQUARED distance), :217 */
+    int32_t apply_define_result_k; /* 1: k<=5 -> topk=3, k<10 -> topk=4 (src/builder.rs:225-233) */
+} asb_build_params;
+
+typedef struct {
+    int64_t n_items, n_features, n_clusters, nnz;
+    double lambda_min, lambda_max, lambda_sum; /* src/eigenmaps.rs:372-382 */
+    double radius;
+    int64_t max_clusters;
+    double ms_cluster, ms_laplacian, ms_taumode, ms_total; /* device stage times */
+} asb_index_info;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* stream: a cudaStream_t (or NULL: the library creates its own non-blocking stream). */
+int asb_ctx_create(int device, void *stream, asb_ctx **out);
+void asb_ctx_destroy(asb_ctx *ctx);
+const char *asb_last_error(asb_ctx *ctx);
+const char *asb_status_string(int status);
+const char *asb_version(void);
+/* number of kernels THIS library launched on the context since creation (bench evidence) */
+int64_t asb_kernel_launches(asb_ctx *ctx);
+/* device time of the most recent top-level call's dominant kernel(s), ms, measured with
+ * CUDA events on the context's stream (0 if none). */
+double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
+
+/* ---- stage 1: clustering ------------------------------------------------------------ */
+/* Two-NN scan: replaces the distance pass of estimate_intrinsic_dimension
+ * (src/clustering.rs:118-145).  For each sample row the two smallest Euclidean distances
+ * to every OTHER row.  sample_idx (host or device, int64[s]) is produced by the host
+ * (StdRng shuffle, :113-116).  d1/d2: f64[s]. */
+int asb_twonn_distances(asb_ctx *ctx, const double *rows, int64_t n, int64_t f,
+                        const int64_t *sample_idx, int64_t s, double *d1, double *d2);
+
+/* Incremental leader clustering in row order: replaces
+ * run_incremental_clustering_with_sampling + nearest_centroid (src/clustering.rs:547-928)
+ * for the deterministic configuration (with_seed, with_inline_sampling(None)).
+ * centroids: f64[max_clusters*f] (first x rows valid), assignments: int64[n] (-1 = None),
+ * sizes: uint64[max_clusters]. */
+int asb_cluster_incremental(asb_ctx *ctx, const double *rows, int64_t n, int64_t f,
+                            int64_t max_clusters, double radius, double *centroids,
+                            int64_t *assignments, uint64_t *sizes, int64_t *x_out);
+
+/* ---- stage 2: feature-graph Laplacian ----------------------------------------------- */
+/* upper bound of stored entries: f * (1 + 2*(topk+1)) */
+int64_t asb_laplacian_max_nnz(int64_t f, int64_t topk);
+/* Replaces GraphFactory::build_laplacian_matrix_from_k_cluster (src/graph.rs:149-204) ->
+ * build_laplacian_matrix (src/laplacian.rs:122-417).  centroids: X x F; output CSR F x F:
+ * indptr int64[f+1], indices int64[capacity], data f64[capacity]. */
+int asb_build_feature_laplacian(asb_ctx *ctx, const double *centroids, int64_t x, int64_t f,
+                                const asb_graph_params *params, int64_t *indptr,
+                                int64_t *indices, double *data, int64_t capacity,
+                                int64_t *nnz_out);
+
+/* ---- stage 3: taumode --------------------------------------------------------------- */
+/* Replaces TauMode::compute_taumode_lambdas_parallel (src/taumode.rs:174-312): per item
+ * tau = select_tau(item values) (:87-127), lambda = synthetic lambda (:552-660).
+ * stats (optional, host f64[3]) = {min, max, sum} of lambdas (src/eigenmaps.rs:372-382).
+ * norms2 (optional, f64[n]) receives sum(x^2) per item (reused by search). */
+int asb_compute_taumode(asb_ctx *ctx, const double *items, int64_t n, int64_t f,
+                        const int64_t *indptr, const int64_t *indices, const double *data,
+                        int32_t tau_mode, double tau_value, double *lambdas, double *norms2,
+                        double *stats);
+
+/* Replaces ArrowSpace::prepare_query_item (src/core.rs:533-549) for a batch of queries.
+ * Returns ASB_ERR_NONFINITE_QUERY if any query value is NaN/Inf. */
+int asb_prepare_query_lambdas(asb_ctx *ctx, const double *queries, int64_t nq, int64_t f,
+                              const int64_t *indptr, const int64_t *indices,
+                              const double *data, int32_t tau_mode, double tau_value,
+                              double *lambda_q);
+
+/* ---- stage 5: search ---------------------------------------------------------------- */
+/* Replaces ArrowSpace::search_lambda_aware (src/core.rs:760-798) for a batch: score =
+ * alpha*cos + (1-alpha)*(1 - min(|lq - li|, 1)); stable descending order (ties -> lower
+ * index); count[q] = min(k, n).  idx: int64[nq*k], score: f64[nq*k], count: int64[nq].
+ * index_offset is added to every returned index (row-sharded multi-GPU search).
+ * norms2 may be NULL (computed internally).  k <= 128. */
+int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const double *lambdas,
+                                  const double *norms2, int64_t n, int64_t f,
+                                  const double *queries, const double *lambda_q, int64_t nq,
+                                  int64_t k, double alpha, int64_t index_offset,
+                                  int64_t *idx, double *score, int64_t *count);
+
+/* k-way merge of per-shard top-k lists (multi-GPU search): in_score/in_idx are
+ * [parts][nq][k] (unused tail slots: idx = -1); out [nq][k] ordered by (score desc, idx
+ * asc) -- the order a single-process stable sort gives (src/core.rs:785). */
+int asb_topk_merge(asb_ctx *ctx, const double *in_score, const int64_t *in_idx, int64_t parts,
+                   int64_t nq, int64_t k, double *out_score, int64_t *out_idx,
+                   int64_t *out_count);
+
+/* ---- whole build: ArrowSpaceBuilder::build (src/builder.rs:249-455) ----------------- */
+/* stages 1-3 with every intermediate resident in HBM.  rows may be host (copied once) or
+ * device (borrowed: must outlive the index). */
+int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f,
+                    const asb_build_params *params, asb_index **out);
+void asb_index_destroy(asb_index *index);
+int asb_index_info_get(const asb_index *index, asb_index_info *info);
+/* copy-out accessors (dst host or device). */
+int asb_index_lambdas(asb_ctx *ctx, const asb_index *index, double *dst);       /* f64[n]   */
+int asb_index_centroids(asb_ctx *ctx, const asb_index *index, double *dst);     /* f64[x*f] */
+int asb_index_assignments(asb_ctx *ctx, const asb_index *index, int64_t *dst);  /* i64[n]   */
+int asb_index_cluster_sizes(asb_ctx *ctx, const asb_index *index, uint64_t *dst); /* u64[x] */
+int asb_index_laplacian(asb_ctx *ctx, const asb_index *index, int64_t *indptr,
+                        int64_t *indices, double *data); /* f+1, nnz, nnz */
+/* EigenMaps::search (src/eigenmaps.rs:410-455) for a batch: prepare_query_item +
+ * search_lambda_aware.  lambda_q_out optional (f64[nq]). */
+int asb_index_search(asb_ctx *ctx, const asb_index *index, const double *queries, int64_t nq,
+                     int64_t k, double alpha, int64_t *idx, double *score, int64_t *count,
+                     double *lambda_q_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROWSPACE_B200_H */
