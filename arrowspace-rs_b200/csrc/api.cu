@@ -1,0 +1,612 @@
+// api.cu -- the C ABI (include/arrowspace_b200.h): context, host/device staging, the stage
+// entry points and the device-resident index (ArrowSpaceBuilder::build, src/builder.rs:249-455).
+#include "common.cuh"
+
+#define ASB_VERSION_STRING "arrowspace_b200 0.1.0 (sm_100a)"
+
+struct asb_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0, f = 0, x = 0, nnz = 0, max_clusters = 0;
+    double radius = 0.0;
+    const double *items = nullptr;  // borrowed or owned
+    double *items_owned = nullptr;
+    double *lambdas = nullptr, *norms2 = nullptr, *centroids = nullptr, *stats = nullptr;
+    int64_t *assign = nullptr;
+    unsigned long long *sizes = nullptr;
+    int64_t *indptr = nullptr, *indices = nullptr;
+    double *data = nullptr;
+    GraphPlan plan;
+    int tau_mode = ASB_TAU_MEDIAN;
+    double tau_value = 0.0;
+    double h_stats[3] = {0, 0, 0};
+    double ms_cluster = 0, ms_laplacian = 0, ms_taumode = 0, ms_total = 0;
+};
+
+extern "C" {
+
+const char *asb_version(void) { return ASB_VERSION_STRING; }
+
+const char *asb_status_string(int s) {
+    switch (s) {
+        case ASB_OK: return "ok";
+        case ASB_ERR_INVALID: return "invalid argument";
+        case ASB_ERR_CUDA: return "CUDA error";
+        case ASB_ERR_NCCL: return "NCCL error";
+        case ASB_ERR_NONFINITE_QUERY:
+            return "Query item contains invalid values (NaN or infinity). All values must be finite.";
+        case ASB_ERR_ZERO_LAMBDA: return "Lambda of the item is 0.0, prepare the item before searching";
+        case ASB_ERR_SHAPE: return "items should be at least of shape (2,2)";
+        case ASB_ERR_TOO_SPARSE: return "Resulting laplacian matrix is too sparse";
+        case ASB_ERR_NO_CLUSTERS: return "No clusters created from data";
+        case ASB_ERR_NAN_SCORE: return "NaN score in search (partial_cmp unwrap)";
+        case ASB_ERR_ZERO_NORM: return "zero-magnitude feature column in cosine kNN";
+        case ASB_ERR_EMPTY: return "items cannot be empty / cannot create a arrowspace of one arrow only";
+        case ASB_ERR_DIM: return "dimension mismatch";
+        case ASB_ERR_CAPACITY: return "output buffer too small";
+        case ASB_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+
+int asb_ctx_create(int device, void *stream, asb_ctx **out) {
+    if (!out) return ASB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ASB_ERR_CUDA;  // no CPU fallback: fail loudly
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return ASB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ASB_ERR_CUDA;
+    if (prop.major < 10) return ASB_ERR_CUDA;  // built for sm_100a only
+    asb_ctx *c = new asb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return ASB_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    // keep freed stream-ordered allocations cached in the pool (no per-call cudaMalloc cost)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return ASB_OK;
+}
+
+void asb_ctx_destroy(asb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *asb_last_error(asb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+int64_t asb_kernel_launches(asb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double asb_last_kernel_ms(asb_ctx *ctx, const char *which) {
+    if (!ctx || !which) return 0.0;
+    auto it = ctx->kernel_ms.find(which);
+    return it == ctx->kernel_ms.end() ? 0.0 : it->second;
+}
+
+int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value) {
+    if (!ctx || !key) return ASB_ERR_INVALID;
+    ctx->options[key] = value;
+    return ASB_OK;
+}
+
+int64_t asb_laplacian_max_nnz(int64_t f, int64_t topk) { return f * (1 + 2 * (topk + 1)); }
+
+}  // extern "C"
+
+// ---- helpers --------------------------------------------------------------------------------
+
+static int set_device(asb_ctx *ctx) {
+    if (!ctx) return ASB_ERR_INVALID;
+    ASB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ASB_OK;
+}
+
+// Fetch a CSR given as host or device pointers into host vectors (the graph is tiny).
+static int csr_to_host(asb_ctx *ctx, const int64_t *indptr, const int64_t *indices, const double *data, int64_t f,
+                       std::vector<int64_t> &hp, std::vector<int64_t> &hi, std::vector<double> &hd) {
+    if (!indptr || f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "csr: null indptr or f<=0");
+    hp.resize((size_t)f + 1);
+    if (asb_is_device_ptr(indptr)) {
+        ASB_CUDA(ctx, cudaMemcpyAsync(hp.data(), indptr, (f + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(hp.data(), indptr, (f + 1) * sizeof(int64_t));
+    }
+    const int64_t nnz = hp[f];
+    if (nnz < 0 || nnz > ((int64_t)1 << 30)) ASB_FAIL(ctx, ASB_ERR_INVALID, "csr: bad nnz %lld", (long long)nnz);
+    hi.resize((size_t)nnz);
+    hd.resize((size_t)nnz);
+    if (nnz > 0) {
+        if (!indices || !data) ASB_FAIL(ctx, ASB_ERR_INVALID, "csr: null indices/data");
+        if (asb_is_device_ptr(indices))
+            ASB_CUDA(ctx, cudaMemcpyAsync(hi.data(), indices, nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            memcpy(hi.data(), indices, nnz * sizeof(int64_t));
+        if (asb_is_device_ptr(data))
+            ASB_CUDA(ctx, cudaMemcpyAsync(hd.data(), data, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            memcpy(hd.data(), data, nnz * sizeof(double));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return ASB_OK;
+}
+
+struct PlanGuard {
+    GraphPlan plan;
+    ~PlanGuard() { plan.release(); }
+};
+
+static int search_status_to_rc(asb_ctx *ctx, int st) {
+    if (st & 2) ASB_FAIL(ctx, ASB_ERR_ZERO_LAMBDA, "Lambda of the item is 0.0, prepare the item before searching");
+    if (st & 1) ASB_FAIL(ctx, ASB_ERR_NAN_SCORE, "NaN score encountered while ranking (reference panics in sort_by)");
+    return ASB_OK;
+}
+
+extern "C" {
+
+// ---- stage 1 --------------------------------------------------------------------------------
+
+int asb_twonn_distances(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const int64_t *sample_idx,
+                        int64_t s, double *d1, double *d2) {
+    ASB_TRY(set_device(ctx));
+    if (!rows || !sample_idx || !d1 || !d2 || n < 2 || f <= 0 || s <= 0)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn: bad arguments");
+    DevIn<double> r;
+    DevIn<int64_t> si;
+    DevOut<double> o1, o2;
+    ASB_TRY(r.init(ctx, rows, (size_t)n * f));
+    ASB_TRY(si.init(ctx, sample_idx, (size_t)s));
+    ASB_TRY(o1.init(ctx, d1, (size_t)s));
+    ASB_TRY(o2.init(ctx, d2, (size_t)s));
+    StageTimer t(ctx, "twonn");
+    ASB_TRY(asb_dev_twonn(ctx, r.ptr, n, f, si.ptr, s, o1.ptr, o2.ptr));
+    t.stop();
+    ASB_TRY(o1.finish(ctx));
+    ASB_TRY(o2.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_cluster_incremental(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, int64_t max_clusters,
+                            double radius, double *centroids, int64_t *assignments, uint64_t *sizes,
+                            int64_t *x_out) {
+    ASB_TRY(set_device(ctx));
+    if (!rows || !centroids || !assignments || !sizes || !x_out)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: null pointer");
+    if (n <= 0 || f <= 0 || max_clusters <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: bad sizes");
+    DevIn<double> r;
+    DevOut<double> c;
+    DevOut<int64_t> a;
+    DevOut<unsigned long long> sz;
+    ASB_TRY(r.init(ctx, rows, (size_t)n * f));
+    ASB_TRY(c.init(ctx, centroids, (size_t)max_clusters * f));
+    ASB_TRY(a.init(ctx, assignments, (size_t)n));
+    ASB_TRY(sz.init(ctx, (unsigned long long *)sizes, (size_t)max_clusters));
+    ASB_CUDA(ctx, cudaMemsetAsync(c.ptr, 0, (size_t)max_clusters * f * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(sz.ptr, 0, (size_t)max_clusters * sizeof(unsigned long long), ctx->stream));
+    StageTimer t(ctx, "cluster");
+    int64_t x = 0;
+    int rc = asb_dev_cluster(ctx, r.ptr, n, f, max_clusters, radius, c.ptr, a.ptr, sz.ptr, &x);
+    t.stop();
+    ASB_TRY(rc);
+    *x_out = x;
+    ASB_TRY(c.finish(ctx));
+    ASB_TRY(a.finish(ctx));
+    ASB_TRY(sz.finish(ctx));
+    return asb_sync(ctx);
+}
+
+// ---- stage 2 --------------------------------------------------------------------------------
+
+int asb_build_feature_laplacian(asb_ctx *ctx, const double *centroids, int64_t x, int64_t f,
+                                const asb_graph_params *params, int64_t *indptr, int64_t *indices, double *data,
+                                int64_t capacity, int64_t *nnz_out) {
+    ASB_TRY(set_device(ctx));
+    if (!centroids || !params || !indptr || !indices || !data || !nnz_out)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "laplacian: null pointer");
+    if (x < 2 || f < 2)
+        ASB_FAIL(ctx, ASB_ERR_SHAPE, "items should be at least of shape (2,2): (%lld,%lld)", (long long)f, (long long)x);
+    if (capacity < f) ASB_FAIL(ctx, ASB_ERR_CAPACITY, "laplacian: capacity < f");
+    DevIn<double> c;
+    DevOut<int64_t> ip, ii;
+    DevOut<double> dd;
+    ASB_TRY(c.init(ctx, centroids, (size_t)x * f));
+    ASB_TRY(ip.init(ctx, indptr, (size_t)f + 1));
+    ASB_TRY(ii.init(ctx, indices, (size_t)capacity));
+    ASB_TRY(dd.init(ctx, data, (size_t)capacity));
+    StageTimer t(ctx, "laplacian");
+    int64_t nnz = 0;
+    int rc = asb_dev_laplacian(ctx, c.ptr, x, f, *params, ip.ptr, ii.ptr, dd.ptr, capacity, &nnz);
+    t.stop();
+    *nnz_out = nnz;
+    ASB_TRY(rc);
+    ASB_TRY(ip.finish(ctx));
+    ASB_TRY(ii.finish(ctx, (size_t)nnz));
+    ASB_TRY(dd.finish(ctx, (size_t)nnz));
+    return asb_sync(ctx);
+}
+
+// ---- stage 3 --------------------------------------------------------------------------------
+
+int asb_compute_taumode(asb_ctx *ctx, const double *items, int64_t n, int64_t f, const int64_t *indptr,
+                        const int64_t *indices, const double *data, int32_t tau_mode, double tau_value,
+                        double *lambdas, double *norms2, double *stats) {
+    ASB_TRY(set_device(ctx));
+    if (!items || !lambdas) ASB_FAIL(ctx, ASB_ERR_INVALID, "taumode: null pointer");
+    if (n <= 0 || f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "taumode: bad sizes");
+    std::vector<int64_t> hp, hi;
+    std::vector<double> hd;
+    ASB_TRY(csr_to_host(ctx, indptr, indices, data, f, hp, hi, hd));
+    PlanGuard pg;
+    ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), f, &pg.plan));
+    DevIn<double> it;
+    DevOut<double> lam, n2;
+    DevTmp<double> st;
+    ASB_TRY(it.init(ctx, items, (size_t)n * f));
+    ASB_TRY(lam.init(ctx, lambdas, (size_t)n));
+    ASB_TRY(n2.init(ctx, norms2, norms2 ? (size_t)n : 0));
+    ASB_TRY(st.init(ctx, 3));
+    StageTimer t(ctx, "taumode");
+    int rc = asb_dev_taumode(ctx, it.ptr, n, f, pg.plan, tau_mode, tau_value, lam.ptr, n2.ptr,
+                             stats ? st.ptr : nullptr, nullptr);
+    t.stop();
+    ASB_TRY(rc);
+    ASB_TRY(lam.finish(ctx));
+    ASB_TRY(n2.finish(ctx));
+    if (stats) {
+        if (asb_is_device_ptr(stats))
+            ASB_CUDA(ctx, cudaMemcpyAsync(stats, st.ptr, 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        else
+            ASB_CUDA(ctx, cudaMemcpyAsync(stats, st.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return asb_sync(ctx);
+}
+
+int asb_prepare_query_lambdas(asb_ctx *ctx, const double *queries, int64_t nq, int64_t f, const int64_t *indptr,
+                              const int64_t *indices, const double *data, int32_t tau_mode, double tau_value,
+                              double *lambda_q) {
+    ASB_TRY(set_device(ctx));
+    if (!queries || !lambda_q) ASB_FAIL(ctx, ASB_ERR_INVALID, "prepare_query: null pointer");
+    if (nq <= 0 || f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "prepare_query: bad sizes");
+    std::vector<int64_t> hp, hi;
+    std::vector<double> hd;
+    ASB_TRY(csr_to_host(ctx, indptr, indices, data, f, hp, hi, hd));
+    PlanGuard pg;
+    ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), f, &pg.plan));
+    DevIn<double> q;
+    DevOut<double> lam;
+    DevTmp<int> flag;
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lam.init(ctx, lambda_q, (size_t)nq));
+    ASB_TRY(flag.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(flag.ptr, 0, sizeof(int), ctx->stream));
+    ASB_TRY(asb_dev_taumode(ctx, q.ptr, nq, f, pg.plan, tau_mode, tau_value, lam.ptr, nullptr, nullptr, flag.ptr));
+    int hflag = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hflag, flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hflag)  // src/core.rs:534-537
+        ASB_FAIL(ctx, ASB_ERR_NONFINITE_QUERY,
+                 "Query item contains invalid values (NaN or infinity). All values must be finite.");
+    ASB_TRY(lam.finish(ctx));
+    return asb_sync(ctx);
+}
+
+// ---- stage 5 --------------------------------------------------------------------------------
+
+int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const double *lambdas, const double *norms2,
+                                  int64_t n, int64_t f, const double *queries, const double *lambda_q, int64_t nq,
+                                  int64_t k, double alpha, int64_t index_offset, int64_t *idx, double *score,
+                                  int64_t *count) {
+    ASB_TRY(set_device(ctx));
+    if (!items || !lambdas || !queries || !lambda_q || !idx || !score)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "search: null pointer");
+    if (n <= 0 || f <= 0 || nq <= 0 || k < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search: bad sizes");
+    if (k == 0) {
+        if (count) {
+            if (asb_is_device_ptr(count)) ASB_CUDA(ctx, cudaMemsetAsync(count, 0, nq * sizeof(int64_t), ctx->stream));
+            else memset(count, 0, nq * sizeof(int64_t));
+        }
+        return asb_sync(ctx);
+    }
+    DevIn<double> it, lam, n2, q, lq;
+    DevOut<int64_t> oi, oc;
+    DevOut<double> os;
+    DevTmp<int64_t> cnt_tmp;
+    DevTmp<int> status;
+    ASB_TRY(it.init(ctx, items, (size_t)n * f));
+    ASB_TRY(lam.init(ctx, lambdas, (size_t)n));
+    ASB_TRY(n2.init(ctx, norms2, norms2 ? (size_t)n : 0));
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lq.init(ctx, lambda_q, (size_t)nq));
+    ASB_TRY(oi.init(ctx, idx, (size_t)nq * k));
+    ASB_TRY(os.init(ctx, score, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, count, count ? (size_t)nq : 0));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_TRY(status.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
+    StageTimer t(ctx, "search");
+    int rc = asb_dev_search(ctx, it.ptr, lam.ptr, n2.ptr, n, f, q.ptr, lq.ptr, nq, k, alpha, index_offset, oi.ptr,
+                            os.ptr, count ? oc.ptr : cnt_tmp.ptr, status.ptr);
+    t.stop();
+    ASB_TRY(rc);
+    int hst = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hst, status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASB_TRY(search_status_to_rc(ctx, hst));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_topk_merge(asb_ctx *ctx, const double *in_score, const int64_t *in_idx, int64_t parts, int64_t nq,
+                   int64_t k, double *out_score, int64_t *out_idx, int64_t *out_count) {
+    ASB_TRY(set_device(ctx));
+    if (!in_score || !in_idx || !out_score || !out_idx) ASB_FAIL(ctx, ASB_ERR_INVALID, "topk_merge: null pointer");
+    if (parts < 1 || nq < 1 || k < 1) ASB_FAIL(ctx, ASB_ERR_INVALID, "topk_merge: bad sizes");
+    DevIn<double> is;
+    DevIn<int64_t> ii;
+    DevOut<double> os;
+    DevOut<int64_t> oi, oc;
+    DevTmp<int64_t> cnt_tmp;
+    ASB_TRY(is.init(ctx, in_score, (size_t)parts * nq * k));
+    ASB_TRY(ii.init(ctx, in_idx, (size_t)parts * nq * k));
+    ASB_TRY(os.init(ctx, out_score, (size_t)nq * k));
+    ASB_TRY(oi.init(ctx, out_idx, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, out_count, out_count ? (size_t)nq : 0));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_TRY(asb_dev_topk_merge(ctx, is.ptr, ii.ptr, parts, nq, k, os.ptr, oi.ptr, out_count ? oc.ptr : cnt_tmp.ptr));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
+// ---- whole build ----------------------------------------------------------------------------
+
+void asb_index_destroy(asb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->items_owned);
+    cudaFree(ix->lambdas);
+    cudaFree(ix->norms2);
+    cudaFree(ix->centroids);
+    cudaFree(ix->stats);
+    cudaFree(ix->assign);
+    cudaFree(ix->sizes);
+    cudaFree(ix->indptr);
+    cudaFree(ix->indices);
+    cudaFree(ix->data);
+    ix->plan.release();
+    cudaStreamSynchronize(ix->stream);
+    delete ix;
+}
+
+int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const asb_build_params *bp,
+                    asb_index **out) {
+    ASB_TRY(set_device(ctx));
+    if (!rows || !bp || !out) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: null pointer");
+    *out = nullptr;
+    if (n <= 0) ASB_FAIL(ctx, ASB_ERR_EMPTY, "items cannot be empty");  // src/core.rs:416
+    if (n <= 1) ASB_FAIL(ctx, ASB_ERR_EMPTY, "cannot create a arrowspace of one arrow only");  // :417-420
+    if (f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: f<=0");
+    if (bp->max_clusters <= 0 || !(bp->radius >= 0.0))
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: max_clusters/radius must come from the host heuristic");
+    asb_graph_params gp = bp->graph;
+    if (bp->apply_define_result_k) {  // src/builder.rs:225-233
+        if (gp.k <= 5) gp.topk = 3;
+        else if (gp.k < 10) gp.topk = 4;
+    }
+    asb_index *ix = new asb_index();
+    ix->device = ctx->device;
+    ix->stream = ctx->stream;
+    ix->n = n;
+    ix->f = f;
+    ix->max_clusters = bp->max_clusters;
+    ix->radius = bp->radius;
+    ix->tau_mode = bp->tau_mode;
+    ix->tau_value = bp->tau_value;
+    struct Guard {
+        asb_index *p;
+        ~Guard() { if (p) asb_index_destroy(p); }
+    } guard{ix};
+
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    struct EvGuard {
+        cudaEvent_t a, b, c, d;
+        ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); }
+    } evg{e0, e1, e2, e3};
+
+    if (asb_is_device_ptr(rows)) {
+        ix->items = rows;
+    } else {
+        ASB_CUDA(ctx, cudaMalloc((void **)&ix->items_owned, (size_t)n * f * sizeof(double)));
+        ASB_CUDA(ctx, cudaMemcpyAsync(ix->items_owned, rows, (size_t)n * f * sizeof(double), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        ix->items = ix->items_owned;
+    }
+    const int64_t cap = asb_laplacian_max_nnz(f, gp.topk);
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->lambdas, (size_t)n * sizeof(double)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->norms2, (size_t)n * sizeof(double)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->centroids, (size_t)bp->max_clusters * f * sizeof(double)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->stats, 3 * sizeof(double)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->assign, (size_t)n * sizeof(int64_t)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->sizes, (size_t)bp->max_clusters * sizeof(unsigned long long)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->indptr, (size_t)(f + 1) * sizeof(int64_t)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->indices, (size_t)cap * sizeof(int64_t)));
+    ASB_CUDA(ctx, cudaMalloc((void **)&ix->data, (size_t)cap * sizeof(double)));
+    ASB_CUDA(ctx, cudaMemsetAsync(ix->centroids, 0, (size_t)bp->max_clusters * f * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(ix->sizes, 0, (size_t)bp->max_clusters * sizeof(unsigned long long), ctx->stream));
+
+    // stage 1: clustering (src/eigenmaps.rs:224-232)
+    cudaEventRecord(e0, ctx->stream);
+    int64_t x = 0;
+    ASB_TRY(asb_dev_cluster(ctx, ix->items, n, f, bp->max_clusters, bp->radius, ix->centroids, ix->assign, ix->sizes, &x));
+    ix->x = x;
+    cudaEventRecord(e1, ctx->stream);
+    // stage 2: feature Laplacian (src/eigenmaps.rs:313-323); assert clustered.shape().0 <= n_items holds
+    int64_t nnz = 0;
+    ASB_TRY(asb_dev_laplacian(ctx, ix->centroids, x, f, gp, ix->indptr, ix->indices, ix->data, cap, &nnz));
+    ix->nnz = nnz;
+    {
+        std::vector<int64_t> hp, hi;
+        std::vector<double> hd;
+        ASB_TRY(csr_to_host(ctx, ix->indptr, ix->indices, ix->data, f, hp, hi, hd));
+        ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), f, &ix->plan));
+    }
+    cudaEventRecord(e2, ctx->stream);
+    // stage 3: taumode (src/eigenmaps.rs:358-383)
+    ASB_TRY(asb_dev_taumode(ctx, ix->items, n, f, ix->plan, bp->tau_mode, bp->tau_value, ix->lambdas, ix->norms2,
+                            ix->stats, nullptr));
+    cudaEventRecord(e3, ctx->stream);
+    ASB_CUDA(ctx, cudaMemcpyAsync(ix->h_stats, ix->stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1); ix->ms_cluster = ms;
+    cudaEventElapsedTime(&ms, e1, e2); ix->ms_laplacian = ms;
+    cudaEventElapsedTime(&ms, e2, e3); ix->ms_taumode = ms;
+    cudaEventElapsedTime(&ms, e0, e3); ix->ms_total = ms;
+    ctx->kernel_ms["build_cluster"] = ix->ms_cluster;
+    ctx->kernel_ms["build_laplacian"] = ix->ms_laplacian;
+    ctx->kernel_ms["build_taumode"] = ix->ms_taumode;
+    ctx->kernel_ms["build_total"] = ix->ms_total;
+    guard.p = nullptr;
+    *out = ix;
+    return ASB_OK;
+}
+
+int asb_index_info_get(const asb_index *ix, asb_index_info *info) {
+    if (!ix || !info) return ASB_ERR_INVALID;
+    info->n_items = ix->n;
+    info->n_features = ix->f;
+    info->n_clusters = ix->x;
+    info->nnz = ix->nnz;
+    info->lambda_min = ix->h_stats[0];
+    info->lambda_max = ix->h_stats[1];
+    info->lambda_sum = ix->h_stats[2];
+    info->radius = ix->radius;
+    info->max_clusters = ix->max_clusters;
+    info->ms_cluster = ix->ms_cluster;
+    info->ms_laplacian = ix->ms_laplacian;
+    info->ms_taumode = ix->ms_taumode;
+    info->ms_total = ix->ms_total;
+    return ASB_OK;
+}
+
+static int copy_out(asb_ctx *ctx, void *dst, const void *src_d, size_t bytes) {
+    if (!dst) ASB_FAIL(ctx, ASB_ERR_INVALID, "copy_out: null destination");
+    if (bytes == 0) return ASB_OK;
+    ASB_CUDA(ctx, cudaMemcpyAsync(dst, src_d, bytes, asb_is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    return asb_sync(ctx);
+}
+
+int asb_index_lambdas(asb_ctx *ctx, const asb_index *ix, double *dst) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    return copy_out(ctx, dst, ix->lambdas, (size_t)ix->n * sizeof(double));
+}
+int asb_index_centroids(asb_ctx *ctx, const asb_index *ix, double *dst) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    return copy_out(ctx, dst, ix->centroids, (size_t)ix->x * ix->f * sizeof(double));
+}
+int asb_index_assignments(asb_ctx *ctx, const asb_index *ix, int64_t *dst) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    return copy_out(ctx, dst, ix->assign, (size_t)ix->n * sizeof(int64_t));
+}
+int asb_index_cluster_sizes(asb_ctx *ctx, const asb_index *ix, uint64_t *dst) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    return copy_out(ctx, dst, ix->sizes, (size_t)ix->x * sizeof(uint64_t));
+}
+int asb_index_laplacian(asb_ctx *ctx, const asb_index *ix, int64_t *indptr, int64_t *indices, double *data) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    ASB_TRY(copy_out(ctx, indptr, ix->indptr, (size_t)(ix->f + 1) * sizeof(int64_t)));
+    ASB_TRY(copy_out(ctx, indices, ix->indices, (size_t)ix->nnz * sizeof(int64_t)));
+    return copy_out(ctx, data, ix->data, (size_t)ix->nnz * sizeof(double));
+}
+
+int asb_index_search(asb_ctx *ctx, const asb_index *ix, const double *queries, int64_t nq, int64_t k, double alpha,
+                     int64_t *idx, double *score, int64_t *count, double *lambda_q_out) {
+    ASB_TRY(set_device(ctx));
+    if (!ix || !queries || !idx || !score) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search: null pointer");
+    if (nq <= 0 || k < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search: bad sizes");
+    const int64_t f = ix->f;
+    DevIn<double> q;
+    DevTmp<double> lq;
+    DevTmp<int> flags;
+    DevTmp<int64_t> cnt_tmp;
+    DevOut<int64_t> oi, oc;
+    DevOut<double> os;
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lq.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 2));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, 2 * sizeof(int), ctx->stream));
+    // prepare_query_item (src/core.rs:533-549): tau from the query values, lambda on gl.matrix
+    StageTimer tq(ctx, "query_lambda");
+    ASB_TRY(asb_dev_taumode(ctx, q.ptr, nq, f, ix->plan, ix->tau_mode, ix->tau_value, lq.ptr, nullptr, nullptr, flags.ptr));
+    tq.stop();
+    int h[2] = {0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(h, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[0])
+        ASB_FAIL(ctx, ASB_ERR_NONFINITE_QUERY,
+                 "Query item contains invalid values (NaN or infinity). All values must be finite.");
+    if (lambda_q_out) ASB_TRY(copy_out(ctx, lambda_q_out, lq.ptr, (size_t)nq * sizeof(double)));
+    if (k == 0) {
+        if (count) {
+            if (asb_is_device_ptr(count)) ASB_CUDA(ctx, cudaMemsetAsync(count, 0, nq * sizeof(int64_t), ctx->stream));
+            else memset(count, 0, nq * sizeof(int64_t));
+        }
+        return asb_sync(ctx);
+    }
+    ASB_TRY(oi.init(ctx, idx, (size_t)nq * k));
+    ASB_TRY(os.init(ctx, score, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, count, count ? (size_t)nq : 0));
+    StageTimer ts(ctx, "search");
+    int rc = asb_dev_search(ctx, ix->items, ix->lambdas, ix->norms2, ix->n, f, q.ptr, lq.ptr, nq, k, alpha, 0, oi.ptr,
+                            os.ptr, count ? oc.ptr : cnt_tmp.ptr, flags.ptr + 1);
+    ts.stop();
+    ASB_TRY(rc);
+    ASB_CUDA(ctx, cudaMemcpyAsync(h + 1, flags.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASB_TRY(search_status_to_rc(ctx, h[1]));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_index_search_lambda_aware(asb_ctx *ctx, const asb_index *ix, const double *queries, const double *lambda_q,
+                                  int64_t nq, int64_t k, double alpha, int64_t *idx, double *score, int64_t *count) {
+    if (!ix) return ASB_ERR_INVALID;
+    return asb_search_lambda_aware_batch(ctx, ix->items, ix->lambdas, ix->norms2, ix->n, ix->f, queries, lambda_q, nq,
+                                         k, alpha, 0, idx, score, count);
+}
+
+}  // extern "C"

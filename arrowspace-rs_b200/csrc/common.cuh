@@ -21,6 +21,7 @@ struct asb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     std::map<std::string, double> kernel_ms;
+    std::map<std::string, double> options;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 

@@ -1,0 +1,555 @@
+// search.cu -- K8 (+K1): dense query x item contraction on the FP64 tensor pipe (DMMA m8n8k4)
+// with the blended lambda-aware score and a running top-k fused into the epilogue, so the
+// Q x N score matrix never exists in HBM.
+//
+// Replaces ArrowSpace::search_lambda_aware (src/core.rs:760-798) with the scoring of
+// ArrowItem::{cosine_similarity, lambda_component_similarity, lambda_similarity}
+// (src/core.rs:135-239) for a batch of queries, and -- in L2 mode -- the distance pass of
+// estimate_intrinsic_dimension (src/clustering.rs:118-145).
+//
+// Tiling: a CTA owns 128 queries x one slab of items and walks the slab in 128-item tiles.
+// Per tile the F dimension is streamed in 16-feature chunks (cp.async, double buffered) into
+// row-major smem tiles with pitch 20 doubles (conflict-free fragment loads); 8 warps (4 x 2)
+// each hold a 32 x 64 accumulator block as 4 x 8 DMMA fragments.  The epilogue turns dots
+// into scores, parks them in smem (aliasing the operand stages) and one warp per query
+// merges the survivors into that query's sorted top-k list (smem, persistent over the slab).
+// Per-slab lists are merged by (score desc, index asc): exactly the order of the reference's
+// stable sort (src/core.rs:785), ties -> lower index.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TQ = 128, TN = 128, KC = 16, PITCH = KC + 4;
+constexpr int kThreads = 256;
+constexpr int STAGE_DOUBLES = (TQ + TN) * PITCH;  // 5120 doubles = 40 KB
+constexpr int SPITCH = 72;                        // score half-tile pitch (doubles)
+constexpr int MODE_COSINE = 0, MODE_L2 = 1;
+constexpr int STATUS_NAN = 1, STATUS_ZERO_LAMBDA = 2;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct SearchArgs {
+    const double *items;     // n x f
+    const double *lambdas;   // n          (cosine mode)
+    const double *norms2;    // n
+    const double *queries;   // nq x f
+    const double *lambda_q;  // nq         (cosine mode)
+    const double *qnorms2;   // nq
+    const long long *self_idx;  // nq      (L2 mode: item index to exclude)
+    long long n, nq;
+    int f, k;
+    double alpha;
+    int nslabs;
+    long long tiles_per_slab;
+    double *part_score;  // nslabs x nq x k
+    int *part_idx;       // nslabs x nq x k
+    int *status;
+};
+
+// Load one KC-wide chunk of `rows` rows starting at row0 into a smem tile [rows][PITCH].
+template <bool VEC>
+__device__ __forceinline__ void load_tile_chunk(double *dst, const double *__restrict__ src, long long row0,
+                                                long long nrows_total, int f, int k0, int tid) {
+    if (VEC) {
+        // 128 rows x 8 chunks of 16 B
+        for (int c = tid; c < 128 * (KC / 2); c += kThreads) {
+            const int r = c / (KC / 2), ch = c % (KC / 2);
+            const long long row = row0 + r;
+            const int col = k0 + ch * 2;
+            const bool ok = row < nrows_total && col < f;
+            const double *g = ok ? src + row * (long long)f + col : src;
+            cp_async16(dst + r * PITCH + ch * 2, g, ok ? 16 : 0);
+        }
+    } else {
+        for (int c = tid; c < 128 * KC; c += kThreads) {
+            const int r = c / KC, ch = c % KC;
+            const long long row = row0 + r;
+            const int col = k0 + ch;
+            const bool ok = row < nrows_total && col < f;
+            const double *g = ok ? src + row * (long long)f + col : src;
+            cp_async8(dst + r * PITCH + ch, g, ok ? 8 : 0);
+        }
+    }
+}
+
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *stages = reinterpret_cast<double *>(smem_raw);     // 2 * STAGE_DOUBLES
+    double *S = stages;                                        // aliases stages: TQ x SPITCH
+    double *sm_nq = stages + 2 * STAGE_DOUBLES;                // TQ
+    double *sm_lq = sm_nq + TQ;                                // TQ
+    double *sm_nx = sm_lq + TQ;                                // TN
+    double *sm_lx = sm_nx + TN;                                // TN
+    double *list_s = sm_lx + TN;                               // TQ * k
+    int *list_i = reinterpret_cast<int *>(list_s + (size_t)TQ * A.k);  // TQ * k
+    int *list_len = list_i + (size_t)TQ * A.k;                 // TQ
+    long long *sm_self = reinterpret_cast<long long *>(list_len + TQ);  // TQ (8B aligned: TQ*k ints + TQ ints even)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int k = A.k, f = A.f;
+
+    const long long q0 = (long long)blockIdx.x * TQ;
+    const int slab = blockIdx.y;
+    const long long ntiles_total = (A.n + TN - 1) / TN;
+    const long long t_begin = (long long)slab * A.tiles_per_slab;
+    long long t_end = t_begin + A.tiles_per_slab;
+    if (t_end > ntiles_total) t_end = ntiles_total;
+
+    for (int q = tid; q < TQ; q += kThreads) {
+        const long long gq = q0 + q;
+        const bool ok = gq < A.nq;
+        const double n2 = ok ? A.qnorms2[gq] : 0.0;
+        sm_nq[q] = (MODE == MODE_COSINE) ? sqrt(n2) : n2;
+        double lq = 0.0;
+        if (MODE == MODE_COSINE) {
+            lq = ok ? A.lambda_q[gq] : 1.0;
+            if (ok && slab == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);  // core.rs:773-776
+        }
+        sm_lq[q] = lq;
+        list_len[q] = 0;
+        if (MODE == MODE_L2) sm_self[q] = ok ? A.self_idx[gq] : -1;
+    }
+    const int nchunks = (f + KC - 1) / KC;
+
+    for (long long t = t_begin; t < t_end; ++t) {
+        const long long i0 = t * TN;
+        __syncthreads();  // S (aliasing the stages) and sm_nx/sm_lx of the previous tile are free
+        for (int c = tid; c < TN; c += kThreads) {
+            const long long gi = i0 + c;
+            const bool ok = gi < A.n;
+            const double n2 = ok ? A.norms2[gi] : 0.0;
+            sm_nx[c] = (MODE == MODE_COSINE) ? sqrt(n2) : n2;
+            sm_lx[c] = (MODE == MODE_COSINE && ok) ? A.lambdas[gi] : 0.0;
+        }
+        double acc[4][8][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        // prologue: chunk 0 -> stage 0
+        load_tile_chunk<VEC>(stages, A.queries, q0, A.nq, f, 0, tid);
+        load_tile_chunk<VEC>(stages + TQ * PITCH, A.items, i0, A.n, f, 0, tid);
+        cp_async_commit();
+        for (int c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks) {
+                double *st = stages + ((c + 1) & 1) * STAGE_DOUBLES;
+                load_tile_chunk<VEC>(st, A.queries, q0, A.nq, f, (c + 1) * KC, tid);
+                load_tile_chunk<VEC>(st + TQ * PITCH, A.items, i0, A.n, f, (c + 1) * KC, tid);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const double *Qs = stages + (c & 1) * STAGE_DOUBLES;
+            const double *Xs = Qs + TQ * PITCH;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
+                double a[4], b[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = Qs[(wm * 32 + i * 8 + gid) * PITCH + kk + tig];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = Xs[(wn * 64 + j * 8 + gid) * PITCH + kk + tig];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            __syncthreads();
+        }
+
+        // ---- epilogue: scores -> smem half tile -> per-query top-k merge
+        for (int half = 0; half < 2; ++half) {
+            if (wn == half) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = wm * 32 + i * 8 + gid;
+                    const double nq = sm_nq[r], lq = sm_lq[r];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double2 sv;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int cl = j * 8 + tig * 2 + u;  // column inside this half
+                            const int c = half * 64 + cl;
+                            const long long gi = i0 + c;
+                            const double dot = acc[i][j][u];
+                            double s;
+                            if (MODE == MODE_COSINE) {
+                                const double denom = nq * sm_nx[c];                 // core.rs:230
+                                const double cosv = denom > 0.0 ? dot / denom : 0.0;  // :231-236
+                                const double ld = fabs(lq - sm_lx[c]);               // :136
+                                const double lam = 1.0 - fmin(ld, 1.0);              // :137
+                                s = A.alpha * cosv + (1.0 - A.alpha) * lam;          // :165
+                                if (gi < A.n && q0 + r < A.nq && s != s) atomicOr(A.status, STATUS_NAN);
+                            } else {
+                                s = -(nq + sm_nx[c] - 2.0 * dot);  // -(|q|^2 + |x|^2 - 2 q.x)
+                                if (s != s) s = -INFINITY;
+                                if (gi == sm_self[r]) s = -INFINITY;  // j != i, clustering.rs:123
+                            }
+                            if (gi >= A.n) s = -INFINITY;
+                            if (u == 0) sv.x = s; else sv.y = s;
+                        }
+                        *reinterpret_cast<double2 *>(&S[r * SPITCH + j * 8 + tig * 2]) = sv;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int qq = 0; qq < TQ / 8; ++qq) {
+                const int q = warp * (TQ / 8) + qq;
+                if (q0 + q >= A.nq) break;
+                int len = list_len[q];
+                double thr = (len == k) ? list_s[(size_t)q * k + k - 1] : -INFINITY;
+                bool full = (len == k);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double s = S[q * SPITCH + e * 32 + lane];
+                    const int li = (int)(i0 - t_begin * TN) + half * 64 + e * 32 + lane;  // index inside slab
+                    // survivors: strictly better than the current k-th (later index loses ties)
+                    unsigned mask = __ballot_sync(0xffffffffu, full ? (s > thr) : (s > -INFINITY));
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const double cs = __shfl_sync(0xffffffffu, s, src);
+                        const int ci = __shfl_sync(0xffffffffu, li, src);
+                        // position = number of entries with score >= cs (sorted descending)
+                        int cnt = 0;
+                        double e0s = 0.0, e1s = 0.0;
+                        int e0i = 0, e1i = 0;
+                        const int p0 = lane, p1 = lane + 32;
+                        if (p0 < len) {
+                            e0s = list_s[(size_t)q * k + p0];
+                            e0i = list_i[(size_t)q * k + p0];
+                        }
+                        if (p1 < len) {
+                            e1s = list_s[(size_t)q * k + p1];
+                            e1i = list_i[(size_t)q * k + p1];
+                        }
+                        cnt = __popc(__ballot_sync(0xffffffffu, p0 < len && e0s >= cs)) +
+                              __popc(__ballot_sync(0xffffffffu, p1 < len && e1s >= cs));
+                        __syncwarp();
+                        if (p0 >= cnt && p0 < len && p0 + 1 < k) {
+                            list_s[(size_t)q * k + p0 + 1] = e0s;
+                            list_i[(size_t)q * k + p0 + 1] = e0i;
+                        }
+                        if (p1 >= cnt && p1 < len && p1 + 1 < k) {
+                            list_s[(size_t)q * k + p1 + 1] = e1s;
+                            list_i[(size_t)q * k + p1 + 1] = e1i;
+                        }
+                        if (lane == 0 && cnt < k) {
+                            list_s[(size_t)q * k + cnt] = cs;
+                            list_i[(size_t)q * k + cnt] = ci;
+                        }
+                        if (len < k) len++;
+                        __syncwarp();
+                        full = (len == k);
+                        if (full) {
+                            thr = list_s[(size_t)q * k + k - 1];
+                            mask &= __ballot_sync(0xffffffffu, s > thr);
+                        }
+                    }
+                }
+                if (lane == 0) list_len[q] = len;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // ---- write this slab's lists
+    for (int c = tid; c < TQ * k; c += kThreads) {
+        const int q = c / k, p = c % k;
+        const long long gq = q0 + q;
+        if (gq >= A.nq) continue;
+        const bool ok = p < list_len[q];
+        const size_t o = ((size_t)slab * A.nq + gq) * k + p;
+        A.part_score[o] = ok ? list_s[(size_t)q * k + p] : -INFINITY;
+        A.part_idx[o] = ok ? list_i[(size_t)q * k + p] + (int)(t_begin * TN) : -1;
+    }
+}
+
+// One warp per query: k-way merge of `parts` lists by (score desc, index asc).
+template <typename IdxT>
+__global__ void __launch_bounds__(256) topk_merge_kernel(const double *__restrict__ in_score,
+                                                         const IdxT *__restrict__ in_idx, int parts,
+                                                         long long nq, int k, long long index_offset,
+                                                         int negate_sqrt, double *__restrict__ out_score,
+                                                         long long *__restrict__ out_idx,
+                                                         long long *__restrict__ out_count) {
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    // each part list is sorted: keep a cursor per part (parts <= 32*4 handled in strides)
+    // simple selection: k rounds of warp arg-best over all candidates not yet taken.
+    const int total = parts * k;
+    int taken = 0;
+    double last_s = INFINITY;
+    long long last_i = -1;
+    for (int r = 0; r < k; ++r) {
+        double bs = -INFINITY;
+        long long bi = -1;
+        for (int c = lane; c < total; c += 32) {
+            const int p = c / k, e = c % k;
+            const size_t o = ((size_t)p * nq + q) * k + e;
+            const long long ii = (long long)in_idx[o];
+            if (ii < 0) continue;
+            const double s = in_score[o];
+            // candidate must come strictly after (last_s, last_i) in (score desc, idx asc) order
+            const bool after = (s < last_s) || (s == last_s && ii > last_i);
+            if (!after) continue;
+            if (bi < 0 || s > bs || (s == bs && ii < bi)) {
+                bs = s;
+                bi = ii;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+                bs = os;
+                bi = oi;
+            }
+        }
+        if (bi < 0) break;
+        if (lane == 0) {
+            out_score[q * k + r] = negate_sqrt ? sqrt(fmax(-bs, 0.0)) : bs;
+            out_idx[q * k + r] = bi + index_offset;
+        }
+        last_s = bs;
+        last_i = bi;
+        taken++;
+    }
+    if (lane == 0) {
+        for (int r = taken; r < k; ++r) {
+            out_score[q * k + r] = negate_sqrt ? INFINITY : -INFINITY;
+            out_idx[q * k + r] = -1;
+        }
+        if (out_count) out_count[q] = taken;
+    }
+}
+
+// Two-NN rescoring: exact direct-form distances for the 4 GEMM-form candidates of each sample
+// (src/clustering.rs:125-130), two smallest -> d1, d2.  One warp per sample.
+__global__ void __launch_bounds__(128) twonn_rescore_kernel(const double *__restrict__ rows, long long n, int f,
+                                                            const long long *__restrict__ sample,
+                                                            const long long *__restrict__ cand_idx, int ncand,
+                                                            long long s, double *__restrict__ d1,
+                                                            double *__restrict__ d2) {
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= s) return;
+    const double *ri = rows + sample[w] * (long long)f;
+    double m1 = INFINITY, m2 = INFINITY;
+    for (int c = 0; c < ncand; ++c) {
+        const long long j = cand_idx[w * ncand + c];
+        if (j < 0) continue;
+        const double *rj = rows + j * (long long)f;
+        double acc = 0.0;
+        for (int t = lane; t < f; t += 32) {
+            const double df = ri[t] - rj[t];
+            acc = fma(df, df, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double d = sqrt(acc);
+        if (d < m1) {
+            m2 = m1;
+            m1 = d;
+        } else if (d < m2) {
+            m2 = d;
+        }
+    }
+    if (lane == 0) {
+        d1[w] = m1;
+        d2[w] = m2;
+    }
+}
+
+size_t search_smem_bytes(int k) {
+    size_t b = (size_t)2 * STAGE_DOUBLES * 8;     // stages (S aliases)
+    b += (size_t)(2 * TQ + 2 * TN) * 8;           // nq, lq, nx, lx
+    b += (size_t)TQ * k * 8 + (size_t)TQ * k * 4; // lists
+    b += (size_t)TQ * 4;                          // len
+    b = (b + 7) & ~(size_t)7;
+    b += (size_t)TQ * 8;                          // self idx
+    return b + 16;
+}
+
+template <int MODE>
+int launch_search(asb_ctx *ctx, SearchArgs &A, int *nslabs_out) {
+    const long long qtiles = (A.nq + TQ - 1) / TQ;
+    const long long ntiles = (A.n + TN - 1) / TN;
+    // enough (query tile, slab) units for ~8 waves over the SMs, each slab >= 4 tiles
+    long long want = ((long long)ctx->sm_count * 8 + qtiles - 1) / qtiles;
+    long long max_slabs = (ntiles + 3) / 4;
+    if (want > max_slabs) want = max_slabs;
+    if (want < 1) want = 1;
+    if (want > 4096) want = 4096;
+    long long tps = (ntiles + want - 1) / want;
+    int nslabs = (int)((ntiles + tps - 1) / tps);
+    A.nslabs = nslabs;
+    A.tiles_per_slab = tps;
+    *nslabs_out = nslabs;
+    return ASB_OK;
+}
+
+}  // namespace
+
+static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_offset, int64_t *idx_d,
+                      double *score_d, int64_t *count_d) {
+    const int k = A.k;
+    if (k < 1 || k > 64) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: k=%d outside 1..64", k);
+    if (A.n > 0x7fffff00ll) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: shard larger than 2^31 items");
+    int nslabs = 1;
+    if (mode == MODE_COSINE) launch_search<MODE_COSINE>(ctx, A, &nslabs);
+    else launch_search<MODE_L2>(ctx, A, &nslabs);
+    DevTmp<double> part_s;
+    DevTmp<int> part_i;
+    ASB_TRY(part_s.init(ctx, (size_t)nslabs * A.nq * k));
+    ASB_TRY(part_i.init(ctx, (size_t)nslabs * A.nq * k));
+    A.part_score = part_s.ptr;
+    A.part_idx = part_i.ptr;
+    const size_t smem = search_smem_bytes(k);
+    const bool vec = (A.f % 2 == 0) && (((uintptr_t)A.items & 15) == 0) && (((uintptr_t)A.queries & 15) == 0);
+    dim3 grid((unsigned)((A.nq + TQ - 1) / TQ), (unsigned)nslabs);
+#define LAUNCH(M, V)                                                                                        \
+    do {                                                                                                    \
+        ASB_CUDA(ctx, cudaFuncSetAttribute(search_kernel<M, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem));                                                    \
+        search_kernel<M, V><<<grid, kThreads, smem, ctx->stream>>>(A);                                      \
+    } while (0)
+    if (mode == MODE_COSINE) {
+        if (vec) LAUNCH(MODE_COSINE, true); else LAUNCH(MODE_COSINE, false);
+    } else {
+        if (vec) LAUNCH(MODE_L2, true); else LAUNCH(MODE_L2, false);
+    }
+#undef LAUNCH
+    ASB_TRY(asb_check_launch(ctx, "search_kernel"));
+    const int wpb = 8;
+    topk_merge_kernel<int><<<(unsigned)((A.nq + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        part_s.ptr, part_i.ptr, nslabs, A.nq, k, index_offset, mode == MODE_L2 ? 1 : 0, score_d,
+        (long long *)idx_d, (long long *)count_d);
+    ASB_TRY(asb_check_launch(ctx, "topk_merge_kernel"));
+    return ASB_OK;
+}
+
+int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,
+                   int64_t n, int64_t f, const double *queries_d, const double *lambda_q_d, int64_t nq,
+                   int64_t k, double alpha, int64_t index_offset, int64_t *idx_d, double *score_d,
+                   int64_t *count_d, int *status_d) {
+    if (n <= 0 || f <= 0 || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search: empty input");
+    DevTmp<double> qn2, xn2;
+    ASB_TRY(qn2.init(ctx, (size_t)nq));
+    ASB_TRY(asb_dev_norms2(ctx, queries_d, nq, f, qn2.ptr));
+    if (!norms2_d) {
+        ASB_TRY(xn2.init(ctx, (size_t)n));
+        ASB_TRY(asb_dev_norms2(ctx, items_d, n, f, xn2.ptr));
+        norms2_d = xn2.ptr;
+    }
+    SearchArgs A{};
+    A.items = items_d;
+    A.lambdas = lambdas_d;
+    A.norms2 = norms2_d;
+    A.queries = queries_d;
+    A.lambda_q = lambda_q_d;
+    A.qnorms2 = qn2.ptr;
+    A.self_idx = nullptr;
+    A.n = n;
+    A.nq = nq;
+    A.f = (int)f;
+    A.k = (int)(k < n ? k : n);
+    A.alpha = alpha;
+    A.status = status_d;
+    // lists are k_eff wide; outputs are k wide: merge writes k_eff columns, pad the rest
+    if (A.k != k) {
+        // k > n: run with k_eff = n into temporaries, then scatter into the k-wide outputs
+        DevTmp<double> ts;
+        DevTmp<int64_t> ti;
+        ASB_TRY(ts.init(ctx, (size_t)nq * A.k));
+        ASB_TRY(ti.init(ctx, (size_t)nq * A.k));
+        ASB_TRY(run_search(ctx, MODE_COSINE, A, index_offset, ti.ptr, ts.ptr, count_d));
+        ASB_CUDA(ctx, cudaMemsetAsync(idx_d, 0xff, (size_t)nq * k * sizeof(int64_t), ctx->stream));
+        ASB_CUDA(ctx, cudaMemsetAsync(score_d, 0, (size_t)nq * k * sizeof(double), ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpy2DAsync(idx_d, k * sizeof(int64_t), ti.ptr, A.k * sizeof(int64_t),
+                                        A.k * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpy2DAsync(score_d, k * sizeof(double), ts.ptr, A.k * sizeof(double),
+                                        A.k * sizeof(double), nq, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ASB_OK;
+    }
+    return run_search(ctx, MODE_COSINE, A, index_offset, idx_d, score_d, count_d);
+}
+
+int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, const int64_t *sample_d, int64_t s,
+                  double *d1_d, double *d2_d) {
+    if (n < 2 || f <= 0 || s <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn: n=%lld s=%lld", (long long)n, (long long)s);
+    // gather the sample rows (they are the "queries" of the contraction)
+    DevTmp<double> q, qn2, xn2, cs;
+    DevTmp<int64_t> ci, cc;
+    DevTmp<int> status;
+    ASB_TRY(q.init(ctx, (size_t)s * f));
+    ASB_TRY(qn2.init(ctx, (size_t)s));
+    ASB_TRY(xn2.init(ctx, (size_t)n));
+    const int ncand = (int)(n - 1 < 4 ? n - 1 : 4);
+    ASB_TRY(cs.init(ctx, (size_t)s * ncand));
+    ASB_TRY(ci.init(ctx, (size_t)s * ncand));
+    ASB_TRY(cc.init(ctx, (size_t)s));
+    ASB_TRY(status.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
+    std::vector<int64_t> hs((size_t)s);
+    ASB_CUDA(ctx, cudaMemcpyAsync(hs.data(), sample_d, s * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t t = 0; t < s; ++t) {
+        if (hs[t] < 0 || hs[t] >= n) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn: sample index %lld out of range", (long long)hs[t]);
+        ASB_CUDA(ctx, cudaMemcpyAsync(q.ptr + t * f, rows_d + hs[t] * f, f * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ASB_TRY(asb_dev_norms2(ctx, q.ptr, s, f, qn2.ptr));
+    ASB_TRY(asb_dev_norms2(ctx, rows_d, n, f, xn2.ptr));
+    SearchArgs A{};
+    A.items = rows_d;
+    A.norms2 = xn2.ptr;
+    A.queries = q.ptr;
+    A.qnorms2 = qn2.ptr;
+    A.self_idx = (const long long *)sample_d;
+    A.n = n;
+    A.nq = s;
+    A.f = (int)f;
+    A.k = ncand;
+    A.alpha = 0.0;
+    A.status = status.ptr;
+    ASB_TRY(run_search(ctx, MODE_L2, A, 0, ci.ptr, cs.ptr, cc.ptr));
+    const int wpb = 4;
+    twonn_rescore_kernel<<<(unsigned)((s + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        rows_d, (long long)n, (int)f, (const long long *)sample_d, (const long long *)ci.ptr, ncand, (long long)s,
+        d1_d, d2_d);
+    return asb_check_launch(ctx, "twonn_rescore_kernel");
+}
+
+int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in_idx_d, int64_t parts, int64_t nq,
+                       int64_t k, double *out_score_d, int64_t *out_idx_d, int64_t *out_count_d) {
+    if (parts < 1 || nq < 1 || k < 1) ASB_FAIL(ctx, ASB_ERR_INVALID, "topk_merge: bad sizes");
+    const int wpb = 8;
+    topk_merge_kernel<long long><<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        in_score_d, (const long long *)in_idx_d, (int)parts, (long long)nq, (int)k, 0, 0, out_score_d,
+        (long long *)out_idx_d, (long long *)out_count_d);
+    return asb_check_launch(ctx, "topk_merge_kernel");
+}

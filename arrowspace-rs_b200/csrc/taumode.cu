@@ -165,6 +165,10 @@ taumode_kernel(const double *__restrict__ items, long long n, int f,
         double v_rb = 0.0, v_ra = 0.0;
         for (int iter = 0;; ++iter) {
             if (!__syncthreads_or(!done)) break;
+            if (iter > 200 && !done) {  // cannot happen (bisection bounds the passes); never hang the GPU
+                done = true;
+                tau = __longlong_as_double(0x7ff8000000000000ll);
+            }
             double pv = 0.0;
             if (!done) {
                 const double lo_f = (lo == -INFINITY) ? vmin : lo;

@@ -98,6 +98,9 @@ int64_t asb_kernel_launches(asb_ctx *ctx);
 /* device time of the most recent top-level call's dominant kernel(s), ms, measured with
  * CUDA events on the context's stream (0 if none). */
 double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
+/* debug / test switches.  "cluster_force_exact" (0|1): take every clustering decision from the
+ * reference-arithmetic path instead of the certified fast path (results are identical). */
+int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
 
 /* ---- stage 1: clustering ------------------------------------------------------------ */
 /* Two-NN scan: replaces the distance pass of estimate_intrinsic_dimension
@@ -182,6 +185,12 @@ int asb_index_laplacian(asb_ctx *ctx, const asb_index *index, int64_t *indptr,
 int asb_index_search(asb_ctx *ctx, const asb_index *index, const double *queries, int64_t nq,
                      int64_t k, double alpha, int64_t *idx, double *score, int64_t *count,
                      double *lambda_q_out);
+
+/* ArrowSpace::search_lambda_aware (src/core.rs:760-798) against the resident index with
+ * caller-prepared query lambdas (the reference's two-step prepare_query_item + search). */
+int asb_index_search_lambda_aware(asb_ctx *ctx, const asb_index *index, const double *queries,
+                                  const double *lambda_q, int64_t nq, int64_t k, double alpha,
+                                  int64_t *idx, double *score, int64_t *count);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,80 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, and refuses to run without a GPU (no CPU fallback).  No compute calls here."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    hdr = (ROOT / "include" / "arrowspace_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(asb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported(asb):
+    lib = asb.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/arrowspace_b200.h but not exported"
+
+
+def test_python_binding_covers_header(asb):
+    assert sorted(asb.ABI_SYMBOLS) == _declared_symbols()
+
+
+def test_struct_layouts(asb):
+    # POD structs must match the C layout (8-byte aligned doubles / int64)
+    assert ctypes.sizeof(asb.host.GraphParamsC) == 64
+    assert ctypes.sizeof(asb.host.BuildParamsC) == 64 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(asb.host.IndexInfoC) == 13 * 8
+
+
+def test_status_strings(asb):
+    lib = asb.load_library()
+    assert lib.asb_status_string(0) == b"ok"
+    assert b"Lambda of the item is 0.0" in lib.asb_status_string(5)   # core.rs:773-776 message
+    assert b"invalid values (NaN or infinity)" in lib.asb_status_string(4)  # core.rs:534-537
+    assert lib.asb_laplacian_max_nnz(384, 4) == 384 * 11
+
+
+def test_no_cpu_fallback(asb):
+    """Without a GPU the product path fails loudly instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(asb.ArrowSpaceError) as ei:
+        asb.Context(0)
+    assert ei.value.status == 2
+
+
+def test_product_does_not_reference_oracle():
+    """The shipped package must not import / link the oracle."""
+    pkg = ROOT / "arrowspace-rs_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        txt = p.read_text()
+        if p.name == "_build.py":
+            continue  # builds the checker, never loads it
+        assert "arrowspace_oracle" not in txt and "oracle_binding" not in txt, p
+
+
+def test_builder_defaults_and_define_result_k(asb):
+    """Defaults of src/builder.rs:59-91 and define_result_k (:225-233); no GPU needed."""
+    b = asb.ArrowSpaceBuilder.__new__(asb.ArrowSpaceBuilder)
+    asb.ArrowSpaceBuilder.__init__(b, ctx=object())
+    assert (b.lambda_eps, b.lambda_k, b.lambda_topk, b.lambda_p, b.lambda_sigma) == (1e-3, 6, 3, 2.0, None)
+    assert b.normalise is False and b.sparsity_check is False and b.use_dims_reduction is False
+    assert b.synthesis == asb.TauMode.Median and b.deterministic_clustering is False
+    b.define_result_k()
+    assert b.lambda_topk == 4            # k=6 < 10
+    b.with_lambda_graph(0.5, 5, 9, 2.0, None).define_result_k()
+    assert b.lambda_topk == 3            # k<=5
+    b.with_lambda_graph(0.5, 12, 7, 2.0, 0.25).define_result_k()
+    assert b.lambda_topk == 7            # k>=10 leaves topk alone
+    b.with_seed(7)
+    assert b.deterministic_clustering and b.clustering_seed == 7
+    assert str(asb.TauMode.Percentile(0.25)) == "Percentile(0.25)" and str(asb.TauMode.Median) == "Median"

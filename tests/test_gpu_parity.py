@@ -1,0 +1,461 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): CSR indptr/indices and top-k id lists
+bit-exact (score gaps < 1e-9 excepted), cluster outputs bit-exact, lambda within 1e-9 relative.
+All tests here need a B200: ``pytest -m gpu``."""
+import numpy as np
+import pytest
+
+from oracle_binding import TAU_FIXED, TAU_MEAN, TAU_MEDIAN, TAU_PERCENTILE
+
+pytestmark = pytest.mark.gpu
+
+LAMBDA_RTOL = 1e-9      # north_star: lambda-tau within 1e-9 relative in f64
+SCORE_GAP = 1e-9        # top-k ids may differ only where the score gap is below this
+
+
+def _tm(asb, mode, value=0.0):
+    return asb.TauMode(mode, value)
+
+
+def _assert_lambda_close(got, want, rtol=LAMBDA_RTOL):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w)
+    ok = ~nan_w
+    err = np.abs(got[ok] - want[ok])
+    tol = rtol * np.maximum(np.abs(want[ok]), 1e-300) + 1e-15
+    bad = err > tol
+    assert not bad.any(), f"max rel err {np.max(err / np.maximum(np.abs(want[ok]), 1e-300))}"
+
+
+def _graph(oracle, cent, **kw):
+    p = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    p.update(kw)
+    return oracle.feature_laplacian(cent, **p)
+
+
+# =============================================================================== taumode (K5-K7)
+@pytest.mark.parametrize("mode,value", [(TAU_MEDIAN, 0.0), (TAU_MEAN, 0.0), (TAU_PERCENTILE, 0.25),
+                                        (TAU_PERCENTILE, 0.9), (TAU_FIXED, 0.3), (TAU_FIXED, -1.0)])
+def test_taumode_proteins(ctx, asb, oracle, golden, mode, value):
+    db = golden["proteins"]
+    csr = _graph(oracle, db[:20])
+    want = oracle.compute_taumode(db, csr, mode, value)
+    lam, n2, stats = ctx.compute_taumode(db, csr, _tm(asb, mode, value), want_norms=True)
+    _assert_lambda_close(lam, want)
+    assert np.allclose(n2, (db * db).sum(1), rtol=1e-14)
+    assert np.isclose(stats[0], want.min(), rtol=1e-9) and np.isclose(stats[1], want.max(), rtol=1e-9)
+    assert np.isclose(stats[2], want.sum(), rtol=1e-9)
+    assert want.std() > 0 and np.all((want >= 0) & (want <= 1))   # tests/test_taumode.rs:162-315
+
+
+def test_taumode_quora_odd_and_even_lengths(ctx, asb, oracle, golden):
+    q = golden["quora"]                                  # 15 x 384, signed values -> many taus hit the floor
+    csr = _graph(oracle, np.abs(q), eps=0.9, topk=6)
+    for mode, value in [(TAU_MEDIAN, 0.0), (TAU_MEAN, 0.0), (TAU_PERCENTILE, 0.5)]:
+        for data in (q, np.abs(q)):
+            want = oracle.compute_taumode(data, csr, mode, value)
+            lam, _, _ = ctx.compute_taumode(data, csr, _tm(asb, mode, value))
+            _assert_lambda_close(lam, want)
+    # odd feature count (F=383): median takes the single middle element
+    qo = np.ascontiguousarray(np.abs(q[:, :383]))
+    csr_o = _graph(oracle, qo, eps=0.9, topk=6)
+    want = oracle.compute_taumode(qo, csr_o, TAU_MEDIAN)
+    lam, _, _ = ctx.compute_taumode(qo, csr_o, _tm(asb, TAU_MEDIAN))
+    _assert_lambda_close(lam, want)
+
+
+def test_taumode_tau_selection_exact(ctx, asb, oracle):
+    """With L = I the synthetic lambda is tau/(1+tau): isolates select_tau (taumode.rs:87-127),
+    including duplicates, negative values (floor) and every rank of Percentile."""
+    rng = np.random.RandomState(3)
+    f = 37
+    eye = (np.arange(f + 1, dtype=np.int64), np.arange(f, dtype=np.int64), np.ones(f))
+    rows = [rng.rand(f), np.round(rng.rand(f) * 4) / 4, np.full(f, 0.5), -rng.rand(f), rng.randn(f),
+            np.concatenate([np.zeros(20), rng.rand(17)]), rng.rand(f) * 1e-12, rng.rand(f) * 1e6]
+    x = np.ascontiguousarray(np.vstack(rows))
+    for mode, value in [(TAU_MEDIAN, 0)] + [(TAU_PERCENTILE, p) for p in np.linspace(0, 1, 13)] + [(TAU_MEAN, 0)]:
+        want = oracle.compute_taumode(x, eye, mode, float(value))
+        lam, _, _ = ctx.compute_taumode(x, eye, _tm(asb, mode, float(value)))
+        assert np.allclose(lam, want, rtol=1e-14, atol=0), (mode, value)
+    xe = np.ascontiguousarray(x[:, :36])                 # even length -> 0.5*(a+b)
+    eye_e = (np.arange(37, dtype=np.int64), np.arange(36, dtype=np.int64), np.ones(36))
+    want = oracle.compute_taumode(xe, eye_e, TAU_MEDIAN)
+    lam, _, _ = ctx.compute_taumode(xe, eye_e, _tm(asb, TAU_MEDIAN))
+    assert np.allclose(lam, want, rtol=1e-14, atol=0)
+
+
+def test_taumode_nonfinite_items(ctx, asb, oracle, golden):
+    db = golden["proteins"].copy()
+    csr = _graph(oracle, db[:20])
+    db[5, 3] = np.nan
+    db[9, 0] = np.inf
+    want = oracle.compute_taumode(db, csr, TAU_MEDIAN)
+    lam, _, _ = ctx.compute_taumode(db, csr, _tm(asb, TAU_MEDIAN))
+    _assert_lambda_close(lam, want)
+
+
+@pytest.mark.parametrize("n,f", [(10_000, 128), (4_097, 384), (777, 1024), (300, 2000)])
+def test_taumode_synthetic(ctx, asb, oracle, n, f):
+    x = asb.synth.protein_like(n, f, seed=42)
+    cent, _, _ = oracle.cluster_incremental(x[:2000], min(64, n // 10), 1.5 * f * 0.0025 * 2)
+    csr = _graph(oracle, cent)
+    assert csr[0][-1] > f, "graph must be non-degenerate"
+    want = oracle.compute_taumode(x, csr, TAU_MEDIAN)
+    lam, _, _ = ctx.compute_taumode(x, csr, _tm(asb, TAU_MEDIAN))
+    _assert_lambda_close(lam, want)
+    assert np.all(np.isfinite(want)) and want.std() > 0
+
+
+def test_prepare_query_item(ctx, asb, oracle, golden):
+    db = golden["proteins"]
+    csr = _graph(oracle, db[:20])
+    aspace = asb.ArrowSpace(db, asb.TauMode.Median, ctx)
+    gl = asb.GraphLaplacian(*csr, nnodes=64, graph_params=None)
+    q = db[3] * 1.02
+    want = oracle.prepare_query_item(q, csr, TAU_MEDIAN)
+    got = aspace.prepare_query_item(q, gl)
+    assert abs(got - want) <= LAMBDA_RTOL * abs(want)
+    assert abs(aspace.prepare_query_item(q, gl) - got) <= 1e-10 * abs(got)   # tests/test_querying_proj.rs:161-169
+    bad = q.copy()
+    bad[2] = np.nan
+    with pytest.raises(asb.ArrowSpaceError) as ei:       # tests/test_querying_proj.rs:261-291
+        aspace.prepare_query_item(bad, gl)
+    assert ei.value.status == 4
+    with pytest.raises(asb.ArrowSpaceError) as ei:       # wrong dimension, core.rs:510-516
+        aspace.prepare_query_item(q[:10], gl)
+    assert ei.value.status == 12
+
+
+# ================================================================================== search (K8)
+def _assert_topk_equal(idx, score, count, widx, wscore, wcount):
+    idx, score, count = np.asarray(idx), np.asarray(score), np.asarray(count)
+    assert np.array_equal(count, wcount)
+    for q in range(idx.shape[0]):
+        c = int(count[q])
+        assert np.allclose(score[q, :c], wscore[q, :c], rtol=0, atol=1e-12), q
+        if not np.array_equal(idx[q, :c], widx[q, :c]):
+            for r in np.nonzero(idx[q, :c] != widx[q, :c])[0]:
+                # allowed only inside a group of scores closer than SCORE_GAP
+                near = np.abs(wscore[q, :c] - wscore[q, r]) < SCORE_GAP
+                assert near.sum() > 1 and idx[q, r] in widx[q, :c][near], (q, r)
+
+
+def test_search_paper_answer(ctx, asb, oracle, golden):
+    """paper.md:123-133 / examples/01_compare_cosine.rs:1 through the GPU path."""
+    db = golden["proteins"]
+    aspace = asb.ArrowSpace(db, asb.TauMode.Median, ctx)
+    aspace.lambdas = np.full(64, 0.25)
+    res = aspace.search_lambda_aware(asb.ArrowItem.new(db[3] * 1.02, 0.3), 3, 1.0)
+    assert [i for i, _ in res] == [3, 6, 0]
+    for (_, s), want in zip(res, (1.000000, 0.999573, 0.999325)):
+        assert abs(s - want) < 5e-7
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.9, 0.7, 0.0])
+@pytest.mark.parametrize("k", [1, 3, 10, 33, 64])
+def test_search_proteins_parity(ctx, asb, oracle, golden, alpha, k):
+    db = golden["proteins"]
+    csr = _graph(oracle, db[:20])
+    lam = oracle.compute_taumode(db, csr, TAU_MEDIAN)
+    queries = np.ascontiguousarray(db[[3, 10, 40, 63]] * 1.02)
+    lq = np.array([oracle.prepare_query_item(q, csr, TAU_MEDIAN) for q in queries])
+    want = oracle.search_lambda_aware_batch(db, lam, queries, lq, k, alpha)
+    got = ctx.search_lambda_aware_batch(db, lam, queries, lq, k, alpha)
+    _assert_topk_equal(*got, *want)
+
+
+@pytest.mark.parametrize("n,f,nq", [(10_000, 128, 100), (5_001, 384, 33), (3_000, 25, 7), (200, 770, 130)])
+def test_search_synthetic_parity(ctx, asb, oracle, n, f, nq):
+    x = asb.synth.protein_like(n, f, seed=42)
+    cent, _, _ = oracle.cluster_incremental(x[:2000], 50, 1.5 * f * 0.0025 * 2)
+    csr = _graph(oracle, cent)
+    lam = oracle.compute_taumode(x, csr, TAU_MEDIAN)
+    queries, _ = asb.synth.queries_from_items(x, nq, seed=43)
+    lq = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq, 10, 0.7)
+    got = ctx.search_lambda_aware_batch(x, lam, queries, lq, 10, 0.7)
+    _assert_topk_equal(*got, *want)
+    idx, score, _ = got
+    assert np.all(np.diff(np.asarray(score), axis=1) <= 0)       # descending, test_querying_proj.rs:369-399
+    assert np.all((np.asarray(idx) >= 0) & (np.asarray(idx) < n))
+
+
+def test_search_ties_and_edges(ctx, asb, oracle, golden):
+    db = golden["proteins"]
+    dup = np.ascontiguousarray(np.vstack([db[:8]] * 40))          # 320 rows, every row 40 times
+    lam = np.full(320, 0.5)
+    q = np.ascontiguousarray(db[[2, 5]])
+    lq = np.array([0.5, 0.4])
+    for k in (1, 7, 41, 64):
+        want = oracle.search_lambda_aware_batch(dup, lam, q, lq, k, 0.7)
+        got = ctx.search_lambda_aware_batch(dup, lam, q, lq, k, 0.7)
+        assert np.array_equal(np.asarray(got[0])[:, :k], want[0][:, :k])   # exact ties -> lower index first
+    # k >= N returns all N (core.rs:786); k == 0 returns nothing
+    idx, score, count = ctx.search_lambda_aware_batch(db[:5], np.full(5, 0.3), q, lq, 64, 0.7)
+    assert count.tolist() == [5, 5]
+    want = oracle.search_lambda_aware_batch(db[:5], np.full(5, 0.3), q, lq, 64, 0.7)
+    assert np.array_equal(np.asarray(idx)[:, :5], want[0][:, :5])
+    _, _, count = ctx.search_lambda_aware_batch(db, np.full(64, 0.3), q, lq, 0, 0.7)
+    assert count.tolist() == [0, 0]
+    with pytest.raises(asb.ArrowSpaceError) as ei:                # core.rs:773-776
+        ctx.search_lambda_aware_batch(db, np.full(64, 0.3), q, np.array([0.5, 0.0]), 3, 0.7)
+    assert ei.value.status == 5
+    bad = db.copy()
+    bad[7, 7] = np.nan
+    with pytest.raises(asb.ArrowSpaceError) as ei:                # core.rs:785 unwrap on NaN
+        ctx.search_lambda_aware_batch(bad, np.full(64, 0.3), q, lq, 3, 0.7)
+    assert ei.value.status == 9
+    zero = db.copy()
+    zero[4] = 0.0                                                 # zero vector -> cosine 0 (core.rs:231-236)
+    want = oracle.search_lambda_aware_batch(zero, np.full(64, 0.3), q, lq, 64, 0.7)
+    got = ctx.search_lambda_aware_batch(zero, np.full(64, 0.3), q, lq, 64, 0.7)
+    _assert_topk_equal(*got, *want)
+
+
+def test_topk_merge_matches_single_shard(ctx, asb, oracle):
+    x = asb.synth.protein_like(4_000, 64, seed=5)
+    lam = np.linspace(0.1, 0.9, 4_000)
+    queries, _ = asb.synth.queries_from_items(x, 20, seed=6)
+    lq = np.full(20, 0.5)
+    k = 10
+    full = ctx.search_lambda_aware_batch(x, lam, queries, lq, k, 0.7)
+    parts_s, parts_i = [], []
+    bounds = [0, 1000, 1001, 2500, 4000]                          # ragged shards incl. a 1-row shard
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        i, s, c = ctx.search_lambda_aware_batch(np.ascontiguousarray(x[a:b]), lam[a:b], queries, lq, k, 0.7,
+                                                index_offset=a)
+        i, s = np.asarray(i).copy(), np.asarray(s).copy()
+        for q in range(20):
+            i[q, int(c[q]):] = -1
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi, mc = ctx.topk_merge(np.stack(parts_s), np.stack(parts_i), len(parts_s), 20, k)
+    assert np.array_equal(mi, np.asarray(full[0])) and np.array_equal(ms, np.asarray(full[1]))
+    assert mc.tolist() == [k] * 20
+
+
+# ============================================================================== Laplacian (K3+K4)
+def _assert_csr_equal(got, want):
+    gip, gii, gdd = got
+    wip, wii, wdd = want
+    assert np.array_equal(gip, wip), "indptr must be bit-exact"
+    assert np.array_equal(gii, wii), "indices must be bit-exact"
+    assert np.allclose(gdd, wdd, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(eps=0.2, topk=3), dict(eps=1.0, topk=7, sigma=None),
+                                dict(self_included=True), dict(rectified=True), dict(p=1.5, sigma=0.1),
+                                dict(eps=1e-3, topk=4, sigma=None)])
+def test_laplacian_proteins(ctx, asb, oracle, golden, kw):
+    cent = golden["proteins"][:20]
+    p = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    p.update(kw)
+    want = oracle.feature_laplacian(cent, **p)
+    gp = asb.GraphParams(p["eps"], p["k"], p["topk"], p["p"], p["sigma"], self_included=p.get("self_included", False),
+                         rectified=p.get("rectified", False))
+    got = ctx.build_feature_laplacian(cent, gp)
+    _assert_csr_equal(got, want)
+
+
+@pytest.mark.parametrize("x,f,topk,k", [(100, 128, 4, 12), (316, 384, 4, 12), (200, 1024, 12, 20), (40, 33, 3, 6)])
+def test_laplacian_synthetic(ctx, asb, oracle, x, f, topk, k):
+    rows = asb.synth.protein_like(4000, f, seed=11)
+    cent, _, _ = oracle.cluster_incremental(rows, x, 1.5 * f * 0.0025 * 2)
+    want = oracle.feature_laplacian(cent, eps=0.5, k=k, topk=topk, p=2.0, sigma=0.25)
+    got = ctx.build_feature_laplacian(cent, asb.GraphParams(0.5, k, topk, 2.0, 0.25))
+    _assert_csr_equal(got, want)
+    ip, ii, dd = got
+    dense = np.zeros((f, f))
+    for r in range(f):
+        dense[r, ii[ip[r]:ip[r + 1]]] = dd[ip[r]:ip[r + 1]]
+    assert np.array_equal(dense, dense.T) and np.all(np.abs(dense.sum(1)) < 1e-12)   # test_laplacian.rs:51-152
+
+
+def test_laplacian_inline_sparsification(ctx, asb, oracle):
+    """mean degree > 10 -> keep the top half by w*sqrt(deg_i*deg_j) (laplacian.rs:229-280)."""
+    rows = asb.synth.protein_like(3000, 256, seed=12)
+    cent, _, _ = oracle.cluster_incremental(rows, 64, 1.5 * 256 * 0.0025 * 2)
+    want = oracle.feature_laplacian(cent, eps=1.0, k=20, topk=14, p=2.0, sigma=0.25)
+    got = ctx.build_feature_laplacian(cent, asb.GraphParams(1.0, 20, 14, 2.0, 0.25))
+    _assert_csr_equal(got, want)
+    assert want[0][-1] < 256 * (1 + 2 * 15) * 0.8            # sparsification really happened
+
+
+def test_laplacian_errors(ctx, asb, golden):
+    gp = asb.GraphParams(0.5, 6, 3, 2.0, None)
+    with pytest.raises(asb.ArrowSpaceError) as ei:               # laplacian.rs:129-134
+        ctx.build_feature_laplacian(golden["proteins"][:1], gp)
+    assert ei.value.status == 6
+    with pytest.raises(asb.ArrowSpaceError) as ei:               # graph.rs:185-193
+        ctx.build_feature_laplacian(golden["quora"], asb.GraphParams(1e-9, 6, 3, 2.0, None, sparsity_check=True))
+    assert ei.value.status == 7
+    z = golden["proteins"][:10].copy()
+    z[:, 5] = 0.0
+    with pytest.raises(asb.ArrowSpaceError) as ei:               # zero-magnitude feature column
+        ctx.build_feature_laplacian(z, gp)
+    assert ei.value.status == 10
+    with pytest.raises(asb.ArrowSpaceError) as ei:               # StandardScaler path stays on the host
+        ctx.build_feature_laplacian(golden["proteins"][:10], asb.GraphParams(0.5, 6, 3, 2.0, None, normalise=True))
+    assert ei.value.status == 14
+
+
+# ================================================================================ clustering (K2)
+def _assert_cluster_equal(got, want):
+    gc, ga, gs = got
+    wc, wa, ws = want
+    assert gc.shape == wc.shape, (gc.shape, wc.shape)
+    assert np.array_equal(ga, wa), "assignments must be identical"
+    assert np.array_equal(gs, ws), "cluster sizes must be identical"
+    assert np.array_equal(gc.view(np.uint64), wc.view(np.uint64)), "centroids must be bit-identical"
+
+
+@pytest.mark.parametrize("n,f,maxk,rscale", [(5_000, 64, 40, 1.0), (20_000, 128, 100, 1.0), (3_000, 384, 316, 0.6),
+                                             (2_000, 33, 7, 1.0), (4_000, 130, 1001, 0.2), (500, 24, 3, 3.0)])
+def test_cluster_parity(ctx, asb, oracle, n, f, maxk, rscale):
+    x = asb.synth.protein_like(n, f, seed=21)
+    radius = rscale * 1.5 * f * 0.0025 * 2
+    want = oracle.cluster_incremental(x, maxk, radius)
+    got = ctx.cluster_incremental(x, maxk, radius)
+    _assert_cluster_equal(got, want)
+    assert (want[1] >= 0).sum() > 0
+
+
+def test_cluster_exact_path_and_ties(ctx, asb, oracle):
+    """Integer-valued data makes many distances tie exactly -> the certified fast path must hand
+    those rows to the reference-arithmetic path; forcing that path for ALL rows gives the same
+    result."""
+    rng = np.random.RandomState(9)
+    x = np.ascontiguousarray(rng.randint(0, 3, size=(3000, 16)).astype(np.float64))
+    for radius in (2.0, 4.0, 7.0):
+        want = oracle.cluster_incremental(x, 24, radius)
+        got = ctx.cluster_incremental(x, 24, radius)
+        _assert_cluster_equal(got, want)
+    assert ctx.kernel_ms("cluster_exact_rows") > 0
+    y = asb.synth.protein_like(3_000, 64, seed=22)
+    want = oracle.cluster_incremental(y, 30, 0.5)
+    ctx.set_option("cluster_force_exact", 1)
+    try:
+        got = ctx.cluster_incremental(y, 30, 0.5)
+        assert ctx.kernel_ms("cluster_exact_rows") == 3_000 - 1
+    finally:
+        ctx.set_option("cluster_force_exact", 0)
+    _assert_cluster_equal(got, want)
+
+
+def test_cluster_nan_rows_and_duplicates(ctx, asb, oracle):
+    x = asb.synth.protein_like(1_000, 32, seed=23)
+    x[10] = x[3]                      # exact duplicate of an earlier row
+    x[500, 4] = np.nan                # NaN row: never nearest to anything (clustering.rs:922)
+    x[700] = x[3]
+    want = oracle.cluster_incremental(x, 20, 0.3)
+    got = ctx.cluster_incremental(x, 20, 0.3)
+    gc, ga, gs = got
+    wc, wa, ws = want
+    assert np.array_equal(ga, wa) and np.array_equal(gs, ws)
+    assert np.array_equal(np.isnan(gc), np.isnan(wc))
+    m = ~np.isnan(wc)
+    assert np.array_equal(gc[m], wc[m])
+
+
+# ==================================================================================== Two-NN (K1)
+@pytest.mark.parametrize("n,f,s", [(5_000, 64, 100), (2_000, 384, 500), (300, 25, 300)])
+def test_twonn_parity(ctx, asb, oracle, n, f, s):
+    x = asb.synth.protein_like(n, f, seed=31)
+    x[17] = x[5]                      # exact duplicate -> d1 == 0 for both
+    si = asb.heuristics.sample_indices(n, s, 129)
+    si[0], si[1] = 5, 17
+    w1, w2 = oracle.twonn_distances(x, si)
+    g1, g2 = ctx.twonn_distances(x, si)
+    assert g1[0] == 0.0 and g1[1] == 0.0
+    assert np.allclose(g1, w1, rtol=1e-9, atol=0) and np.allclose(g2, w2, rtol=1e-9, atol=0)
+    assert asb.heuristics.intrinsic_dim_from_distances(n, f, g1, g2) == oracle.intrinsic_dim(n, f, w1, w2)
+
+
+# =============================================================== whole build + stage equivalence
+def _oracle_build(oracle, x, maxk, radius, gp, mode=TAU_MEDIAN, value=0.0):
+    cent, asg, sizes = oracle.cluster_incremental(x, maxk, radius)
+    csr = oracle.feature_laplacian(cent, **gp)
+    lam = oracle.compute_taumode(x, csr, mode, value)
+    return cent, asg, sizes, csr, lam
+
+
+@pytest.mark.parametrize("n,f,maxk", [(10_000, 128, 100), (3_000, 384, 150)])
+def test_build_matches_oracle_and_stages(ctx, asb, oracle, n, f, maxk):
+    """ArrowSpaceBuilder::build vs the oracle pipeline, and the reference's own stage-equivalence
+    contract (tests/test_eigenmaps.rs:117-329): monolithic build == the four EigenMaps stages."""
+    x = asb.synth.protein_like(n, f, seed=42)
+    radius = 1.5 * f * 0.0025 * 2
+    gp = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    cent, asg, sizes, csr, lam = _oracle_build(oracle, x, maxk, radius, gp)
+
+    def builder():
+        return (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(0.5, 12, 4, 2.0, 0.25)
+                .with_synthesis(asb.TauMode.Median).with_seed(42).with_inline_sampling(None)
+                .with_dims_reduction(False, None).with_cluster_params(maxk, radius))
+
+    aspace, gl = builder().build(x)
+    _assert_cluster_equal((gl.init_data, aspace.cluster_assignments, aspace.cluster_sizes), (cent, asg, sizes))
+    _assert_csr_equal(gl.csr, csr)
+    _assert_lambda_close(aspace.lambdas, lam)
+    assert gl.shape() == (f, f) and gl.nnodes == n               # tests/test_builder.rs:272,339
+    info = aspace.index_info()
+    assert info.n_clusters == cent.shape[0] and info.nnz == csr[0][-1]
+    assert np.isclose(info.lambda_min, lam.min(), rtol=1e-9) and np.isclose(info.lambda_sum, lam.sum(), rtol=1e-9)
+
+    b = builder()
+    out = asb.ArrowSpace.start_clustering(b, x)
+    gl2 = out.aspace.eigenmaps(b, out.centroids, n)
+    out.aspace.compute_taumode(gl2)
+    assert np.array_equal(out.aspace.cluster_assignments, aspace.cluster_assignments)
+    assert np.array_equal(out.aspace.cluster_sizes, aspace.cluster_sizes)
+    _assert_csr_equal(gl2.csr, gl.csr)
+    assert np.allclose(out.aspace.lambdas, aspace.lambdas, rtol=1e-12, atol=0)
+
+    queries, src = asb.synth.queries_from_items(x, 50, seed=43)
+    lq_want = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    idx, score, count, lq = aspace.search_batch(queries, 10, 0.7)           # EigenMaps::search, batched
+    _assert_lambda_close(lq, lq_want)
+    _assert_topk_equal(idx, score, count, *want)
+    one = out.aspace.search(queries[0], gl2, 10, 0.7)                       # EigenMaps::search, single
+    assert [i for i, _ in one] == want[0][0].tolist()
+    res = aspace.search_lambda_aware(asb.ArrowItem.new(queries[1], float(lq_want[1])), 10, 0.7)
+    assert [i for i, _ in res] == want[0][1].tolist()
+    # alpha = 1: the source item is the best hit (query = item x 1.02 has cosine 1)
+    idx1, _, _, _ = aspace.search_batch(queries, 1, 1.0)
+    assert (np.asarray(idx1)[:, 0] == src).mean() > 0.9
+
+
+def test_builder_defaults_give_degenerate_graph(ctx, asb):
+    """Literal builder defaults (eps=1e-3) on generic data: empty graph -> lambda == 0 -> the search
+    panics in the reference (core.rs:773-776); here ASB_ERR_ZERO_LAMBDA."""
+    x = asb.synth.protein_like(2_000, 64, seed=42)
+    b = (asb.ArrowSpaceBuilder.new(ctx).with_seed(1).with_inline_sampling(None).with_cluster_params(32, 0.5))
+    aspace, gl = b.build(x)
+    assert gl.nnz() == 64 and np.all(aspace.lambdas == 0.0)
+    with pytest.raises(asb.ArrowSpaceError) as ei:
+        aspace.search(x[0] * 1.02, gl, 3, 0.7)
+    assert ei.value.status == 5
+    with pytest.raises(asb.ArrowSpaceError) as ei:               # core.rs:416-420
+        asb.ArrowSpaceBuilder.new(ctx).with_inline_sampling(None).with_cluster_params(2, 1.0).build(x[:1])
+    assert ei.value.status == 11
+
+
+def test_device_resident_inputs(ctx, asb, oracle):
+    """torch CUDA tensors are used in place (zero copy) and give the same answers as host arrays."""
+    import torch
+    x = asb.synth.protein_like(6_000, 128, seed=42)
+    cent, _, _ = oracle.cluster_incremental(x[:2000], 50, 1.5 * 128 * 0.0025 * 2)
+    csr = _graph(oracle, cent)
+    xd = torch.from_numpy(x).cuda()
+    lam_h, n2_h, _ = ctx.compute_taumode(x, csr, asb.TauMode.Median, want_norms=True)
+    lam_d, n2_d, _ = ctx.compute_taumode(xd, csr, asb.TauMode.Median, want_norms=True)
+    assert lam_d.is_cuda and np.array_equal(lam_d.cpu().numpy(), lam_h)
+    queries, _ = asb.synth.queries_from_items(x, 64, seed=43)
+    qd = torch.from_numpy(queries).cuda()
+    lq_d = ctx.prepare_query_lambdas(qd, csr, asb.TauMode.Median)
+    idx_d, sc_d, cnt_d = ctx.search_lambda_aware_batch(xd, lam_d, qd, lq_d, 10, 0.7, norms2=n2_d)
+    idx_h, sc_h, cnt_h = ctx.search_lambda_aware_batch(x, lam_h, queries, lq_d.cpu().numpy(), 10, 0.7)
+    assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.array_equal(sc_d.cpu().numpy(), sc_h)
