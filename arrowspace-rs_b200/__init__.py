@@ -8,4 +8,4 @@ from .host import (  # noqa: F401
     ABI_SYMBOLS, ArrowItem, ArrowSpace, ArrowSpaceBuilder, ArrowSpaceError, ClusteredOutput, Context, GraphLaplacian,
     GraphParams, TauMode, TAUDEFAULT, TAU_FLOOR, default_context, load_library,
 )
-from . import host, heuristics, synth  # noqa: F401
+from . import host, heuristics, parallel, synth  # noqa: F401

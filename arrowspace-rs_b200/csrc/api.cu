@@ -89,6 +89,10 @@ void asb_ctx_destroy(asb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->ktimers) {
+        if (kv.second.a) cudaEventDestroy(kv.second.a);
+        if (kv.second.b) cudaEventDestroy(kv.second.b);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -99,6 +103,15 @@ const char *asb_last_error(asb_ctx *ctx) { return ctx ? ctx->last_error.c_str() 
 int64_t asb_kernel_launches(asb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 double asb_last_kernel_ms(asb_ctx *ctx, const char *which) {
     if (!ctx || !which) return 0.0;
+    auto kt = ctx->ktimers.find(which);
+    if (kt != ctx->ktimers.end() && kt->second.b) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(kt->second.b) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, kt->second.a, kt->second.b) == cudaSuccess)
+            return ms;
+        cudaGetLastError();
+        return 0.0;
+    }
     auto it = ctx->kernel_ms.find(which);
     return it == ctx->kernel_ms.end() ? 0.0 : it->second;
 }
@@ -212,6 +225,52 @@ int asb_cluster_incremental(asb_ctx *ctx, const double *rows, int64_t n, int64_t
     ASB_TRY(c.finish(ctx));
     ASB_TRY(a.finish(ctx));
     ASB_TRY(sz.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_cluster_incremental_resume(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, int64_t max_clusters,
+                                   double radius, double *centroids, int64_t *assignments, uint64_t *sizes,
+                                   int64_t *x_inout) {
+    ASB_TRY(set_device(ctx));
+    if (!rows || !centroids || !assignments || !sizes || !x_inout)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster_resume: null pointer");
+    if (n <= 0 || f <= 0 || max_clusters <= 0 || *x_inout < 0 || *x_inout > max_clusters)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster_resume: bad sizes");
+    DevIn<double> r;
+    DevOut<int64_t> a;
+    ASB_TRY(r.init(ctx, rows, (size_t)n * f));
+    ASB_TRY(a.init(ctx, assignments, (size_t)n));
+    // centroids / sizes are in-out: stage them both ways when they live on the host
+    const bool cdev = asb_is_device_ptr(centroids), sdev = asb_is_device_ptr(sizes);
+    DevTmp<double> ctmp;
+    DevTmp<unsigned long long> stmp;
+    double *c_d = centroids;
+    unsigned long long *s_d = (unsigned long long *)sizes;
+    if (!cdev) {
+        ASB_TRY(ctmp.init(ctx, (size_t)max_clusters * f));
+        ASB_CUDA(ctx, cudaMemcpyAsync(ctmp.ptr, centroids, (size_t)max_clusters * f * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        c_d = ctmp.ptr;
+    }
+    if (!sdev) {
+        ASB_TRY(stmp.init(ctx, (size_t)max_clusters));
+        ASB_CUDA(ctx, cudaMemcpyAsync(stmp.ptr, sizes, (size_t)max_clusters * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        s_d = stmp.ptr;
+    }
+    StageTimer t(ctx, "cluster");
+    int64_t x = 0;
+    int rc = asb_dev_cluster(ctx, r.ptr, n, f, max_clusters, radius, c_d, a.ptr, s_d, &x, *x_inout);
+    t.stop();
+    ASB_TRY(rc);
+    *x_inout = x;
+    if (!cdev)
+        ASB_CUDA(ctx, cudaMemcpyAsync(centroids, c_d, (size_t)max_clusters * f * sizeof(double), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    if (!sdev)
+        ASB_CUDA(ctx, cudaMemcpyAsync(sizes, s_d, (size_t)max_clusters * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    ASB_TRY(a.finish(ctx));
     return asb_sync(ctx);
 }
 

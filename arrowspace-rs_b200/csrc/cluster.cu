@@ -38,6 +38,7 @@ struct ClusterArgs {
     long long n;
     int f;
     int max_k;
+    int init_k;  // centroids already present in `centroids`/`sizes` (pipeline hand-off)
     double radius;
     double *centroids;  // [max_k][f] global: output, and live storage when !cent_in_smem
     long long *assign;
@@ -116,7 +117,18 @@ __global__ void __launch_bounds__(1024, 1) cluster_kernel(ClusterArgs A) {
 
     for (int s = tid; s < slots; s += blockDim.x) cnt[s] = 0ull;
     for (long long r = 0; r < kRing - 1; ++r) issue_row(r);
-    int kc = 0;
+    int kc = A.init_k;
+    __syncthreads();
+    for (int s = warp; s < slots; s += nw) {  // resume: adopt the state left by the previous shard
+        const int c = s * ncta + rank;
+        if (c >= kc) break;
+        if (A.cent_in_smem) {
+            double *cv = cent_s + (size_t)s * cp;
+            const double *src = A.centroids + (size_t)c * f;
+            for (int j = lane; j < f; j += 32) cv[j] = src[j];
+        }
+        if (lane == 0) cnt[s] = A.sizes[c];
+    }
     int n_exact = 0;
     const double r_half = A.radius * 0.5, r_full = A.radius, r_relax = A.radius * 1.5;
     __syncthreads();
@@ -371,11 +383,13 @@ size_t cluster_smem_bytes(int f, int slots, bool cent_in_smem) {
 }  // namespace
 
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
-                    double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host) {
+                    double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host,
+                    int64_t init_k) {
     if (n <= 0 || f <= 0 || max_clusters <= 0)
         ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: n=%lld f=%lld max_clusters=%lld", (long long)n, (long long)f,
                  (long long)max_clusters);
     if (f > 16384 || max_clusters > (1 << 20)) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "cluster: f or max_clusters too large");
+    if (init_k < 0 || init_k > max_clusters) ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: init_k=%lld", (long long)init_k);
     ASB_CUDA(ctx, cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     const size_t smem_cap = 227 * 1024;
     ClusterArgs A{};
@@ -383,6 +397,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     A.n = n;
     A.f = (int)f;
     A.max_k = (int)max_clusters;
+    A.init_k = (int)init_k;
     A.radius = radius;
     A.centroids = centroids_d;
     A.assign = (long long *)assign_d;
@@ -426,7 +441,10 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             cudaGetLastError();
             continue;
         }
-        e = cudaLaunchKernelEx(&cfg, cluster_kernel, A);
+        {
+            KernelTimer kt(ctx, "cluster_kernel");
+            e = cudaLaunchKernelEx(&cfg, cluster_kernel, A);
+        }
         if (e != cudaSuccess) {
             cudaGetLastError();
             continue;

@@ -13,7 +13,12 @@
 
 #include "../../include/arrowspace_b200.h"
 
+struct KTimerEvents {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
 struct asb_ctx {
+    std::map<std::string, KTimerEvents> ktimers;  // per-kernel device timers (see KernelTimer)
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -178,6 +183,22 @@ struct StageTimer {
     }
 };
 
+// Brackets ONE kernel launch with CUDA events on the launching stream; the elapsed time is
+// resolved lazily by asb_last_kernel_ms(name) (the roofline numbers of bench.py come from here).
+struct KernelTimer {
+    asb_ctx *ctx;
+    KTimerEvents *ev;
+    KernelTimer(asb_ctx *c, const char *name) : ctx(c) {
+        ev = &ctx->ktimers[name];
+        if (!ev->a) {
+            cudaEventCreate(&ev->a);
+            cudaEventCreate(&ev->b);
+        }
+        cudaEventRecord(ev->a, ctx->stream);
+    }
+    ~KernelTimer() { cudaEventRecord(ev->b, ctx->stream); }
+};
+
 // ---- internal stage entry points on DEVICE pointers (used by the C ABI and asb_index) ----
 
 struct DeviceCsr {  // device-resident CSR of the feature graph (int64 as at the ABI)
@@ -221,7 +242,7 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
 int asb_dev_norms2(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, double *norms2_d);
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters,
                     double radius, double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d,
-                    int64_t *x_out_host);
+                    int64_t *x_out_host, int64_t init_k = 0);
 int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_t f,
                       const asb_graph_params &gp, int64_t *indptr_d, int64_t *indices_d, double *data_d,
                       int64_t capacity, int64_t *nnz_host);

@@ -437,10 +437,13 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
                                            (int)smem));                                                    \
         search_kernel<M, V><<<grid, kThreads, smem, ctx->stream>>>(A);                                      \
     } while (0)
-    if (mode == MODE_COSINE) {
-        if (vec) LAUNCH(MODE_COSINE, true); else LAUNCH(MODE_COSINE, false);
-    } else {
-        if (vec) LAUNCH(MODE_L2, true); else LAUNCH(MODE_L2, false);
+    {
+        KernelTimer kt(ctx, mode == MODE_COSINE ? "search_kernel" : "twonn_kernel");
+        if (mode == MODE_COSINE) {
+            if (vec) LAUNCH(MODE_COSINE, true); else LAUNCH(MODE_COSINE, false);
+        } else {
+            if (vec) LAUNCH(MODE_L2, true); else LAUNCH(MODE_L2, false);
+        }
     }
 #undef LAUNCH
     ASB_TRY(asb_check_launch(ctx, "search_kernel"));

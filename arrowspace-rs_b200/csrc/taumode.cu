@@ -372,8 +372,11 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(items_d, (long long)n, f, plan.entries, plan.row_ptr,
-                                                         tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
+    {
+        KernelTimer kt(ctx, "taumode_kernel");
+        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(items_d, (long long)n, f, plan.entries, plan.row_ptr,
+                                                             tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
+    }
     return asb_check_launch(ctx, "taumode_kernel");
 }
 

@@ -88,6 +88,7 @@ ABI_SYMBOLS = {
     "asb_ctx_set_option": (C.c_int, [_P, C.c_char_p, _D]),
     "asb_twonn_distances": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _P]),
     "asb_cluster_incremental": (C.c_int, [_P, _P, _I64, _I64, _I64, _D, _P, _P, _P, C.POINTER(_I64)]),
+    "asb_cluster_incremental_resume": (C.c_int, [_P, _P, _I64, _I64, _I64, _D, _P, _P, _P, C.POINTER(_I64)]),
     "asb_laplacian_max_nnz": (_I64, [_I64, _I64]),
     "asb_build_feature_laplacian": (C.c_int, [_P, _P, _I64, _I64, C.POINTER(GraphParamsC), _P, _P, _P, _I64,
                                               C.POINTER(_I64)]),
@@ -218,6 +219,24 @@ class Context:
         self.check(self.lib.asb_cluster_incremental(self.handle, _ptr(rows), n, f, int(max_clusters), float(radius),
                                                     _ptr(cent), _ptr(asg), _ptr(sizes), C.byref(x)))
         return cent[: x.value].copy(), asg, sizes[: x.value].copy()
+
+    def cluster_incremental_resume(self, rows, max_clusters: int, radius: float, centroids, sizes, x: int,
+                                   assignments=None):
+        """Continue the walk from (centroids[:x], sizes[:x]); buffers are updated in place.
+        Returns (x_new, assignments)."""
+        rows = _as_f64_matrix(rows)
+        n, f = _shape2(rows)
+        if assignments is None:
+            if _is_device(rows):
+                import torch
+                assignments = torch.empty(n, dtype=torch.int64, device=rows.device)
+            else:
+                assignments = np.empty(n, dtype=np.int64)
+        xx = _I64(int(x))
+        self.check(self.lib.asb_cluster_incremental_resume(self.handle, _ptr(rows), n, f, int(max_clusters),
+                                                           float(radius), _ptr(centroids), _ptr(assignments),
+                                                           _ptr(sizes), C.byref(xx)))
+        return xx.value, assignments
 
     def build_feature_laplacian(self, centroids, gp: "GraphParams"):
         centroids = _as_f64_matrix(centroids)

@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py -- lambda-tau build items/s + lambda-aware search QPS@k=10 on B200 (BASELINE.json).
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+    Two-NN scan (K1) -> incremental clustering (K2) -> feature Laplacian (K3+K4) -> taumode (K5+K6)
+    = ArrowSpaceBuilder::build, then prepare_query (K7) + search_lambda_aware k=10 (K8) for Q queries.
+Workload at N=1: BASELINE configs[2] "1M x 384 lambda-tau build + 10k-query lambda-aware search k=10
+on 1 B200" (the configuration the metric is quoted on; 3.07 GB, fits one GPU).  At N>1 every rank
+holds its own 1M x 384 shard of one virtual dataset (weak scaling, row sharding).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+`value` = items/s of the whole build with inputs resident in HBM; `e2e` = the same through the
+public host-buffer API (pinned host rows -> H2D inside the timed region, results read back).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+GRAPH = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)   # with_lambda_graph(0.5, 12, 4, 2.0, Some(0.25))
+ALPHA, TOPK = 0.7, 10
+DATA_SEED, QUERY_SEED = 42, 43
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="items per GPU")
+    ap.add_argument("--f", type=int, default=384)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak():
+    p = ROOT / "profiles" / "r01_fp64_peak.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["dmma_tflops"]), float(d["dfma_tflops"])
+    return 34.1, 36.7
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/asb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def cluster_inputs(n_global: int, f: int, sample_rows: np.ndarray):
+    """(max_clusters, radius): max_clusters = step1_bounds k_max with id_est = F;
+    radius = the seeded pilot rule (heuristics.pilot_radius), both printed with the result."""
+    import arrowspace_b200 as asb
+    _, k_max = asb.heuristics.step1_bounds(n_global, f, f)
+    radius = asb.heuristics.pilot_radius(sample_rows, k_max, asb.heuristics.CLUSTERING_SEED)
+    return int(k_max), float(radius)
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be
+    compiled here -- DESIGN.md) on the box's host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import arrowspace_b200 as asb
+    from oracle_binding import Oracle, TAU_MEDIAN
+    o = Oracle()
+    cores = o.num_threads()
+    n, f = args.n, args.f
+    n_s = min(n, 20_000)            # rows of the build sample
+    n_items_search = min(n, 200_000)
+    q_s = max(cores, 16)
+    x = asb.synth.protein_like(n_items_search, f, seed=DATA_SEED)
+    maxk, radius = cluster_inputs(n * args.gpus, f, x[: min(len(x), 50_000)])
+    queries = asb.synth.rows_at(asb.synth.query_indices(n_items_search, q_s, QUERY_SEED), f, DATA_SEED) * 1.02
+    si = asb.heuristics.sample_indices(n_s, 500, 129)
+    build_t, search_t = [], []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        o.twonn_distances(x[:n_s], si)
+        cent, asg, sizes = o.cluster_incremental(x[:n_s], maxk, radius)
+        csr = o.feature_laplacian(cent, **GRAPH)
+        lam_s = o.compute_taumode(x[:n_s], csr, TAU_MEDIAN)
+        t1 = time.perf_counter()
+        lam = o.compute_taumode(x, csr, TAU_MEDIAN)
+        lq = o.compute_taumode(queries, csr, TAU_MEDIAN)
+        t2 = time.perf_counter()
+        o.search_lambda_aware_batch(x, lam, queries, lq, TOPK, ALPHA)
+        t3 = time.perf_counter()
+        if step >= args.warmup:
+            build_t.append(t1 - t0)
+            search_t.append(t3 - t2)
+    bt, st = float(np.mean(build_t)), float(np.mean(search_t))
+    items_s = n_s / bt
+    # search cost is linear in N: QPS at the full N = measured QPS x (sample items / N)
+    qps = (q_s / st) * (n_items_search / n)
+    sample = (f"build: first {n_s} rows of the {n}x{f} workload (Two-NN 500 samples + sequential clustering + Laplacian "
+              f"+ taumode); search: {q_s} queries x {n_items_search} items, QPS scaled by {n_items_search}/{n}")
+    line = {
+        "impl": "reference", "metric": "lambda_tau_build_items_per_s", "value": items_s, "unit": "items/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (bt + st) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}x{f} lambda-tau build + {args.nq}-query lambda-aware search k={TOPK} (bounded sample)",
+                   "max_clusters": maxk, "radius": radius, "graph": GRAPH, "taumode": "Median", "alpha": ALPHA},
+        "search_qps": qps,
+        "cpu_baseline": {"value": items_s, "unit": "items/s", "cores": cores, "kind": "port", "sample": sample,
+                         "search_qps": qps},
+        "e2e": {"value": items_s, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import arrowspace_b200 as asb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    asb._build.build_cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = asb.Context(local_rank, stream=stream if stream else None)
+
+    n, f, nq = args.n, args.f, args.nq
+    n_global = n * world
+    lo = rank * n
+    t_gen = time.perf_counter()
+    rows_h = torch.empty((n, f), dtype=torch.float64).pin_memory()
+    asb.synth.protein_like(n, f, seed=DATA_SEED, out=rows_h.numpy(), row0=lo)
+    q_idx = asb.synth.query_indices(n_global, nq, QUERY_SEED)
+    queries_h = torch.from_numpy(asb.synth.rows_at(q_idx, f, DATA_SEED) * 1.02).pin_memory()
+    t_gen = time.perf_counter() - t_gen
+    rows_d = rows_h.to(dev, non_blocking=True)
+    queries_d = queries_h.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    maxk, radius = cluster_inputs(n_global, f, rows_h.numpy()[: min(n, 50_000)])
+    if world > 1:
+        t = torch.tensor([radius], dtype=torch.float64, device=dev)
+        dist.broadcast(t, src=0)
+        radius = float(t.item())
+    gp = asb.GraphParams(GRAPH["eps"], GRAPH["k"], GRAPH["topk"], GRAPH["p"], GRAPH["sigma"])
+    tm = asb.TauMode.Median
+    sample_idx = torch.from_numpy(asb.heuristics.sample_indices(n, 500, 129)).to(dev)
+    d1 = torch.empty(500, dtype=torch.float64, device=dev)
+    d2 = torch.empty(500, dtype=torch.float64, device=dev)
+    lib = ctx.lib
+    import ctypes as C
+
+    def builder():
+        return (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(GRAPH["eps"], GRAPH["k"], GRAPH["topk"], GRAPH["p"],
+                                                                 GRAPH["sigma"])
+                .with_synthesis(tm).with_seed(DATA_SEED).with_inline_sampling(None).with_dims_reduction(False, None)
+                .with_cluster_params(maxk, radius))
+
+    compute = asb.parallel.GpuCompute(ctx)
+    kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": []}
+    stage_acc = {"twonn": [], "cluster": [], "laplacian": [], "taumode": [], "search": []}
+
+    def twonn():
+        ctx.check(lib.asb_twonn_distances(ctx.handle, rows_d.data_ptr(), n, f, sample_idx.data_ptr(), 500,
+                                          d1.data_ptr(), d2.data_ptr()))
+
+    def step_resident(record: bool):
+        """One step with every input already resident in HBM.  Returns (build_ms, search_ms)."""
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        twonn()
+        if world == 1:
+            bp = asb.host.BuildParamsC(gp.to_c(), tm.mode, tm.value, maxk, radius, 0)
+            h = C.c_void_p()
+            ctx.check(lib.asb_index_build(ctx.handle, rows_d.data_ptr(), n, f, C.byref(bp), C.byref(h)))
+            e[1].record()
+            idx = torch.empty((nq, TOPK), dtype=torch.int64, device=dev)
+            score = torch.empty((nq, TOPK), dtype=torch.float64, device=dev)
+            count = torch.empty(nq, dtype=torch.int64, device=dev)
+            ctx.check(lib.asb_index_search(ctx.handle, h, queries_d.data_ptr(), nq, TOPK, ALPHA, idx.data_ptr(),
+                                           score.data_ptr(), count.data_ptr(), None))
+            e[2].record()
+            torch.cuda.synchronize()
+            info = asb.host.IndexInfoC()
+            lib.asb_index_info_get(h, C.byref(info))
+            if record:
+                stage_acc["cluster"].append(info.ms_cluster)
+                stage_acc["laplacian"].append(info.ms_laplacian)
+                stage_acc["taumode"].append(info.ms_taumode)
+            result = (idx, score, info)
+            lib.asb_index_destroy(h)
+        else:
+            index = asb.parallel.build_sharded(compute, dist, rows_d, lo, n_global, gp, tm, maxk, radius,
+                                               comm_device=dev, rank=rank, world=world)
+            e[1].record()
+            idx, score, count = asb.parallel.search_sharded(compute, dist, index, queries_d, TOPK, ALPHA,
+                                                            comm_device=dev, world=world)
+            e[2].record()
+            torch.cuda.synchronize()
+            result = (idx, score, index)
+        if record:
+            for kname in kernel_acc:
+                kernel_acc[kname].append(ctx.kernel_ms(kname))
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    build_ms, search_ms = [], []
+    t_start.record()
+    last = None
+    for _ in range(args.steps):
+        b, s, last = step_resident(True)
+        build_ms.append(b)
+        search_ms.append(s)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    launches = ctx.kernel_launches - launches0
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = max_over_ranks(total_ms)
+    build_ms_mean = max_over_ranks(float(np.mean(build_ms)))
+    search_ms_mean = max_over_ranks(float(np.mean(search_ms)))
+    ms_per_step = total_ms / args.steps
+    items_per_s = n_global / (build_ms_mean * 1e-3)
+    qps = nq / (search_ms_mean * 1e-3)
+
+    # ---- end to end through the host-buffer API (pinned host -> H2D inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e_build, e2e_search = [], []
+        h2d = n * f * 8 + nq * f * 8
+        d2h = 0
+        for it in range(1 + max(1, min(args.steps, 2))):
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                aspace, gl = builder().build(rows_h.numpy())          # H2D of the rows + D2H of every output
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                idx, score, count, lq = aspace.search_batch(queries_h.numpy(), TOPK, ALPHA)
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                d2h = (aspace.lambdas.nbytes + gl.init_data.nbytes + aspace.cluster_assignments.nbytes +
+                       aspace.cluster_sizes.nbytes + gl.indptr.nbytes + gl.indices.nbytes + gl.data.nbytes +
+                       idx.nbytes + score.nbytes + count.nbytes + lq.nbytes)
+                aspace._release()
+            else:
+                rd = rows_h.to(dev, non_blocking=True)
+                qd = queries_h.to(dev, non_blocking=True)
+                index = asb.parallel.build_sharded(compute, dist, rd, lo, n_global, gp, tm, maxk, radius,
+                                                   comm_device=dev, rank=rank, world=world)
+                lam_h = index.lambdas.cpu()
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                idx, score, count = asb.parallel.search_sharded(compute, dist, index, qd, TOPK, ALPHA,
+                                                                comm_device=dev, world=world)
+                idx_h, score_h = idx.cpu(), score.cpu()
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                d2h = lam_h.numel() * 8 + idx_h.numel() * 8 + score_h.numel() * 8
+                del rd, qd, index
+            if it > 0:
+                e2e_build.append(max_over_ranks((t1 - t0) * 1e3))
+                e2e_search.append(max_over_ranks((t2 - t1) * 1e3))
+        e2e = {"value": n_global / (float(np.mean(e2e_build)) * 1e-3), "unit": "items/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "search_qps": nq / (float(np.mean(e2e_search)) * 1e-3),
+               "build_ms": float(np.mean(e2e_build)), "search_ms": float(np.mean(e2e_search))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines (algorithmic work per launch / CUDA-event duration of that kernel)
+    hbm_peak, peak_src = measured_peaks()
+    dmma_peak, dfma_peak = fp64_peak()
+    kms = {k: float(np.mean(v)) if v else 0.0 for k, v in kernel_acc.items()}
+    info_nnz = None
+    if world == 1:
+        info_nnz = int(last[2].nnz)
+    kernels = {}
+    if kms["taumode_kernel"] > 0:
+        by = n * (8 * f + 16)        # read the item once, write lambda + norm  (8F + 8 per item)
+        ach = by / (kms["taumode_kernel"] * 1e-3) / 1e9
+        kernels["taumode_kernel"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": ach / hbm_peak, "ms": kms["taumode_kernel"], "traffic": None}
+    if kms["search_kernel"] > 0:
+        fl = 2.0 * nq * n * f
+        ach = fl / (kms["search_kernel"] * 1e-3) / 1e12
+        kernels["search_kernel"] = {"bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                                    "frac": ach / dmma_peak, "ms": kms["search_kernel"], "traffic": None,
+                                    "peak_source": "FP64 DMMA m8n8k4 micro-benchmark on this pool "
+                                                   "(profiles/r01_fp64_peak.json); DFMA peak %.1f" % dfma_peak}
+    if kms["twonn_kernel"] > 0:
+        fl = 2.0 * 500 * n * f
+        ach = fl / (kms["twonn_kernel"] * 1e-3) / 1e12
+        kernels["twonn_kernel"] = {"bound": "tensor", "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s",
+                                   "frac": ach / dmma_peak, "ms": kms["twonn_kernel"], "traffic": None}
+    if kms["cluster_kernel"] > 0:
+        by = n * 8 * f
+        ach = by / (kms["cluster_kernel"] * 1e-3) / 1e9
+        kernels["cluster_kernel"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": ach / hbm_peak, "ms": kms["cluster_kernel"], "traffic": None,
+                                     "note": "order-dependent walk: latency bound by design (one cluster "
+                                             "barrier per row), rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
+                                     "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
+    dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+    roofline = dict(kernels[dominant], kernel=dominant, peak_kind=peak_src) if dominant else None
+
+    line = {
+        "metric": "lambda_tau_build_items_per_s", "value": items_per_s, "unit": "items/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n_global}x{f} lambda-tau build ({n} rows/GPU) + {nq}-query lambda-aware search k={TOPK}",
+                   "build": "Two-NN scan + incremental clustering + feature Laplacian + taumode (ArrowSpaceBuilder::build)",
+                   "max_clusters": maxk, "radius": radius, "graph": GRAPH, "taumode": "Median", "alpha": ALPHA,
+                   "l2": "inputs (3.07 GB items per GPU) larger than the 126 MB L2; no flush needed",
+                   "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "nnz_laplacian": info_nnz, "data_gen_s": t_gen},
+        "search_qps": qps, "build_ms": build_ms_mean, "search_ms": search_ms_mean,
+        "stages_ms": {k: float(np.mean(v)) for k, v in stage_acc.items() if v},
+        "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+    }
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only)
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle_binding import Oracle, TAU_MEDIAN
+        o = Oracle()
+        cores = o.num_threads()
+        n_s = min(n, 20_000)
+        n_items_search = min(n, 200_000)
+        q_s = max(cores, 16)
+        xs = rows_h.numpy()
+        t0 = time.perf_counter()
+        o.twonn_distances(xs[:n_s], asb.heuristics.sample_indices(n_s, 500, 129))
+        cent, asg, sizes = o.cluster_incremental(xs[:n_s], maxk, radius)
+        csr = o.feature_laplacian(cent, **GRAPH)
+        lam_s = o.compute_taumode(xs[:n_s], csr, TAU_MEDIAN)
+        t1 = time.perf_counter()
+        lam = o.compute_taumode(xs[:n_items_search], csr, TAU_MEDIAN)
+        lq = o.compute_taumode(queries_h.numpy()[:q_s], csr, TAU_MEDIAN)
+        t2 = time.perf_counter()
+        o.search_lambda_aware_batch(xs[:n_items_search], lam, queries_h.numpy()[:q_s], lq, TOPK, ALPHA)
+        t3 = time.perf_counter()
+        line["cpu_baseline"] = {
+            "value": n_s / (t1 - t0), "unit": "items/s", "cores": cores, "kind": "port",
+            "sample": f"build on the first {n_s} rows (clustering is sequential in the reference's deterministic "
+                      f"mode); search {q_s} queries x {n_items_search} items scaled to N={n}",
+            "search_qps": (q_s / (t3 - t2)) * (n_items_search / n), "build_s": t1 - t0, "search_s": t3 - t2}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,14 @@ int asb_cluster_incremental(asb_ctx *ctx, const double *rows, int64_t n, int64_t
                             int64_t max_clusters, double radius, double *centroids,
                             int64_t *assignments, uint64_t *sizes, int64_t *x_out);
 
+/* Same walk, continuing from an existing state: centroids/sizes hold *x_inout centroids on
+ * entry and the updated state on exit.  Processing shard 0, then shard 1 resumed from shard 0's
+ * state, ... equals one call over the concatenated rows -- the order-preserving hand-off used
+ * when the items are row-sharded over several GPUs (the centroid state travels, not the rows). */
+int asb_cluster_incremental_resume(asb_ctx *ctx, const double *rows, int64_t n, int64_t f,
+                                   int64_t max_clusters, double radius, double *centroids,
+                                   int64_t *assignments, uint64_t *sizes, int64_t *x_inout);
+
 /* ---- stage 2: feature-graph Laplacian ----------------------------------------------- */
 /* upper bound of stored entries: f * (1 + 2*(topk+1)) */
 int64_t asb_laplacian_max_nnz(int64_t f, int64_t topk);

@@ -203,10 +203,16 @@ def test_search_ties_and_edges(ctx, asb, oracle, golden):
         ctx.search_lambda_aware_batch(db, np.full(64, 0.3), q, np.array([0.5, 0.0]), 3, 0.7)
     assert ei.value.status == 5
     bad = db.copy()
-    bad[7, 7] = np.nan
-    with pytest.raises(asb.ArrowSpaceError) as ei:                # core.rs:785 unwrap on NaN
+    bad[7, 7] = np.inf                                            # inf item: cos = inf/inf = NaN
+    with pytest.raises(asb.ArrowSpaceError) as ei:                # core.rs:785 partial_cmp().unwrap() on NaN
         ctx.search_lambda_aware_batch(bad, np.full(64, 0.3), q, lq, 3, 0.7)
     assert ei.value.status == 9
+    bad[7, 7] = np.nan                                            # NaN item: norm NaN -> `denom > 0` false -> cos 0
+    lam_nan = np.full(64, 0.3)
+    lam_nan[9] = np.nan                                           # NaN lambda: f64::min(NaN, 1) = 1 -> lam term 0
+    want = oracle.search_lambda_aware_batch(bad, lam_nan, q, lq, 64, 0.7)
+    got = ctx.search_lambda_aware_batch(bad, lam_nan, q, lq, 64, 0.7)
+    _assert_topk_equal(*got, *want)
     zero = db.copy()
     zero[4] = 0.0                                                 # zero vector -> cosine 0 (core.rs:231-236)
     want = oracle.search_lambda_aware_batch(zero, np.full(64, 0.3), q, lq, 64, 0.7)
