@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(256) norms2_kernel(const double *__restrict__ 
 template <int TI>
 int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const GraphPlan &plan, int tau_mode,
                    double tau_value, double *lambdas_d, double *norms2_d, int *flag_d) {
+    // flag_d != nullptr <=> query preparation (K7); timed under its own name
+    const char *timer_name = flag_d ? "query_taumode_kernel" : "taumode_kernel";
     constexpr int P = kWarps * (32 / TI);
     const size_t smem = ((size_t)f * (TI + 1) + (size_t)4 * P * TI) * sizeof(double);
     auto kern = taumode_kernel<TI>;
@@ -373,7 +375,7 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
     {
-        KernelTimer kt(ctx, "taumode_kernel");
+        KernelTimer kt(ctx, timer_name);
         kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(items_d, (long long)n, f, plan.entries, plan.row_ptr,
                                                              tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
     }

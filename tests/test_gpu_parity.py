@@ -464,4 +464,5 @@ def test_device_resident_inputs(ctx, asb, oracle):
     lq_d = ctx.prepare_query_lambdas(qd, csr, asb.TauMode.Median)
     idx_d, sc_d, cnt_d = ctx.search_lambda_aware_batch(xd, lam_d, qd, lq_d, 10, 0.7, norms2=n2_d)
     idx_h, sc_h, cnt_h = ctx.search_lambda_aware_batch(x, lam_h, queries, lq_d.cpu().numpy(), 10, 0.7)
-    assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.array_equal(sc_d.cpu().numpy(), sc_h)
+    # norms come from two kernels with different summation orders -> scores agree to an ulp or two
+    assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.allclose(sc_d.cpu().numpy(), sc_h, rtol=0, atol=1e-14)
