@@ -44,7 +44,7 @@ struct ClusterArgs {
     long long *assign;
     unsigned long long *sizes;
     int *x_out;
-    int *stats;  // [0] rows through the exact path
+    int *stats;  // [0] rows through the exact path, [1] blocks (blocked kernel)
     int cent_in_smem;
     int slots_per_cta;
     int force_exact;
@@ -77,7 +77,13 @@ __device__ __forceinline__ bool lex_less(double d1, int c1, double d2, int c2) {
     return d1 < d2 || (d1 == d2 && c1 < c2);
 }
 
-__global__ void __launch_bounds__(1024, 1) cluster_kernel(ClusterArgs A) {
+}  // namespace
+
+#include "cluster_block.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(1024, 1) cluster_rowwise_kernel(ClusterArgs A) {
     cg::cluster_group cluster = cg::this_cluster();
     const int ncta = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -390,7 +396,6 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
                  (long long)max_clusters);
     if (f > 16384 || max_clusters > (1 << 20)) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "cluster: f or max_clusters too large");
     if (init_k < 0 || init_k > max_clusters) ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: init_k=%lld", (long long)init_k);
-    ASB_CUDA(ctx, cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     const size_t smem_cap = 227 * 1024;
     ClusterArgs A{};
     A.rows = rows_d;
@@ -406,60 +411,84 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         auto it = ctx->options.find("cluster_force_exact");
         A.force_exact = (it != ctx->options.end() && it->second != 0.0) ? 1 : 0;
     }
+    bool want_rowwise = false;
+    {
+        auto it = ctx->options.find("cluster_rowwise");
+        want_rowwise = (it != ctx->options.end() && it->second != 0.0);
+    }
     A.vec = (f % 2 == 0) && (((uintptr_t)rows_d & 15) == 0);
     DevTmp<int> scratch;
-    ASB_TRY(scratch.init(ctx, 2));
-    ASB_CUDA(ctx, cudaMemsetAsync(scratch.ptr, 0, 2 * sizeof(int), ctx->stream));
+    ASB_TRY(scratch.init(ctx, 4));
+    ASB_CUDA(ctx, cudaMemsetAsync(scratch.ptr, 0, 4 * sizeof(int), ctx->stream));
     A.x_out = scratch.ptr;
     A.stats = scratch.ptr + 1;
 
-    int launched = 0;
-    for (int ncta : {16, 8, 4, 2, 1}) {
-        const int slots = (int)((max_clusters + ncta - 1) / ncta);
-        bool in_smem = cluster_smem_bytes((int)f, slots, true) <= smem_cap;
-        size_t smem = cluster_smem_bytes((int)f, slots, in_smem);
-        if (smem > smem_cap) continue;
-        int nwarps = slots < 4 ? 4 : (slots > 32 ? 32 : slots);
-        A.cent_in_smem = in_smem ? 1 : 0;
-        A.slots_per_cta = slots;
-        ASB_CUDA(ctx, cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ncta);
-        cfg.blockDim = dim3(nwarps * 32);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = ncta;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        int max_clusters_active = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters_active, cluster_kernel, &cfg);
-        if (e != cudaSuccess || max_clusters_active < 1) {
-            cudaGetLastError();
-            continue;
+    // variant 0/1: blocked kernel with B = 16 / 8 rows per cluster barrier; 2: row-wise kernel
+    int launched = 0, variant_used = -1;
+    for (int variant = want_rowwise ? 2 : 0; variant < 3 && !launched; ++variant) {
+        for (int ncta : {16, 8, 4, 2, 1}) {
+            const int slots = (int)((max_clusters + ncta - 1) / ncta);
+            auto bytes = [&](bool in_smem) -> size_t {
+                if (variant == 0) return cluster_block_smem_bytes<16>((int)f, slots, (int)max_clusters, in_smem);
+                if (variant == 1) return cluster_block_smem_bytes<8>((int)f, slots, (int)max_clusters, in_smem);
+                return cluster_smem_bytes((int)f, slots, in_smem);
+            };
+            const bool in_smem = bytes(true) <= smem_cap;
+            const size_t smem = bytes(in_smem);
+            if (smem > smem_cap) continue;
+            const int nwarps = slots < 4 ? 4 : (slots > 32 ? 32 : slots);
+            A.cent_in_smem = in_smem ? 1 : 0;
+            A.slots_per_cta = slots;
+            const void *fn = variant == 0   ? (const void *)cluster_block_kernel<16>
+                             : variant == 1 ? (const void *)cluster_block_kernel<8>
+                                            : (const void *)cluster_rowwise_kernel;
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ncta);
+            cfg.blockDim = dim3(nwarps * 32);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = ncta;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int max_clusters_active = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters_active, fn, &cfg);
+            if (e != cudaSuccess || max_clusters_active < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            void *args[] = {(void *)&A};
+            {
+                KernelTimer kt(ctx, "cluster_kernel");
+                e = cudaLaunchKernelExC(&cfg, fn, args);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            launched = ncta;
+            variant_used = variant;
+            break;
         }
-        {
-            KernelTimer kt(ctx, "cluster_kernel");
-            e = cudaLaunchKernelEx(&cfg, cluster_kernel, A);
-        }
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            continue;
-        }
-        launched = ncta;
-        break;
     }
     if (!launched) ASB_FAIL(ctx, ASB_ERR_CUDA, "cluster: no cluster configuration could be launched");
     ctx->launches++;
-    int h[2] = {0, 0};
-    ASB_CUDA(ctx, cudaMemcpyAsync(h, scratch.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    int h[3] = {0, 0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(h, scratch.ptr, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *x_out_host = h[0];
     ctx->kernel_ms["cluster_exact_rows"] = (double)h[1];
     ctx->kernel_ms["cluster_ncta"] = (double)launched;
+    ctx->kernel_ms["cluster_blocks"] = (double)h[2];
+    ctx->kernel_ms["cluster_variant"] = (double)variant_used;
     if (h[0] == 0) ASB_FAIL(ctx, ASB_ERR_NO_CLUSTERS, "No clusters created from data");  // clustering.rs:869-874
     return ASB_OK;
 }

@@ -1,0 +1,537 @@
+// cluster_block.cuh -- K2, blocked variant: the same order-dependent walk as cluster_rowwise_kernel
+// (src/clustering.rs:547-928) but B rows per cluster barrier instead of one.
+//
+// Per block of B rows (B = 16 or 8):
+//   1. every warp computes the fast squared distances from ALL B rows to the centroid(s) it owns
+//      (B independent accumulators -> the FP64 pipe is throughput- not latency-bound), reduced
+//      over lanes with a transposing butterfly (16 shuffles instead of 80);
+//   2. per row: CTA arg-min over its centroids, then the 16 x 16 all-to-all through distributed
+//      shared memory -- ONE cluster barrier per block;
+//   3. every CTA derives, redundantly and identically, the decisions for the rows IN ORDER.  Row 0
+//      sees the exact snapshot.  Row i > 0 sees centroids that rows 0..i-1 of the block may have
+//      moved; a running-mean update moves centroid b by exactly |x - c_b| / k_new, so by the
+//      triangle inequality the true distance of any later row to b lies within +-disp[b] of its
+//      snapshot distance.  The decision for row i is taken from the snapshot only when that
+//      interval arithmetic CERTIFIES it (arg-min separated, no threshold inside the interval);
+//      the first row that cannot be certified ends the block and becomes row 0 of the next one.
+//      A row that creates a centroid also ends the block (later rows need distances to it).
+//      Row 0 itself falls back to the reference-arithmetic exact path when its margins are below
+//      delta (same rule as the row-wise kernel).
+//   4. owner warps apply the committed updates in row order with the reference's own IEEE
+//      operations; rank 0 writes the assignments.
+// Rows stream through a shared-memory ring filled by 1-D bulk async copies (cp.async.bulk, the
+// TMA engine; SASS UBLKCP) completing on per-slot mbarriers.
+#pragma once
+
+namespace {
+
+constexpr int kNone = 0x7fffffff;
+
+struct __align__(16) GRow {
+    double bd, sd;  // best / second best squared snapshot distance
+    double sb, ss;  // their square roots
+    int bc;
+    int pad;
+};
+
+struct __align__(16) Dec {
+    double knew;
+    int action;  // 0 new centroid, 1 running-mean update, 2 count only, 3 drop
+    int target;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity));
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Sum B per-lane partial accumulators over the 32 lanes with a transposing butterfly; on return
+// acc[0] of lane L holds the total of row (L >> kShift), kShift = 1 (B = 16) or 2 (B = 8).
+template <int B>
+__device__ __forceinline__ void transpose_reduce(double (&acc)[B], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int cur = B; cur > 1; cur >>= 1) {
+        const int half = cur >> 1;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int h = 0; h < half; ++h) {
+            const double send = upper ? acc[h] : acc[h + half];
+            const double keep = upper ? acc[h + half] : acc[h];
+            acc[h] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    for (; off > 0; off >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
+}
+
+template <int B>
+__global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
+    constexpr int R = 2 * B;                       // ring rows
+    constexpr int kShift = (B == 16) ? 1 : 2;      // lane -> row after transpose_reduce
+    constexpr int TCH = 4;                         // feature chunk = 32 * TCH
+    cg::cluster_group cluster = cg::this_cluster();
+    const int ncta = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const int f = A.f;
+    const int cp = f | 1;
+    const int fpad = (f + 1) & ~1;
+    const int slots = A.slots_per_cta;
+    const int maxk = A.max_k;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                    // R * fpad
+    double *D = ring + (size_t)R * fpad;                                    // slots * B
+    double *disp = D + (size_t)slots * B;                                   // maxk (accumulated displacement)
+    double *wred_d = disp + ((maxk + 1) & ~1);                              // 32
+    Xch *xch = reinterpret_cast<Xch *>(wred_d + 32);                        // [2][16][B]
+    Xch *xch_exact = xch + 2 * 16 * B;                                      // [2][16]
+    GRow *G = reinterpret_cast<GRow *>(xch_exact + 32);                     // B
+    Dec *dec = reinterpret_cast<Dec *>(G + B);                              // B
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(dec + B);  // R mbarriers
+    unsigned long long *cnt = full + R;                                     // maxk (replicated counts)
+    int *wred_c = reinterpret_cast<int *>(cnt + maxk);                      // 32
+    int *ctl = wred_c + 32;                                                 // [0] n_commit [1] exact flag [2] kc
+    int *modlist = ctl + 4;                                                 // B
+    double *cent_s = reinterpret_cast<double *>(modlist + B + ((B + 4) & 1));  // slots * cp (8B aligned)
+
+    auto cptr = [&](int slot) -> double * {
+        return A.cent_in_smem ? cent_s + (size_t)slot * cp : A.centroids + ((size_t)slot * ncta + rank) * f;
+    };
+    auto rowptr = [&](long long r) -> const double * { return ring + (size_t)(r & (R - 1)) * fpad; };
+
+    // ---- init
+    if (tid == 0) {
+        for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < maxk; c += blockDim.x) {
+        cnt[c] = (c < A.init_k) ? A.sizes[c] : 0ull;
+        disp[c] = 0.0;
+    }
+    int kc = A.init_k;
+    for (int s = warp; s < slots; s += nw) {  // resume: adopt the state left by the previous shard
+        const int c = s * ncta + rank;
+        if (c >= kc) break;
+        if (A.cent_in_smem) {
+            double *cv = cent_s + (size_t)s * cp;
+            const double *src = A.centroids + (size_t)c * f;
+            for (int j = lane; j < f; j += 32) cv[j] = src[j];
+        }
+    }
+    const double r_half = A.radius * 0.5, r_full = A.radius, r_relax = A.radius * 1.5;
+    const unsigned row_bytes = (unsigned)f * 8u;
+    long long next_fetch = 0;
+    long long r0 = 0;
+    int n_exact = 0;
+    long long n_blocks = 0;
+    __syncthreads();
+    cluster.sync();
+
+    while (r0 < A.n) {
+        const int par = (int)(n_blocks & 1);
+        // ---- fetch rows [next_fetch, min(n, r0 + R))
+        long long fetch_to = r0 + R;
+        if (fetch_to > A.n) fetch_to = A.n;
+        if (A.vec) {
+            if (tid == 0) {
+                for (long long r = next_fetch; r < fetch_to; ++r) {
+                    unsigned long long *bar = &full[r & (R - 1)];
+                    mbar_expect_tx(bar, row_bytes);
+                    bulk_g2s(ring + (size_t)(r & (R - 1)) * fpad, A.rows + r * (long long)f, row_bytes, bar);
+                }
+            }
+        } else {
+            for (long long r = next_fetch; r < fetch_to; ++r) {
+                double *dst = ring + (size_t)(r & (R - 1)) * fpad;
+                const double *src = A.rows + r * (long long)f;
+                for (int j = tid; j < f; j += blockDim.x) dst[j] = src[j];
+            }
+            __syncthreads();
+        }
+        next_fetch = fetch_to;
+        const int nb = (int)((A.n - r0) < B ? (A.n - r0) : B);
+        if (A.vec) {
+            for (int i = 0; i < nb; ++i) {
+                const long long r = r0 + i;
+                mbar_wait(&full[r & (R - 1)], (unsigned)((r / R) & 1));
+            }
+        }
+
+        // ---- 1. fast distances: this warp's centroid(s) x the block's rows
+        for (int s = warp; s < slots; s += nw) {
+            const int c = s * ncta + rank;
+            if (c >= kc) break;
+            const double *cv = cptr(s);
+            double acc[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) acc[i] = 0.0;
+            for (int j0 = 0; j0 < f; j0 += 32 * TCH) {
+                double cr[TCH];
+                bool ok[TCH];
+#pragma unroll
+                for (int t = 0; t < TCH; ++t) {
+                    const int j = j0 + lane + 32 * t;
+                    ok[t] = j < f;
+                    cr[t] = ok[t] ? cv[j] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < B; ++i) {
+                    if (i < nb) {
+                        const double *row = rowptr(r0 + i);
+#pragma unroll
+                        for (int t = 0; t < TCH; ++t) {
+                            if (ok[t]) {
+                                const double df = row[j0 + lane + 32 * t] - cr[t];
+                                acc[i] = fma(df, df, acc[i]);
+                            }
+                        }
+                    }
+                }
+            }
+            transpose_reduce<B>(acc, lane);
+            double tot = acc[0];
+            if (!(tot == tot)) tot = INFINITY;  // NaN never wins (`d2 < best` is false)
+            if ((lane & ((1 << kShift) - 1)) == 0) D[(size_t)s * B + (lane >> kShift)] = tot;
+        }
+        __syncthreads();
+
+        // ---- 2. per row: arg-min over this CTA's centroids, all-to-all through DSMEM
+        const int my_valid = kc > rank ? (kc - rank + ncta - 1) / ncta : 0;  // my centroids < kc
+        for (int i = warp; i < nb; i += nw) {
+            double bd = INFINITY, sd = INFINITY;
+            int bc = kNone;
+            for (int s = lane; s < my_valid; s += 32) {
+                const double d = D[(size_t)s * B + i];
+                const int c = s * ncta + rank;
+                if (lex_less(d, c, bd, bc)) {
+                    sd = bd;
+                    bd = d;
+                    bc = c;
+                } else if (d < sd) {
+                    sd = d;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double obd = __shfl_xor_sync(0xffffffffu, bd, o);
+                const double osd = __shfl_xor_sync(0xffffffffu, sd, o);
+                const int obc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (lex_less(obd, obc, bd, bc)) {
+                    sd = fmin(fmin(sd, osd), bd);
+                    bd = obd;
+                    bc = obc;
+                } else {
+                    sd = fmin(fmin(sd, osd), obd);
+                }
+            }
+            if (lane < ncta) {
+                Xch *remote = cluster.map_shared_rank(xch, lane) + ((size_t)par * 16 + rank) * B + i;
+                Xch v;
+                v.best_d = bd;
+                v.second_d = sd;
+                v.best_c = bc;
+                v.pad = 0;
+                *remote = v;
+            }
+        }
+        cluster.sync();
+
+        // ---- 3a. per row: reduce the 16 CTA entries -> G[i]
+        for (int i = warp; i < nb; i += nw) {
+            const Xch *e = xch + ((size_t)par * 16) * B + i;
+            double bd = lane < ncta ? e[(size_t)lane * B].best_d : INFINITY;
+            double sd = lane < ncta ? e[(size_t)lane * B].second_d : INFINITY;
+            int bc = lane < ncta ? e[(size_t)lane * B].best_c : kNone;
+            for (int o = 8; o > 0; o >>= 1) {
+                const double obd = __shfl_xor_sync(0xffffffffu, bd, o);
+                const double osd = __shfl_xor_sync(0xffffffffu, sd, o);
+                const int obc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (lex_less(obd, obc, bd, bc)) {
+                    sd = fmin(fmin(sd, osd), bd);
+                    bd = obd;
+                    bc = obc;
+                } else {
+                    sd = fmin(fmin(sd, osd), obd);
+                }
+            }
+            if (lane == 0) {
+                GRow g;
+                g.bd = bd;
+                g.sd = sd;
+                g.sb = sqrt(bd);
+                g.ss = sqrt(sd);
+                g.bc = bc;
+                g.pad = 0;
+                G[i] = g;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3b. in-order resolve with interval certification (one thread, identical in every CTA)
+        if (tid == 0) {
+            int n_commit = 0, exact = 0, nmod = 0, kcl = kc;
+            double dmax = 0.0;
+            bool created = false;
+            for (int i = 0; i < nb && !created; ++i) {
+                const GRow g = G[i];
+                int action, target;
+                double knew = 0.0;
+                if (kcl == 0) {
+                    action = 0;
+                    target = 0;
+                } else {
+                    const int b = (g.bc == kNone) ? 0 : g.bc;
+                    const double mod_b = disp[b];
+                    bool ok = !A.force_exact && (g.bd < INFINITY);
+                    double lo2, hi2, hi_b;
+                    if (dmax == 0.0) {  // nothing moved yet in this block: the snapshot is the state
+                        hi_b = g.sb;
+                        if (!(g.sd > g.bd * (1.0 + kDelta))) ok = false;
+                        lo2 = g.bd * (1.0 - kDelta);
+                        hi2 = g.bd * (1.0 + kDelta);
+                    } else {
+                        hi_b = g.sb + mod_b;
+                        const double lo_b = fmax(g.sb - mod_b, 0.0);
+                        if (!((g.ss - dmax) > hi_b * (1.0 + kDelta))) ok = false;
+                        lo2 = lo_b * lo_b * (1.0 - kDelta);
+                        hi2 = hi_b * hi_b * (1.0 + kDelta);
+                    }
+                    if ((r_half >= lo2 && r_half <= hi2) || (r_full >= lo2 && r_full <= hi2) ||
+                        (r_relax >= lo2 && r_relax <= hi2))
+                        ok = false;
+                    if (!ok) {
+                        if (i == 0) exact = 1;
+                        break;
+                    }
+                    const double d2 = g.bd;  // any value of the certified interval gives the same outcome
+                    if (kcl < maxk && d2 > r_half) {
+                        action = 0;
+                        target = kcl;
+                    } else if (d2 <= r_full) {
+                        action = 1;
+                        target = b;
+                    } else if (d2 <= r_relax) {
+                        action = 2;
+                        target = b;
+                    } else {
+                        action = 3;
+                        target = -1;
+                    }
+                    if (action == 1) {
+                        knew = (double)cnt[b] + 1.0;
+                        if (mod_b == 0.0) modlist[nmod++] = b;
+                        const double nd = mod_b + (hi_b / knew) * (1.0 + 1e-9) + 1e-300;  // |c' - c| = |x - c| / k_new
+                        disp[b] = nd;
+                        dmax = fmax(dmax, nd);
+                    }
+                }
+                if (action == 0) {
+                    cnt[target] = 1ull;
+                    kcl++;
+                    created = true;
+                } else if (action == 1 || action == 2) {
+                    cnt[target] += 1ull;
+                }
+                Dec dd;
+                dd.knew = knew;
+                dd.action = action;
+                dd.target = target;
+                dec[i] = dd;
+                n_commit++;
+            }
+            for (int m = 0; m < nmod; ++m) disp[modlist[m]] = 0.0;
+            ctl[0] = n_commit;
+            ctl[1] = exact;
+            ctl[2] = kcl;
+        }
+        __syncthreads();
+        int n_commit = ctl[0];
+        const int exact = ctl[1];
+
+        if (exact) {
+            // ---- exact path for row r0: reference arithmetic for every candidate within delta
+            n_exact++;
+            const GRow g = G[0];
+            const double hi = g.bd * (1.0 + kDelta);
+            const double *row = rowptr(r0);
+            double my_d = INFINITY;
+            int my_c = kNone;
+            for (int s = tid; s < my_valid; s += blockDim.x) {
+                const int c = s * ncta + rank;
+                if (A.force_exact || D[(size_t)s * B] <= hi || !(hi < INFINITY)) {
+                    const double *cv = cptr(s);
+                    double d2 = 0.0;
+                    for (int j = 0; j < f; ++j) {  // src/clustering.rs:917-921
+                        const double diff = __dsub_rn(row[j], cv[j]);
+                        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+                    }
+                    if (!(d2 == d2)) d2 = INFINITY;
+                    if (lex_less(d2, c, my_d, my_c)) {
+                        my_d = d2;
+                        my_c = c;
+                    }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, my_d, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, my_c, o);
+                if (lex_less(od, oc, my_d, my_c)) {
+                    my_d = od;
+                    my_c = oc;
+                }
+            }
+            if (lane == 0) {
+                wred_d[warp] = my_d;
+                wred_c[warp] = my_c;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double bd = lane < nw ? wred_d[lane] : INFINITY;
+                int bc = lane < nw ? wred_c[lane] : kNone;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double obd = __shfl_xor_sync(0xffffffffu, bd, o);
+                    const int obc = __shfl_xor_sync(0xffffffffu, bc, o);
+                    if (lex_less(obd, obc, bd, bc)) {
+                        bd = obd;
+                        bc = obc;
+                    }
+                }
+                if (lane < ncta) {
+                    Xch *remote = cluster.map_shared_rank(xch_exact, lane) + par * 16 + rank;
+                    Xch v;
+                    v.best_d = bd;
+                    v.second_d = INFINITY;
+                    v.best_c = bc;
+                    v.pad = 0;
+                    *remote = v;
+                }
+            }
+            cluster.sync();
+            if (tid == 0) {
+                double bd = INFINITY;
+                int bc = kNone;
+                for (int q = 0; q < ncta; ++q) {
+                    const Xch e = xch_exact[par * 16 + q];
+                    if (lex_less(e.best_d, e.best_c, bd, bc)) {
+                        bd = e.best_d;
+                        bc = e.best_c;
+                    }
+                }
+                const int b = (bc == kNone) ? 0 : bc;
+                int action, target;
+                double knew = 0.0;
+                int kcl = ctl[2];
+                if (kcl < maxk && bd > r_half) {
+                    action = 0;
+                    target = kcl;
+                    cnt[target] = 1ull;
+                    kcl++;
+                } else if (bd <= r_full) {
+                    action = 1;
+                    target = b;
+                    knew = (double)cnt[b] + 1.0;
+                    cnt[b] += 1ull;
+                } else if (bd <= r_relax) {
+                    action = 2;
+                    target = b;
+                    cnt[b] += 1ull;
+                } else {
+                    action = 3;
+                    target = -1;
+                }
+                Dec dd;
+                dd.knew = knew;
+                dd.action = action;
+                dd.target = target;
+                dec[0] = dd;
+                ctl[0] = 1;
+                ctl[2] = kcl;
+            }
+            __syncthreads();
+            n_commit = 1;
+        }
+        kc = ctl[2];
+
+        // ---- 4. apply the committed decisions in row order (owner warps), write assignments
+        for (int i = 0; i < n_commit; ++i) {
+            const Dec dd = dec[i];
+            if (dd.action == 3) continue;
+            const int owner = dd.target % ncta, slot = dd.target / ncta;
+            if (owner != rank || warp != slot % nw) continue;
+            double *cv = cptr(slot);
+            const double *row = rowptr(r0 + i);
+            if (dd.action == 0) {
+                for (int j = lane; j < f; j += 32) cv[j] = row[j];
+            } else if (dd.action == 1) {
+                for (int j = lane; j < f; j += 32) {
+                    const double c0 = cv[j];
+                    cv[j] = __dadd_rn(c0, __ddiv_rn(__dsub_rn(row[j], c0), dd.knew));  // :748
+                }
+            }
+        }
+        if (rank == 0 && tid < n_commit) A.assign[r0 + tid] = (long long)dec[tid].target;
+        r0 += n_commit;
+        n_blocks++;
+        __syncthreads();  // ring slots, D, G, dec are free for the next block
+    }
+    cluster.sync();
+    // ---- write back
+    for (int s = warp; s < slots; s += nw) {
+        const int c = s * ncta + rank;
+        if (c >= kc) break;
+        if (A.cent_in_smem) {
+            const double *cv = cent_s + (size_t)s * cp;
+            double *dst = A.centroids + (size_t)c * f;
+            for (int j = lane; j < f; j += 32) dst[j] = cv[j];
+        }
+    }
+    if (rank == 0) {
+        for (int c = tid; c < kc; c += blockDim.x) A.sizes[c] = cnt[c];
+        if (tid == 0) {
+            A.x_out[0] = kc;
+            A.stats[0] = n_exact;
+            A.stats[1] = (int)(n_blocks > 0x7fffffff ? 0x7fffffff : n_blocks);
+        }
+    }
+}
+
+template <int B>
+size_t cluster_block_smem_bytes(int f, int slots, int maxk, bool cent_in_smem) {
+    const int fpad = (f + 1) & ~1;
+    size_t b = (size_t)2 * B * fpad * 8;            // ring
+    b += (size_t)slots * B * 8;                     // D
+    b += (size_t)((maxk + 1) & ~1) * 8;             // disp
+    b += 32 * 8;                                    // wred_d
+    b += (size_t)(2 * 16 * B + 32) * sizeof(Xch);   // xch + xch_exact
+    b += (size_t)B * sizeof(GRow);
+    b += (size_t)B * sizeof(Dec);
+    b += (size_t)2 * B * 8;                         // mbarriers
+    b += (size_t)maxk * 8;                          // cnt
+    b += 32 * 4 + 4 * 4 + (size_t)(B + 2) * 4;      // wred_c, ctl, modlist
+    if (cent_in_smem) b += (size_t)slots * (f | 1) * 8;
+    return b + 64;
+}
+
+}  // namespace

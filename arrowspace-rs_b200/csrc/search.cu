@@ -9,8 +9,9 @@
 //
 // Tiling: a CTA owns 128 queries x one slab of items and walks the slab in 128-item tiles.
 // Per tile the F dimension is streamed in 16-feature chunks (cp.async, double buffered) into
-// row-major smem tiles with pitch 20 doubles (conflict-free fragment loads); 8 warps (4 x 2)
-// each hold a 32 x 64 accumulator block as 4 x 8 DMMA fragments.  The epilogue turns dots
+// row-major smem tiles with pitch 20 doubles (conflict-free fragment loads); 16 warps (4 x 4)
+// each hold a 32 x 32 accumulator block as 4 x 4 DMMA fragments (4 warps per scheduler keep the
+// FP64 tensor pipe issuing: with 2 per scheduler it idled half the time, profiles/r01_v1_search).  The epilogue turns dots
 // into scores, parks them in smem (aliasing the operand stages) and one warp per query
 // merges the survivors into that query's sorted top-k list (smem, persistent over the slab).
 // Per-slab lists are merged by (score desc, index asc): exactly the order of the reference's
@@ -20,7 +21,8 @@
 namespace {
 
 constexpr int TQ = 128, TN = 128, KC = 16, PITCH = KC + 4;
-constexpr int kThreads = 256;
+constexpr int kWarps = 16;               // 4 (queries) x 4 (items) warps, 32 x 32 accumulators each
+constexpr int kThreads = kWarps * 32;
 constexpr int STAGE_DOUBLES = (TQ + TN) * PITCH;  // 5120 doubles = 40 KB
 constexpr int SPITCH = 72;                        // score half-tile pitch (doubles)
 constexpr int MODE_COSINE = 0, MODE_L2 = 1;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
     long long *sm_self = reinterpret_cast<long long *>(list_len + TQ);  // TQ (8B aligned: TQ*k ints + TQ ints even)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp >> 2, wn = warp & 3;
     const int gid = lane >> 2, tig = lane & 3;
     const int k = A.k, f = A.f;
 
@@ -141,11 +143,11 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
             sm_nx[c] = (MODE == MODE_COSINE) ? sqrt(n2) : n2;
             sm_lx[c] = (MODE == MODE_COSINE && ok) ? A.lambdas[gi] : 0.0;
         }
-        double acc[4][8][2];
+        double acc[4][4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         // prologue: chunk 0 -> stage 0
         load_tile_chunk<VEC>(stages, A.queries, q0, A.nq, f, 0, tid);
@@ -166,32 +168,32 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
             const double *Xs = Qs + TQ * PITCH;
 #pragma unroll
             for (int kk = 0; kk < KC; kk += 4) {
-                double a[4], b[8];
+                double a[4], b[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[i] = Qs[(wm * 32 + i * 8 + gid) * PITCH + kk + tig];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b[j] = Xs[(wn * 64 + j * 8 + gid) * PITCH + kk + tig];
+                for (int j = 0; j < 4; ++j) b[j] = Xs[(wn * 32 + j * 8 + gid) * PITCH + kk + tig];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
             __syncthreads();
         }
 
         // ---- epilogue: scores -> smem half tile -> per-query top-k merge
         for (int half = 0; half < 2; ++half) {
-            if (wn == half) {
+            if ((wn >> 1) == half) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = wm * 32 + i * 8 + gid;
                     const double nq = sm_nq[r], lq = sm_lq[r];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         double2 sv;
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            const int cl = j * 8 + tig * 2 + u;  // column inside this half
+                            const int cl = (wn & 1) * 32 + j * 8 + tig * 2 + u;  // column inside this half
                             const int c = half * 64 + cl;
                             const long long gi = i0 + c;
                             const double dot = acc[i][j][u];
@@ -211,13 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
                             if (gi >= A.n) s = -INFINITY;
                             if (u == 0) sv.x = s; else sv.y = s;
                         }
-                        *reinterpret_cast<double2 *>(&S[r * SPITCH + j * 8 + tig * 2]) = sv;
+                        *reinterpret_cast<double2 *>(&S[r * SPITCH + (wn & 1) * 32 + j * 8 + tig * 2]) = sv;
                     }
                 }
             }
             __syncthreads();
-            for (int qq = 0; qq < TQ / 8; ++qq) {
-                const int q = warp * (TQ / 8) + qq;
+            for (int qq = 0; qq < TQ / kWarps; ++qq) {
+                const int q = warp * (TQ / kWarps) + qq;
                 if (q0 + q >= A.nq) break;
                 int len = list_len[q];
                 double thr = (len == k) ? list_s[(size_t)q * k + k - 1] : -INFINITY;

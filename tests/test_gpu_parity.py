@@ -328,6 +328,43 @@ def test_cluster_parity(ctx, asb, oracle, n, f, maxk, rscale):
     assert (want[1] >= 0).sum() > 0
 
 
+@pytest.mark.parametrize("n,f,maxk,rscale", [(60_000, 64, 100, 1.0), (30_000, 128, 316, 0.8), (8_000, 770, 64, 1.0),
+                                             (5_000, 33, 40, 0.7)])
+def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rscale):
+    """Long walks exercise the blocked kernel's interval certification (counts grow, displacements
+    shrink, blocks get longer); the row-wise kernel must give the same bits."""
+    x = asb.synth.protein_like(n, f, seed=77)
+    radius = rscale * 1.5 * f * 0.0025 * 2
+    want = oracle.cluster_incremental(x, maxk, radius)
+    got = ctx.cluster_incremental(x, maxk, radius)
+    _assert_cluster_equal(got, want)
+    assert ctx.kernel_ms("cluster_variant") in (0.0, 1.0)
+    blocks = ctx.kernel_ms("cluster_blocks")
+    assert 0 < blocks <= n
+    ctx.set_option("cluster_rowwise", 1)
+    try:
+        got = ctx.cluster_incremental(x, maxk, radius)
+        assert ctx.kernel_ms("cluster_variant") == 2.0
+    finally:
+        ctx.set_option("cluster_rowwise", 0)
+    _assert_cluster_equal(got, want)
+
+
+def test_cluster_resume_equals_single_walk(ctx, asb, oracle):
+    """Shard 0, then shard 1 resumed from shard 0's state == one walk (the multi-GPU hand-off)."""
+    x = asb.synth.protein_like(9_000, 96, seed=78)
+    radius = 1.5 * 96 * 0.0025 * 2
+    maxk = 80
+    want = oracle.cluster_incremental(x, maxk, radius)
+    cent = np.zeros((maxk, 96))
+    sizes = np.zeros(maxk, dtype=np.uint64)
+    k, asg = 0, []
+    for a, b in [(0, 1), (1, 4000), (4000, 4001), (4001, 9000)]:
+        k, part = ctx.cluster_incremental_resume(np.ascontiguousarray(x[a:b]), maxk, radius, cent, sizes, k)
+        asg.append(part)
+    _assert_cluster_equal((cent[:k], np.concatenate(asg), sizes[:k]), want)
+
+
 def test_cluster_exact_path_and_ties(ctx, asb, oracle):
     """Integer-valued data makes many distances tie exactly -> the certified fast path must hand
     those rows to the reference-arithmetic path; forcing that path for ALL rows gives the same
