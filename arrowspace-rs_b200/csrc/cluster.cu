@@ -48,7 +48,8 @@ struct ClusterArgs {
     int cent_in_smem;
     int slots_per_cta;
     int force_exact;
-    int vec;  // rows 16B-copyable
+    int vec;   // rows 16B-copyable
+    int vec2;  // centroid storage 16B-loadable (blocked kernel, LDS.128 distance loop)
 };
 
 struct __align__(16) Xch {
@@ -436,9 +437,11 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             const bool in_smem = bytes(true) <= smem_cap;
             const size_t smem = bytes(in_smem);
             if (smem > smem_cap) continue;
-            const int nwarps = slots < 4 ? 4 : (slots > 32 ? 32 : slots);
+            const int wcap = variant < 2 ? 24 : 32;  // blocked kernels are compiled for <= 768 threads
+            const int nwarps = slots < 4 ? 4 : (slots > wcap ? wcap : slots);
             A.cent_in_smem = in_smem ? 1 : 0;
             A.slots_per_cta = slots;
+            A.vec2 = (A.vec && (in_smem || (((uintptr_t)centroids_d & 15) == 0))) ? 1 : 0;
             const void *fn = variant == 0   ? (const void *)cluster_block_kernel<16>
                              : variant == 1 ? (const void *)cluster_block_kernel<8>
                                             : (const void *)cluster_rowwise_kernel;

@@ -38,7 +38,18 @@ struct __align__(16) Dec {
     double knew;
     int action;  // 0 new centroid, 1 running-mean update, 2 count only, 3 drop
     int target;
+    int owner;   // CTA rank that stores the target centroid
+    int slot;    // slot inside that CTA
+    int owarp;   // warp of that CTA that owns the slot
+    int pad;
 };
+
+constexpr int kGroup = 8;  // rows per bulk copy / mbarrier
+
+__host__ __device__ inline int block_cent_pitch(int f) {
+    const int fpad = (f + 1) & ~1;
+    return ((fpad / 2) & 1) ? fpad : fpad + 2;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -85,19 +96,56 @@ __device__ __forceinline__ void transpose_reduce(double (&acc)[B], int lane) {
     for (; off > 0; off >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
 }
 
+// acc[i] += sum over T features (j0 + lane + 32 t) of (row_i - c)^2 for the B rows of the block.
+template <int B, int T>
+__device__ __forceinline__ void dist_chunk(double (&acc)[B], const double *__restrict__ cv, const double *ring,
+                                           int s0, int ring_mask, int fpad, int j0, int lane) {
+    double cr[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) cr[t] = cv[j0 + lane + 32 * t];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        const double *row = ring + (size_t)((s0 + i) & ring_mask) * fpad + j0 + lane;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double df = row[32 * t] - cr[t];
+            acc[i] = fma(df, df, acc[i]);
+        }
+    }
+}
+
+// Same with 16-byte shared-memory loads: the lane owns the feature pairs (j0 + 2 lane + 64 t, +1).
+template <int B, int T>
+__device__ __forceinline__ void dist_chunk2(double (&acc)[B], const double *__restrict__ cv, const double *ring,
+                                            int s0, int ring_mask, int fpad, int j0, int lane) {
+    double2 cr[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) cr[t] = *reinterpret_cast<const double2 *>(cv + j0 + 2 * lane + 64 * t);
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        const double *row = ring + (size_t)((s0 + i) & ring_mask) * fpad + j0 + 2 * lane;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double2 x = *reinterpret_cast<const double2 *>(row + 64 * t);
+            const double d0 = x.x - cr[t].x, d1 = x.y - cr[t].y;
+            acc[i] = fma(d0, d0, acc[i]);
+            acc[i] = fma(d1, d1, acc[i]);
+        }
+    }
+}
+
 template <int B>
-__global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
-    constexpr int R = 2 * B;                       // ring rows
+__global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
+    constexpr int R = 4 * kGroup;                  // ring rows (4 groups of 8; B <= 16 spans <= 3 groups)
     constexpr int kShift = (B == 16) ? 1 : 2;      // lane -> row after transpose_reduce
-    constexpr int TCH = 4;                         // feature chunk = 32 * TCH
     cg::cluster_group cluster = cg::this_cluster();
     const int ncta = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
     const int f = A.f;
-    const int cp = f | 1;
     const int fpad = (f + 1) & ~1;
+    const int cp = block_cent_pitch(f);  // even (16 B rows) with an odd number of 16 B granules
     const int slots = A.slots_per_cta;
     const int maxk = A.max_k;
 
@@ -110,12 +158,13 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
     Xch *xch_exact = xch + 2 * 16 * B;                                      // [2][16]
     GRow *G = reinterpret_cast<GRow *>(xch_exact + 32);                     // B
     Dec *dec = reinterpret_cast<Dec *>(G + B);                              // B
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(dec + B);  // R mbarriers
-    unsigned long long *cnt = full + R;                                     // maxk (replicated counts)
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(dec + B);  // 4 group mbarriers
+    unsigned long long *cnt = full + 4;                                     // maxk (replicated counts)
     int *wred_c = reinterpret_cast<int *>(cnt + maxk);                      // 32
     int *ctl = wred_c + 32;                                                 // [0] n_commit [1] exact flag [2] kc
     int *modlist = ctl + 4;                                                 // B
-    double *cent_s = reinterpret_cast<double *>(modlist + B + ((B + 4) & 1));  // slots * cp (8B aligned)
+    double *cent_s = reinterpret_cast<double *>(
+        (reinterpret_cast<uintptr_t>(modlist + B) + 15) & ~(uintptr_t)15);  // slots * cp, 16 B aligned
 
     auto cptr = [&](int slot) -> double * {
         return A.cent_in_smem ? cent_s + (size_t)slot * cp : A.centroids + ((size_t)slot * ncta + rank) * f;
@@ -124,7 +173,7 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
 
     // ---- init
     if (tid == 0) {
-        for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < 4; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int c = tid; c < maxk; c += blockDim.x) {
@@ -143,7 +192,8 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
     }
     const double r_half = A.radius * 0.5, r_full = A.radius, r_relax = A.radius * 1.5;
     const unsigned row_bytes = (unsigned)f * 8u;
-    long long next_fetch = 0;
+    long long next_fetch = 0;   // rows [0, next_fetch) have been requested (multiple of kGroup, or n)
+    long long waited_groups = 0;  // groups [0, waited_groups) are known to have landed
     long long r0 = 0;
     int n_exact = 0;
     long long n_blocks = 0;
@@ -152,15 +202,19 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
 
     while (r0 < A.n) {
         const int par = (int)(n_blocks & 1);
-        // ---- fetch rows [next_fetch, min(n, r0 + R))
-        long long fetch_to = r0 + R;
+        // ---- fetch whole groups of 8 rows up to group (r0/8 + 3): the slot of that group held group
+        //      r0/8 - 1, every row of which is already committed
+        long long fetch_to = (r0 / kGroup + 4) * kGroup;
         if (fetch_to > A.n) fetch_to = A.n;
         if (A.vec) {
             if (tid == 0) {
-                for (long long r = next_fetch; r < fetch_to; ++r) {
-                    unsigned long long *bar = &full[r & (R - 1)];
-                    mbar_expect_tx(bar, row_bytes);
-                    bulk_g2s(ring + (size_t)(r & (R - 1)) * fpad, A.rows + r * (long long)f, row_bytes, bar);
+                for (long long r = next_fetch; r < fetch_to; r += kGroup) {
+                    const long long g = r / kGroup;
+                    const long long rows_in = (A.n - r) < kGroup ? (A.n - r) : kGroup;
+                    unsigned long long *bar = &full[g & 3];
+                    const unsigned bytes = (unsigned)rows_in * row_bytes;
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(ring + (size_t)(r & (R - 1)) * fpad, A.rows + r * (long long)f, bytes, bar);
                 }
             }
         } else {
@@ -174,13 +228,14 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
         next_fetch = fetch_to;
         const int nb = (int)((A.n - r0) < B ? (A.n - r0) : B);
         if (A.vec) {
-            for (int i = 0; i < nb; ++i) {
-                const long long r = r0 + i;
-                mbar_wait(&full[r & (R - 1)], (unsigned)((r / R) & 1));
-            }
+            const long long g_last = (r0 + nb - 1) / kGroup;
+            for (; waited_groups <= g_last; ++waited_groups)
+                mbar_wait(&full[waited_groups & 3], (unsigned)((waited_groups >> 2) & 1));
         }
 
-        // ---- 1. fast distances: this warp's centroid(s) x the block's rows
+        // ---- 1. fast distances: this warp's centroid(s) x the block's rows (rows >= nb read stale
+        //      ring slots; their results are never consumed)
+        const int s0 = (int)(r0 & (R - 1));
         for (int s = warp; s < slots; s += nw) {
             const int c = s * ncta + rank;
             if (c >= kc) break;
@@ -188,27 +243,21 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
             double acc[B];
 #pragma unroll
             for (int i = 0; i < B; ++i) acc[i] = 0.0;
-            for (int j0 = 0; j0 < f; j0 += 32 * TCH) {
-                double cr[TCH];
-                bool ok[TCH];
-#pragma unroll
-                for (int t = 0; t < TCH; ++t) {
-                    const int j = j0 + lane + 32 * t;
-                    ok[t] = j < f;
-                    cr[t] = ok[t] ? cv[j] : 0.0;
-                }
+            int j0 = 0;
+            if (A.vec2) {
+                for (; j0 + 384 <= f; j0 += 384) dist_chunk2<B, 6>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+                for (; j0 + 128 <= f; j0 += 128) dist_chunk2<B, 2>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+                for (; j0 + 64 <= f; j0 += 64) dist_chunk2<B, 1>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+            }
+            for (; j0 + 384 <= f; j0 += 384) dist_chunk<B, 12>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+            for (; j0 + 128 <= f; j0 += 128) dist_chunk<B, 4>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+            for (; j0 + 32 <= f; j0 += 32) dist_chunk<B, 1>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
+            if (j0 + lane < f) {
+                const double cr = cv[j0 + lane];
 #pragma unroll
                 for (int i = 0; i < B; ++i) {
-                    if (i < nb) {
-                        const double *row = rowptr(r0 + i);
-#pragma unroll
-                        for (int t = 0; t < TCH; ++t) {
-                            if (ok[t]) {
-                                const double df = row[j0 + lane + 32 * t] - cr[t];
-                                acc[i] = fma(df, df, acc[i]);
-                            }
-                        }
-                    }
+                    const double df = ring[(size_t)((s0 + i) & (R - 1)) * fpad + j0 + lane] - cr;
+                    acc[i] = fma(df, df, acc[i]);
                 }
             }
             transpose_reduce<B>(acc, lane);
@@ -289,82 +338,155 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
         }
         __syncthreads();
 
-        // ---- 3b. in-order resolve with interval certification (one thread, identical in every CTA)
-        if (tid == 0) {
-            int n_commit = 0, exact = 0, nmod = 0, kcl = kc;
-            double dmax = 0.0;
-            bool created = false;
-            for (int i = 0; i < nb && !created; ++i) {
-                const GRow g = G[i];
-                int action, target;
-                double knew = 0.0;
-                if (kcl == 0) {
-                    action = 0;
-                    target = 0;
-                } else {
-                    const int b = (g.bc == kNone) ? 0 : g.bc;
-                    const double mod_b = disp[b];
-                    bool ok = !A.force_exact && (g.bd < INFINITY);
-                    double lo2, hi2, hi_b;
-                    if (dmax == 0.0) {  // nothing moved yet in this block: the snapshot is the state
-                        hi_b = g.sb;
-                        if (!(g.sd > g.bd * (1.0 + kDelta))) ok = false;
-                        lo2 = g.bd * (1.0 - kDelta);
-                        hi2 = g.bd * (1.0 + kDelta);
-                    } else {
-                        hi_b = g.sb + mod_b;
-                        const double lo_b = fmax(g.sb - mod_b, 0.0);
-                        if (!((g.ss - dmax) > hi_b * (1.0 + kDelta))) ok = false;
-                        lo2 = lo_b * lo_b * (1.0 - kDelta);
-                        hi2 = hi_b * hi_b * (1.0 + kDelta);
-                    }
-                    if ((r_half >= lo2 && r_half <= hi2) || (r_full >= lo2 && r_full <= hi2) ||
-                        (r_relax >= lo2 && r_relax <= hi2))
-                        ok = false;
-                    if (!ok) {
-                        if (i == 0) exact = 1;
-                        break;
-                    }
-                    const double d2 = g.bd;  // any value of the certified interval gives the same outcome
-                    if (kcl < maxk && d2 > r_half) {
-                        action = 0;
-                        target = kcl;
-                    } else if (d2 <= r_full) {
-                        action = 1;
-                        target = b;
-                    } else if (d2 <= r_relax) {
-                        action = 2;
-                        target = b;
-                    } else {
-                        action = 3;
-                        target = -1;
-                    }
-                    if (action == 1) {
-                        knew = (double)cnt[b] + 1.0;
-                        if (mod_b == 0.0) modlist[nmod++] = b;
-                        const double nd = mod_b + (hi_b / knew) * (1.0 + 1e-9) + 1e-300;  // |c' - c| = |x - c| / k_new
-                        disp[b] = nd;
-                        dmax = fmax(dmax, nd);
-                    }
+        // ---- 3b. resolve the block's rows IN ORDER (warp 0, identical in every CTA).
+        //      Lane i holds row i's summary.  Fast path (saturated state, the steady state of a long
+        //      walk): all rows are certified at once against the worst-case total displacement E of
+        //      the block, E >= sum_j (sb_j + E) / (cnt_j + 1); duplicates of a target get their k_new
+        //      in row order from a match mask.  Otherwise: the sequential interval-certified loop.
+        if (warp == 0) {
+            GRow g;
+            g.bd = g.sd = g.sb = g.ss = INFINITY;
+            g.bc = kNone;
+            if (lane < nb) g = G[lane];
+            int n_commit = 0, exact = 0, kcl = kc;
+            int my_action = 3, my_target = -1;
+            double my_knew = 0.0;
+            bool done = false;
+            if (!A.force_exact && kc == maxk) {
+                const int b = (g.bc == kNone) ? 0 : g.bc;
+                const unsigned long long cb = cnt[b];
+                const float inv = lane < nb ? 1.0f / (float)(cb + 1ull) : 0.0f;
+                float qsum = inv;
+                double esum = lane < nb ? g.sb * (double)inv : 0.0;
+                for (int o = 16; o > 0; o >>= 1) {
+                    qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+                    esum += __shfl_xor_sync(0xffffffffu, esum, o);
                 }
-                if (action == 0) {
-                    cnt[target] = 1ull;
-                    kcl++;
-                    created = true;
-                } else if (action == 1 || action == 2) {
-                    cnt[target] += 1ull;
+                bool ok = (qsum < 0.25f) && (esum < INFINITY);
+                const double E = esum / (1.0 - (double)qsum) * 1.001 + 1e-300;
+                const double hi_b = g.sb + E, lo_b = fmax(g.sb - E, 0.0);
+                const double lo2 = lo_b * lo_b * (1.0 - kDelta), hi2 = hi_b * hi_b * (1.0 + kDelta);
+                bool row_ok = (g.bd < INFINITY) && ((g.ss - E) > hi_b * (1.0 + kDelta)) &&
+                              !((r_full >= lo2 && r_full <= hi2) || (r_relax >= lo2 && r_relax <= hi2));
+                if (lane >= nb) row_ok = true;
+                ok = ok && __all_sync(0xffffffffu, row_ok);
+                if (ok) {
+                    int action = 3;
+                    if (lane < nb) action = (g.bd <= r_full) ? 1 : ((g.bd <= r_relax) ? 2 : 3);
+                    const bool counts = (action == 1 || action == 2);
+                    const unsigned m = __match_any_sync(0xffffffffu, counts ? b : (-1 - lane));
+                    const int lower = __popc(m & ((1u << lane) - 1u));
+                    if (counts) {
+                        my_knew = (double)(cb + (unsigned long long)lower) + 1.0;
+                        if ((m >> lane) == 1u) cnt[b] = cb + (unsigned long long)__popc(m);  // highest lane of the group
+                    }
+                    my_action = action;
+                    my_target = counts ? b : -1;
+                    n_commit = nb;
+                    done = true;
                 }
-                Dec dd;
-                dd.knew = knew;
-                dd.action = action;
-                dd.target = target;
-                dec[i] = dd;
-                n_commit++;
             }
-            for (int m = 0; m < nmod; ++m) disp[modlist[m]] = 0.0;
-            ctl[0] = n_commit;
-            ctl[1] = exact;
-            ctl[2] = kcl;
+            if (!done) {
+                int nmod = 0;
+                double dmax = 0.0;
+                bool created = false;
+                for (int i = 0; i < nb && !created; ++i) {
+                    const double bd = __shfl_sync(0xffffffffu, g.bd, i);
+                    const double sd = __shfl_sync(0xffffffffu, g.sd, i);
+                    const double sb = __shfl_sync(0xffffffffu, g.sb, i);
+                    const double ss = __shfl_sync(0xffffffffu, g.ss, i);
+                    const int bc = __shfl_sync(0xffffffffu, g.bc, i);
+                    int action, target;
+                    double knew = 0.0;
+                    if (kcl == 0) {
+                        action = 0;
+                        target = 0;
+                    } else {
+                        const int b = (bc == kNone) ? 0 : bc;
+                        const double mod_b = disp[b];
+                        const unsigned long long cb = cnt[b];
+                        bool ok = !A.force_exact && (bd < INFINITY);
+                        double lo2, hi2, hi_b;
+                        if (dmax == 0.0) {  // nothing moved yet in this block: the snapshot is the state
+                            hi_b = sb;
+                            if (!(sd > bd * (1.0 + kDelta))) ok = false;
+                            lo2 = bd * (1.0 - kDelta);
+                            hi2 = bd * (1.0 + kDelta);
+                        } else {
+                            hi_b = sb + mod_b;
+                            const double lo_b = fmax(sb - mod_b, 0.0);
+                            if (!((ss - dmax) > hi_b * (1.0 + kDelta))) ok = false;
+                            lo2 = lo_b * lo_b * (1.0 - kDelta);
+                            hi2 = hi_b * hi_b * (1.0 + kDelta);
+                        }
+                        if ((r_half >= lo2 && r_half <= hi2) || (r_full >= lo2 && r_full <= hi2) ||
+                            (r_relax >= lo2 && r_relax <= hi2))
+                            ok = false;
+                        if (!ok) {
+                            if (i == 0) exact = 1;
+                            break;
+                        }
+                        const double d2 = bd;  // any value of the certified interval gives the same outcome
+                        if (kcl < maxk && d2 > r_half) {
+                            action = 0;
+                            target = kcl;
+                        } else if (d2 <= r_full) {
+                            action = 1;
+                            target = b;
+                        } else if (d2 <= r_relax) {
+                            action = 2;
+                            target = b;
+                        } else {
+                            action = 3;
+                            target = -1;
+                        }
+                        if (action == 1) {
+                            knew = (double)cb + 1.0;
+                            // |c' - c| = |x - c| / k_new; a float reciprocal with 1e-3 slack bounds it from above
+                            const double nd = mod_b + hi_b * (double)(1.001f / (float)knew) + 1e-300;
+                            if (lane == 0) {
+                                if (mod_b == 0.0) modlist[nmod] = b;
+                                disp[b] = nd;
+                            }
+                            if (mod_b == 0.0) nmod++;
+                            dmax = fmax(dmax, nd);
+                        }
+                        if (lane == 0 && (action == 1 || action == 2)) cnt[b] = cb + 1ull;
+                    }
+                    if (action == 0) {
+                        if (lane == 0) cnt[target] = 1ull;
+                        kcl++;
+                        created = true;
+                    }
+                    if (lane == i) {
+                        my_action = action;
+                        my_target = target;
+                        my_knew = knew;
+                    }
+                    n_commit++;
+                    __syncwarp();
+                }
+                __syncwarp();
+                if (lane == 0)
+                    for (int m = 0; m < nmod; ++m) disp[modlist[m]] = 0.0;
+            }
+            if (lane < n_commit) {  // decision records, owner coordinates computed in parallel
+                Dec dd;
+                dd.knew = my_knew;
+                dd.action = my_action;
+                dd.target = my_target;
+                const int tt = my_target < 0 ? 0 : my_target;
+                dd.owner = tt % ncta;
+                dd.slot = tt / ncta;
+                dd.owarp = dd.slot % nw;
+                dd.pad = 0;
+                dec[lane] = dd;
+            }
+            if (lane == 0) {
+                ctl[0] = n_commit;
+                ctl[1] = exact;
+                ctl[2] = kcl;
+            }
         }
         __syncthreads();
         int n_commit = ctl[0];
@@ -465,6 +587,11 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
                 dd.knew = knew;
                 dd.action = action;
                 dd.target = target;
+                const int tt = target < 0 ? 0 : target;
+                dd.owner = tt % ncta;
+                dd.slot = tt / ncta;
+                dd.owarp = dd.slot % nw;
+                dd.pad = 0;
                 dec[0] = dd;
                 ctl[0] = 1;
                 ctl[2] = kcl;
@@ -477,10 +604,8 @@ __global__ void __launch_bounds__(1024, 1) cluster_block_kernel(ClusterArgs A) {
         // ---- 4. apply the committed decisions in row order (owner warps), write assignments
         for (int i = 0; i < n_commit; ++i) {
             const Dec dd = dec[i];
-            if (dd.action == 3) continue;
-            const int owner = dd.target % ncta, slot = dd.target / ncta;
-            if (owner != rank || warp != slot % nw) continue;
-            double *cv = cptr(slot);
+            if (dd.action == 3 || dd.owner != rank || dd.owarp != warp) continue;
+            double *cv = cptr(dd.slot);
             const double *row = rowptr(r0 + i);
             if (dd.action == 0) {
                 for (int j = lane; j < f; j += 32) cv[j] = row[j];
@@ -527,11 +652,11 @@ size_t cluster_block_smem_bytes(int f, int slots, int maxk, bool cent_in_smem) {
     b += (size_t)(2 * 16 * B + 32) * sizeof(Xch);   // xch + xch_exact
     b += (size_t)B * sizeof(GRow);
     b += (size_t)B * sizeof(Dec);
-    b += (size_t)2 * B * 8;                         // mbarriers
+    b += (size_t)4 * 8;                             // group mbarriers
     b += (size_t)maxk * 8;                          // cnt
     b += 32 * 4 + 4 * 4 + (size_t)(B + 2) * 4;      // wred_c, ctl, modlist
-    if (cent_in_smem) b += (size_t)slots * (f | 1) * 8;
-    return b + 64;
+    if (cent_in_smem) b += (size_t)slots * block_cent_pitch(f) * 8;
+    return b + 96;
 }
 
 }  // namespace

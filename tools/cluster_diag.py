@@ -1,0 +1,18 @@
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import arrowspace_b200 as asb, torch, numpy as np
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+f = 384
+ctx = asb.Context(0)
+x = asb.synth.protein_like(n, f, seed=42)
+xd = torch.from_numpy(x).cuda()
+_, kmax = asb.heuristics.step1_bounds(1_000_000, f, f)
+radius = asb.heuristics.pilot_radius(x, kmax, 128)
+for upto in (2_000, 20_000, n):
+    for it in range(2):
+        ctx.cluster_incremental(xd[:upto], kmax, radius)
+    print(f"rows={upto} ms={ctx.kernel_ms('cluster_kernel'):.2f} blocks={ctx.kernel_ms('cluster_blocks'):.0f} "
+          f"rows/block={upto/max(ctx.kernel_ms('cluster_blocks'),1):.2f} exact={ctx.kernel_ms('cluster_exact_rows'):.0f} "
+          f"us/row={1e3*ctx.kernel_ms('cluster_kernel')/upto:.3f} us/block={1e3*ctx.kernel_ms('cluster_kernel')/max(ctx.kernel_ms('cluster_blocks'),1):.2f}")
