@@ -41,7 +41,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES]
-    deps = srcs + [CSRC / "common.cuh", ROOT / "include" / "arrowspace_b200.h"]
+    deps = srcs + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "arrowspace_b200.h"]
     if force or _stale(LIB_PATH, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, srcs)]
         if verbose:

@@ -134,10 +134,60 @@ __device__ __forceinline__ void dist_chunk2(double (&acc)[B], const double *__re
     }
 }
 
+// Register tile of 2 centroids x 8 rows: every row element fetched from shared memory feeds two
+// centroids (the distance loop was shared-memory-bandwidth bound with one centroid per warp,
+// profiles/r01_cluster_v4).  acc[c * 8 + i]; 16-byte loads, lane owns features (j0 + 2 lane + 64 t, +1).
+template <int T>
+__device__ __forceinline__ void dist_tile2x8_v2(double (&acc)[16], const double *__restrict__ cv0,
+                                                const double *__restrict__ cv1, const double *ring, int s0,
+                                                int ring_mask, int fpad, int j0, int lane) {
+    double2 c0[T], c1[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        c0[t] = *reinterpret_cast<const double2 *>(cv0 + j0 + 2 * lane + 64 * t);
+        c1[t] = *reinterpret_cast<const double2 *>(cv1 + j0 + 2 * lane + 64 * t);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double *row = ring + (size_t)((s0 + i) & ring_mask) * fpad + j0 + 2 * lane;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double2 x = *reinterpret_cast<const double2 *>(row + 64 * t);
+            double d;
+            d = x.x - c0[t].x; acc[i] = fma(d, d, acc[i]);
+            d = x.y - c0[t].y; acc[i] = fma(d, d, acc[i]);
+            d = x.x - c1[t].x; acc[8 + i] = fma(d, d, acc[8 + i]);
+            d = x.y - c1[t].y; acc[8 + i] = fma(d, d, acc[8 + i]);
+        }
+    }
+}
+// scalar variant: lane owns features j0 + lane + 32 t
+template <int T>
+__device__ __forceinline__ void dist_tile2x8(double (&acc)[16], const double *__restrict__ cv0,
+                                             const double *__restrict__ cv1, const double *ring, int s0,
+                                             int ring_mask, int fpad, int j0, int lane) {
+    double c0[T], c1[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        c0[t] = cv0[j0 + lane + 32 * t];
+        c1[t] = cv1[j0 + lane + 32 * t];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double *row = ring + (size_t)((s0 + i) & ring_mask) * fpad + j0 + lane;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double x = row[32 * t];
+            double d;
+            d = x - c0[t]; acc[i] = fma(d, d, acc[i]);
+            d = x - c1[t]; acc[8 + i] = fma(d, d, acc[8 + i]);
+        }
+    }
+}
+
 template <int B>
 __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
     constexpr int R = 4 * kGroup;                  // ring rows (4 groups of 8; B <= 16 spans <= 3 groups)
-    constexpr int kShift = (B == 16) ? 1 : 2;      // lane -> row after transpose_reduce
     cg::cluster_group cluster = cg::this_cluster();
     const int ncta = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -233,37 +283,47 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
                 mbar_wait(&full[waited_groups & 3], (unsigned)((waited_groups >> 2) & 1));
         }
 
-        // ---- 1. fast distances: this warp's centroid(s) x the block's rows (rows >= nb read stale
-        //      ring slots; their results are never consumed)
+        // ---- 1. fast distances.  Work item = (pair of this CTA's centroids) x (8 consecutive rows of the
+        //      block); items go round-robin to the warps.  Rows >= nb read stale ring slots and a pair's
+        //      missing second centroid is a duplicate of the first; those results are never consumed.
         const int s0 = (int)(r0 & (R - 1));
-        for (int s = warp; s < slots; s += nw) {
-            const int c = s * ncta + rank;
-            if (c >= kc) break;
-            const double *cv = cptr(s);
-            double acc[B];
+        {
+            const int my_n = kc > rank ? (kc - rank + ncta - 1) / ncta : 0;  // my centroids < kc
+            const int npairs = (my_n + 1) >> 1;
+            const int nitems = npairs * (B / 8);
+            for (int it = warp; it < nitems; it += nw) {
+                const int pair = it / (B / 8), half = it % (B / 8);
+                const int sl0 = 2 * pair, sl1 = (2 * pair + 1 < my_n) ? 2 * pair + 1 : 2 * pair;
+                const double *cv0 = cptr(sl0), *cv1 = cptr(sl1);
+                const int sh = (s0 + 8 * half) & (R - 1);
+                double acc[16];
 #pragma unroll
-            for (int i = 0; i < B; ++i) acc[i] = 0.0;
-            int j0 = 0;
-            if (A.vec2) {
-                for (; j0 + 384 <= f; j0 += 384) dist_chunk2<B, 6>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-                for (; j0 + 128 <= f; j0 += 128) dist_chunk2<B, 2>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-                for (; j0 + 64 <= f; j0 += 64) dist_chunk2<B, 1>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-            }
-            for (; j0 + 384 <= f; j0 += 384) dist_chunk<B, 12>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-            for (; j0 + 128 <= f; j0 += 128) dist_chunk<B, 4>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-            for (; j0 + 32 <= f; j0 += 32) dist_chunk<B, 1>(acc, cv, ring, s0, R - 1, fpad, j0, lane);
-            if (j0 + lane < f) {
-                const double cr = cv[j0 + lane];
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+                int j0 = 0;
+                if (A.vec2) {
+                    for (; j0 + 128 <= f; j0 += 128) dist_tile2x8_v2<2>(acc, cv0, cv1, ring, sh, R - 1, fpad, j0, lane);
+                    for (; j0 + 64 <= f; j0 += 64) dist_tile2x8_v2<1>(acc, cv0, cv1, ring, sh, R - 1, fpad, j0, lane);
+                }
+                for (; j0 + 64 <= f; j0 += 64) dist_tile2x8<2>(acc, cv0, cv1, ring, sh, R - 1, fpad, j0, lane);
+                for (; j0 + 32 <= f; j0 += 32) dist_tile2x8<1>(acc, cv0, cv1, ring, sh, R - 1, fpad, j0, lane);
+                if (j0 + lane < f) {
+                    const double a0 = cv0[j0 + lane], a1 = cv1[j0 + lane];
 #pragma unroll
-                for (int i = 0; i < B; ++i) {
-                    const double df = ring[(size_t)((s0 + i) & (R - 1)) * fpad + j0 + lane] - cr;
-                    acc[i] = fma(df, df, acc[i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const double x = ring[(size_t)((sh + i) & (R - 1)) * fpad + j0 + lane];
+                        double d;
+                        d = x - a0; acc[i] = fma(d, d, acc[i]);
+                        d = x - a1; acc[8 + i] = fma(d, d, acc[8 + i]);
+                    }
+                }
+                transpose_reduce<16>(acc, lane);  // lane L now holds element L >> 1 = c * 8 + i
+                double tot = acc[0];
+                if (!(tot == tot)) tot = INFINITY;  // NaN never wins (`d2 < best` is false)
+                if ((lane & 1) == 0) {
+                    const int e = lane >> 1, cidx = e >> 3, i = e & 7;
+                    if (cidx == 0 || sl1 != sl0) D[(size_t)(cidx ? sl1 : sl0) * B + 8 * half + i] = tot;
                 }
             }
-            transpose_reduce<B>(acc, lane);
-            double tot = acc[0];
-            if (!(tot == tot)) tot = INFINITY;  // NaN never wins (`d2 < best` is false)
-            if ((lane & ((1 << kShift) - 1)) == 0) D[(size_t)s * B + (lane >> kShift)] = tot;
         }
         __syncthreads();
 
@@ -602,18 +662,28 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
         kc = ctl[2];
 
         // ---- 4. apply the committed decisions in row order (owner warps), write assignments
-        for (int i = 0; i < n_commit; ++i) {
-            const Dec dd = dec[i];
-            if (dd.action == 3 || dd.owner != rank || dd.owarp != warp) continue;
-            double *cv = cptr(dd.slot);
-            const double *row = rowptr(r0 + i);
-            if (dd.action == 0) {
-                for (int j = lane; j < f; j += 32) cv[j] = row[j];
-            } else if (dd.action == 1) {
-                for (int j = lane; j < f; j += 32) {
-                    const double c0 = cv[j];
-                    cv[j] = __dadd_rn(c0, __ddiv_rn(__dsub_rn(row[j], c0), dd.knew));  // :748
+        {
+            bool mine = false;
+            if (lane < n_commit) {
+                const Dec dd = dec[lane];
+                mine = dd.action != 3 && dd.owner == rank && dd.owarp == warp;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const Dec dd = dec[i];
+                double *cv = cptr(dd.slot);
+                const double *row = rowptr(r0 + i);
+                if (dd.action == 0) {
+                    for (int j = lane; j < f; j += 32) cv[j] = row[j];
+                } else if (dd.action == 1) {
+                    for (int j = lane; j < f; j += 32) {
+                        const double c0 = cv[j];
+                        cv[j] = __dadd_rn(c0, __ddiv_rn(__dsub_rn(row[j], c0), dd.knew));  // :748
+                    }
                 }
+                __syncwarp();
             }
         }
         if (rank == 0 && tid < n_commit) A.assign[r0 + tid] = (long long)dec[tid].target;
