@@ -219,12 +219,21 @@ struct GraphPlan {  // built from a CSR (host side, tiny), lives in device memor
     GraphEntry *entries = nullptr;  // all stored entries, row-major order
     int32_t *row_ptr = nullptr;     // f+1
     int64_t f = 0, nnz = 0;
+    // symmetric form (taumode_sym.cuh): undirected edges i<j with w = -L_ij, per-row residuals
+    void *sym_edges = nullptr;      // SymEdge[nedges]
+    double *resid = nullptr;        // f
+    int64_t nedges = 0;
+    bool is_sym = false, all_pos = false;
     cudaStream_t stream = nullptr;
     void release() {
         if (entries) cudaFreeAsync(entries, stream);
         if (row_ptr) cudaFreeAsync(row_ptr, stream);
+        if (sym_edges) cudaFreeAsync(sym_edges, stream);
+        if (resid) cudaFreeAsync(resid, stream);
         entries = nullptr;
         row_ptr = nullptr;
+        sym_edges = nullptr;
+        resid = nullptr;
     }
 };
 

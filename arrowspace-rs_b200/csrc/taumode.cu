@@ -358,6 +358,12 @@ __global__ void __launch_bounds__(256) norms2_kernel(const double *__restrict__ 
     if (lane == 0) out[w] = s;
 }
 
+}  // namespace
+
+#include "taumode_sym.cuh"
+
+namespace {
+
 template <int TI>
 int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const GraphPlan &plan, int tau_mode,
                    double tau_value, double *lambdas_d, double *norms2_d, int *flag_d) {
@@ -365,7 +371,14 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     const char *timer_name = flag_d ? "query_taumode_kernel" : "taumode_kernel";
     constexpr int P = kWarps * (32 / TI);
     const size_t smem = ((size_t)f * (TI + 1) + (size_t)4 * P * TI) * sizeof(double);
-    auto kern = taumode_kernel<TI>;
+    bool generic = !plan.is_sym;
+    {
+        auto it = ctx->options.find("taumode_generic");
+        if (it != ctx->options.end() && it->second != 0.0) generic = true;
+    }
+    const void *kern = generic ? (const void *)taumode_kernel<TI>
+                               : (plan.all_pos ? (const void *)taumode_sym_kernel<TI, true>
+                                               : (const void *)taumode_sym_kernel<TI, false>);
     ASB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ASB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -376,8 +389,18 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     if (grid < 1) grid = 1;
     {
         KernelTimer kt(ctx, timer_name);
-        kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(items_d, (long long)n, f, plan.entries, plan.row_ptr,
-                                                             tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
+        if (generic) {
+            taumode_kernel<TI><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
+                items_d, (long long)n, f, plan.entries, plan.row_ptr, tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
+        } else if (plan.all_pos) {
+            taumode_sym_kernel<TI, true><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
+                items_d, (long long)n, f, (const SymEdge *)plan.sym_edges, (int)plan.nedges, plan.resid, tau_mode,
+                tau_value, lambdas_d, norms2_d, flag_d);
+        } else {
+            taumode_sym_kernel<TI, false><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
+                items_d, (long long)n, f, (const SymEdge *)plan.sym_edges, (int)plan.nedges, plan.resid, tau_mode,
+                tau_value, lambdas_d, norms2_d, flag_d);
+        }
     }
     return asb_check_launch(ctx, "taumode_kernel");
 }
@@ -414,6 +437,59 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
                                       ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(plan->row_ptr, rp.data(), (f + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
                                   ctx->stream));
+    // ---- symmetric form: is L_ij == L_ji bit for bit for every stored off-diagonal?
+    std::vector<SymEdge> sym;
+    std::vector<double> resid((size_t)f, 0.0);
+    bool is_sym = true, all_pos = true;
+    auto find = [&](int64_t r, int64_t c, double *out) -> bool {  // rows are short; linear scan
+        for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e)
+            if (indices[e] == c) {
+                *out = data[e];
+                return true;
+            }
+        return false;
+    };
+    for (int64_t i = 0; i < f && is_sym; ++i) {
+        double diag = 0.0, wsum = 0.0;
+        int64_t last_col = -1;
+        for (int64_t e = indptr[i]; e < indptr[i + 1]; ++e) {
+            const int64_t j = indices[e];
+            if (j <= last_col) is_sym = false;  // duplicates / unsorted: use the generic kernel
+            last_col = j;
+            if (j == i) {
+                diag = data[e];
+                continue;
+            }
+            double back;
+            if (!find(j, i, &back) || memcmp(&back, &data[e], sizeof(double)) != 0) {
+                is_sym = false;
+                break;
+            }
+            const double w = -data[e];
+            wsum += w;  // ascending j, like the degree sum of src/laplacian.rs:369
+            if (!(w > 0.0)) all_pos = false;
+            if (j > i) {
+                SymEdge se;
+                se.w = w;
+                se.i = (int)i;
+                se.j = (int)j;
+                sym.push_back(se);
+            }
+        }
+        resid[i] = diag - wsum;
+    }
+    plan->is_sym = is_sym;
+    plan->all_pos = is_sym && all_pos;
+    plan->nedges = is_sym ? (int64_t)sym.size() : 0;
+    if (is_sym) {
+        ASB_CUDA(ctx, cudaMallocAsync(&plan->sym_edges, (sym.size() > 0 ? sym.size() : 1) * sizeof(SymEdge), ctx->stream));
+        ASB_CUDA(ctx, cudaMallocAsync((void **)&plan->resid, f * sizeof(double), ctx->stream));
+        if (!sym.empty())
+            ASB_CUDA(ctx, cudaMemcpyAsync(plan->sym_edges, sym.data(), sym.size() * sizeof(SymEdge),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(plan->resid, resid.data(), f * sizeof(double), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    }
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     return ASB_OK;
 }

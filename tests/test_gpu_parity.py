@@ -108,6 +108,66 @@ def test_taumode_synthetic(ctx, asb, oracle, n, f):
     assert np.all(np.isfinite(want)) and want.std() > 0
 
 
+def test_taumode_generic_and_symmetric_kernels_agree(ctx, asb, oracle, golden):
+    """Symmetric graphs take the edge-once kernel, anything else the generic CSR kernel; both must
+    match the oracle (non-symmetric, positive off-diagonal and diagonal-free matrices included)."""
+    x = asb.synth.protein_like(3_000, 128, seed=42)
+    cent, _, _ = oracle.cluster_incremental(x[:2000], 50, 1.5 * 128 * 0.0025 * 2)
+    csr = _graph(oracle, cent)
+    want = oracle.compute_taumode(x, csr, TAU_MEDIAN)
+    lam_sym, _, _ = ctx.compute_taumode(x, csr, _tm(asb, TAU_MEDIAN))
+    ctx.set_option("taumode_generic", 1)
+    try:
+        lam_gen, _, _ = ctx.compute_taumode(x, csr, _tm(asb, TAU_MEDIAN))
+    finally:
+        ctx.set_option("taumode_generic", 0)
+    _assert_lambda_close(lam_sym, want)
+    _assert_lambda_close(lam_gen, want)
+    rng = np.random.RandomState(5)
+    f = 24
+    db = golden["proteins"]
+    for kind in ("nonsym", "mixed_sign_sym", "no_diag"):
+        dense = np.zeros((f, f))
+        for _ in range(60):
+            i, j = rng.randint(0, f, 2)
+            if i == j:
+                continue
+            v = -rng.rand() if kind != "mixed_sign_sym" else rng.randn()
+            dense[i, j] = v
+            if kind != "nonsym":
+                dense[j, i] = v
+        if kind != "no_diag":
+            dense[np.arange(f), np.arange(f)] = rng.rand(f) + 0.5
+        ip, ii, dd = [0], [], []
+        for r in range(f):
+            for c in range(f):
+                if dense[r, c] != 0.0:
+                    ii.append(c)
+                    dd.append(dense[r, c])
+            ip.append(len(ii))
+        g = (np.array(ip, dtype=np.int64), np.array(ii, dtype=np.int64), np.array(dd))
+        for mode, value in [(TAU_MEDIAN, 0.0), (TAU_FIXED, 0.4)]:
+            want = oracle.compute_taumode(db, g, mode, value)
+            lam, _, _ = ctx.compute_taumode(db, g, _tm(asb, mode, value))
+            _assert_lambda_close(lam, want, rtol=1e-9)
+
+
+def test_taumode_heavy_duplicates_and_extremes(ctx, asb, oracle):
+    """Selection corner cases: long runs of equal values around the median, huge / tiny magnitudes."""
+    rng = np.random.RandomState(11)
+    f = 96
+    eye = (np.arange(f + 1, dtype=np.int64), np.arange(f, dtype=np.int64), np.ones(f))
+    rows = [np.concatenate([np.zeros(60), rng.rand(36)]), np.concatenate([np.full(50, 0.25), rng.rand(46)]),
+            np.repeat(rng.rand(12), 8), np.full(f, 7.0), rng.rand(f) * 1e-300, rng.rand(f) * 1e300,
+            np.concatenate([rng.rand(40), np.full(16, 0.5), rng.rand(40)]), np.sort(rng.rand(f)), -np.sort(rng.rand(f)),
+            np.exp(rng.randn(f) * 20)]
+    x = np.ascontiguousarray(np.vstack(rows))
+    for mode, value in [(TAU_MEDIAN, 0)] + [(TAU_PERCENTILE, p) for p in (0.0, 0.1, 0.33, 0.5, 0.52, 0.9, 1.0)]:
+        want = oracle.compute_taumode(x, eye, mode, float(value))
+        lam, _, _ = ctx.compute_taumode(x, eye, _tm(asb, mode, float(value)))
+        assert np.allclose(lam, want, rtol=1e-14, atol=0, equal_nan=True), (mode, value, lam, want)
+
+
 def test_prepare_query_item(ctx, asb, oracle, golden):
     db = golden["proteins"]
     csr = _graph(oracle, db[:20])
