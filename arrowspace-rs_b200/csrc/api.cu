@@ -444,8 +444,11 @@ int asb_topk_merge(asb_ctx *ctx, const double *in_score, const int64_t *in_idx, 
 
 void asb_index_destroy(asb_index *ix) {
     if (!ix) return;
+    // Independent of the creating context (it may already be gone at interpreter shutdown):
+    // cudaFree synchronises with outstanding work on the memory and accepts stream-ordered
+    // allocations as well.
     cudaSetDevice(ix->device);
-    cudaStreamSynchronize(ix->stream);
+    cudaDeviceSynchronize();
     cudaFree(ix->items_owned);
     cudaFree(ix->lambdas);
     cudaFree(ix->norms2);
@@ -456,8 +459,11 @@ void asb_index_destroy(asb_index *ix) {
     cudaFree(ix->indptr);
     cudaFree(ix->indices);
     cudaFree(ix->data);
-    ix->plan.release();
-    cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->plan.entries);
+    cudaFree(ix->plan.row_ptr);
+    cudaFree(ix->plan.sym_edges);
+    cudaFree(ix->plan.resid);
+    cudaGetLastError();
     delete ix;
 }
 

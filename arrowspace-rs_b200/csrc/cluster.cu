@@ -49,6 +49,7 @@ struct ClusterArgs {
     int slots_per_cta;
     int force_exact;
     int vec;   // rows 16B-copyable
+    long long *phase_times;  // optional: 8 cycle counters of CTA 0 / thread 0 (debug option)
     int vec2;  // centroid storage 16B-loadable (blocked kernel, LDS.128 distance loop)
 };
 
@@ -423,6 +424,17 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ASB_CUDA(ctx, cudaMemsetAsync(scratch.ptr, 0, 4 * sizeof(int), ctx->stream));
     A.x_out = scratch.ptr;
     A.stats = scratch.ptr + 1;
+    DevTmp<long long> ptimes;
+    bool want_times = false;
+    {
+        auto it = ctx->options.find("cluster_phase_times");
+        want_times = (it != ctx->options.end() && it->second != 0.0);
+    }
+    if (want_times) {
+        ASB_TRY(ptimes.init(ctx, 8));
+        ASB_CUDA(ctx, cudaMemsetAsync(ptimes.ptr, 0, 8 * sizeof(long long), ctx->stream));
+        A.phase_times = ptimes.ptr;
+    }
 
     // variant 0/1: blocked kernel with B = 16 / 8 rows per cluster barrier; 2: row-wise kernel
     int launched = 0, variant_used = -1;
@@ -489,6 +501,12 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *x_out_host = h[0];
     ctx->kernel_ms["cluster_exact_rows"] = (double)h[1];
+    if (want_times) {
+        long long ht[8];
+        ASB_CUDA(ctx, cudaMemcpyAsync(ht, ptimes.ptr, sizeof(ht), cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 8; ++k) ctx->kernel_ms[std::string("cluster_phase") + std::to_string(k)] = (double)ht[k];
+    }
     ctx->kernel_ms["cluster_ncta"] = (double)launched;
     ctx->kernel_ms["cluster_blocks"] = (double)h[2];
     ctx->kernel_ms["cluster_variant"] = (double)variant_used;

@@ -250,6 +250,16 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
     __syncthreads();
     cluster.sync();
 
+    long long tphase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define ASB_TICK(k)                                  \
+    do {                                             \
+        if (A.phase_times) {                         \
+            const long long _t = clock64();          \
+            tphase[k] += _t - tlast;                 \
+            tlast = _t;                              \
+        }                                            \
+    } while (0)
     while (r0 < A.n) {
         const int par = (int)(n_blocks & 1);
         // ---- fetch whole groups of 8 rows up to group (r0/8 + 3): the slot of that group held group
@@ -276,13 +286,17 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
             __syncthreads();
         }
         next_fetch = fetch_to;
-        const int nb = (int)((A.n - r0) < B ? (A.n - r0) : B);
+        // keep block starts aligned to the copy groups: after a short block the next one stops at a group
+        // boundary, so that the following block's rows were all requested one block ahead
+        int nb = B - (int)(r0 & (kGroup - 1));
+        if ((long long)nb > A.n - r0) nb = (int)(A.n - r0);
         if (A.vec) {
             const long long g_last = (r0 + nb - 1) / kGroup;
             for (; waited_groups <= g_last; ++waited_groups)
                 mbar_wait(&full[waited_groups & 3], (unsigned)((waited_groups >> 2) & 1));
         }
 
+        ASB_TICK(0);  // fetch issue + wait for rows
         // ---- 1. fast distances.  Work item = (pair of this CTA's centroids) x (8 consecutive rows of the
         //      block); items go round-robin to the warps.  Rows >= nb read stale ring slots and a pair's
         //      missing second centroid is a duplicate of the first; those results are never consumed.
@@ -327,6 +341,7 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
         }
         __syncthreads();
 
+        ASB_TICK(1);  // phase 1 + barrier
         // ---- 2. per row: arg-min over this CTA's centroids, all-to-all through DSMEM
         const int my_valid = kc > rank ? (kc - rank + ncta - 1) / ncta : 0;  // my centroids < kc
         for (int i = warp; i < nb; i += nw) {
@@ -365,7 +380,9 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
                 *remote = v;
             }
         }
+        ASB_TICK(2);  // phase 2
         cluster.sync();
+        ASB_TICK(3);  // cluster barrier
 
         // ---- 3a. per row: reduce the 16 CTA entries -> G[i]
         for (int i = warp; i < nb; i += nw) {
@@ -398,6 +415,7 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
         }
         __syncthreads();
 
+        ASB_TICK(4);  // 3a + barrier
         // ---- 3b. resolve the block's rows IN ORDER (warp 0, identical in every CTA).
         //      Lane i holds row i's summary.  Fast path (saturated state, the steady state of a long
         //      walk): all rows are certified at once against the worst-case total displacement E of
@@ -549,6 +567,7 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
             }
         }
         __syncthreads();
+        ASB_TICK(5);  // resolve + barrier
         int n_commit = ctl[0];
         const int exact = ctl[1];
 
@@ -690,6 +709,7 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
         r0 += n_commit;
         n_blocks++;
         __syncthreads();  // ring slots, D, G, dec are free for the next block
+        ASB_TICK(6);  // exact path (if any) + apply + barrier
     }
     cluster.sync();
     // ---- write back
@@ -708,6 +728,8 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
             A.x_out[0] = kc;
             A.stats[0] = n_exact;
             A.stats[1] = (int)(n_blocks > 0x7fffffff ? 0x7fffffff : n_blocks);
+            if (A.phase_times)
+                for (int k = 0; k < 8; ++k) A.phase_times[k] = tphase[k];
         }
     }
 }

@@ -471,8 +471,10 @@ class ArrowSpace:
 
     # -- index handle ---------------------------------------------------------------------
     def _release(self):
-        if self._index is not None:
-            self.ctx.lib.asb_index_destroy(self._index)
+        if getattr(self, "_index", None) is not None:
+            lib = getattr(self.ctx, "lib", None)
+            if lib is not None:
+                lib.asb_index_destroy(self._index)
             self._index = None
 
     def __del__(self):  # pragma: no cover

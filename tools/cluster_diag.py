@@ -6,6 +6,7 @@ import arrowspace_b200 as asb, torch, numpy as np
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 f = 384
 ctx = asb.Context(0)
+ctx.set_option('cluster_phase_times', 1)
 x = asb.synth.protein_like(n, f, seed=42)
 xd = torch.from_numpy(x).cuda()
 _, kmax = asb.heuristics.step1_bounds(1_000_000, f, f)
@@ -16,3 +17,7 @@ for upto in (2_000, 20_000, n):
     print(f"rows={upto} ms={ctx.kernel_ms('cluster_kernel'):.2f} blocks={ctx.kernel_ms('cluster_blocks'):.0f} "
           f"rows/block={upto/max(ctx.kernel_ms('cluster_blocks'),1):.2f} exact={ctx.kernel_ms('cluster_exact_rows'):.0f} "
           f"us/row={1e3*ctx.kernel_ms('cluster_kernel')/upto:.3f} us/block={1e3*ctx.kernel_ms('cluster_kernel')/max(ctx.kernel_ms('cluster_blocks'),1):.2f}")
+    ph = [ctx.kernel_ms(f"cluster_phase{k}") for k in range(7)]
+    tot = sum(ph) or 1
+    names = ["fetch+wait", "phase1", "phase2", "cluster.sync", "3a", "resolve", "apply"]
+    print("   cycles/block:", {n: round(v / max(ctx.kernel_ms('cluster_blocks'), 1)) for n, v in zip(names, ph)})
