@@ -66,9 +66,23 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+CPP_EXAMPLE = ROOT / "tools" / "cpp_example"
+
+
+def build_cpp_example(force: bool = False) -> Path:
+    """The C++ host mirror (include/arrowspace_b200.hpp) compiled against the C ABI."""
+    src = ROOT / "tools" / "cpp_example.cpp"
+    if force or _stale(CPP_EXAMPLE, [src, ROOT / "include" / "arrowspace_b200.hpp", ROOT / "include" / "arrowspace_b200.h"]):
+        gxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else (shutil.which("g++") or "g++")
+        subprocess.run([gxx, "-std=c++17", "-O2", f"-I{ROOT / 'include'}", str(src), f"-L{PKG_DIR}", "-larrowspace_b200",
+                        f"-Wl,-rpath,{PKG_DIR}", "-o", str(CPP_EXAMPLE)], check=True)
+    return CPP_EXAMPLE
+
+
 def build_all(force: bool = False) -> None:
     build_cuda(force=force)
     build_oracle(force=force)
+    build_cpp_example(force=force)
 
 
 if __name__ == "__main__":

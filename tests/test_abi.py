@@ -78,3 +78,13 @@ def test_builder_defaults_and_define_result_k(asb):
     b.with_seed(7)
     assert b.deterministic_clustering and b.clustering_seed == 7
     assert str(asb.TauMode.Percentile(0.25)) == "Percentile(0.25)" and str(asb.TauMode.Median) == "Median"
+
+
+def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(asb):
+    import subprocess
+    import torch
+    exe = asb._build.build_cpp_example()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr

@@ -563,3 +563,12 @@ def test_device_resident_inputs(ctx, asb, oracle):
     idx_h, sc_h, cnt_h = ctx.search_lambda_aware_batch(x, lam_h, queries, lq_d.cpu().numpy(), 10, 0.7)
     # norms come from two kernels with different summation orders -> scores agree to an ulp or two
     assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.allclose(sc_d.cpu().numpy(), sc_h, rtol=0, atol=1e-14)
+
+
+def test_cpp_host_mirror(asb):
+    """include/arrowspace_b200.hpp (the compiled-language host mirror) end to end: build + search."""
+    import subprocess
+    exe = asb._build.build_cpp_example()
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "top: 3 (1.000000)" in out.stdout
