@@ -42,9 +42,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="items per GPU")
-    ap.add_argument("--f", type=int, default=384)
-    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--items", dest="n", type=int, default=1_000_000, help="items per GPU")
+    ap.add_argument("--features", dest="f", type=int, default=384)
+    ap.add_argument("--queries", dest="nq", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -404,8 +404,8 @@ def run_b200(args):
         ach = by / (kms["cluster_kernel"] * 1e-3) / 1e9
         kernels["cluster_kernel"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": ach / hbm_peak, "ms": kms["cluster_kernel"], "traffic": None,
-                                     "note": "order-dependent walk: latency bound by design (one cluster "
-                                             "barrier per row), rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
+                                     "note": "order-dependent walk: dependency bound by design (one cluster "
+                                             "barrier per block of <=16 rows), rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
                                      "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
     dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = dict(kernels[dominant], kernel=dominant, peak_kind=peak_src) if dominant else None
