@@ -20,10 +20,9 @@
 
 namespace {
 
-constexpr int TQ = 128, TN = 128, KC = 16, PITCH = KC + 4;
+constexpr int TQ = 128, TN = 128;
 constexpr int kWarps = 16;               // 4 (queries) x 4 (items) warps, 32 x 32 accumulators each
 constexpr int kThreads = kWarps * 32;
-constexpr int STAGE_DOUBLES = (TQ + TN) * PITCH;  // 5120 doubles = 40 KB
 constexpr int SPITCH = 72;                        // score half-tile pitch (doubles)
 constexpr int MODE_COSINE = 0, MODE_L2 = 1;
 constexpr int STATUS_NAN = 1, STATUS_ZERO_LAMBDA = 2;
@@ -66,9 +65,10 @@ struct SearchArgs {
 };
 
 // Load one KC-wide chunk of `rows` rows starting at row0 into a smem tile [rows][PITCH].
-template <bool VEC>
+template <bool VEC, int KC>
 __device__ __forceinline__ void load_tile_chunk(double *dst, const double *__restrict__ src, long long row0,
                                                 long long nrows_total, int f, int k0, int tid) {
+    constexpr int PITCH = KC + 4;
     if (VEC) {
         // 128 rows x 8 chunks of 16 B
         for (int c = tid; c < 128 * (KC / 2); c += kThreads) {
@@ -91,8 +91,13 @@ __device__ __forceinline__ void load_tile_chunk(double *dst, const double *__res
     }
 }
 
-template <int MODE, bool VEC>
+template <int MODE, bool VEC, int KC>
 __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
+    constexpr int PITCH = KC + 4;                     // pitch = 4 (mod 16) doubles: conflict-free fragments
+    constexpr int STAGE_DOUBLES = (TQ + TN) * PITCH;  // one pipeline stage (both operands)
+    constexpr int CPR = KC / 2;                       // 16 B chunks per row
+    constexpr int RPP = kThreads / CPR;               // rows covered per pass of the copy threads
+    constexpr int NPT = TQ / RPP;                     // chunks per thread per operand
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *stages = reinterpret_cast<double *>(smem_raw);     // 2 * STAGE_DOUBLES
     double *S = stages;                                        // aliases stages: TQ x SPITCH
@@ -132,6 +137,15 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
         if (MODE == MODE_L2) sm_self[q] = ok ? A.self_idx[gq] : -1;
     }
     const int nchunks = (f + KC - 1) / KC;
+    const int lr = tid / CPR, lch = (tid % CPR) * 2;
+    const double *gq[NPT];
+    bool okq[NPT];
+#pragma unroll
+    for (int m = 0; m < NPT; ++m) {
+        const long long row = q0 + lr + RPP * m;
+        okq[m] = row < A.nq;
+        gq[m] = A.queries + (okq[m] ? row : 0) * (long long)f + lch;
+    }
 
     for (long long t = t_begin; t < t_end; ++t) {
         const long long i0 = t * TN;
@@ -149,16 +163,36 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        // prologue: chunk 0 -> stage 0
-        load_tile_chunk<VEC>(stages, A.queries, q0, A.nq, f, 0, tid);
-        load_tile_chunk<VEC>(stages + TQ * PITCH, A.items, i0, A.n, f, 0, tid);
-        cp_async_commit();
+        // Per-thread copy descriptors (VEC path): thread t moves the 16 B chunk (row t/8 + 64 m, cols 2 (t%8))
+        // of each operand, m = 0, 1; only the feature offset changes from chunk to chunk.
+        const double *gx[NPT];
+        bool okx[NPT];
+#pragma unroll
+        for (int m = 0; m < NPT; ++m) {
+            const long long row = i0 + lr + RPP * m;
+            okx[m] = row < A.n;
+            gx[m] = A.items + (okx[m] ? row : 0) * (long long)f + lch;
+        }
+        auto issue_chunk = [&](int chunk) {
+            double *st = stages + (chunk & 1) * STAGE_DOUBLES;
+            const int k0 = chunk * KC;
+            if (VEC) {
+                const bool colok = k0 + lch < f;
+#pragma unroll
+                for (int m = 0; m < NPT; ++m) {
+                    cp_async16(st + (lr + RPP * m) * PITCH + lch, gq[m] + k0, (okq[m] && colok) ? 16 : 0);
+                    cp_async16(st + TQ * PITCH + (lr + RPP * m) * PITCH + lch, gx[m] + k0, (okx[m] && colok) ? 16 : 0);
+                }
+            } else {
+                load_tile_chunk<false, KC>(st, A.queries, q0, A.nq, f, k0, tid);
+                load_tile_chunk<false, KC>(st + TQ * PITCH, A.items, i0, A.n, f, k0, tid);
+            }
+            cp_async_commit();
+        };
+        issue_chunk(0);
         for (int c = 0; c < nchunks; ++c) {
             if (c + 1 < nchunks) {
-                double *st = stages + ((c + 1) & 1) * STAGE_DOUBLES;
-                load_tile_chunk<VEC>(st, A.queries, q0, A.nq, f, (c + 1) * KC, tid);
-                load_tile_chunk<VEC>(st + TQ * PITCH, A.items, i0, A.n, f, (c + 1) * KC, tid);
-                cp_async_commit();
+                issue_chunk(c + 1);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
@@ -386,8 +420,8 @@ __global__ void __launch_bounds__(128) twonn_rescore_kernel(const double *__rest
     }
 }
 
-size_t search_smem_bytes(int k) {
-    size_t b = (size_t)2 * STAGE_DOUBLES * 8;     // stages (S aliases)
+size_t search_smem_bytes(int k, int kc) {
+    size_t b = (size_t)2 * (TQ + TN) * (kc + 4) * 8;  // stages (S aliases)
     b += (size_t)(2 * TQ + 2 * TN) * 8;           // nq, lq, nx, lx
     b += (size_t)TQ * k * 8 + (size_t)TQ * k * 4; // lists
     b += (size_t)TQ * 4;                          // len
@@ -430,14 +464,22 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
     ASB_TRY(part_i.init(ctx, (size_t)nslabs * A.nq * k));
     A.part_score = part_s.ptr;
     A.part_idx = part_i.ptr;
-    const size_t smem = search_smem_bytes(k);
+    int kc = 32;  // deeper chunks halve the barrier count; fall back when the top-k lists need the space
+    if (search_smem_bytes(k, kc) > 220 * 1024) kc = 16;
+    const size_t smem = search_smem_bytes(k, kc);
     const bool vec = (A.f % 2 == 0) && (((uintptr_t)A.items & 15) == 0) && (((uintptr_t)A.queries & 15) == 0);
     dim3 grid((unsigned)((A.nq + TQ - 1) / TQ), (unsigned)nslabs);
-#define LAUNCH(M, V)                                                                                        \
-    do {                                                                                                    \
-        ASB_CUDA(ctx, cudaFuncSetAttribute(search_kernel<M, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem));                                                    \
-        search_kernel<M, V><<<grid, kThreads, smem, ctx->stream>>>(A);                                      \
+#define LAUNCH(M, V)                                                                                           \
+    do {                                                                                                       \
+        if (kc == 32) {                                                                                        \
+            ASB_CUDA(ctx, cudaFuncSetAttribute(search_kernel<M, V, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem));                                                   \
+            search_kernel<M, V, 32><<<grid, kThreads, smem, ctx->stream>>>(A);                                 \
+        } else {                                                                                               \
+            ASB_CUDA(ctx, cudaFuncSetAttribute(search_kernel<M, V, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem));                                                   \
+            search_kernel<M, V, 16><<<grid, kThreads, smem, ctx->stream>>>(A);                                 \
+        }                                                                                                      \
     } while (0)
     {
         KernelTimer kt(ctx, mode == MODE_COSINE ? "search_kernel" : "twonn_kernel");
