@@ -1,5 +1,7 @@
 // api.cu -- the C ABI (include/arrowspace_b200.h): context, host/device staging, the stage
 // entry points and the device-resident index (ArrowSpaceBuilder::build, src/builder.rs:249-455).
+#include <algorithm>
+
 #include "common.cuh"
 
 #define ASB_VERSION_STRING "arrowspace_b200 0.1.0 (sm_100a)"
@@ -414,6 +416,120 @@ int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const doubl
     ASB_TRY(oi.finish(ctx));
     ASB_TRY(os.finish(ctx));
     ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_search_lambda_aware_hybrid_batch(asb_ctx *ctx, const double *items, const double *lambdas, const double *norms2,
+                                         int64_t n, int64_t f, const double *queries, const double *lambda_q,
+                                         int64_t nq, int64_t k, double alpha, int64_t *idx, double *score,
+                                         int64_t *count) {
+    ASB_TRY(set_device(ctx));
+    if (!items || !lambdas || !queries || !lambda_q || !idx || !score)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "hybrid search: null pointer");
+    if (n <= 0 || f <= 0 || nq <= 0 || k < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "hybrid search: bad sizes");
+    std::vector<int64_t> h_idx((size_t)nq * (k ? k : 1), -1), h_cnt((size_t)nq, 0);
+    std::vector<double> h_sc((size_t)nq * (k ? k : 1), 0.0);
+    if (k > 0) {  // k == 0 -> empty (src/core.rs:810-812)
+        DevIn<double> it, lam, n2, q, lq;
+        DevTmp<int64_t> i1, i2, c1, c2;
+        DevTmp<double> s1, s2, xn2;
+        DevTmp<int> status;
+        ASB_TRY(it.init(ctx, items, (size_t)n * f));
+        ASB_TRY(lam.init(ctx, lambdas, (size_t)n));
+        ASB_TRY(n2.init(ctx, norms2, norms2 ? (size_t)n : 0));
+        ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+        ASB_TRY(lq.init(ctx, lambda_q, (size_t)nq));
+        ASB_TRY(i1.init(ctx, (size_t)nq * k));
+        ASB_TRY(i2.init(ctx, (size_t)nq * k));
+        ASB_TRY(s1.init(ctx, (size_t)nq * k));
+        ASB_TRY(s2.init(ctx, (size_t)nq * k));
+        ASB_TRY(c1.init(ctx, (size_t)nq));
+        ASB_TRY(c2.init(ctx, (size_t)nq));
+        ASB_TRY(status.init(ctx, 1));
+        ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
+        const double *n2p = n2.ptr;
+        if (!n2p) {
+            ASB_TRY(xn2.init(ctx, (size_t)n));
+            ASB_TRY(asb_dev_norms2(ctx, it.ptr, n, f, xn2.ptr));
+            n2p = xn2.ptr;
+        }
+        StageTimer t(ctx, "hybrid_search");
+        ASB_TRY(asb_dev_search(ctx, it.ptr, lam.ptr, n2p, n, f, q.ptr, lq.ptr, nq, k, alpha, 0, i1.ptr, s1.ptr, c1.ptr,
+                               status.ptr));
+        ASB_TRY(asb_dev_search(ctx, it.ptr, lam.ptr, n2p, n, f, q.ptr, lq.ptr, nq, k, 1.0, 0, i2.ptr, s2.ptr, c2.ptr,
+                               status.ptr));
+        t.stop();
+        std::vector<int64_t> a_i((size_t)nq * k), b_i((size_t)nq * k), a_c((size_t)nq), b_c((size_t)nq);
+        std::vector<double> a_s((size_t)nq * k), b_s((size_t)nq * k);
+        int hst = 0;
+        ASB_CUDA(ctx, cudaMemcpyAsync(a_i.data(), i1.ptr, a_i.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(b_i.data(), i2.ptr, b_i.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(a_s.data(), s1.ptr, a_s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(b_s.data(), s2.ptr, b_s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(a_c.data(), c1.ptr, a_c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(b_c.data(), c2.ptr, b_c.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(&hst, status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hst & 1) ASB_FAIL(ctx, ASB_ERR_NAN_SCORE, "NaN score encountered while ranking");
+        // union + re-rank on the host: 2k candidates per query (src/core.rs:897-924)
+        struct Cand { int64_t i; double s; };
+        std::vector<Cand> u;
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            u.clear();
+            const int64_t ca = a_c[qi], cb = b_c[qi];
+            auto has = [&](int64_t id) {
+                for (auto &c : u) if (c.i == id) return true;
+                return false;
+            };
+            for (int64_t r = 0; r < cb; ++r)  // high semantic matches, scored by cosine
+                if (b_s[qi * k + r] > 0.9999) u.push_back({b_i[qi * k + r], b_s[qi * k + r]});
+            for (int64_t r = 0; r < ca; ++r)  // lambda top-k, or_insert
+                if (!has(a_i[qi * k + r])) u.push_back({a_i[qi * k + r], a_s[qi * k + r]});
+            if (cb > 0 && !has(b_i[qi * k])) u.push_back({b_i[qi * k], b_s[qi * k]});  // semantic top-1
+            std::sort(u.begin(), u.end(), [](const Cand &x, const Cand &y) { return x.s > y.s || (x.s == y.s && x.i < y.i); });
+            const int64_t outn = (int64_t)u.size() < k ? (int64_t)u.size() : k;
+            for (int64_t r = 0; r < outn; ++r) {
+                h_idx[qi * k + r] = u[r].i;
+                h_sc[qi * k + r] = u[r].s;
+            }
+            h_cnt[qi] = outn;
+        }
+    }
+    auto put = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (!dst || bytes == 0) return ASB_OK;
+        if (asb_is_device_ptr(dst)) {
+            ASB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            memcpy(dst, src, bytes);
+        }
+        return ASB_OK;
+    };
+    if (k > 0) {
+        ASB_TRY(put(idx, h_idx.data(), (size_t)nq * k * 8));
+        ASB_TRY(put(score, h_sc.data(), (size_t)nq * k * 8));
+    }
+    ASB_TRY(put(count, h_cnt.data(), (size_t)nq * 8));
+    return ASB_OK;
+}
+
+int asb_range_search(asb_ctx *ctx, const double *lambdas, int64_t n, double lambda_q, double eps, int64_t index_offset,
+                     int64_t *idx, double *dist, int64_t capacity, int64_t *count_out) {
+    ASB_TRY(set_device(ctx));
+    if (!lambdas || !idx || !dist || !count_out) ASB_FAIL(ctx, ASB_ERR_INVALID, "range_search: null pointer");
+    if (n <= 0 || capacity < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "range_search: bad sizes");
+    DevIn<double> lam;
+    DevOut<int64_t> oi;
+    DevOut<double> od;
+    ASB_TRY(lam.init(ctx, lambdas, (size_t)n));
+    ASB_TRY(oi.init(ctx, idx, (size_t)capacity));
+    ASB_TRY(od.init(ctx, dist, (size_t)capacity));
+    int64_t cnt = 0;
+    int rc = asb_dev_range_search(ctx, lam.ptr, n, lambda_q, eps, index_offset, oi.ptr, od.ptr, capacity, &cnt);
+    *count_out = cnt;
+    ASB_TRY(rc);
+    ASB_TRY(oi.finish(ctx, (size_t)cnt));
+    ASB_TRY(od.finish(ctx, (size_t)cnt));
     return asb_sync(ctx);
 }
 

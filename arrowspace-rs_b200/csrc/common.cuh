@@ -255,5 +255,8 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
 int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_t f,
                       const asb_graph_params &gp, int64_t *indptr_d, int64_t *indices_d, double *data_d,
                       int64_t capacity, int64_t *nnz_host);
+int asb_dev_range_search(asb_ctx *ctx, const double *lambdas_d, int64_t n, double lambda_q, double eps,
+                         int64_t index_offset, int64_t *idx_d, double *dist_d, int64_t capacity,
+                         int64_t *count_host);
 int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in_idx_d, int64_t parts,
                        int64_t nq, int64_t k, double *out_score_d, int64_t *out_idx_d, int64_t *out_count_d);

@@ -1,0 +1,111 @@
+// extras.cu -- "next" rows of SURVEY 8f (rank 1): range_search (src/core.rs:944-976) as an ordered
+// stream compaction over the lambda array (HBM bound: 8 B read per item, 16 B written per hit).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kItemsPerBlock = 4096;  // 256 threads x 16
+
+// pass 1: hits per block ; pass 2 (WRITE): ordered emit using the scanned block offsets.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) range_kernel(const double *__restrict__ lam, long long n, double lq, double eps,
+                                                    long long *__restrict__ block_counts,
+                                                    const long long *__restrict__ block_offsets,
+                                                    long long index_offset, long long *__restrict__ idx,
+                                                    double *__restrict__ dist) {
+    __shared__ int warp_counts[8];
+    __shared__ int warp_base[8];
+    const long long base = (long long)blockIdx.x * kItemsPerBlock;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long out = WRITE ? block_offsets[blockIdx.x] : 0;
+    int total = 0;
+    // warp w owns the contiguous 512-item slice [base + 512 w, +512): order is preserved
+    for (int it = 0; it < 16; ++it) {
+        const long long i = base + (long long)warp * 512 + it * 32 + lane;
+        double d = 0.0;
+        bool hit = false;
+        if (i < n) {
+            d = lq - lam[i];       // signed difference, as written in the reference (:962)
+            hit = d <= eps;        // :963
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (WRITE) {
+            // all warps need the counts of the warps before them: computed once below (first iteration)
+            if (it == 0) {
+                // count this warp's hits over its whole slice first
+                int c = 0;
+                for (int jt = 0; jt < 16; ++jt) {
+                    const long long j = base + (long long)warp * 512 + jt * 32 + lane;
+                    const bool h = (j < n) && ((lq - lam[j]) <= eps);
+                    c += __popc(__ballot_sync(0xffffffffu, h));
+                }
+                if (lane == 0) warp_counts[warp] = c;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int acc = 0;
+                    for (int w = 0; w < 8; ++w) {
+                        warp_base[w] = acc;
+                        acc += warp_counts[w];
+                    }
+                }
+                __syncthreads();
+                out += warp_base[warp];
+            }
+            if (hit) {
+                const long long o = out + __popc(m & ((1u << lane) - 1u));
+                idx[o] = i + index_offset;
+                dist[o] = d;
+            }
+            out += __popc(m);
+        } else {
+            total += __popc(m);
+        }
+    }
+    if (!WRITE) {
+        if (lane == 0) warp_counts[warp] = total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = 0;
+            for (int w = 0; w < 8; ++w) acc += warp_counts[w];
+            block_counts[blockIdx.x] = acc;
+        }
+    }
+}
+
+}  // namespace
+
+// lambdas_d: device; outputs device (capacity entries).  Returns the number of hits in *count_host;
+// when it exceeds capacity nothing is written and ASB_ERR_CAPACITY is returned.
+int asb_dev_range_search(asb_ctx *ctx, const double *lambdas_d, int64_t n, double lambda_q, double eps,
+                         int64_t index_offset, int64_t *idx_d, double *dist_d, int64_t capacity,
+                         int64_t *count_host) {
+    if (n <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "range_search: n<=0");
+    const long long nblocks = (n + kItemsPerBlock - 1) / kItemsPerBlock;
+    DevTmp<long long> counts, offsets;
+    ASB_TRY(counts.init(ctx, (size_t)nblocks));
+    ASB_TRY(offsets.init(ctx, (size_t)nblocks));
+    range_kernel<false><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(lambdas_d, (long long)n, lambda_q, eps, counts.ptr,
+                                                                   nullptr, 0, nullptr, nullptr);
+    ASB_TRY(asb_check_launch(ctx, "range_kernel<count>"));
+    std::vector<long long> hc((size_t)nblocks), ho((size_t)nblocks);
+    ASB_CUDA(ctx, cudaMemcpyAsync(hc.data(), counts.ptr, nblocks * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long acc = 0;
+    for (long long b = 0; b < nblocks; ++b) {
+        ho[b] = acc;
+        acc += hc[b];
+    }
+    *count_host = acc;
+    if (acc > capacity) ASB_FAIL(ctx, ASB_ERR_CAPACITY, "range_search: %lld hits exceed capacity %lld", acc, (long long)capacity);
+    if (acc == 0) return ASB_OK;
+    ASB_CUDA(ctx, cudaMemcpyAsync(offsets.ptr, ho.data(), nblocks * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        KernelTimer kt(ctx, "range_kernel");
+        range_kernel<true><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(lambdas_d, (long long)n, lambda_q, eps, nullptr,
+                                                                      offsets.ptr, (long long)index_offset,
+                                                                      (long long *)idx_d, dist_d);
+    }
+    ASB_TRY(asb_check_launch(ctx, "range_kernel<write>"));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host offsets vector goes out of scope
+    return ASB_OK;
+}

@@ -96,6 +96,8 @@ ABI_SYMBOLS = {
     "asb_prepare_query_lambdas": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, C.c_int32, _D, _P]),
     "asb_search_lambda_aware_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _I64, _P, _P,
                                                 _P]),
+    "asb_search_lambda_aware_hybrid_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P]),
+    "asb_range_search": (C.c_int, [_P, _P, _I64, _D, _D, _I64, _P, _P, _I64, C.POINTER(_I64)]),
     "asb_topk_merge": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "asb_index_build": (C.c_int, [_P, _P, _I64, _I64, C.POINTER(BuildParamsC), C.POINTER(_P)]),
     "asb_index_destroy": (None, [_P]),
@@ -307,6 +309,30 @@ class Context:
                                                           _ptr(queries), _ptr(lambda_q), nq, int(k), float(alpha),
                                                           int(index_offset), _ptr(idx), _ptr(score), _ptr(count)))
         return idx, score, count
+
+    def search_lambda_aware_hybrid_batch(self, items, lambdas, queries, lambda_q, k: int, alpha: float, norms2=None):
+        items = _as_f64_matrix(items)
+        queries = _as_f64_matrix(queries)
+        n, f = _shape2(items)
+        nq, fq = _shape2(queries)
+        if fq != f:
+            raise ArrowSpaceError(ASB_ERR_DIM, f"Query dimension {fq} doesn't match index original dimension {f}")
+        idx = np.full((nq, max(k, 1)), -1, dtype=np.int64)
+        score = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        count = np.zeros(nq, dtype=np.int64)
+        self.check(self.lib.asb_search_lambda_aware_hybrid_batch(
+            self.handle, _ptr(items), _ptr(lambdas), _ptr(norms2), n, f, _ptr(queries), _ptr(lambda_q), nq, int(k),
+            float(alpha), _ptr(idx), _ptr(score), _ptr(count)))
+        return idx, score, count
+
+    def range_search(self, lambdas, lambda_q: float, eps: float, index_offset: int = 0):
+        n = int(lambdas.shape[0])
+        idx = np.empty(n, dtype=np.int64)
+        dist = np.empty(n, dtype=np.float64)
+        cnt = _I64(0)
+        self.check(self.lib.asb_range_search(self.handle, _ptr(lambdas), n, float(lambda_q), float(eps),
+                                             int(index_offset), _ptr(idx), _ptr(dist), n, C.byref(cnt)))
+        return idx[: cnt.value].copy(), dist[: cnt.value].copy()
 
     def topk_merge(self, in_score, in_idx, parts: int, nq: int, k: int):
         if _is_device(in_score):
@@ -580,6 +606,23 @@ class ArrowSpace:
             return idx, score, count
         items, lambdas, norms2 = self._device_items()
         return self.ctx.search_lambda_aware_batch(items, lambdas, queries, lambda_q, k, alpha, norms2=norms2)
+
+    def search_lambda_aware_hybrid(self, query: ArrowItem, k: int, alpha: float) -> List[Tuple[int, float]]:
+        """``ArrowSpace::search_lambda_aware_hybrid`` (src/core.rs:802-928)."""
+        q = np.ascontiguousarray(query.item, dtype=np.float64).reshape(1, -1)
+        items, lambdas, norms2 = self._device_items()
+        idx, score, count = self.ctx.search_lambda_aware_hybrid_batch(
+            items, lambdas, q, np.array([query.lambda_], dtype=np.float64), k, alpha, norms2=norms2)
+        return [(int(idx[0][r]), float(score[0][r])) for r in range(int(count[0]))]
+
+    def range_search(self, query: ArrowItem, gl: GraphLaplacian, eps: float) -> List[Tuple[int, float]]:
+        """``ArrowSpace::range_search`` (src/core.rs:944-976): the query lambda is re-prepared when it is
+        (relatively) zero, then every item with ``lambda_q - lambda_i <= eps`` is returned in index order."""
+        lam_q = query.lambda_
+        if abs(lam_q) <= 1e-9:  # relative_eq!(query.lambda, 0.0, epsilon = 1e-9), :953
+            lam_q = self.prepare_query_item(query.item, gl)
+        idx, dist = self.ctx.range_search(self.lambdas, lam_q, eps)
+        return [(int(i), float(d)) for i, d in zip(idx, dist)]
 
     def search(self, item, gl: GraphLaplacian, k: int, alpha: float) -> List[Tuple[int, float]]:
         """``EigenMaps::search`` (src/eigenmaps.rs:410-455) = prepare_query_item + search_lambda_aware."""

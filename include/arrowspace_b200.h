@@ -167,6 +167,24 @@ int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const doubl
                                   int64_t k, double alpha, int64_t index_offset,
                                   int64_t *idx, double *score, int64_t *count);
 
+/* ---- "next" rows ---------------------------------------------------- */
+/* Replaces ArrowSpace::search_lambda_aware_hybrid (src/core.rs:802-928) for a batch: the union of
+ * {cosine > 0.9999} (scored by cosine), the lambda-aware top-k (scored alpha*cos+(1-alpha)*lam
+ * unless already present) and the semantic top-1, sorted by that score, truncated to k.  Built
+ * from two fused searches (blended, and alpha = 1).  Score ties (unspecified in the reference:
+ * rayon fold + sort_unstable) resolve to the lower index.  count[q] <= k. */
+int asb_search_lambda_aware_hybrid_batch(asb_ctx *ctx, const double *items, const double *lambdas,
+                                         const double *norms2, int64_t n, int64_t f,
+                                         const double *queries, const double *lambda_q, int64_t nq,
+                                         int64_t k, double alpha, int64_t *idx, double *score,
+                                         int64_t *count);
+/* Replaces the scan of ArrowSpace::range_search (src/core.rs:959-969): every item with
+ * lambda_q - lambda_i <= eps (signed difference, as written), in index order.  idx/dist hold
+ * `capacity` entries; *count_out receives the number of hits (ASB_ERR_CAPACITY if larger). */
+int asb_range_search(asb_ctx *ctx, const double *lambdas, int64_t n, double lambda_q, double eps,
+                     int64_t index_offset, int64_t *idx, double *dist, int64_t capacity,
+                     int64_t *count_out);
+
 /* k-way merge of per-shard top-k lists (multi-GPU search): in_score/in_idx are
  * [parts][nq][k] (unused tail slots: idx = -1); out [nq][k] ordered by (score desc, idx
  * asc) -- the order a single-process stable sort gives (src/core.rs:785). */

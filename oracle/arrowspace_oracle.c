@@ -551,3 +551,109 @@ int aso_search_lambda_aware_batch(const double *items, const double *lambdas, in
     (void)threads;
     return rc_all;
 }
+
+/* ------------------------------------------------ "next" rows */
+
+typedef struct {
+    double s;
+    int64_t i;
+} hs_t;
+
+static int cmp_hs_desc(const void *a, const void *b) {
+    const hs_t *x = (const hs_t *)a, *y = (const hs_t *)b;
+    if (x->s > y->s) return -1;
+    if (x->s < y->s) return 1;
+    return (x->i > y->i) - (x->i < y->i); /* reference: unspecified (rayon fold + sort_unstable) */
+}
+
+/* src/core.rs:802-928.  Union of {cos > 0.9999} (scored by cosine), the lambda-aware top-k
+ * (scored alpha*cos + (1-alpha)*lam unless already present) and the semantic top-1 (cosine),
+ * sorted by that score, truncated to k.  Ties (unspecified in the reference) -> lower index. */
+int aso_search_lambda_aware_hybrid(const double *items, const double *lambdas, int64_t n, int64_t f,
+                                   const double *q, double lambda_q, int64_t k, double alpha,
+                                   int64_t *idx_out, double *score_out, int64_t *count_out) {
+    if (n <= 0 || f <= 0 || k < 0) return ASO_ERR_INVALID;
+    *count_out = 0;
+    if (k == 0) return ASO_OK; /* :810-812 */
+    double beta = 1.0 - alpha;
+    double *cosv = (double *)malloc((size_t)n * sizeof(double));
+    hs_t *ls = (hs_t *)malloc((size_t)n * sizeof(hs_t));
+    double nq2 = 0.0;
+    for (int64_t j = 0; j < f; ++j) nq2 += q[j] * q[j];
+    int64_t sem_i = 0;
+    double sem_s = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *xr = items + i * f;
+        double nx2 = 0.0, dot = 0.0;
+        for (int64_t j = 0; j < f; ++j) nx2 += xr[j] * xr[j];
+        double denom = sqrt(nq2) * sqrt(nx2);
+        if (denom > 0.0) {
+            for (int64_t j = 0; j < f; ++j) dot += q[j] * xr[j];
+            cosv[i] = dot / denom;
+        } else {
+            cosv[i] = 0.0;
+        }
+        double lam = 1.0 - fmin(fabs(lambda_q - lambdas[i]), 1.0);
+        ls[i].s = alpha * cosv[i] + beta * lam; /* :834 */
+        ls[i].i = i;
+        if (cosv[i] > sem_s) { /* :837-839 */
+            sem_s = cosv[i];
+            sem_i = i;
+        }
+    }
+    qsort(ls, (size_t)n, sizeof(hs_t), cmp_hs_desc);
+    int64_t kk = k < n ? k : n;
+    /* union */
+    int64_t cap = kk + 1, cnt = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (cosv[i] > 0.9999) cap++;
+    hs_t *u = (hs_t *)malloc((size_t)cap * sizeof(hs_t));
+    unsigned char *in = (unsigned char *)calloc((size_t)n, 1);
+    for (int64_t i = 0; i < n; ++i)
+        if (cosv[i] > 0.9999) { /* :842-844, :902-905 */
+            u[cnt].i = i;
+            u[cnt].s = cosv[i];
+            cnt++;
+            in[i] = 1;
+        }
+    for (int64_t r = 0; r < kk; ++r) /* :908-911 or_insert */
+        if (!in[ls[r].i]) {
+            u[cnt] = ls[r];
+            cnt++;
+            in[ls[r].i] = 1;
+        }
+    if (!in[sem_i]) { /* :914-915 */
+        u[cnt].i = sem_i;
+        u[cnt].s = sem_s;
+        cnt++;
+    }
+    qsort(u, (size_t)cnt, sizeof(hs_t), cmp_hs_desc);
+    int64_t outn = cnt < k ? cnt : k;
+    for (int64_t r = 0; r < outn; ++r) {
+        idx_out[r] = u[r].i;
+        score_out[r] = u[r].s;
+    }
+    *count_out = outn;
+    free(cosv);
+    free(ls);
+    free(u);
+    free(in);
+    return ASO_OK;
+}
+
+/* src/core.rs:944-976 (after the lambda==0 re-preparation, which is host logic): every item with
+ * lambda_q - lambda_i <= eps (signed difference, as written), in index order. */
+int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double eps, int64_t *idx_out,
+                     double *dist_out, int64_t *count_out) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double d = lambda_q - lambdas[i];
+        if (d <= eps) {
+            idx_out[c] = i;
+            dist_out[c] = d;
+            c++;
+        }
+    }
+    *count_out = c;
+    return ASO_OK;
+}

@@ -124,6 +124,13 @@ int aso_search_lambda_aware_batch(const double *items, const double *lambdas, in
                                   int64_t nq, int64_t k, double alpha, int64_t *idx_out,
                                   double *score_out, int64_t *count_out, int threads);
 
+/* src/core.rs:802-928 and :944-976 */
+int aso_search_lambda_aware_hybrid(const double *items, const double *lambdas, int64_t n, int64_t f,
+                                   const double *q, double lambda_q, int64_t k, double alpha,
+                                   int64_t *idx_out, double *score_out, int64_t *count_out);
+int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double eps, int64_t *idx_out,
+                     double *dist_out, int64_t *count_out);
+
 int aso_num_threads(void);
 
 #ifdef __cplusplus

@@ -53,6 +53,8 @@ class Oracle:
         lib.aso_feature_laplacian.argtypes = [_P, _I64, _I64, C.POINTER(LapParams), _P, _P, _P, C.POINTER(_I64)]
         lib.aso_search_lambda_aware.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_search_lambda_aware_batch.argtypes = [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P, C.c_int]
+        lib.aso_search_lambda_aware_hybrid.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
+        lib.aso_range_search.argtypes = [_P, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_num_threads.restype = C.c_int
         self.lib = lib
 
@@ -164,3 +166,24 @@ class Oracle:
         self._chk(self.lib.aso_search_lambda_aware_batch(_p(items), _p(lambdas), n, f, _p(queries), _p(lambda_q), nq, k,
                                                          alpha, _p(idx), _p(sc), _p(cnt), threads))
         return idx, sc, cnt
+
+    def search_lambda_aware_hybrid(self, items, lambdas, q, lambda_q, k, alpha):
+        items = np.ascontiguousarray(items, dtype=np.float64)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        n, f = items.shape
+        idx = np.full(max(k, 1), -1, dtype=np.int64)
+        sc = np.zeros(max(k, 1), dtype=np.float64)
+        cnt = _I64(0)
+        self._chk(self.lib.aso_search_lambda_aware_hybrid(_p(items), _p(lambdas), n, f, _p(q), lambda_q, k, alpha,
+                                                          _p(idx), _p(sc), C.byref(cnt)))
+        return [(int(idx[r]), float(sc[r])) for r in range(cnt.value)]
+
+    def range_search(self, lambdas, lambda_q, eps):
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        n = len(lambdas)
+        idx = np.empty(max(n, 1), dtype=np.int64)
+        dist = np.empty(max(n, 1), dtype=np.float64)
+        cnt = _I64(0)
+        self._chk(self.lib.aso_range_search(_p(lambdas), n, lambda_q, eps, _p(idx), _p(dist), C.byref(cnt)))
+        return idx[: cnt.value].copy(), dist[: cnt.value].copy()

@@ -572,3 +572,53 @@ def test_cpp_host_mirror(asb):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "top: 3 (1.000000)" in out.stdout
+
+
+# ===================================================== "next" rows: hybrid + range search
+def test_hybrid_search_parity(ctx, asb, oracle, golden):
+    """search_lambda_aware_hybrid (core.rs:802-928): union of {cos > 0.9999}, lambda top-k, semantic top-1."""
+    db = golden["proteins"]
+    csr = _graph(oracle, db[:20])
+    lam = oracle.compute_taumode(db, csr, TAU_MEDIAN)
+    dup = np.ascontiguousarray(np.vstack([db, db[:8] * 1.00001, db[3:4] * 2.0]))   # several cos > 0.9999 hits
+    lam_d = np.concatenate([lam, lam[:8] + 0.3, lam[3:4] + 0.5])
+    aspace = asb.ArrowSpace(dup, asb.TauMode.Median, ctx)
+    aspace.lambdas = lam_d
+    for qi in (3, 10, 63):
+        for k in (1, 3, 10, 40):
+            for alpha in (0.9, 0.5):
+                q = asb.ArrowItem.new(db[qi] * 1.02, float(lam[qi]))
+                want = oracle.search_lambda_aware_hybrid(dup, lam_d, q.item, q.lambda_, k, alpha)
+                got = aspace.search_lambda_aware_hybrid(q, k, alpha)
+                assert [i for i, _ in got] == [i for i, _ in want], (qi, k, alpha)
+                assert np.allclose([s for _, s in got], [s for _, s in want], rtol=0, atol=1e-12)
+    assert aspace.search_lambda_aware_hybrid(asb.ArrowItem.new(db[0], 0.3), 0, 0.7) == []   # core.rs:810-812
+    x = asb.synth.protein_like(5_000, 128, seed=42)
+    lam5 = np.linspace(0.2, 0.6, 5_000)
+    queries, _ = asb.synth.queries_from_items(x, 12, seed=43)
+    idx, score, count = ctx.search_lambda_aware_hybrid_batch(x, lam5, queries, np.full(12, 0.4), 10, 0.7)
+    for qn in range(12):
+        want = oracle.search_lambda_aware_hybrid(x, lam5, queries[qn], 0.4, 10, 0.7)
+        assert idx[qn, :count[qn]].tolist() == [i for i, _ in want]
+
+
+def test_range_search_parity(ctx, asb, oracle, golden):
+    """range_search (core.rs:944-976): signed lambda difference <= eps, index order, re-prepared zero lambda."""
+    rng = np.random.RandomState(1)
+    for n in (1, 31, 4096, 4097, 50_000):
+        lam = rng.rand(n)
+        for lq, eps in [(0.5, 0.1), (0.5, -0.2), (2.0, 0.5), (0.0, 10.0), (0.3, 0.0)]:
+            widx, wdist = oracle.range_search(lam, lq, eps)
+            gidx, gdist = ctx.range_search(lam, lq, eps)
+            assert np.array_equal(gidx, widx) and np.array_equal(gdist, wdist), (n, lq, eps)
+    db = golden["proteins"]
+    csr = _graph(oracle, db[:20])
+    aspace = asb.ArrowSpace(db, asb.TauMode.Median, ctx)
+    gl = asb.GraphLaplacian(*csr, nnodes=64, graph_params=None)
+    aspace.compute_taumode(gl)
+    q = db[5] * 1.02
+    lq = oracle.prepare_query_item(q, csr, TAU_MEDIAN)
+    want = oracle.range_search(aspace.lambdas, lq, 0.01)
+    got = aspace.range_search(asb.ArrowItem.new(q, 0.0), gl, 0.01)            # lambda 0 -> re-prepared (:953-957)
+    assert [i for i, _ in got] == want[0].tolist()
+    assert np.allclose([d for _, d in got], want[1], rtol=0, atol=1e-12)

@@ -232,3 +232,21 @@ def test_host_heuristics_match_oracle(oracle, asb):
     d1 = rng.rand(50) + 0.5
     d2 = d1 * (1.0 + rng.rand(50))
     assert h.intrinsic_dim_from_distances(1000, 64, d1, d2) == oracle.intrinsic_dim(1000, 64, d1, d2)
+
+
+# ---- "next" rows: hybrid / range search semantics (src/core.rs:802-976) -----------------------------
+def test_hybrid_and_range_semantics(oracle, golden):
+    db = golden["proteins"]
+    lam = np.linspace(0.1, 0.9, 64)
+    q = db[3] * 1.02
+    # alpha = 1: the lambda top-k is the cosine top-k, so hybrid == plain search (paper answer again)
+    res = oracle.search_lambda_aware_hybrid(db, lam, q, 0.3, 3, 1.0)
+    assert [i for i, _ in res] == [3, 6, 0]
+    # an item with cos > 0.9999 is kept with its COSINE as score even when its lambda is far away
+    far = lam.copy()
+    far[3] = 5.0
+    res = oracle.search_lambda_aware_hybrid(db, far, q, 0.3, 2, 0.1)
+    assert res[0][0] == 3 and abs(res[0][1] - 1.0) < 1e-12
+    assert oracle.search_lambda_aware_hybrid(db, lam, q, 0.3, 0, 0.7) == []
+    idx, dist = oracle.range_search(np.array([0.1, 0.5, 0.9]), 0.5, 0.1)
+    assert idx.tolist() == [1, 2] and np.allclose(dist, [0.0, -0.4])        # signed difference, one-sided
