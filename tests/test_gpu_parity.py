@@ -580,8 +580,10 @@ def test_hybrid_search_parity(ctx, asb, oracle, golden):
     db = golden["proteins"]
     csr = _graph(oracle, db[:20])
     lam = oracle.compute_taumode(db, csr, TAU_MEDIAN)
-    dup = np.ascontiguousarray(np.vstack([db, db[:8] * 1.00001, db[3:4] * 2.0]))   # several cos > 0.9999 hits
-    lam_d = np.concatenate([lam, lam[:8] + 0.3, lam[3:4] + 0.5])
+    rng = np.random.RandomState(4)
+    near = db[:8] + 0.004 * rng.rand(8, 24)              # cos ~ 0.99995 > 0.9999, distinct from the originals
+    dup = np.ascontiguousarray(np.vstack([db, near]))   # several cos > 0.9999 hits per query
+    lam_d = np.concatenate([lam, lam[:8] + 0.3])
     aspace = asb.ArrowSpace(dup, asb.TauMode.Median, ctx)
     aspace.lambdas = lam_d
     for qi in (3, 10, 63):
