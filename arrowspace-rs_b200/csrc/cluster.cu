@@ -49,6 +49,8 @@ struct ClusterArgs {
     int slots_per_cta;
     int force_exact;
     int vec;   // rows 16B-copyable
+    const float *rows32;                  // FP32 copy of the rows (cluster_f32_kernel)
+    const unsigned long long *max_norm2_bits;  // bit pattern of max finite |x|^2 over rows and initial centroids
     long long *phase_times;  // optional: 8 cycle counters of CTA 0 / thread 0 (debug option)
     int vec2;  // centroid storage 16B-loadable (blocked kernel, LDS.128 distance loop)
 };
@@ -82,6 +84,7 @@ __device__ __forceinline__ bool lex_less(double d1, int c1, double d2, int c2) {
 }  // namespace
 
 #include "cluster_block.cuh"
+#include "cluster_f32.cuh"
 
 namespace {
 
@@ -436,12 +439,22 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         A.phase_times = ptimes.ptr;
     }
 
-    // variant 0/1: blocked kernel with B = 16 / 8 rows per cluster barrier; 2: row-wise kernel
-    int launched = 0, variant_used = -1;
-    for (int variant = want_rowwise ? 2 : 0; variant < 3 && !launched; ++variant) {
+    // variant -1: FP32-prefilter kernel, 32 rows per cluster barrier; 0/1: FP64 blocked kernel with
+    // B = 16 / 8; 2: row-wise kernel
+    bool allow_f32 = (f % 4 == 0) && (((uintptr_t)rows_d & 15) == 0) && !want_rowwise;
+    {
+        auto it = ctx->options.find("cluster_no_f32");
+        if (it != ctx->options.end() && it->second != 0.0) allow_f32 = false;
+    }
+    DevTmp<float> rows32;
+    DevTmp<unsigned long long> maxn2;
+    int launched = 0, variant_used = -9;
+    for (int variant = want_rowwise ? 2 : (allow_f32 ? -1 : 0); variant < 3 && !launched; ++variant) {
         for (int ncta : {16, 8, 4, 2, 1}) {
             const int slots = (int)((max_clusters + ncta - 1) / ncta);
             auto bytes = [&](bool in_smem) -> size_t {
+                if (variant == -1)
+                    return in_smem ? cluster_f32_smem_bytes((int)f, slots, (int)max_clusters) : (size_t)1 << 30;
                 if (variant == 0) return cluster_block_smem_bytes<16>((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 1) return cluster_block_smem_bytes<8>((int)f, slots, (int)max_clusters, in_smem);
                 return cluster_smem_bytes((int)f, slots, in_smem);
@@ -449,12 +462,31 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             const bool in_smem = bytes(true) <= smem_cap;
             const size_t smem = bytes(in_smem);
             if (smem > smem_cap) continue;
-            const int wcap = variant < 2 ? 24 : 32;  // blocked kernels are compiled for <= 768 threads
+            if (variant == -1 && !rows32.ptr) {  // one streaming pass: FP32 copy of the rows + max |x|^2
+                ASB_TRY(rows32.init(ctx, (size_t)n * f));
+                ASB_TRY(maxn2.init(ctx, 1));
+                ASB_CUDA(ctx, cudaMemsetAsync(maxn2.ptr, 0, sizeof(unsigned long long), ctx->stream));
+                {
+                    KernelTimer kt(ctx, "cluster_prep_kernel");
+                    rows_to_f32_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(rows_d, (long long)n, (int)f,
+                                                                                       rows32.ptr, maxn2.ptr);
+                }
+                ASB_TRY(asb_check_launch(ctx, "rows_to_f32_kernel"));
+                if (init_k > 0) {
+                    rows_to_f32_kernel<<<(unsigned)((init_k + 7) / 8), 256, 0, ctx->stream>>>(
+                        centroids_d, (long long)init_k, (int)f, nullptr, maxn2.ptr);
+                    ASB_TRY(asb_check_launch(ctx, "rows_to_f32_kernel(centroids)"));
+                }
+                A.rows32 = rows32.ptr;
+                A.max_norm2_bits = maxn2.ptr;
+            }
+            const int wcap = variant < 2 ? 24 : 32;  // launch bounds of the variants
             const int nwarps = slots < 4 ? 4 : (slots > wcap ? wcap : slots);
             A.cent_in_smem = in_smem ? 1 : 0;
             A.slots_per_cta = slots;
             A.vec2 = (A.vec && (in_smem || (((uintptr_t)centroids_d & 15) == 0))) ? 1 : 0;
-            const void *fn = variant == 0   ? (const void *)cluster_block_kernel<16>
+            const void *fn = variant == -1  ? (const void *)cluster_f32_kernel
+                             : variant == 0 ? (const void *)cluster_block_kernel<16>
                              : variant == 1 ? (const void *)cluster_block_kernel<8>
                                             : (const void *)cluster_rowwise_kernel;
             if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||

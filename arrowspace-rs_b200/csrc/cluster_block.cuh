@@ -250,14 +250,19 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
     __syncthreads();
     cluster.sync();
 
-    long long tphase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    __shared__ long long tphase[8];  // debug phase timers (thread 0 only)
+    if (tid == 0)
+        for (int k = 0; k < 8; ++k) tphase[k] = 0;
     long long tlast = clock64();
 #define ASB_TICK(k)                                  \
     do {                                             \
         if (A.phase_times) {                         \
-            const long long _t = clock64();          \
-            tphase[k] += _t - tlast;                 \
-            tlast = _t;                              \
+            if (tid == 0) {                          \
+                const long long _t = clock64();      \
+                tphase[k] += _t - tlast;             \
+                tlast = _t;                          \
+            }                                        \
+            __syncwarp(); /* aligned barriers follow */ \
         }                                            \
     } while (0)
     while (r0 < A.n) {

@@ -398,9 +398,16 @@ def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rsc
     want = oracle.cluster_incremental(x, maxk, radius)
     got = ctx.cluster_incremental(x, maxk, radius)
     _assert_cluster_equal(got, want)
-    assert ctx.kernel_ms("cluster_variant") in (0.0, 1.0)
+    assert ctx.kernel_ms("cluster_variant") in ((-1.0, 0.0, 1.0) if f % 4 == 0 else (0.0, 1.0))
     blocks = ctx.kernel_ms("cluster_blocks")
     assert 0 < blocks <= n
+    ctx.set_option("cluster_no_f32", 1)      # FP64 blocked kernel
+    try:
+        got = ctx.cluster_incremental(x, maxk, radius)
+        assert ctx.kernel_ms("cluster_variant") in (0.0, 1.0)
+    finally:
+        ctx.set_option("cluster_no_f32", 0)
+    _assert_cluster_equal(got, want)
     ctx.set_option("cluster_rowwise", 1)
     try:
         got = ctx.cluster_incremental(x, maxk, radius)

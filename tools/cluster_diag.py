@@ -6,7 +6,12 @@ import arrowspace_b200 as asb, torch, numpy as np
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 f = 384
 ctx = asb.Context(0)
-ctx.set_option('cluster_phase_times', 1)
+import os
+if os.environ.get('DIAG_TIMES', '1') == '1':
+    ctx.set_option('cluster_phase_times', 1)
+if os.environ.get('DIAG_NOF32', '0') == '1':
+    ctx.set_option('cluster_no_f32', 1)
+print('diag start', flush=True)
 x = asb.synth.protein_like(n, f, seed=42)
 xd = torch.from_numpy(x).cuda()
 _, kmax = asb.heuristics.step1_bounds(1_000_000, f, f)
