@@ -12,7 +12,9 @@
 //     feed the same interval arithmetic as the centroid displacements, so a decision is still only
 //     taken when it is CERTIFIED; everything else goes through the reference-arithmetic FP64 path.
 //     FP64 rows are needed only by the owner warp that applies an update (read straight from
-//     global memory, L2-prefetched one block ahead) and by the exact path.
+//     global memory, L2-prefetched one block ahead) and by the exact path.  The update of block k
+//     overlaps with the distance phase of block k+1 (per-centroid done/need counters instead of a
+//     CTA barrier).
 // Outputs are bit-identical to the reference for every input, like the other two variants.
 #pragma once
 
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
     int *wred_c = reinterpret_cast<int *>(xrow64 + f);                         // 32
     int *ctl = wred_c + 32;                                                    // 4
     int *modlist = ctl + 4;                                                    // B
-    double *cent64 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(modlist + B) + 15) & ~(uintptr_t)15);
+    int *upd_need = modlist + B;                                               // slots4: updates committed per own slot
+    int *upd_done = upd_need + slots4;                                         // slots4: updates applied per own slot
+    double *cent64 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(upd_done + slots4) + 15) & ~(uintptr_t)15);
 
     const double xmax = sqrt(__longlong_as_double((long long)*A.max_norm2_bits)) * (1.0 + 1e-6);
     const double eta = 3e-7 * xmax;                  // input rounding: 2u(|x| + |c|) <= 2.4e-7 * max|x|
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
         disp[c] = 0.0;
     }
     for (int j = tid; j < slots4 * f; j += blockDim.x) cent32[j] = 0.0f;
+    for (int j = tid; j < 2 * slots4; j += blockDim.x) upd_need[j] = 0;  // upd_need and upd_done are contiguous
     int kc = A.init_k;
     __syncthreads();
     for (int s = warp; s < slots; s += nw) {  // resume: adopt the state left by the previous shard
@@ -227,6 +232,13 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
                 if (split > 4) split = 4;
                 const int off_a = ring_off(rbase), off_b = ring_off(rbase + split);
                 const int s0 = 4 * quad;
+                if (lane < 4) {  // the owner warps of these centroids may still be applying the previous block
+                    const volatile int *dn = upd_done + s0 + lane;
+                    const int need = upd_need[s0 + lane];
+                    while (*dn < need) {
+                    }
+                }
+                __syncwarp();
                 const float *p0 = c32(s0), *p1 = c32(s0 + 1), *p2 = c32(s0 + 2), *p3 = c32(s0 + 3);
                 float acc[16];
 #pragma unroll
@@ -459,6 +471,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
                 dd.owarp = dd.slot % nw;
                 dd.pad = 0;
                 dec[lane] = dd;
+                if ((my_action == 0 || my_action == 1) && dd.owner == rank) atomicAdd(&upd_need[dd.slot], 1);
             }
             if (lane == 0) {
                 ctl[0] = n_commit;
@@ -575,6 +588,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
                 dd.owarp = dd.slot % nw;
                 dd.pad = 0;
                 dec[0] = dd;
+                if ((action == 0 || action == 1) && dd.owner == rank) upd_need[dd.slot] += 1;
                 ctl[0] = 1;
                 ctl[2] = kcl;
             }
@@ -621,14 +635,19 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
                     }
                 }
                 __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *((volatile int *)(upd_done + dd.slot)) = upd_done[dd.slot] + 1;
             }
         }
         if (rank == 0 && tid < n_commit) A.assign[r0 + tid] = (long long)dec[tid].target;
         r0 += n_commit;
         n_blocks++;
-        __syncthreads();
+        // No CTA barrier here: the owner warps finish their updates while the other warps start the next
+        // block; phase 1 waits per centroid (upd_done >= upd_need).  Everything else the next block
+        // overwrites (ring slots, D, dec, ctl) is only written after barriers the owner warps also join.
         ASB_TICK(6);
     }
+    __syncthreads();
     cluster.sync();
     for (int s = warp; s < slots; s += nw) {
         const int c = s * ncta + rank;
@@ -663,6 +682,7 @@ size_t cluster_f32_smem_bytes(int f, int slots, int maxk) {
     b += 32 * 8;                                       // wred_d
     b += (size_t)f * 8;                                // xrow64
     b += 32 * 4 + 4 * 4 + (size_t)kB32 * 4;            // wred_c, ctl, modlist
+    b += (size_t)slots4 * 4 * 2;                       // upd_need, upd_done
     b += (size_t)slots * block_cent_pitch(f) * 8;      // cent64
     return b + 96;
 }
