@@ -407,6 +407,16 @@ def run_b200(args):
                                      "note": "order-dependent walk: dependency bound by design (one cluster "
                                              "barrier per block of <=16 rows), rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
                                      "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
+    # DRAM traffic per launch from `ncu --set full` captures (profiles/r01_final_ncu_summary.csv,
+    # profiles/r01_v1_*): only quoted for the configuration they were captured on.
+    if n == 1_000_000 and f == 384 and world == 1:
+        if "cluster_kernel" in kernels:
+            kernels["cluster_kernel"]["traffic"] = 4.66e9   # 4.64 GB read (f32 rows + f64 rows for updates) + 19 MB written
+        if "taumode_kernel" in kernels:
+            kernels["taumode_kernel"]["traffic"] = 3.11e9   # 5 x (614.5 MB read + 7.1 MB written) measured on 200k items
+        if "search_kernel" in kernels:
+            kernels["search_kernel"]["traffic_note"] = ("ncu on 200k items x 2048 queries: 670 MB read for a 614 MB "
+                                                        "item set (L2 serves the per-query-tile re-reads)")
     dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = dict(kernels[dominant], kernel=dominant, peak_kind=peak_src) if dominant else None
 
