@@ -371,14 +371,7 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     const char *timer_name = flag_d ? "query_taumode_kernel" : "taumode_kernel";
     constexpr int P = kWarps * (32 / TI);
     const size_t smem = ((size_t)f * (TI + 1) + (size_t)4 * P * TI) * sizeof(double);
-    bool generic = !plan.is_sym;
-    {
-        auto it = ctx->options.find("taumode_generic");
-        if (it != ctx->options.end() && it->second != 0.0) generic = true;
-    }
-    const void *kern = generic ? (const void *)taumode_kernel<TI>
-                               : (plan.all_pos ? (const void *)taumode_sym_kernel<TI, true>
-                                               : (const void *)taumode_sym_kernel<TI, false>);
+    const void *kern = (const void *)taumode_kernel<TI>;
     ASB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ASB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -389,18 +382,8 @@ int launch_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int f, const 
     if (grid < 1) grid = 1;
     {
         KernelTimer kt(ctx, timer_name);
-        if (generic) {
-            taumode_kernel<TI><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
-                items_d, (long long)n, f, plan.entries, plan.row_ptr, tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
-        } else if (plan.all_pos) {
-            taumode_sym_kernel<TI, true><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
-                items_d, (long long)n, f, (const SymEdge *)plan.sym_edges, (int)plan.nedges, plan.resid, tau_mode,
-                tau_value, lambdas_d, norms2_d, flag_d);
-        } else {
-            taumode_sym_kernel<TI, false><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
-                items_d, (long long)n, f, (const SymEdge *)plan.sym_edges, (int)plan.nedges, plan.resid, tau_mode,
-                tau_value, lambdas_d, norms2_d, flag_d);
-        }
+        taumode_kernel<TI><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
+            items_d, (long long)n, f, plan.entries, plan.row_ptr, tau_mode, tau_value, lambdas_d, norms2_d, flag_d);
     }
     return asb_check_launch(ctx, "taumode_kernel");
 }
@@ -480,12 +463,14 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
     }
     plan->is_sym = is_sym;
     plan->all_pos = is_sym && all_pos;
-    plan->nedges = is_sym ? (int64_t)sym.size() : 0;
+    std::vector<SymEdge> sched;
+    if (is_sym) asb_schedule_edges(sym, sched);  // conflict-free steps of 32 edges (padded)
+    plan->nedges = is_sym ? (int64_t)sched.size() : 0;
     if (is_sym) {
-        ASB_CUDA(ctx, cudaMallocAsync(&plan->sym_edges, (sym.size() > 0 ? sym.size() : 1) * sizeof(SymEdge), ctx->stream));
+        ASB_CUDA(ctx, cudaMallocAsync(&plan->sym_edges, (sched.size() > 0 ? sched.size() : 1) * sizeof(SymEdge), ctx->stream));
         ASB_CUDA(ctx, cudaMallocAsync((void **)&plan->resid, f * sizeof(double), ctx->stream));
-        if (!sym.empty())
-            ASB_CUDA(ctx, cudaMemcpyAsync(plan->sym_edges, sym.data(), sym.size() * sizeof(SymEdge),
+        if (!sched.empty())
+            ASB_CUDA(ctx, cudaMemcpyAsync(plan->sym_edges, sched.data(), sched.size() * sizeof(SymEdge),
                                           cudaMemcpyHostToDevice, ctx->stream));
         ASB_CUDA(ctx, cudaMemcpyAsync(plan->resid, resid.data(), f * sizeof(double), cudaMemcpyHostToDevice,
                                       ctx->stream));
@@ -503,6 +488,44 @@ int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, c
                  (long long)plan.f, (long long)f);
     if (tau_mode < ASB_TAU_FIXED || tau_mode > ASB_TAU_PERCENTILE)
         ASB_FAIL(ctx, ASB_ERR_INVALID, "taumode: unknown tau mode %d", tau_mode);
+    bool generic = !plan.is_sym;
+    {
+        auto it = ctx->options.find("taumode_generic");
+        if (it != ctx->options.end() && it->second != 0.0) generic = true;
+    }
+    if (!generic && (size_t)f * sizeof(double) <= 200 * 1024) {
+        // one warp per item; as many warps per CTA as the private shared-memory copies allow
+        int wpc = kTauWarps;
+        while (wpc > 1 && (size_t)wpc * f * sizeof(double) > 96 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * f * sizeof(double);
+        const void *kern = plan.all_pos ? (const void *)taumode_warp_kernel<true> : (const void *)taumode_warp_kernel<false>;
+        ASB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        ASB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTauWarps * 32, smem));
+        if (per_sm < 1) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "taumode: item does not fit shared memory (f=%lld)", (long long)f);
+        long long grid = (long long)ctx->sm_count * per_sm;
+        const long long need = (n + wpc - 1) / wpc;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        const int nsteps = (int)(plan.nedges / 32);
+        {
+            KernelTimer kt(ctx, nonfinite_flag_d ? "query_taumode_kernel" : "taumode_kernel");
+            if (plan.all_pos)
+                taumode_warp_kernel<true><<<(unsigned)grid, kTauWarps * 32, smem, ctx->stream>>>(
+                    items_d, (long long)n, (int)f, (const SymEdge *)plan.sym_edges, nsteps, plan.resid, tau_mode,
+                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc);
+            else
+                taumode_warp_kernel<false><<<(unsigned)grid, kTauWarps * 32, smem, ctx->stream>>>(
+                    items_d, (long long)n, (int)f, (const SymEdge *)plan.sym_edges, nsteps, plan.resid, tau_mode,
+                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc);
+        }
+        ASB_TRY(asb_check_launch(ctx, "taumode_warp_kernel"));
+        if (stats_d) {
+            lambda_stats_kernel<<<1, 1024, 0, ctx->stream>>>(lambdas_d, (long long)n, stats_d);
+            ASB_TRY(asb_check_launch(ctx, "lambda_stats_kernel"));
+        }
+        return ASB_OK;
+    }
     const size_t budget = 227 * 1024 - 1024;
     auto fits = [&](int ti) { return ((size_t)f * (ti + 1) + 4 * 256) * sizeof(double) <= budget; };
     int rc;
