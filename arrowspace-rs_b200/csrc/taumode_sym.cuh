@@ -29,6 +29,15 @@ struct __align__(16) SymEdge {
     int i, j;  // i < j
 };
 
+__device__ __forceinline__ SymEdge ld_edge(const SymEdge *p) {  // one 16-byte read-only load
+    const int4 r = __ldg(reinterpret_cast<const int4 *>(p));
+    SymEdge e;
+    e.w = __hiloint2double(r.y, r.x);
+    e.i = r.z;
+    e.j = r.w;
+    return e;
+}
+
 constexpr int kSelCap = 8;
 constexpr int kTauWarps = 8;
 
@@ -71,7 +80,7 @@ taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const 
             const SymEdge *sp = sched + lane;
             int s = 0;
             for (; s + 2 <= nsteps; s += 2) {
-                const SymEdge e0 = sp[(size_t)s * 32], e1 = sp[(size_t)(s + 1) * 32];
+                const SymEdge e0 = ld_edge(sp + (size_t)s * 32), e1 = ld_edge(sp + (size_t)(s + 1) * 32);
                 const double a0 = xs[e0.i], b0 = xs[e0.j], a1 = xs[e1.i], b1 = xs[e1.j];
                 const double d0 = a0 - b0, d1 = a1 - b1;
                 const double c0 = e0.w * (d0 * d0), c1 = e1.w * (d1 * d1);
@@ -93,7 +102,7 @@ taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const 
                 }
             }
             for (; s < nsteps; ++s) {
-                const SymEdge e0 = sp[(size_t)s * 32];
+                const SymEdge e0 = ld_edge(sp + (size_t)s * 32);
                 const double d0 = xs[e0.i] - xs[e0.j];
                 const double c0 = e0.w * (d0 * d0);
                 if (ALLPOS) {
@@ -179,43 +188,43 @@ taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const 
                     c_hi = c_p;
                 }
             }
-            // ---- extraction: the values inside [lo, hi) (when few) and the largest finite value below lo
+            // ---- extraction: the <= 8 finite values inside [lo, hi) are gathered one per lane (ballot order),
+            //      ranked with 8 shuffles; also the largest finite value below lo
             const bool small = (c_hi - c_lo <= kSelCap);
-            double v[kSelCap];
-#pragma unroll
-            for (int q = 0; q < kSelCap; ++q) v[q] = INFINITY;
+            double mine = INFINITY;  // lane q < nv holds the q-th gathered value
+            int nv = 0;
             double below = -INFINITY;
             for (int j0 = 0; j0 < f; j0 += 32) {
                 const int j = j0 + lane;
                 const double x = j < f ? xs[j] : __longlong_as_double(0x7ff8000000000000ll);
                 const bool fin = fabs(x) < INFINITY;
                 if (fin && x < lo) below = fmax(below, x);
-                unsigned m = __ballot_sync(0xffffffffu, small && fin && x >= lo && x < hi);
-                while (m) {
-                    const int srcl = __ffs(m) - 1;
-                    m &= m - 1;
-                    // sorted insert into v[] (uniform across the warp, static indices only)
-                    double carry = __shfl_sync(0xffffffffu, x, srcl);
-#pragma unroll
-                    for (int q = 0; q < kSelCap; ++q) {
-                        const double lo_v = fmin(v[q], carry), hi_v = fmax(v[q], carry);
-                        v[q] = lo_v;
-                        carry = hi_v;
-                    }
+                const unsigned m = __ballot_sync(0xffffffffu, small && fin && x >= lo && x < hi);
+                if (m) {  // warp-uniform
+                    const int want = lane - nv;  // lanes nv .. nv+popc(m)-1 fetch the (want+1)-th set bit's value
+                    const int cntm = __popc(m);
+                    const int srcl = (want >= 0 && want < cntm) ? (int)__fns(m, 0, want + 1) : lane;
+                    const double xv = __shfl_sync(0xffffffffu, x, srcl);
+                    if (want >= 0 && want < cntm) mine = xv;
+                    nv += cntm;
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
             double v_rb, v_ra;
             if (small) {
-                const int k = rb - c_lo;
-                v_rb = v[0];
-                v_ra = below;
+                // rank of my value among the gathered ones (ties broken by lane) -> fetch ranks k and k-1
+                int rank = 0;
 #pragma unroll
                 for (int q = 0; q < kSelCap; ++q) {
-                    if (q == k) v_rb = v[q];
-                    if (q == k - 1) v_ra = v[q];
+                    const double o = __shfl_sync(0xffffffffu, mine, q);
+                    rank += (q < nv && (o < mine || (o == mine && q < lane))) ? 1 : 0;
                 }
+                const int k = rb - c_lo;
+                const unsigned has_k = __ballot_sync(0xffffffffu, lane < nv && rank == k);
+                const unsigned has_km1 = __ballot_sync(0xffffffffu, lane < nv && rank == k - 1);
+                v_rb = __shfl_sync(0xffffffffu, mine, has_k ? __ffs(has_k) - 1 : 0);
+                v_ra = has_km1 ? __shfl_sync(0xffffffffu, mine, __ffs(has_km1) - 1) : below;
             } else {  // every finite value inside the bracket equals lo
                 v_rb = lo;
                 v_ra = (rb - 1 >= c_lo) ? lo : below;
