@@ -449,12 +449,16 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     DevTmp<float> rows32;
     DevTmp<unsigned long long> maxn2;
     int launched = 0, variant_used = -9;
-    for (int variant = want_rowwise ? 2 : (allow_f32 ? -1 : 0); variant < 3 && !launched; ++variant) {
+    int first_variant = want_rowwise ? 2 : (allow_f32 ? -1 : 0);
+    {
+        auto it = ctx->options.find("cluster_first_variant");  // diagnostics/tests: skip the faster variants
+        if (it != ctx->options.end() && (int)it->second > first_variant && (int)it->second <= 2) first_variant = (int)it->second;
+    }
+    for (int variant = first_variant; variant < 3 && !launched; ++variant) {
         for (int ncta : {16, 8, 4, 2, 1}) {
             const int slots = (int)((max_clusters + ncta - 1) / ncta);
             auto bytes = [&](bool in_smem) -> size_t {
-                if (variant == -1)
-                    return in_smem ? cluster_f32_smem_bytes((int)f, slots, (int)max_clusters) : (size_t)1 << 30;
+                if (variant == -1) return cluster_f32_smem_bytes((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 0) return cluster_block_smem_bytes<16>((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 1) return cluster_block_smem_bytes<8>((int)f, slots, (int)max_clusters, in_smem);
                 return cluster_smem_bytes((int)f, slots, in_smem);
@@ -485,7 +489,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             A.cent_in_smem = in_smem ? 1 : 0;
             A.slots_per_cta = slots;
             A.vec2 = (A.vec && (in_smem || (((uintptr_t)centroids_d & 15) == 0))) ? 1 : 0;
-            const void *fn = variant == -1  ? (const void *)cluster_f32_kernel
+            const void *fn = variant == -1  ? (in_smem ? (const void *)cluster_f32_kernel<true> : (const void *)cluster_f32_kernel<false>)
                              : variant == 0 ? (const void *)cluster_block_kernel<16>
                              : variant == 1 ? (const void *)cluster_block_kernel<8>
                                             : (const void *)cluster_rowwise_kernel;

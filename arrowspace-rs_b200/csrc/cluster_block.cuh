@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(768, 1) cluster_block_kernel(ClusterArgs A) {
 template <int B>
 size_t cluster_block_smem_bytes(int f, int slots, int maxk, bool cent_in_smem) {
     const int fpad = (f + 1) & ~1;
-    size_t b = (size_t)2 * B * fpad * 8;            // ring
+    size_t b = (size_t)4 * kGroup * fpad * 8;       // ring (R rows, independent of B)
     b += (size_t)slots * B * 8;                     // D
     b += (size_t)((maxk + 1) & ~1) * 8;             // disp
     b += 32 * 8;                                    // wred_d

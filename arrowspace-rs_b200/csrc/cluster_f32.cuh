@@ -106,6 +106,7 @@ __device__ __forceinline__ bool lex_less_f(float d1, int c1, float d2, int c2) {
     return d1 < d2 || (d1 == d2 && c1 < c2);
 }
 
+template <bool CSMEM>
 __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
     constexpr int B = kB32;
     constexpr int RROWS = kRingGroups * kGroup;
@@ -144,7 +145,12 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
     const double eta = 3e-7 * xmax;                  // input rounding: 2u(|x| + |c|) <= 2.4e-7 * max|x|
     const double rho = (double)(f + 32) * 5.97e-8;   // FP32 accumulation + sqrt + conversions
 
-    auto c64 = [&](int slot) -> double * { return cent64 + (size_t)slot * cp; };
+    // FP64 centroids: distributed shared memory when they fit, else the (L2-resident) global array --
+    // only the owner warp (updates) and the exact path ever touch them
+    auto c64 = [&](int slot) -> double * {
+        if (CSMEM) return cent64 + (size_t)slot * cp;
+        return A.centroids + ((size_t)slot * ncta + rank) * f;
+    };
     auto c32 = [&](int slot) -> float * { return cent32 + (size_t)slot * f; };
     auto ring_off = [&](long long r) -> int { return (int)(((r >> 3) % kRingGroups) * kGroup + (r & 7)) * f; };
 
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
         const double *src = A.centroids + (size_t)c * f;
         for (int j = lane; j < f; j += 32) {
             const double v = src[j];
-            c64(s)[j] = v;
+            if (CSMEM) c64(s)[j] = v;
             c32(s)[j] = (float)v;
         }
     }
@@ -652,9 +658,11 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
     for (int s = warp; s < slots; s += nw) {
         const int c = s * ncta + rank;
         if (c >= kc) break;
-        const double *cv = c64(s);
-        double *dst = A.centroids + (size_t)c * f;
-        for (int j = lane; j < f; j += 32) dst[j] = cv[j];
+        if (CSMEM) {
+            const double *cv = c64(s);
+            double *dst = A.centroids + (size_t)c * f;
+            for (int j = lane; j < f; j += 32) dst[j] = cv[j];
+        }
     }
     if (rank == 0) {
         for (int c = tid; c < kc; c += blockDim.x) A.sizes[c] = cnt[c];
@@ -668,7 +676,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32_kernel(ClusterArgs A) {
     }
 }
 
-size_t cluster_f32_smem_bytes(int f, int slots, int maxk) {
+size_t cluster_f32_smem_bytes(int f, int slots, int maxk, bool cent64_in_smem) {
     const int slots4 = (slots + 3) & ~3;
     size_t b = (size_t)kRingGroups * kGroup * f * 4;   // ring (f32)
     b += (size_t)slots4 * f * 4;                       // cent32
@@ -683,7 +691,7 @@ size_t cluster_f32_smem_bytes(int f, int slots, int maxk) {
     b += (size_t)f * 8;                                // xrow64
     b += 32 * 4 + 4 * 4 + (size_t)kB32 * 4;            // wred_c, ctl, modlist
     b += (size_t)slots4 * 4 * 2;                       // upd_need, upd_done
-    b += (size_t)slots * block_cent_pitch(f) * 8;      // cent64
+    if (cent64_in_smem) b += (size_t)slots * block_cent_pitch(f) * 8;  // cent64
     return b + 96;
 }
 
