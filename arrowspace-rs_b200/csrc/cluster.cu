@@ -53,6 +53,8 @@ struct ClusterArgs {
     const unsigned long long *max_norm2_bits;  // bit pattern of max finite |x|^2 over rows and initial centroids
     long long *phase_times;  // optional: 8 cycle counters of CTA 0 / thread 0 (debug option)
     int vec2;  // centroid storage 16B-loadable (blocked kernel, LDS.128 distance loop)
+    const double *rows_n2;  // |fl32(row)|^2 in FP64 (pipelined kernel: distances via dot products)
+    int tick_tid;           // thread of CTA 0 that owns the debug phase timers
 };
 
 struct __align__(16) Xch {
@@ -85,6 +87,7 @@ __device__ __forceinline__ bool lex_less(double d1, int c1, double d2, int c2) {
 
 #include "cluster_block.cuh"
 #include "cluster_f32.cuh"
+#include "cluster_f32p.cuh"
 
 namespace {
 
@@ -433,23 +436,39 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         auto it = ctx->options.find("cluster_phase_times");
         want_times = (it != ctx->options.end() && it->second != 0.0);
     }
+    {
+        auto it = ctx->options.find("cluster_tick_tid");
+        A.tick_tid = it != ctx->options.end() ? (int)it->second : 0;
+    }
     if (want_times) {
-        ASB_TRY(ptimes.init(ctx, 8));
-        ASB_CUDA(ctx, cudaMemsetAsync(ptimes.ptr, 0, 8 * sizeof(long long), ctx->stream));
+        ASB_TRY(ptimes.init(ctx, 48));
+        ASB_CUDA(ctx, cudaMemsetAsync(ptimes.ptr, 0, 48 * sizeof(long long), ctx->stream));
         A.phase_times = ptimes.ptr;
     }
 
-    // variant -1: FP32-prefilter kernel, 32 rows per cluster barrier; 0/1: FP64 blocked kernel with
-    // B = 16 / 8; 2: row-wise kernel
+    // variant -2: pipelined FP32-prefilter kernel (resolve of block b overlaps the distances of b+1);
+    // -1: FP32-prefilter kernel, 32 rows per cluster barrier; 0/1: FP64 blocked kernel with B = 16 / 8;
+    // 2: row-wise kernel
     bool allow_f32 = (f % 4 == 0) && (((uintptr_t)rows_d & 15) == 0) && !want_rowwise;
     {
         auto it = ctx->options.find("cluster_no_f32");
         if (it != ctx->options.end() && it->second != 0.0) allow_f32 = false;
     }
     DevTmp<float> rows32;
+    DevTmp<double> rows_n2;
     DevTmp<unsigned long long> maxn2;
+    int rows32_pitch = -1;
     int launched = 0, variant_used = -9;
-    int first_variant = want_rowwise ? 2 : (allow_f32 ? -1 : 0);
+    bool allow_pipe = !want_rowwise && (((uintptr_t)rows_d & 15) == 0);
+    {
+        auto it = ctx->options.find("cluster_no_f32");
+        if (it != ctx->options.end() && it->second != 0.0) allow_pipe = false;
+    }
+    int first_variant = want_rowwise ? 2 : (allow_pipe ? -2 : (allow_f32 ? -1 : 0));
+    {
+        auto it = ctx->options.find("cluster_no_pipeline");
+        if (first_variant == -2 && it != ctx->options.end() && it->second != 0.0) first_variant = -1;
+    }
     {
         auto it = ctx->options.find("cluster_first_variant");  // diagnostics/tests: skip the faster variants
         if (it != ctx->options.end() && (int)it->second > first_variant && (int)it->second <= 2) first_variant = (int)it->second;
@@ -458,38 +477,45 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         for (int ncta : {16, 8, 4, 2, 1}) {
             const int slots = (int)((max_clusters + ncta - 1) / ncta);
             auto bytes = [&](bool in_smem) -> size_t {
+                if (variant == -2) return cluster_f32p_smem_bytes((int)f, slots, (int)max_clusters);
                 if (variant == -1) return cluster_f32_smem_bytes((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 0) return cluster_block_smem_bytes<16>((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 1) return cluster_block_smem_bytes<8>((int)f, slots, (int)max_clusters, in_smem);
                 return cluster_smem_bytes((int)f, slots, in_smem);
             };
-            const bool in_smem = bytes(true) <= smem_cap;
+            const bool in_smem = variant != -2 && bytes(true) <= smem_cap;
             const size_t smem = bytes(in_smem);
             if (smem > smem_cap) continue;
-            if (variant == -1 && !rows32.ptr) {  // one streaming pass: FP32 copy of the rows + max |x|^2
-                ASB_TRY(rows32.init(ctx, (size_t)n * f));
-                ASB_TRY(maxn2.init(ctx, 1));
+            if (variant == -1 && !allow_f32) continue;
+            const int pitch32 = variant == -2 ? f32p_pitch((int)f) : (int)f;
+            if (variant < 0 && rows32_pitch != pitch32) {  // one streaming pass: FP32 copy of the rows + max |x|^2
+                ASB_TRY(rows32.init(ctx, (size_t)n * pitch32));
+                if (!rows_n2.ptr) ASB_TRY(rows_n2.init(ctx, (size_t)n));
+                if (!maxn2.ptr) ASB_TRY(maxn2.init(ctx, 1));
                 ASB_CUDA(ctx, cudaMemsetAsync(maxn2.ptr, 0, sizeof(unsigned long long), ctx->stream));
                 {
                     KernelTimer kt(ctx, "cluster_prep_kernel");
-                    rows_to_f32_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(rows_d, (long long)n, (int)f,
-                                                                                       rows32.ptr, maxn2.ptr);
+                    rows_to_f32_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(
+                        rows_d, (long long)n, (int)f, rows32.ptr, maxn2.ptr, rows_n2.ptr, pitch32);
                 }
                 ASB_TRY(asb_check_launch(ctx, "rows_to_f32_kernel"));
                 if (init_k > 0) {
                     rows_to_f32_kernel<<<(unsigned)((init_k + 7) / 8), 256, 0, ctx->stream>>>(
-                        centroids_d, (long long)init_k, (int)f, nullptr, maxn2.ptr);
+                        centroids_d, (long long)init_k, (int)f, nullptr, maxn2.ptr, nullptr, (int)f);
                     ASB_TRY(asb_check_launch(ctx, "rows_to_f32_kernel(centroids)"));
                 }
+                rows32_pitch = pitch32;
                 A.rows32 = rows32.ptr;
+                A.rows_n2 = rows_n2.ptr;
                 A.max_norm2_bits = maxn2.ptr;
             }
             const int wcap = variant < 2 ? 24 : 32;  // launch bounds of the variants
-            const int nwarps = slots < 4 ? 4 : (slots > wcap ? wcap : slots);
+            const int nwarps = variant == -2 ? 24 : (slots < 4 ? 4 : (slots > wcap ? wcap : slots));
             A.cent_in_smem = in_smem ? 1 : 0;
             A.slots_per_cta = slots;
             A.vec2 = (A.vec && (in_smem || (((uintptr_t)centroids_d & 15) == 0))) ? 1 : 0;
-            const void *fn = variant == -1  ? (in_smem ? (const void *)cluster_f32_kernel<true> : (const void *)cluster_f32_kernel<false>)
+            const void *fn = variant == -2  ? (const void *)cluster_f32p_kernel
+                             : variant == -1  ? (in_smem ? (const void *)cluster_f32_kernel<true> : (const void *)cluster_f32_kernel<false>)
                              : variant == 0 ? (const void *)cluster_block_kernel<16>
                              : variant == 1 ? (const void *)cluster_block_kernel<8>
                                             : (const void *)cluster_rowwise_kernel;
@@ -538,10 +564,10 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     *x_out_host = h[0];
     ctx->kernel_ms["cluster_exact_rows"] = (double)h[1];
     if (want_times) {
-        long long ht[8];
+        long long ht[48];
         ASB_CUDA(ctx, cudaMemcpyAsync(ht, ptimes.ptr, sizeof(ht), cudaMemcpyDeviceToHost, ctx->stream));
         ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int k = 0; k < 8; ++k) ctx->kernel_ms[std::string("cluster_phase") + std::to_string(k)] = (double)ht[k];
+        for (int k = 0; k < 48; ++k) ctx->kernel_ms[std::string("cluster_phase") + std::to_string(k)] = (double)ht[k];
     }
     ctx->kernel_ms["cluster_ncta"] = (double)launched;
     ctx->kernel_ms["cluster_blocks"] = (double)h[2];

@@ -38,20 +38,29 @@ struct __align__(16) GRow32 {
 // rows (f64) -> rows32 (f32) + max finite squared norm.  One warp per row.
 __global__ void __launch_bounds__(256) rows_to_f32_kernel(const double *__restrict__ rows, long long n, int f,
                                                           float *__restrict__ rows32,
-                                                          unsigned long long *__restrict__ max_norm2_bits) {
+                                                          unsigned long long *__restrict__ max_norm2_bits,
+                                                          double *__restrict__ rows_n2, int pitch) {
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= n) return;
     const double *r = rows + w * (long long)f;
-    float *o = rows32 ? rows32 + w * (long long)f : nullptr;
-    double s = 0.0;
+    float *o = rows32 ? rows32 + w * (long long)pitch : nullptr;  // pitch >= f; the padding is zero
+    double s = 0.0, s32 = 0.0;
     for (int j = lane; j < f; j += 32) {
         const double v = __ldg(r + j);
-        if (o) o[j] = (float)v;
+        const float vf = (float)v;
+        if (o) o[j] = vf;
         s = fma(v, v, s);
+        s32 = fma((double)vf, (double)vf, s32);
     }
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (o)
+        for (int j = f + lane; j < pitch; j += 32) o[j] = 0.0f;
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        s32 += __shfl_xor_sync(0xffffffffu, s32, off);
+    }
     if (lane == 0 && s < INFINITY) atomicMax(max_norm2_bits, (unsigned long long)__double_as_longlong(s));
+    if (lane == 0 && rows_n2) rows_n2[w] = s32;  // squared norm of the FP32-rounded row (FP64, ~1e-16 relative)
 }
 
 // acc[c * 4 + i] += |row_i - cent_c|^2 over the 128 features (j0 + 4 lane .. +3), FP32, 16-byte loads:

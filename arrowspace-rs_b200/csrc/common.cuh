@@ -139,6 +139,8 @@ struct DevTmp {
     T *ptr = nullptr;
     cudaStream_t stream = nullptr;
     int init(asb_ctx *ctx, size_t count) {
+        if (ptr) cudaFreeAsync(ptr, stream);  // re-init: release the previous buffer (stream-ordered)
+        ptr = nullptr;
         stream = ctx->stream;
         if (count == 0) count = 1;
         ASB_CUDA(ctx, cudaMallocAsync((void **)&ptr, count * sizeof(T), stream));

@@ -400,16 +400,17 @@ def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rsc
     _assert_cluster_equal(got, want)
     blocks = ctx.kernel_ms("cluster_blocks")
     assert 0 < blocks <= n
-    # -1: FP32-prefilter kernel, 0/1: FP64 blocked kernel (16 / 8 rows per barrier), 2: row-wise kernel.
+    # -2: pipelined FP32-prefilter kernel (default), -1: FP32-prefilter kernel, 0/1: FP64 blocked kernel
+    # (16 / 8 rows per barrier), 2: row-wise kernel.
     # A variant that does not fit shared memory for this shape falls through to the next one.
     seen = {ctx.kernel_ms("cluster_variant")}
-    for first in (0, 1, 2):
+    for first in (-1, 0, 1, 2):
         ctx.set_option("cluster_first_variant", first)
         try:
             got = ctx.cluster_incremental(x, maxk, radius)
             used = ctx.kernel_ms("cluster_variant")
         finally:
-            ctx.set_option("cluster_first_variant", -1)
+            ctx.set_option("cluster_first_variant", -9)
         assert used >= first
         seen.add(used)
         _assert_cluster_equal(got, want)
