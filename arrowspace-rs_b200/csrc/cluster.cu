@@ -510,7 +510,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
                 A.max_norm2_bits = maxn2.ptr;
             }
             const int wcap = variant < 2 ? 24 : 32;  // launch bounds of the variants
-            const int nwarps = variant == -2 ? 24 : (slots < 4 ? 4 : (slots > wcap ? wcap : slots));
+            const int nwarps = variant == -2 ? 16 : (slots < 4 ? 4 : (slots > wcap ? wcap : slots));
             A.cent_in_smem = in_smem ? 1 : 0;
             A.slots_per_cta = slots;
             A.vec2 = (A.vec && (in_smem || (((uintptr_t)centroids_d & 15) == 0))) ? 1 : 0;

@@ -35,6 +35,7 @@ namespace {
         }                                            \
     } while (0)
 
+constexpr int kXBuf = 4;       // all-to-all buffers: a peer CTA can run up to three exchanges ahead of the slowest reader
 constexpr int kPipeGroups = 8;  // ring = 8 groups of 8 rows: the block being read + the next one in flight
 
 // shared::cta address -> the same location in CTA `rank` of the cluster (shared::cluster window)
@@ -90,7 +91,7 @@ __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) 
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-__global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
+__global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     constexpr int B = kB32;
     constexpr int NG = kPipeGroups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -108,21 +109,21 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
     float *ring = reinterpret_cast<float *>(smem_raw);                         // NG * 8 * fp
     float *cent32 = ring + (size_t)NG * kGroup * fp;                           // slots4 * fp
     float *Dall = cent32 + (size_t)slots4 * fp;                                // [2][slots4 * B]
-    Xch32 *xch = reinterpret_cast<Xch32 *>(Dall + (size_t)2 * slots4 * B);     // [2][16][B]
-    Xch32 *part_all = xch + 2 * 16 * B;                                        // [2][slots4 / 8][B] per-tile arg-min
+    Xch32 *xch = reinterpret_cast<Xch32 *>(Dall + (size_t)2 * slots4 * B);     // [kXBuf][16][B]
+    Xch32 *part_all = xch + kXBuf * 16 * B;                                    // [2][slots4 / 8][B] per-tile arg-min
     Xch *xch_exact = reinterpret_cast<Xch *>(part_all + 2 * (slots4 / 8) * B);  // [2][16]
     GRow32 *G = reinterpret_cast<GRow32 *>(xch_exact + 32);                    // B
     Dec *dec_all = reinterpret_cast<Dec *>(G + B);                             // [2][B]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(dec_all + 2 * B);  // NG mbarriers
-    unsigned long long *xbar = full + NG;                                      // 2: all-to-all landed (per parity)
-    unsigned long long *cnt = xbar + 2;                                        // maxk (replicated counts)
+    unsigned long long *xbar = full + NG;                                      // kXBuf: all-to-all landed (per buffer)
+    unsigned long long *cnt = xbar + kXBuf;                                    // maxk (replicated counts)
     double *disp = reinterpret_cast<double *>(cnt + maxk);                     // maxk
     double *wred_d = disp + maxk;                                              // 32
     double *ctld_all = wred_d + 32;                                            // [2]: displacement bound of the block
     double *xrow64 = ctld_all + 2;                                              // f (exact path row)
     int *wred_c = reinterpret_cast<int *>(xrow64 + f);                         // 32
     int *ctl_all = wred_c + 32;                                                // [2][4]
-    int *item_ctr = ctl_all + 8;                                               // 2 (+2 pad)
+    int *item_ctr = ctl_all + 8;                                               // [2] work counter, [2] items finished
     int *modlist = item_ctr + 4;                                               // B
 
     const double xmax = sqrt(__longlong_as_double((long long)*A.max_norm2_bits)) * (1.0 + 1e-6);
@@ -148,10 +149,9 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
 
     if (tid == 0) {
         for (int s = 0; s < NG; ++s) mbar_init(&full[s], 1);
-        mbar_init(&xbar[0], 1);
-        mbar_init(&xbar[1], 1);
+        for (int k = 0; k < kXBuf; ++k) mbar_init(&xbar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        item_ctr[0] = item_ctr[1] = 0;
+        item_ctr[0] = item_ctr[1] = item_ctr[2] = item_ctr[3] = 0;
     }
     for (int c = tid; c < maxk; c += blockDim.x) {
         cnt[c] = (c < A.init_k) ? A.sizes[c] : 0ull;
@@ -172,15 +172,26 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
     long long r0 = 0, n_blocks = 0;
     int n_exact = 0;
     __shared__ long long tphase[8];  // debug phase timers (thread 0 only)
+    __shared__ long long arr_t[32], arr_hist[32], arr_late[32];
+    if (tid < 32) arr_t[tid] = arr_hist[tid] = arr_late[tid] = 0;
     if (tid == 0)
         for (int k = 0; k < 8; ++k) tphase[k] = 0;
     long long tlast = clock64();
 
+    // Warp roles.  Warp 0 is the control warp (arg-min, all-to-all, resolve): its chain of dependent
+    // instructions is the critical path.  The tensor-core tile needs few warps (one per 8 centroids x 16 rows),
+    // so the rest apply the centroid updates, each on its own slice of the features.
+    const int ncomp = (nw - 1) / 2;            // warps 1 .. ncomp compute distances in the pipelined steady state
+    const int first_apply = ncomp + 1;         // warps first_apply .. nw-1 apply updates
+    const int napply = nw - first_apply;
+    const bool is_compute = warp >= 1 && warp <= ncomp;
+    const bool is_apply = warp >= first_apply;
+    const int feat_per_apply = (f + napply - 1) / napply;
     // ---- row ring: groups [ring_lo, ring_hi) are resident or in flight.  Every thread tracks, per slot,
     // the parity of the latest copy (issued) and whether it has already observed it landing (waited).
     long long ring_lo = 0, ring_hi = 0;
     unsigned issued = 0u, waited = 0xffffffffu;
-    const bool fetcher = (tid == blockDim.x - 32);
+    const bool fetcher = (tid == ncomp * 32);  // lane 0 of the last compute warp
     auto need_groups = [&](long long ga, long long gb) {
         if (ga < ring_lo || ga > ring_hi) ring_lo = ring_hi = ga;  // rows were dropped from the ring: restart here
         for (long long g = ring_hi; g < gb; ++g) {
@@ -210,6 +221,36 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
     };
 
     int my_n = 0;
+    // (one warp; lane = row) merge the per-tile arg-mins of this CTA, then one 16-byte store per peer CTA and row
+    // that also completes 16 tx-bytes on the peer's mbarrier: instruction k carries the 32 rows' entries to peer k
+    // (contiguous 512 bytes) -- no staging, no fence, no barrier round trip.  Exchange number `seq` uses buffer
+    // seq % kXBuf; every CTA performs the same sequence of exchanges.
+    auto send_block = [&](int nbk, const Xch32 *part, int seq) {
+        float bd = INFINITY, sd = INFINITY;
+        int bc = kNone;
+        const int xb = seq & (kXBuf - 1);
+        if (lane < nbk) {
+            const int ntile = (my_n + 7) >> 3;
+            for (int nt = 0; nt < ntile; ++nt) {
+                const Xch32 v = part[nt * B + lane];
+                merge_best(bd, sd, bc, v.bd, v.sd, v.bc);
+            }
+            const unsigned dst = smem_u32(xch + ((size_t)xb * 16 + rank) * B + lane);
+            const unsigned bar = smem_u32(&xbar[xb]);
+            for (int peer = 0; peer < ncta; ++peer)
+                st_async_16(mapa_u32(dst, peer), mapa_u32(bar, peer), __float_as_uint(bd), __float_as_uint(sd),
+                            (unsigned)bc, 0u);
+        }
+        __syncwarp();
+    };
+    // (warp 0) wait until exchange `seq` (16 x nbk entries of 16 bytes) has landed in this CTA
+    auto recv_block = [&](int nbk, int seq) {
+        const int xb = seq & (kXBuf - 1);
+        if (lane == 0) mbar_expect_tx(&xbar[xb], (unsigned)(ncta * nbk * (int)sizeof(Xch32)));
+        __syncwarp();
+        mbar_wait(&xbar[xb], (unsigned)((seq / kXBuf) & 1));
+    };
+
     // ---- q = |c|^2 - 2 <x, c> for the rows of block [rb, rb + nbk) and this CTA's centroids on the tensor cores
     // (mma.sync m16n8k8 TF32, 3xTF32 split, FP32 accumulate); the squared distance is |x|^2 + q.
     // Work item = (8 centroids) x (2 ring groups = 16 rows) over all features.  Thread (g, t) of the warp loads
@@ -218,7 +259,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
     // is all a dot product needs.  |c|^2 comes from the very registers fed to the MMAs, so a centroid that is
     // being rewritten while it is read still yields the distance to the vector actually read.
     // ctr == nullptr: static round-robin over the warps, else a shared work counter.
-    auto phase1 = [&](long long rb, int nbk, float *D, Xch32 *part, int *ctr, int w0, int wn) {
+    auto phase1 = [&](long long rb, int nbk, float *D, Xch32 *part, int *ctr, int w0, int wn, int seq) {
         const int ntile = (my_n + 7) >> 3;
         const long long g0 = rb / kGroup;
         const int lead = (int)(rb & (kGroup - 1));
@@ -228,6 +269,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
         const int g = lane >> 2, t = lane & 3;
         int it;
         if (ctr) {
+            if (nitems == 0 && warp == w0) send_block(nbk, part, seq);  // this CTA holds no centroid: all-infinite entries
             it = 0;
             if (lane == 0) it = atomicAdd(ctr, 1);
             it = __shfl_sync(0xffffffffu, it, 0);
@@ -324,8 +366,19 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
                 }
             }
             if (ctr) {
-                if (lane == 0) it = atomicAdd(ctr, 1);
+                // the warp that finishes the last item of the block sends the block's entries right away
+                __threadfence_block();
+                int fin = 0;
+                if (lane == 0) {
+                    fin = atomicAdd(ctr + 2, 1);
+                    it = atomicAdd(ctr, 1);
+                }
+                fin = __shfl_sync(0xffffffffu, fin, 0);
                 it = __shfl_sync(0xffffffffu, it, 0);
+                if (fin == nitems - 1) {
+                    __threadfence_block();
+                    send_block(nbk, part, seq);
+                }
             } else {
                 it += wn;
             }
@@ -342,47 +395,15 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
             tq = t;
         }
     };
-    // (warp 0; lane = row) merge the per-tile arg-mins of this CTA, then one 16-byte store per peer CTA and row that
-    // also completes 16 tx-bytes on the peer's mbarrier: instruction k carries the 32 rows' entries to peer k
-    // (contiguous 512 bytes), no staging, no fence, no barrier round trip
-    auto phase2 = [&](int nbk, const Xch32 *part, int par) {
-        probe(-1, 0.0);
-        float bd = INFINITY, sd = INFINITY;
-        int bc = kNone;
-        if (lane < nbk) {
-            const int ntile = (my_n + 7) >> 3;
-            for (int nt = 0; nt < ntile; ++nt) {
-                const Xch32 v = part[nt * B + lane];
-                merge_best(bd, sd, bc, v.bd, v.sd, v.bc);
-            }
-        }
-        probe(40, (double)bd);
-        if (lane < nbk) {
-            const unsigned dst = smem_u32(xch + ((size_t)par * 16 + rank) * B + lane);
-            const unsigned bar = smem_u32(&xbar[par]);
-            for (int peer = 0; peer < ncta; ++peer)
-                st_async_16(mapa_u32(dst, peer), mapa_u32(bar, peer), __float_as_uint(bd), __float_as_uint(sd),
-                            (unsigned)bc, 0u);
-        }
-        __syncwarp();
-        probe(42, 0.0);
-    };
-
     __syncthreads();
     cluster.sync();
 
-    // Warp roles.  Warp 0 is the control warp (arg-min, all-to-all, resolve): its chain of dependent
-    // instructions is the critical path.  The tensor-core tile needs few warps (one per 8 centroids x 16 rows),
-    // so the rest apply the centroid updates, each on its own slice of the features.
-    const int ncomp = (nw - 1) / 2;            // warps 1 .. ncomp compute distances in the pipelined steady state
-    const int first_apply = ncomp + 1;         // warps first_apply .. nw-1 apply updates
-    const int napply = nw - first_apply;
-    const bool is_compute = warp >= 1 && warp <= ncomp;
-    const bool is_apply = warp >= first_apply;
-    const int feat_per_apply = (f + napply - 1) / napply;
-    long long warp_wait = 0;  // debug: cycles this warp spent waiting at the per-block CTA barrier
     bool have = false;     // the distances + all-to-all of the block at r0 are already in flight (speculated)
     int cur = 0;           // distance buffer / exchange parity of the block at r0
+    double nx_ahead = 0.0; // (warp 0) squared norm of row `lane` of the speculated next block
+    int xs_next = 0;       // next unused exchange sequence number
+    int xs_cur = 0;        // exchange that carries the entries of the block at r0
+    int xs_stale = -1, stale_rows = 0;  // a speculative exchange that was sent but will not be used (drained below)
     double E1 = 0.0, E2 = 0.0;  // certified displacement bounds of the two preceding blocks
     while (r0 < A.n) {
         int nb = B - (int)(r0 & (kGroup - 1));  // blocks end on group boundaries
@@ -394,13 +415,18 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
         double P = 0.0;
         if (!have) {
             __syncthreads();  // every update is applied; nobody reads the ring, D or dec of earlier blocks
-            if (warp != 0) {  // the control warp never reads the row ring
+            if (is_compute) {  // only the compute warps read the row ring
                 const long long ga = r0 / kGroup;
                 need_groups(ga, (ga + NG) < g_total ? (ga + NG) : g_total);
             }
-            if (warp != 0) phase1(r0, nb, Dbuf(cur), Pbuf(cur), nullptr, 1, nw - 1);
+            if (is_compute) phase1(r0, nb, Dbuf(cur), Pbuf(cur), nullptr, 1, ncomp, 0);
+            if (xs_stale >= 0) {  // consume the exchange of the dropped speculative block (keeps the barrier phases in step)
+                if (warp == 0) recv_block(stale_rows, xs_stale);
+                xs_stale = -1;
+            }
             __syncthreads();
-            if (warp == 0) phase2(nb, Pbuf(cur), cur);
+            xs_cur = xs_next++;
+            if (warp == 0) send_block(nb, Pbuf(cur), xs_cur);
         } else {
             P = E1 + E2;
         }
@@ -409,14 +435,14 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
         const long long r0n = r0 + nb;
         const int nbn = (A.n - r0n) < (long long)B ? (int)(A.n - r0n) : B;
         const bool spec = !A.force_exact && kc == maxk && r0n < A.n;
-        if (spec && warp != 0) {
+        if (spec && is_compute) {
             const long long ga = r0n / kGroup;
             need_groups(ga, (ga + NG) < g_total ? (ga + NG) : g_total);
         }
-        if (is_apply) {   // L2-prefetch the FP64 rows the updates of the next block will read
+        if (is_compute) {   // L2-prefetch the FP64 rows the updates of the next block will read
             const long long lines_per_row = ((long long)f * 8 + 127) / 128;
             const long long first = r0n * lines_per_row, total = (long long)B * lines_per_row;
-            const int na = napply * 32, ia = tid - first_apply * 32;
+            const int na = ncomp * 32, ia = tid - 32;
             for (long long l = (long long)rank * na + ia; l < total; l += (long long)ncta * na) {
                 const long long byte = (first + l) * 128;
                 if (byte < A.n * (long long)f * 8)
@@ -427,30 +453,41 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
 
         // ---- resolve the rows of this block IN ORDER (warp 0, identical in every CTA); lane i holds row i
         if (warp == 0) {
-            const double nx = (lane < nb) ? __ldg(A.rows_n2 + r0 + lane) : 0.0;  // in flight during the wait
-            // the 16 x nb entries of this block land in xch[cur] with 16 tx-bytes each
-            if (lane == 0) mbar_expect_tx(&xbar[cur], (unsigned)(ncta * nb * (int)sizeof(Xch32)));
-            __syncwarp();
-            mbar_wait(&xbar[cur], (unsigned)((n_blocks >> 1) & 1));
+            // |x|^2 of this block's rows: loaded one block ahead when the block was speculated (an HBM round trip
+            // would otherwise sit on the critical path)
+            const double nx = have ? nx_ahead : ((lane < nb) ? __ldg(A.rows_n2 + r0 + lane) : 0.0);
+            if (spec) nx_ahead = (lane < nbn) ? __ldg(A.rows_n2 + r0n + lane) : 0.0;
+            recv_block(nb, xs_cur);  // the 16 x nb entries of this block, 16 tx-bytes each
             ASB_TICKP(1);
             probe(-1, 0.0);
             GRow32 g;
             g.bd = g.sb_hi = g.sb_lo = g.ss_lo = INFINITY;
             g.bc = kNone;
             if (lane < nb) {  // reduce the 16 CTA entries of row `lane`, attach the certified distance bounds
-                const Xch32 *e = xch + ((size_t)cur * 16) * B + lane;
-                float bd = INFINITY, sd = INFINITY;
-                int bc = kNone;
-                for (int q = 0; q < ncta; ++q) {
-                    const Xch32 v = e[(size_t)q * B];
-                    if (lex_less_f(v.bd, v.bc, bd, bc)) {
-                        sd = fminf(fminf(sd, v.sd), bd);
-                        bd = v.bd;
-                        bc = v.bc;
-                    } else {
-                        sd = fminf(fminf(sd, v.sd), v.bd);
+                const Xch32 *e = xch + ((size_t)(xs_cur & (kXBuf - 1)) * 16) * B + lane;
+                // 4 interleaved merge chains over the 16 CTA entries (depth 4 + 2 instead of 16)
+                float b4[4], s4[4];
+                int c4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    b4[k] = s4[k] = INFINITY;
+                    c4[k] = kNone;
+                }
+#pragma unroll
+                for (int q0 = 0; q0 < 16; q0 += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (q0 + k < ncta) {
+                            const Xch32 v = e[(size_t)(q0 + k) * B];
+                            merge_best(b4[k], s4[k], c4[k], v.bd, v.sd, v.bc);
+                        }
                     }
                 }
+                merge_best(b4[0], s4[0], c4[0], b4[1], s4[1], c4[1]);
+                merge_best(b4[2], s4[2], c4[2], b4[3], s4[3], c4[3]);
+                merge_best(b4[0], s4[0], c4[0], b4[2], s4[2], c4[2]);
+                const float bd = b4[0], sd = s4[0];
+                const int bc = c4[0];
                 const double d2b = nx + (double)bd, d2s = nx + (double)sd;  // squared distances, +- delta
                 g.bd = fmax(d2b, 0.0);
                 // FP32 square roots (2 ulp incl. the conversion) with outward slack
@@ -479,7 +516,9 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
                 }
                 bool ok = (qsum < 0.9f) && (esum < INFINITY);
                 // own displacement of the block: E >= sum_j (sb_hi_j + P + E) / (cnt_j + 1)
-                const double E = (esum + P * (double)qsum) / (1.0 - (double)qsum) * 1.001 + 1e-300;
+                // (upper bound of 1 / (1 - qsum) from directed FP32 roundings instead of an FP64 division)
+                const double E =
+                    (esum + P * (double)qsum) * (double)__frcp_ru(__fsub_rd(1.0f, qsum)) * 1.001 + 1e-300;
                 const double T = P + E;  // staleness + everything earlier rows of the block can add
                 const double hi_b = g.sb_hi + T, lo_b = fmax(g.sb_lo - T, 0.0);
                 const double lo2 = lo_b * lo_b * (1.0 - 1e-12), hi2 = hi_b * hi_b * (1.0 + 1e-12);
@@ -597,23 +636,32 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
                 ctl[1] = exact;
                 ctl[2] = kcl;
                 ctld[0] = e_own;
-                item_ctr[(n_blocks + 1) & 1] = 0;  // the work counter of the next iteration
+                item_ctr[(n_blocks + 1) & 1] = 0;  // the work counters of the next iteration
+                item_ctr[2 + ((n_blocks + 1) & 1)] = 0;
             }
             __syncwarp();
             probe(46, 0.0);
             ASB_TICKP(2);
         }
         // ---- meanwhile: distances of the next block (warp 0 joins when it has resolved this one)
-        if (spec && is_compute) phase1(r0n, nbn, Dbuf(cur ^ 1), Pbuf(cur ^ 1), &item_ctr[n_blocks & 1], 1, ncomp);
+        const int xs_spec = xs_next;  // exchange of the speculative block (sent by the compute warp that finishes it)
+        if (spec) xs_next++;
+        if (spec && is_compute)
+            phase1(r0n, nbn, Dbuf(cur ^ 1), Pbuf(cur ^ 1), &item_ctr[n_blocks & 1], 1, ncomp, xs_spec);
         ASB_TICKP(3);
         {
-            long long tb = 0, te = 0;
-            if (A.phase_times) asm volatile("mov.u64 %0, %%clock64;" : "=l"(tb)::"memory");
+            long long tb = 0;
+            if (A.phase_times) {
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(tb)::"memory");
+                if (lane == 0) arr_t[warp] = tb;
+            }
             __syncthreads();
-            if (A.phase_times) {  // BAR.SYNC defers its blocking: read the clock behind a load that needs it
-                const int probe = *reinterpret_cast<volatile int *>(ctl_all);
-                asm volatile("mov.u64 %0, %%clock64;" : "=l"(te) : "r"(probe) : "memory");
-                warp_wait += te - tb;
+            if (A.phase_times && tid == 0) {  // debug: which warp arrived last, and how long after the control warp
+                int last = 0;
+                for (int w = 1; w < nw; ++w)
+                    if (arr_t[w] > arr_t[last]) last = w;
+                arr_hist[last] += 1;
+                arr_late[last] += arr_t[last] - arr_t[0];
             }
         }
         ASB_TICKP(4);
@@ -739,10 +787,14 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
         kc = kc_new;
 
         if (rank == 0 && tid < n_commit) A.assign[r0 + tid] = (long long)dec[tid].target;
-        // ---- all-to-all of the next block first (the cluster barrier must not wait for the updates) ...
-        if (ok_spec && warp == 0) phase2(nbn, Pbuf(cur ^ 1), cur ^ 1);
+        if (ok_spec) {
+            xs_cur = xs_spec;
+        } else if (spec) {
+            xs_stale = xs_spec;
+            stale_rows = nbn;
+        }
         ASB_TICKP(5);
-        // ---- ... then apply the committed decisions in row order.  The update c += (x - c) / k is element-wise,
+        // ---- apply the committed decisions in row order.  The update c += (x - c) / k is element-wise,
         // so the apply warps split the FEATURES: every apply warp handles its slice of every row this CTA owns
         // (FP64 row and centroid from global memory, both centroid copies written; the slice of the centroid
         // stays in registers across consecutive rows of one slot, the next row is loaded ahead).
@@ -872,7 +924,7 @@ __global__ void __launch_bounds__(768, 1) cluster_f32p_kernel(ClusterArgs A) {
     __syncthreads();
     if (rank == 0 && tid == 0 && A.phase_times)
         for (int k = 0; k < 8; ++k) A.phase_times[k] = tphase[k];
-    if (rank == 0 && lane == 0 && A.phase_times) A.phase_times[8 + warp] = warp_wait;
+    if (rank == 0 && tid < 24 && A.phase_times) A.phase_times[8 + tid] = arr_hist[tid] * 1000000ll + (arr_hist[tid] ? arr_late[tid] / arr_hist[tid] : 0);
 }
 
 size_t cluster_f32p_smem_bytes(int f, int slots, int maxk) {
@@ -881,11 +933,11 @@ size_t cluster_f32p_smem_bytes(int f, int slots, int maxk) {
     size_t b = (size_t)kPipeGroups * kGroup * fp * 4;  // ring (f32)
     b += (size_t)slots8 * fp * 4;                      // cent32
     b += (size_t)2 * slots8 * kB32 * 4;                // D (two buffers)
-    b += (size_t)(2 * 16 + 2 * (slots8 / 8)) * kB32 * sizeof(Xch32);  // xch, per-tile arg-mins
+    b += (size_t)(kXBuf * 16 + 2 * (slots8 / 8)) * kB32 * sizeof(Xch32);  // xch, per-tile arg-mins
     b += 32 * sizeof(Xch);                             // xch_exact
     b += (size_t)kB32 * sizeof(GRow32);
     b += (size_t)2 * kB32 * sizeof(Dec);
-    b += (size_t)kPipeGroups * 8 + 2 * 8;              // mbarriers
+    b += (size_t)kPipeGroups * 8 + kXBuf * 8;          // mbarriers
     b += (size_t)maxk * 8 * 2;                         // cnt, disp
     b += 32 * 8 + 2 * 8;                               // wred_d, ctld
     b += (size_t)f * 8;                                // xrow64

@@ -33,7 +33,8 @@ for upto in (n // 2, n):
         names = ["nonspec p1+p2", "w0 cluster wait", "w0 resolve", "w0 spec p1", "S1 barrier", "apply", "p2+arrive"]
     print("   cycles/block:", {n: round(v / max(ctx.kernel_ms('cluster_blocks'), 1)) for n, v in zip(names, ph)})
     if ctx.kernel_ms('cluster_variant') == -2:
-        print("   barrier wait cycles/block per warp:", [round(ctx.kernel_ms(f"cluster_phase{8 + w}") / max(ctx.kernel_ms('cluster_blocks'), 1)) for w in range(24)])
+        print("   last arriver at the block barrier (warp: count, mean cycles after warp 0):",
+              {w: (int(ctx.kernel_ms(f"cluster_phase{8 + w}")) // 1000000, int(ctx.kernel_ms(f"cluster_phase{8 + w}")) % 1000000) for w in range(24) if ctx.kernel_ms(f"cluster_phase{8 + w}") > 0})
         nb_ = max(ctx.kernel_ms('cluster_blocks'), 1)
         print("   warp 0 detail cycles/block:", {k: round(ctx.kernel_ms(f"cluster_phase{i}") / nb_) for k, i in
               [("p2 argmin", 40), ("p2 fence", 41), ("p2 bulk issue", 42), ("res reduce16+bounds", 43), ("res fast cert", 44), ("res slow path", 45), ("res dec write", 46)]})
