@@ -85,6 +85,18 @@ __device__ __forceinline__ void merge_best(float &bd, float &sd, int &bc, float 
         sd = fminf(fminf(sd, osd), obd);
     }
 }
+// RN(a / b) from y = RN(1 / b) with two FMA correction steps (Markstein): q0 = RN(a y) is within 2 ulp of a / b,
+// q1 = RN(q0 + (a - b q0) y) is faithful, and one more step from a faithful quotient with a correctly rounded
+// reciprocal yields the correctly rounded quotient (b is a cluster count, an integer below 2^52, so its significand
+// is never all ones -- the one exception of the theorem).  The residuals a - b q are exact in an FMA as long as
+// nothing under- or overflows: operands outside [1e-280, 1e280] (and non-finite ones) take the library division.
+__device__ __forceinline__ double div_by_count(double a, double b, double y) {
+    const double aa = fabs(a);
+    if (!(aa >= 1e-280 && aa <= 1e280)) return a == 0.0 ? a / b : __ddiv_rn(a, b);
+    const double q0 = __dmul_rn(a, y);
+    const double q1 = __fma_rn(__fma_rn(-q0, b, a), y, q0);
+    return __fma_rn(__fma_rn(-q1, b, a), y, q1);
+}
 // x = hi + lo exactly; hi has 10 explicit mantissa bits (a TF32 number), |lo| < 2^-10 |x|
 __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
     hi = __float_as_uint(x) & 0xffffe000u;
@@ -809,8 +821,9 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
             const int jhi = (jlo + feat_per_apply) < f ? (jlo + feat_per_apply) : f;
             constexpr int T = 4;
             if (feat_per_apply <= 32 * T) {
-                // software pipeline: the row slice AND the centroid slice of the next row are in flight while the
-                // current row is applied (a row that hits the same slot as its predecessor takes the fresh registers)
+                // software pipeline: the row slice, the centroid slice and the reciprocal of the count of the NEXT row
+                // are in flight while the current row is applied (a row that hits the same slot as its predecessor
+                // takes the fresh registers)
                 double cw[T], xv[T];
                 int i = todo ? __ffs(todo) - 1 : -1;
                 todo &= todo - 1;
@@ -818,6 +831,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                 dd.slot = -1;
                 dd.action = 3;
                 dd.knew = 1.0;
+                double yk = 1.0;
                 if (i >= 0) {
                     dd = dec[i];
                     const double *row = A.rows + (r0 + i) * (long long)f;
@@ -828,11 +842,12 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                         xv[t] = j < jhi ? __ldg(row + j) : 0.0;
                         cw[t] = (j < jhi && dd.action != 0) ? cv[j] : 0.0;
                     }
+                    yk = __drcp_rn(dd.action != 0 ? dd.knew : 1.0);
                 }
                 while (i >= 0) {
                     const int inext = todo ? __ffs(todo) - 1 : -1;
                     todo &= todo - 1;
-                    double xn[T], cnx[T];
+                    double xn[T], cnx[T], yn = 1.0;
                     Dec dn = dd;
                     bool fresh = false;  // the next row needs a centroid slice from memory
                     if (inext >= 0) {
@@ -846,16 +861,17 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                             xn[t] = j < jhi ? __ldg(row + j) : 0.0;
                             cnx[t] = (j < jhi && fresh) ? cvn[j] : 0.0;
                         }
+                        yn = __drcp_rn(dn.action != 0 ? dn.knew : 1.0);
                     }
                     double *cv = c64(dd.slot);
                     float *cf = c32(dd.slot);
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
                         const int j = jlo + lane + 32 * t;
-                        if (j < jhi) {  // (lanes past the slice would divide 0 by k: the slow path of the division)
+                        if (j < jhi) {
                             double v = xv[t];
-                            if (dd.action != 0)
-                                v = __dadd_rn(cw[t], __ddiv_rn(__dsub_rn(v, cw[t]), dd.knew));  // :748
+                            if (dd.action != 0)  // c + (x - c) / k, src/clustering.rs:748
+                                v = __dadd_rn(cw[t], div_by_count(__dsub_rn(v, cw[t]), dd.knew, yk));
                             cw[t] = v;
                             cv[j] = v;
                             cf[j] = (float)v;
@@ -869,6 +885,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                         }
                     }
                     dd = dn;
+                    yk = yn;
                     i = inext;
                 }
             } else {
