@@ -404,8 +404,10 @@ def run_b200(args):
         ach = by / (kms["cluster_kernel"] * 1e-3) / 1e9
         kernels["cluster_kernel"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": ach / hbm_peak, "ms": kms["cluster_kernel"], "traffic": None,
-                                     "note": "order-dependent walk: dependency bound by design (one cluster "
-                                             "barrier per block of <=16 rows), rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
+                                     "note": "order-dependent walk: dependency bound by design (32-row blocks, the "
+                                             "resolve of block b overlaps the tensor-core distance tile of block b+1), "
+                                             "rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
+                                     "variant": ctx.kernel_ms("cluster_variant"),
                                      "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
     # DRAM traffic per launch from `ncu --set full` captures (profiles/r01_final_ncu_summary.csv,
     # profiles/r01_v1_*): only quoted for the configuration they were captured on.
@@ -418,7 +420,12 @@ def run_b200(args):
             kernels["search_kernel"]["traffic_note"] = ("ncu on 200k items x 2048 queries: 670 MB read for a 614 MB "
                                                         "item set (L2 serves the per-query-tile re-reads)")
     dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
-    roofline = dict(kernels[dominant], kernel=dominant, peak_kind=peak_src) if dominant else None
+    roofline = dict(kernels[dominant], kernel=dominant) if dominant else None
+    if roofline is not None:
+        # HBM peaks come from MEASURED_PEAKS.json (or the profiling guide's fallback); that file has no FP64 entry,
+        # so FP64 tensor-bound kernels are held against the DMMA rate measured on this pool by tools/fp64_peak.cu
+        roofline["peak_kind"] = peak_src if roofline["bound"] == "hbm" else \
+            "measured on this pool by tools/fp64_peak.cu (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure"
 
     line = {
         "metric": "lambda_tau_build_items_per_s", "value": items_per_s, "unit": "items/s", "n_gpus": world,
