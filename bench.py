@@ -183,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": items_s, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------- B200 arm
@@ -201,6 +201,9 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout at VERSION level; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     asb._build.build_cuda()
     stream = torch.cuda.current_stream().cuda_stream
@@ -467,13 +470,28 @@ def run_b200(args):
             "sample": f"build on the first {n_s} rows (clustering is sequential in the reference's deterministic "
                       f"mode); search {q_s} queries x {n_items_search} items scaled to N={n}",
             "search_qps": (q_s / (t3 - t2)) * (n_items_search / n), "build_s": t1 - t0, "search_s": t3 - t2}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _emit(line: dict) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else that writes to fd 1 while the
+    bench runs (NCCL's version banner, library chatter) has been pointed at stderr."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
