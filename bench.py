@@ -416,7 +416,7 @@ def run_b200(args):
     # profiles/r01_v1_*): only quoted for the configuration they were captured on.
     if n == 1_000_000 and f == 384 and world == 1:
         if "cluster_kernel" in kernels:
-            kernels["cluster_kernel"]["traffic"] = 4.66e9   # 4.64 GB read (f32 rows + f64 rows for updates) + 19 MB written
+            kernels["cluster_kernel"]["traffic"] = 4.67e9   # ncu (profiles/r01_v6_launches.md): 2.32 GB read + 10.5 MB written per 500k rows
         if "taumode_kernel" in kernels:
             kernels["taumode_kernel"]["traffic"] = 3.11e9   # 5 x (614.5 MB read + 7.1 MB written) measured on 200k items
         if "search_kernel" in kernels:

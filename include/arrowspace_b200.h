@@ -98,8 +98,16 @@ int64_t asb_kernel_launches(asb_ctx *ctx);
 /* device time of the most recent top-level call's dominant kernel(s), ms, measured with
  * CUDA events on the context's stream (0 if none). */
 double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
-/* debug / test switches.  "cluster_force_exact" (0|1): take every clustering decision from the
- * reference-arithmetic path instead of the certified fast path (results are identical). */
+/* debug / test switches (results are identical whatever they are set to):
+ *   "cluster_force_exact" (0|1)   take every clustering decision from the reference-arithmetic path instead of
+ *                                 the certified fast path;
+ *   "cluster_first_variant" (v)   start the clustering kernel selection at variant v: -2 pipelined tensor-core
+ *                                 kernel (default), -1 FP32 blocked, 0 / 1 FP64 blocked (16 / 8 rows), 2 row-wise;
+ *                                 a variant that does not fit shared memory falls through to the next one;
+ *   "cluster_no_pipeline", "cluster_no_f32", "cluster_rowwise" (0|1)  shorthands for -1, 0 and 2;
+ *   "cluster_phase_times" (0|1), "cluster_tick_tid" (t)  per-block cycle probes, read back with
+ *                                 asb_last_kernel_ms(ctx, "cluster_phaseN");
+ *   "taumode_generic" (0|1)       use the generic CSR kernel even for a symmetric graph. */
 int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
 
 /* ---- stage 1: clustering ------------------------------------------------------------ */
