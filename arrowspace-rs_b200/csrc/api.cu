@@ -18,7 +18,11 @@ struct asb_index {
     unsigned long long *sizes = nullptr;
     int64_t *indptr = nullptr, *indices = nullptr;
     double *data = nullptr;
-    GraphPlan plan;
+    GraphPlan plan;       // feature Laplacian: query lambdas (and item lambdas unless spectral)
+    GraphPlan plan_sig;   // spectral signals (Laplacian-of-Laplacian): item lambdas when spectral
+    int64_t *sig_indptr = nullptr, *sig_indices = nullptr;
+    double *sig_data = nullptr;
+    int64_t sig_nnz = 0;
     int tau_mode = ASB_TAU_MEDIAN;
     double tau_value = 0.0;
     double h_stats[3] = {0, 0, 0};
@@ -579,6 +583,13 @@ void asb_index_destroy(asb_index *ix) {
     cudaFree(ix->plan.row_ptr);
     cudaFree(ix->plan.sym_edges);
     cudaFree(ix->plan.resid);
+    cudaFree(ix->plan_sig.entries);
+    cudaFree(ix->plan_sig.row_ptr);
+    cudaFree(ix->plan_sig.sym_edges);
+    cudaFree(ix->plan_sig.resid);
+    cudaFree(ix->sig_indptr);
+    cudaFree(ix->sig_indices);
+    cudaFree(ix->sig_data);
     cudaGetLastError();
     delete ix;
 }
@@ -655,11 +666,33 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
         std::vector<double> hd;
         ASB_TRY(csr_to_host(ctx, ix->indptr, ix->indices, ix->data, f, hp, hi, hd));
         ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), f, &ix->plan));
+        if (bp->spectral) {
+            // optional stage (src/eigenmaps.rs:325-345 -> src/graph.rs:211-231): signals = the same Laplacian
+            // construction run on dense(L)^T, i.e. with the F rows of L as the "items" and its F columns as nodes
+            std::vector<double> dense((size_t)f * f, 0.0);
+            for (int64_t r = 0; r < f; ++r)
+                for (int64_t e = hp[r]; e < hp[r + 1]; ++e) dense[(size_t)r * f + hi[e]] = hd[e];
+            DevTmp<double> dense_d;
+            ASB_TRY(dense_d.init(ctx, (size_t)f * f));
+            ASB_CUDA(ctx, cudaMemcpyAsync(dense_d.ptr, dense.data(), (size_t)f * f * sizeof(double), cudaMemcpyHostToDevice,
+                                          ctx->stream));
+            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_indptr, (size_t)(f + 1) * sizeof(int64_t)));
+            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_indices, (size_t)cap * sizeof(int64_t)));
+            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_data, (size_t)cap * sizeof(double)));
+            int64_t snnz = 0;
+            ASB_TRY(asb_dev_laplacian(ctx, dense_d.ptr, f, f, gp, ix->sig_indptr, ix->sig_indices, ix->sig_data, cap, &snnz));
+            ix->sig_nnz = snnz;
+            std::vector<int64_t> sp, si;
+            std::vector<double> sd;
+            ASB_TRY(csr_to_host(ctx, ix->sig_indptr, ix->sig_indices, ix->sig_data, f, sp, si, sd));
+            ASB_TRY(asb_graph_plan_from_host(ctx, sp.data(), si.data(), sd.data(), f, &ix->plan_sig));
+        }
     }
     cudaEventRecord(e2, ctx->stream);
-    // stage 3: taumode (src/eigenmaps.rs:358-383)
-    ASB_TRY(asb_dev_taumode(ctx, ix->items, n, f, ix->plan, bp->tau_mode, bp->tau_value, ix->lambdas, ix->norms2,
-                            ix->stats, nullptr));
+    // stage 3: taumode (src/eigenmaps.rs:358-383); the items read the signals graph when it exists
+    // (src/taumode.rs:195-200), queries never do (src/core.rs:548)
+    ASB_TRY(asb_dev_taumode(ctx, ix->items, n, f, bp->spectral ? ix->plan_sig : ix->plan, bp->tau_mode, bp->tau_value,
+                            ix->lambdas, ix->norms2, ix->stats, nullptr));
     cudaEventRecord(e3, ctx->stream);
     ASB_CUDA(ctx, cudaMemcpyAsync(ix->h_stats, ix->stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -692,6 +725,7 @@ int asb_index_info_get(const asb_index *ix, asb_index_info *info) {
     info->ms_laplacian = ix->ms_laplacian;
     info->ms_taumode = ix->ms_taumode;
     info->ms_total = ix->ms_total;
+    info->nnz_signals = ix->sig_nnz;
     return ASB_OK;
 }
 
@@ -729,6 +763,15 @@ int asb_index_laplacian(asb_ctx *ctx, const asb_index *ix, int64_t *indptr, int6
     ASB_TRY(copy_out(ctx, indptr, ix->indptr, (size_t)(ix->f + 1) * sizeof(int64_t)));
     ASB_TRY(copy_out(ctx, indices, ix->indices, (size_t)ix->nnz * sizeof(int64_t)));
     return copy_out(ctx, data, ix->data, (size_t)ix->nnz * sizeof(double));
+}
+
+int asb_index_signals(asb_ctx *ctx, const asb_index *ix, int64_t *indptr, int64_t *indices, double *data) {
+    ASB_TRY(set_device(ctx));
+    if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
+    if (!ix->sig_indptr) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_signals: the index was built without spectral signals");
+    ASB_TRY(copy_out(ctx, indptr, ix->sig_indptr, (size_t)(ix->f + 1) * sizeof(int64_t)));
+    ASB_TRY(copy_out(ctx, indices, ix->sig_indices, (size_t)ix->sig_nnz * sizeof(int64_t)));
+    return copy_out(ctx, data, ix->sig_data, (size_t)ix->sig_nnz * sizeof(double));
 }
 
 int asb_index_search(asb_ctx *ctx, const asb_index *ix, const double *queries, int64_t nq, int64_t k, double alpha,

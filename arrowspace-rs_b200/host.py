@@ -60,6 +60,7 @@ class BuildParamsC(C.Structure):
     _fields_ = [
         ("graph", GraphParamsC), ("tau_mode", C.c_int32), ("tau_value", C.c_double),
         ("max_clusters", C.c_int64), ("radius", C.c_double), ("apply_define_result_k", C.c_int32),
+        ("spectral", C.c_int32),
     ]
 
 
@@ -69,7 +70,7 @@ class IndexInfoC(C.Structure):
         ("lambda_min", C.c_double), ("lambda_max", C.c_double), ("lambda_sum", C.c_double),
         ("radius", C.c_double), ("max_clusters", C.c_int64),
         ("ms_cluster", C.c_double), ("ms_laplacian", C.c_double), ("ms_taumode", C.c_double),
-        ("ms_total", C.c_double),
+        ("ms_total", C.c_double), ("nnz_signals", C.c_int64),
     ]
 
 
@@ -107,6 +108,7 @@ ABI_SYMBOLS = {
     "asb_index_assignments": (C.c_int, [_P, _P, _P]),
     "asb_index_cluster_sizes": (C.c_int, [_P, _P, _P]),
     "asb_index_laplacian": (C.c_int, [_P, _P, _P, _P, _P]),
+    "asb_index_signals": (C.c_int, [_P, _P, _P, _P, _P]),
     "asb_index_search": (C.c_int, [_P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P]),
     "asb_index_search_lambda_aware": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _D, _P, _P, _P]),
 }
@@ -492,6 +494,7 @@ class ArrowSpace:
         self.cluster_radius = 0.0
         self.projection_matrix = None
         self.reduced_dim = None
+        self.signals = None  # (indptr, indices, data) of aspace.signals, src/core.rs:370
         self._index = None  # native asb_index*
         self._device_cache = None
 
@@ -541,18 +544,26 @@ class ArrowSpace:
 
     def eigenmaps(self, builder: "ArrowSpaceBuilder", centroids, n_items: int) -> GraphLaplacian:
         """``EigenMaps::eigenmaps`` (src/eigenmaps.rs:292-356)."""
-        if builder.prebuilt_spectral:
-            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "with_spectral(true) is a 'next' row (SURVEY 8f)")
         centroids = _as_f64_matrix(centroids)
         if centroids.shape[0] > n_items:  # graph.rs:168 assert
             raise ArrowSpaceError(ASB_ERR_INVALID, "clustered.shape().0 <= n_items violated")
         gp = builder.graph_params()
         indptr, indices, data = self.ctx.build_feature_laplacian(centroids, gp)
-        return GraphLaplacian(indptr, indices, data, n_items, gp, np.asarray(centroids))
+        gl = GraphLaplacian(indptr, indices, data, n_items, gp, np.asarray(centroids))
+        if builder.prebuilt_spectral:  # src/eigenmaps.rs:325-345 -> GraphFactory::build_spectral_laplacian
+            self.signals = self.build_spectral_laplacian(gl)
+        return gl
+
+    def build_spectral_laplacian(self, gl: GraphLaplacian):
+        """``GraphFactory::build_spectral_laplacian`` (src/graph.rs:211-231): the Laplacian construction run on
+        ``dense(L)^T`` -- the F rows of L are the "items", its F columns the nodes.  Returns the signals CSR."""
+        return self.ctx.build_feature_laplacian(np.ascontiguousarray(gl.to_dense()), gl.graph_params)
 
     def compute_taumode(self, gl: GraphLaplacian) -> None:
-        """``EigenMaps::compute_taumode`` (src/eigenmaps.rs:358-383)."""
-        lam, n2, stats = self.ctx.compute_taumode(self.data, gl.csr, self.taumode, want_norms=True)
+        """``EigenMaps::compute_taumode`` (src/eigenmaps.rs:358-383); reads ``signals`` instead of the feature
+        Laplacian when they exist (src/taumode.rs:195-200)."""
+        graph = self.signals if getattr(self, "signals", None) is not None else gl.csr
+        lam, n2, stats = self.ctx.compute_taumode(self.data, graph, self.taumode, want_norms=True)
         self.lambdas = lam
         self.norms2 = n2
         self.lambda_stats = (stats[0], stats[1], stats[2] / self.nitems)
@@ -765,14 +776,15 @@ class ArrowSpaceBuilder:
             raise ArrowSpaceError(ASB_ERR_UNSUPPORTED,
                                   "inline sampling uses an OS-seeded RNG in the reference (src/sampling.rs:123,184); "
                                   "use with_inline_sampling(None)")
-        if self.use_dims_reduction or self.prebuilt_spectral:
-            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "JL projection / spectral signals are 'next' rows (SURVEY 8f)")
+        if self.use_dims_reduction:
+            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "JL projection is a 'next' row (SURVEY 8f)")
         n, f = _shape2(rows)
         aspace = ArrowSpace(rows, self.synthesis, self.ctx)
         k_opt, radius = self.resolve_cluster_params(rows)
         self.cluster_max_clusters, self.cluster_radius = k_opt, radius
         gp = self.graph_params()
-        bp = BuildParamsC(gp.to_c(), self.synthesis.mode, self.synthesis.value, int(k_opt), float(radius), 0)
+        bp = BuildParamsC(gp.to_c(), self.synthesis.mode, self.synthesis.value, int(k_opt), float(radius), 0,
+                          1 if self.prebuilt_spectral else 0)
         h = _P()
         lib = self.ctx.lib
         self.ctx.check(lib.asb_index_build(self.ctx.handle, _ptr(rows), n, f, C.byref(bp), C.byref(h)))
@@ -798,6 +810,11 @@ class ArrowSpaceBuilder:
         aspace.cluster_radius = radius
         aspace.lambda_stats = (info.lambda_min, info.lambda_max, info.lambda_sum / n)
         gl = GraphLaplacian(indptr, indices, data, n, gp, cent)
+        if self.prebuilt_spectral:
+            snnz = int(info.nnz_signals)
+            sp, si, sd = np.empty(f + 1, dtype=np.int64), np.empty(snnz, dtype=np.int64), np.empty(snnz, dtype=np.float64)
+            self.ctx.check(lib.asb_index_signals(self.ctx.handle, h, _ptr(sp), _ptr(si), _ptr(sd)))
+            aspace.signals = (sp, si, sd)
         return aspace, gl
 
     def __str__(self):  # src/builder.rs:459-524 Display: key=value, ...

@@ -76,6 +76,9 @@ typedef struct {
     int64_t max_clusters; /* builder.cluster_max_clusters, src/eigenmaps.rs:216 */
     double radius;        /* builder.cluster_radius (a SQUARED distance), :217 */
     int32_t apply_define_result_k; /* 1: k<=5 -> topk=3, k<10 -> topk=4 (src/builder.rs:225-233) */
+    int32_t spectral; /* with_spectral (src/builder.rs:157-162): also build the Laplacian-of-Laplacian "signals"
+                       * (src/graph.rs:211-231) and synthesise the ITEM lambdas from it (src/taumode.rs:195-200);
+                       * query lambdas keep using the feature Laplacian (src/core.rs:548) */
 } asb_build_params;
 
 typedef struct {
@@ -84,6 +87,7 @@ typedef struct {
     double radius;
     int64_t max_clusters;
     double ms_cluster, ms_laplacian, ms_taumode, ms_total; /* device stage times */
+    int64_t nnz_signals; /* stored entries of the spectral signals matrix, 0 without with_spectral */
 } asb_index_info;
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -216,6 +220,9 @@ int asb_index_laplacian(asb_ctx *ctx, const asb_index *index, int64_t *indptr,
                         int64_t *indices, double *data); /* f+1, nnz, nnz */
 /* EigenMaps::search (src/eigenmaps.rs:410-455) for a batch: prepare_query_item +
  * search_lambda_aware.  lambda_q_out optional (f64[nq]). */
+/* aspace.signals (src/core.rs:370; F x F CSR, capacity asb_laplacian_max_nnz(F, topk)); ASB_ERR_INVALID when the
+ * index was built without `spectral`. */
+int asb_index_signals(asb_ctx *ctx, const asb_index *idx, int64_t *indptr, int64_t *indices, double *data);
 int asb_index_search(asb_ctx *ctx, const asb_index *index, const double *queries, int64_t nq,
                      int64_t k, double alpha, int64_t *idx, double *score, int64_t *count,
                      double *lambda_q_out);

@@ -77,6 +77,8 @@ class ArrowSpace {
   public:
     int64_t nitems = 0, nfeatures = 0, n_clusters = 0;
     std::vector<double> lambdas;
+    std::vector<int64_t> signals_indptr, signals_indices;  // aspace.signals (with_spectral), CSR F x F
+    std::vector<double> signals_data;
     std::vector<int64_t> cluster_assignments;  // -1 = None
     std::vector<uint64_t> cluster_sizes;
     double cluster_radius = 0.0;
@@ -153,6 +155,7 @@ class ArrowSpaceBuilder {
     }
     ArrowSpaceBuilder &with_synthesis(TauMode t) { synthesis = t; return *this; }           // :142-146
     ArrowSpaceBuilder &with_normalisation(bool v) { normalise = v; return *this; }          // :148-152
+    ArrowSpaceBuilder &with_spectral(bool v) { prebuilt_spectral = v; return *this; }       // :157-162
     ArrowSpaceBuilder &with_sparsity_check(bool v) { sparsity_check = v; return *this; }    // :164-168
     ArrowSpaceBuilder &with_inline_sampling_none() { sampling = false; return *this; }      // :170-179 (None only)
     ArrowSpaceBuilder &with_dims_reduction(bool enable) { use_dims_reduction = enable; return *this; }  // :181-185
@@ -175,6 +178,7 @@ class ArrowSpaceBuilder {
         bp.tau_mode = synthesis.mode; bp.tau_value = synthesis.value;
         bp.max_clusters = cluster_max_clusters; bp.radius = cluster_radius;
         bp.apply_define_result_k = 1;  // define_result_k, :225-233
+        bp.spectral = prebuilt_spectral ? 1 : 0;
         ArrowSpace a;
         a.ctx_ = ctx_;
         ctx_->check(asb_index_build(ctx_->get(), rows, n, f, &bp, &a.index_));
@@ -190,6 +194,12 @@ class ArrowSpaceBuilder {
         ctx_->check(asb_index_cluster_sizes(ctx_->get(), a.index_, a.cluster_sizes.data()));
         ctx_->check(asb_index_centroids(ctx_->get(), a.index_, gl.init_data.data()));
         ctx_->check(asb_index_laplacian(ctx_->get(), a.index_, gl.indptr.data(), gl.indices.data(), gl.data.data()));
+        if (prebuilt_spectral) {  // aspace.signals, src/core.rs:370
+            a.signals_indptr.resize((size_t)f + 1); a.signals_indices.resize((size_t)info.nnz_signals);
+            a.signals_data.resize((size_t)info.nnz_signals);
+            ctx_->check(asb_index_signals(ctx_->get(), a.index_, a.signals_indptr.data(), a.signals_indices.data(),
+                                          a.signals_data.data()));
+        }
         return {std::move(a), std::move(gl)};
     }
 
@@ -197,6 +207,7 @@ class ArrowSpaceBuilder {
     std::optional<double> lambda_sigma; bool normalise = false, sparsity_check = false, sampling = true;
     TauMode synthesis; int64_t cluster_max_clusters = 0; double cluster_radius = 1.0;
     std::optional<uint64_t> clustering_seed; bool deterministic_clustering = false, use_dims_reduction = false;
+    bool prebuilt_spectral = false;
 
   private:
     const Context *ctx_;

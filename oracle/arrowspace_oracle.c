@@ -15,6 +15,21 @@
 #include <omp.h>
 #endif
 
+/* src/graph.rs:211-231: aspace.signals = build_laplacian_matrix(sparse_to_dense(&gl.matrix).transpose(), params,
+ * Some(nitems)).matrix.  aso_feature_laplacian(M, X, F) is build_laplacian_matrix(M^T), so M = dense(L). */
+int aso_spectral_signals(const int64_t *l_indptr, const int64_t *l_indices, const double *l_data, int64_t f,
+                         const aso_lap_params *params, int64_t *indptr, int64_t *indices, double *data,
+                         int64_t *nnz_out) {
+    if (!l_indptr || !l_indices || !l_data || f <= 0) return ASO_ERR_INVALID;
+    double *dense = (double *)calloc((size_t)f * (size_t)f, sizeof(double));
+    if (!dense) return ASO_ERR_INVALID;
+    for (int64_t r = 0; r < f; ++r)
+        for (int64_t e = l_indptr[r]; e < l_indptr[r + 1]; ++e) dense[(size_t)r * f + l_indices[e]] = l_data[e];
+    const int rc = aso_feature_laplacian(dense, f, f, params, indptr, indices, data, nnz_out);
+    free(dense);
+    return rc;
+}
+
 int aso_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -112,6 +112,13 @@ int aso_feature_laplacian(const double *centroids, int64_t x, int64_t f,
                           const aso_lap_params *params, int64_t *indptr, int64_t *indices,
                           double *data, int64_t *nnz_out);
 
+/* GraphFactory::build_spectral_laplacian, src/graph.rs:211-231 -- signals =
+ * build_laplacian_matrix(dense(L)^T, params): the F rows of L are the "items", its F columns the nodes.
+ * L in CSR (F x F); output CSR with the same capacity rule as aso_feature_laplacian. */
+int aso_spectral_signals(const int64_t *l_indptr, const int64_t *l_indices, const double *l_data, int64_t f,
+                         const aso_lap_params *params, int64_t *indptr, int64_t *indices, double *data,
+                         int64_t *nnz_out);
+
 /* src/core.rs:135-239,760-798.  Returns count = min(k,n) in *count_out. */
 int aso_search_lambda_aware(const double *items, const double *lambdas, int64_t n, int64_t f,
                             const double *q, double lambda_q, int64_t k, double alpha,

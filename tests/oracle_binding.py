@@ -51,6 +51,7 @@ class Oracle:
         lib.aso_step1_bounds.restype = None
         lib.aso_step1_bounds.argtypes = [_I64, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)]
         lib.aso_feature_laplacian.argtypes = [_P, _I64, _I64, C.POINTER(LapParams), _P, _P, _P, C.POINTER(_I64)]
+        lib.aso_spectral_signals.argtypes = [_P, _P, _P, _I64, C.POINTER(LapParams), _P, _P, _P, C.POINTER(_I64)]
         lib.aso_search_lambda_aware.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_search_lambda_aware_batch.argtypes = [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P, C.c_int]
         lib.aso_search_lambda_aware_hybrid.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
@@ -139,6 +140,24 @@ class Oracle:
         P = LapParams(eps, k, topk, p, 1 if sigma is not None else 0, sigma if sigma is not None else 0.0,
                       int(normalise), int(sparsity_check), int(self_included), int(rectified))
         self._chk(self.lib.aso_feature_laplacian(_p(c), x, f, C.byref(P), _p(ip), _p(ii), _p(dd), C.byref(nnz)))
+        return ip, ii[: nnz.value].copy(), dd[: nnz.value].copy()
+
+    def spectral_signals(self, csr, eps, k, topk, p, sigma, normalise=False, sparsity_check=False,
+                         self_included=False, rectified=False):
+        """aspace.signals from the feature Laplacian ``csr`` (src/graph.rs:211-231)."""
+        lp = np.ascontiguousarray(csr[0], dtype=np.int64)
+        li = np.ascontiguousarray(csr[1], dtype=np.int64)
+        ld = np.ascontiguousarray(csr[2], dtype=np.float64)
+        f = len(lp) - 1
+        cap = max(f * (1 + 2 * (topk + 1)), f) + 8
+        ip = np.zeros(f + 1, dtype=np.int64)
+        ii = np.zeros(cap, dtype=np.int64)
+        dd = np.zeros(cap, dtype=np.float64)
+        nnz = _I64(0)
+        P = LapParams(eps, k, topk, p, 1 if sigma is not None else 0, sigma if sigma is not None else 0.0,
+                      int(normalise), int(sparsity_check), int(self_included), int(rectified))
+        self._chk(self.lib.aso_spectral_signals(_p(lp), _p(li), _p(ld), f, C.byref(P), _p(ip), _p(ii), _p(dd),
+                                                C.byref(nnz)))
         return ip, ii[: nnz.value].copy(), dd[: nnz.value].copy()
 
     def search_lambda_aware(self, items, lambdas, q, lambda_q, k, alpha):

@@ -31,7 +31,8 @@ def test_struct_layouts(asb):
     # POD structs must match the C layout (8-byte aligned doubles / int64)
     assert ctypes.sizeof(asb.host.GraphParamsC) == 64
     assert ctypes.sizeof(asb.host.BuildParamsC) == 64 + 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(asb.host.IndexInfoC) == 13 * 8
+    assert ctypes.sizeof(asb.host.IndexInfoC) == 14 * 8
+    assert asb.host.BuildParamsC.spectral.offset == asb.host.BuildParamsC.apply_define_result_k.offset + 4
 
 
 def test_status_strings(asb):

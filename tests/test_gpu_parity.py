@@ -538,6 +538,52 @@ def test_build_matches_oracle_and_stages(ctx, asb, oracle, n, f, maxk):
     assert (np.asarray(idx1)[:, 0] == src).mean() > 0.9
 
 
+def test_spectral_signals_build(ctx, asb, oracle):
+    """with_spectral(true) (src/builder.rs:157-162, src/graph.rs:211-231): signals = the Laplacian
+    construction run on dense(L)^T; ITEM lambdas come from the signals graph (src/taumode.rs:195-200), QUERY lambdas
+    keep using the feature Laplacian (src/core.rs:548).  One native call and the staged mirror must both match
+    the oracle composition."""
+    n, f, maxk = 4_000, 128, 80
+    x = asb.synth.protein_like(n, f, seed=42)
+    radius = 1.5 * f * 0.0025 * 2
+    gp = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    cent, asg, sizes = oracle.cluster_incremental(x, maxk, radius)
+    csr = oracle.feature_laplacian(cent, **gp)
+    sig = oracle.spectral_signals(csr, **gp)
+    lam = oracle.compute_taumode(x, sig, TAU_MEDIAN, 0.0)
+    lam_plain = oracle.compute_taumode(x, csr, TAU_MEDIAN, 0.0)
+    assert not np.allclose(lam, lam_plain)          # the two graphs really give different lambdas
+
+    def builder():
+        return (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(0.5, 12, 4, 2.0, 0.25)
+                .with_synthesis(asb.TauMode.Median).with_seed(42).with_inline_sampling(None)
+                .with_dims_reduction(False, None).with_cluster_params(maxk, radius).with_spectral(True))
+
+    aspace, gl = builder().build(x)
+    _assert_csr_equal(gl.csr, csr)
+    _assert_csr_equal(aspace.signals, sig)
+    _assert_lambda_close(aspace.lambdas, lam)
+    assert aspace.index_info().nnz_signals == sig[0][-1]
+
+    b = builder()
+    out = asb.ArrowSpace.start_clustering(b, x)
+    gl2 = out.aspace.eigenmaps(b, out.centroids, n)
+    out.aspace.compute_taumode(gl2)
+    _assert_csr_equal(out.aspace.signals, sig)
+    assert np.allclose(out.aspace.lambdas, aspace.lambdas, rtol=1e-12, atol=0)
+
+    queries, _ = asb.synth.queries_from_items(x, 20, seed=43)
+    lq_want = oracle.compute_taumode(queries, csr, TAU_MEDIAN)       # queries: feature Laplacian, not signals
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    idx, score, count, lq = aspace.search_batch(queries, 10, 0.7)
+    _assert_lambda_close(lq, lq_want)
+    _assert_topk_equal(idx, score, count, *want)
+
+    plain, _ = (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(0.5, 12, 4, 2.0, 0.25).with_seed(42)
+                .with_inline_sampling(None).with_cluster_params(maxk, radius).build(x))
+    assert plain.signals is None and plain.index_info().nnz_signals == 0
+
+
 def test_builder_defaults_give_degenerate_graph(ctx, asb):
     """Literal builder defaults (eps=1e-3) on generic data: empty graph -> lambda == 0 -> the search
     panics in the reference (core.rs:773-776); here ASB_ERR_ZERO_LAMBDA."""

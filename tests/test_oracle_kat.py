@@ -250,3 +250,27 @@ def test_hybrid_and_range_semantics(oracle, golden):
     assert oracle.search_lambda_aware_hybrid(db, lam, q, 0.3, 0, 0.7) == []
     idx, dist = oracle.range_search(np.array([0.1, 0.5, 0.9]), 0.5, 0.1)
     assert idx.tolist() == [1, 2] and np.allclose(dist, [0.0, -0.4])        # signed difference, one-sided
+
+
+def test_spectral_signals_is_the_laplacian_of_the_dense_laplacian(oracle, golden):
+    """SURVEY 8f rank 3 (src/graph.rs:211-231): signals = build_laplacian_matrix(dense(L)^T, params).  The oracle
+    entry point must equal the composition spelled out by hand, and keep the Laplacian invariants
+    (src/tests/test_laplacian.rs:51-152: symmetric, diagonal stored, zero row sums)."""
+    x = golden["proteins"]
+    gp = dict(eps=0.5, k=6, topk=3, p=2.0, sigma=0.25)
+    csr = oracle.feature_laplacian(x, **gp)
+    f = len(csr[0]) - 1
+    dense = np.zeros((f, f))
+    for r in range(f):
+        for e in range(csr[0][r], csr[0][r + 1]):
+            dense[r, csr[1][e]] = csr[2][e]
+    want = oracle.feature_laplacian(dense, **gp)
+    got = oracle.spectral_signals(csr, **gp)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    sig = np.zeros((f, f))
+    for r in range(f):
+        cols = got[1][got[0][r]:got[0][r + 1]]
+        assert r in cols                                   # diagonal always stored
+        sig[r, cols] = got[2][got[0][r]:got[0][r + 1]]
+    assert np.allclose(sig, sig.T, atol=1e-12)
+    assert np.allclose(sig.sum(axis=1), 0.0, atol=1e-9)
