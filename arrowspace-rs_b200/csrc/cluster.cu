@@ -55,6 +55,7 @@ struct ClusterArgs {
     int vec2;  // centroid storage 16B-loadable (blocked kernel, LDS.128 distance loop)
     const double *rows_n2;  // |fl32(row)|^2 in FP64 (pipelined kernel: distances via dot products)
     int tick_tid;           // thread of CTA 0 that owns the debug phase timers
+    int tile_check;         // debug: compare every tensor-core distance with FP64 (pipelined kernel, no speculation)
 };
 
 struct __align__(16) Xch {
@@ -439,6 +440,11 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     {
         auto it = ctx->options.find("cluster_tick_tid");
         A.tick_tid = it != ctx->options.end() ? (int)it->second : 0;
+    }
+    {
+        auto it = ctx->options.find("cluster_check_tile");
+        A.tile_check = (it != ctx->options.end() && it->second != 0.0) ? 1 : 0;
+        if (A.tile_check) want_times = true;  // the result travels in the debug counters
     }
     if (want_times) {
         ASB_TRY(ptimes.init(ctx, 48));

@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     //   * dropped lo*lo term and the TF32 truncation of the lo operands: 3 * 2^-20 |x||c|;
     //   * accumulation: exact products, every mma.sync result within 9 * 2^-23 * max(|acc|, |a_k b_k|) of the
     //     exact sum (aligned, truncating adders of at least 24 bits -- the behaviour reported for NVIDIA tensor
-    //     cores since Volta; `cluster_debug` = 3 measures the real error of every tile against FP64 and
-    //     tests/test_gpu_parity.py asserts it stays below delta / 4).  The main accumulation is split over 4
+    //     cores since Volta; the `cluster_check_tile` option measures the real error of every tile against
+    //     FP64 and tests/test_gpu_parity.py asserts it stays below delta / 4).  The main accumulation is split over 4
     //     independent accumulators, so a chain is nchunk MMAs long, plus 3 FP32 additions and the final FMA;
     //   * |c|^2: 4 chains of 2 * nchunk FMAs + 4 additions.
     // Every centroid is a running mean of rows, so |c| <= max|x|.
@@ -345,6 +345,20 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                 const int grp = (j & 2) ? 2 * mt + 1 : 2 * mt;
                 const int ri = 8 * grp + g - lead;
                 if (slot < my_n && grp < nrg && ri >= 0 && ri < nbk) D[(size_t)slot * B + ri] = q;
+                if (A.tile_check && slot < my_n && grp < nrg && ri >= 0 && ri < nbk && q < INFINITY && delta > 0.0) {
+                    // debug: the same quantity in FP64 from the very FP32 operands (centroids are settled: no
+                    // speculation in this mode); worst |error| / delta over the run, in units of 1e-12
+                    const float *xrow = ring + (size_t)(((g0 + grp) % NG) * kGroup + g) * fp;
+                    const float *crow = c32(slot);
+                    double sc = 0.0, sx = 0.0;
+                    for (int kk = 0; kk < f; ++kk) {
+                        sc = fma((double)crow[kk], (double)crow[kk], sc);
+                        sx = fma((double)xrow[kk], (double)crow[kk], sx);
+                    }
+                    const double ratio = fabs((double)q - (sc - 2.0 * sx)) / delta;
+                    atomicMax(reinterpret_cast<unsigned long long *>(A.phase_times + 47),
+                              (unsigned long long)(ratio * 1e12));
+                }
             }
             // per row: (best, second, best id) over the 8 centroids of the tile -- 2 in this thread, 4 threads per row
 #pragma unroll
@@ -446,7 +460,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
         // ---- speculation: the next block starts where this one ends
         const long long r0n = r0 + nb;
         const int nbn = (A.n - r0n) < (long long)B ? (int)(A.n - r0n) : B;
-        const bool spec = !A.force_exact && kc == maxk && r0n < A.n;
+        const bool spec = !A.force_exact && !A.tile_check && kc == maxk && r0n < A.n;
         if (spec && is_compute) {
             const long long ga = r0n / kGroup;
             need_groups(ga, (ga + NG) < g_total ? (ga + NG) : g_total);

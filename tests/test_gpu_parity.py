@@ -417,6 +417,27 @@ def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rsc
     assert 2.0 in seen
 
 
+@pytest.mark.parametrize("n,f,maxk", [(6_000, 384, 100), (4_000, 132, 64), (3_000, 33, 20)])
+def test_cluster_tensor_tile_error_model(ctx, asb, oracle, n, f, maxk):
+    """The certified decisions of the pipelined kernel rest on an error bound for the 3xTF32 tensor-core
+    distances (exact products, truncating accumulation -- an assumption about the hardware).
+    `cluster_check_tile` recomputes every distance of the walk in FP64 from the same FP32 operands and
+    reports the worst |error| / bound: it has to stay well inside the bound, and the walk stays bit-exact."""
+    x = asb.synth.protein_like(n, f, seed=5)
+    radius = 1.5 * f * 0.0025 * 2
+    want = oracle.cluster_incremental(x, maxk, radius)
+    ctx.set_option("cluster_check_tile", 1)
+    try:
+        got = ctx.cluster_incremental(x, maxk, radius)
+        assert ctx.kernel_ms("cluster_variant") == -2.0
+        worst = ctx.kernel_ms("cluster_phase47") * 1e-12
+    finally:
+        ctx.set_option("cluster_check_tile", 0)
+        ctx.set_option("cluster_phase_times", 0)
+    _assert_cluster_equal(got, want)
+    assert 0.0 < worst < 0.25, worst
+
+
 def test_cluster_resume_equals_single_walk(ctx, asb, oracle):
     """Shard 0, then shard 1 resumed from shard 0's state == one walk (the multi-GPU hand-off)."""
     x = asb.synth.protein_like(9_000, 96, seed=78)
