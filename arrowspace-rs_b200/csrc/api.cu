@@ -423,6 +423,52 @@ int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const doubl
     return asb_sync(ctx);
 }
 
+int asb_search_energy_batch(asb_ctx *ctx, const double *items, const double *lambdas, const double *norms2, int64_t n,
+                            int64_t f, const double *queries, const double *lambda_q, int64_t nq, int64_t k,
+                            double w_lambda, double w_dirichlet, int64_t index_offset, int64_t *idx, double *score,
+                            int64_t *count) {
+    ASB_TRY(set_device(ctx));
+    if (!items || !lambdas || !queries || !lambda_q || !idx || !score)
+        ASB_FAIL(ctx, ASB_ERR_INVALID, "search_energy: null pointer");
+    if (n <= 0 || f <= 0 || nq <= 0 || k < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search_energy: bad sizes");
+    if (k == 0) {  // scored.truncate(0), src/energymaps.rs:398
+        if (count) {
+            if (asb_is_device_ptr(count)) ASB_CUDA(ctx, cudaMemsetAsync(count, 0, nq * sizeof(int64_t), ctx->stream));
+            else memset(count, 0, nq * sizeof(int64_t));
+        }
+        return asb_sync(ctx);
+    }
+    DevIn<double> it, lam, n2, q, lq;
+    DevOut<int64_t> oi, oc;
+    DevOut<double> os;
+    DevTmp<int64_t> cnt_tmp;
+    DevTmp<int> status;
+    ASB_TRY(it.init(ctx, items, (size_t)n * f));
+    ASB_TRY(lam.init(ctx, lambdas, (size_t)n));
+    ASB_TRY(n2.init(ctx, norms2, norms2 ? (size_t)n : 0));
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lq.init(ctx, lambda_q, (size_t)nq));
+    ASB_TRY(oi.init(ctx, idx, (size_t)nq * k));
+    ASB_TRY(os.init(ctx, score, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, count, count ? (size_t)nq : 0));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_TRY(status.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
+    StageTimer t(ctx, "search_energy");
+    int rc = asb_dev_search_energy(ctx, it.ptr, lam.ptr, n2.ptr, n, f, q.ptr, lq.ptr, nq, k, w_lambda, w_dirichlet,
+                                   index_offset, oi.ptr, os.ptr, count ? oc.ptr : cnt_tmp.ptr, status.ptr);
+    t.stop();
+    ASB_TRY(rc);
+    int hst = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hst, status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASB_TRY(search_status_to_rc(ctx, hst));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
 int asb_search_lambda_aware_hybrid_batch(asb_ctx *ctx, const double *items, const double *lambdas, const double *norms2,
                                          int64_t n, int64_t f, const double *queries, const double *lambda_q,
                                          int64_t nq, int64_t k, double alpha, int64_t *idx, double *score,

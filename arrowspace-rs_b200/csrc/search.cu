@@ -24,7 +24,7 @@ constexpr int TQ = 128, TN = 128;
 constexpr int kWarps = 16;               // 4 (queries) x 4 (items) warps, 32 x 32 accumulators each
 constexpr int kThreads = kWarps * 32;
 constexpr int SPITCH = 72;                        // score half-tile pitch (doubles)
-constexpr int MODE_COSINE = 0, MODE_L2 = 1;
+constexpr int MODE_COSINE = 0, MODE_L2 = 1, MODE_ENERGY = 2;
 constexpr int STATUS_NAN = 1, STATUS_ZERO_LAMBDA = 2;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
@@ -56,7 +56,8 @@ struct SearchArgs {
     const long long *self_idx;  // nq      (L2 mode: item index to exclude)
     long long n, nq;
     int f, k;
-    double alpha;
+    double alpha;            // cosine mode: alpha; energy mode: w_lambda
+    double w_dir;            // energy mode: w_dirichlet
     int nslabs;
     long long tiles_per_slab;
     double *part_score;  // nslabs x nq x k
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
             lq = ok ? A.lambda_q[gq] : 1.0;
             if (ok && slab == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);  // core.rs:773-776
         }
+        if (MODE == MODE_ENERGY) lq = ok ? A.lambda_q[gq] : 0.0;
         sm_lq[q] = lq;
         list_len[q] = 0;
         if (MODE == MODE_L2) sm_self[q] = ok ? A.self_idx[gq] : -1;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
             const bool ok = gi < A.n;
             const double n2 = ok ? A.norms2[gi] : 0.0;
             sm_nx[c] = (MODE == MODE_COSINE) ? sqrt(n2) : n2;
-            sm_lx[c] = (MODE == MODE_COSINE && ok) ? A.lambdas[gi] : 0.0;
+            sm_lx[c] = (MODE != MODE_L2 && ok) ? A.lambdas[gi] : 0.0;
         }
         double acc[4][4][2];
 #pragma unroll
@@ -238,6 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
                                 const double ld = fabs(lq - sm_lx[c]);               // :136
                                 const double lam = 1.0 - fmin(ld, 1.0);              // :137
                                 s = A.alpha * cosv + (1.0 - A.alpha) * lam;          // :165
+                                if (gi < A.n && q0 + r < A.nq && s != s) atomicOr(A.status, STATUS_NAN);
+                            } else if (MODE == MODE_ENERGY) {
+                                // src/energymaps.rs:838-895 (score) and :368-407 (search_energy: rank by -score)
+                                const double d = sqrt(fmax(nq + sm_nx[c] - 2.0 * dot, 0.0));   // |q - x|
+                                const double e = fmin(d / (1.0 + d), 1.0);                      // bounded_l2_energy
+                                s = -(A.alpha * fabs(lq - sm_lx[c]) + A.w_dir * e);
                                 if (gi < A.n && q0 + r < A.nq && s != s) atomicOr(A.status, STATUS_NAN);
                             } else {
                                 s = -(nq + sm_nx[c] - 2.0 * dot);  // -(|q|^2 + |x|^2 - 2 q.x)
@@ -420,6 +428,64 @@ __global__ void __launch_bounds__(128) twonn_rescore_kernel(const double *__rest
     }
 }
 
+// Energy search, second pass: exact direct-form scores (src/energymaps.rs:884-894: d_lambda, |q - x| from the
+// difference vector, bounded energy) for the kc candidates of the fused pass, then the best k by
+// (score desc, index asc) -- the reference's stable descending sort.  One warp per query, kc <= 64.
+__global__ void __launch_bounds__(128) energy_rescore_kernel(const double *__restrict__ items, const double *__restrict__ lambdas,
+                                                             int f, const double *__restrict__ queries,
+                                                             const double *__restrict__ lambda_q, long long nq, int kc,
+                                                             int k, long long index_offset, double w_lambda, double w_dir,
+                                                             const long long *__restrict__ cand_idx,
+                                                             const long long *__restrict__ cand_cnt,
+                                                             long long *__restrict__ idx_out, double *__restrict__ score_out,
+                                                             long long *__restrict__ count_out) {
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nq) return;
+    const int cnt = (int)cand_cnt[w];
+    const double *q = queries + w * (long long)f;
+    const double lq = lambda_q[w];
+    double sc[2] = {-INFINITY, -INFINITY};   // candidate c lives in lane c % 32, register c / 32
+    long long id[2] = {-1, -1};
+    for (int c = 0; c < cnt; ++c) {
+        const long long gi = cand_idx[w * kc + c];
+        const double *x = items + (gi - index_offset) * (long long)f;
+        double acc = 0.0;
+        for (int t = lane; t < f; t += 32) {
+            const double df = q[t] - x[t];
+            acc = fma(df, df, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double d = sqrt(acc);
+        const double s = -(w_lambda * fabs(lq - lambdas[gi - index_offset]) + w_dir * fmin(d / (1.0 + d), 1.0));
+        if ((c & 31) == lane) {
+            sc[c >> 5] = s;
+            id[c >> 5] = gi;
+        }
+    }
+    const int kout = k < cnt ? k : cnt;
+    // rank of every candidate = number of candidates that sort before it
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = h * 32 + lane;
+        int rank = 0;
+        for (int o = 0; o < cnt; ++o) {
+            const double os = __shfl_sync(0xffffffffu, sc[o >> 5], o & 31);
+            const long long oi = __shfl_sync(0xffffffffu, id[o >> 5], o & 31);
+            if (c < cnt && (os > sc[h] || (os == sc[h] && oi < id[h]))) rank++;
+        }
+        if (c < cnt && rank < kout) {
+            idx_out[w * k + rank] = id[h];
+            score_out[w * k + rank] = sc[h];
+        }
+    }
+    for (int r = kout + lane; r < k; r += 32) {
+        idx_out[w * k + r] = -1;
+        score_out[w * k + r] = 0.0;
+    }
+    if (lane == 0 && count_out) count_out[w] = kout;
+}
+
 size_t search_smem_bytes(int k, int kc) {
     size_t b = (size_t)2 * (TQ + TN) * (kc + 4) * 8;  // stages (S aliases)
     b += (size_t)(2 * TQ + 2 * TN) * 8;           // nq, lq, nx, lx
@@ -456,8 +522,7 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
     if (k < 1 || k > 64) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: k=%d outside 1..64", k);
     if (A.n > 0x7fffff00ll) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: shard larger than 2^31 items");
     int nslabs = 1;
-    if (mode == MODE_COSINE) launch_search<MODE_COSINE>(ctx, A, &nslabs);
-    else launch_search<MODE_L2>(ctx, A, &nslabs);
+    launch_search<MODE_COSINE>(ctx, A, &nslabs);  // the slab split does not depend on the mode
     DevTmp<double> part_s;
     DevTmp<int> part_i;
     ASB_TRY(part_s.init(ctx, (size_t)nslabs * A.nq * k));
@@ -482,9 +547,11 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
         }                                                                                                      \
     } while (0)
     {
-        KernelTimer kt(ctx, mode == MODE_COSINE ? "search_kernel" : "twonn_kernel");
+        KernelTimer kt(ctx, mode == MODE_COSINE ? "search_kernel" : (mode == MODE_ENERGY ? "energy_kernel" : "twonn_kernel"));
         if (mode == MODE_COSINE) {
             if (vec) LAUNCH(MODE_COSINE, true); else LAUNCH(MODE_COSINE, false);
+        } else if (mode == MODE_ENERGY) {
+            if (vec) LAUNCH(MODE_ENERGY, true); else LAUNCH(MODE_ENERGY, false);
         } else {
             if (vec) LAUNCH(MODE_L2, true); else LAUNCH(MODE_L2, false);
         }
@@ -543,6 +610,52 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
         return ASB_OK;
     }
     return run_search(ctx, MODE_COSINE, A, index_offset, idx_d, score_d, count_d);
+}
+
+int asb_dev_search_energy(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,
+                          int64_t n, int64_t f, const double *queries_d, const double *lambda_q_d, int64_t nq,
+                          int64_t k, double w_lambda, double w_dirichlet, int64_t index_offset, int64_t *idx_d,
+                          double *score_d, int64_t *count_d, int *status_d) {
+    if (n <= 0 || f <= 0 || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search_energy: empty input");
+    if (k < 1 || k > 60) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search_energy: k=%lld outside 1..60", (long long)k);
+    DevTmp<double> qn2, xn2, cs;
+    DevTmp<int64_t> ci, cc;
+    ASB_TRY(qn2.init(ctx, (size_t)nq));
+    ASB_TRY(asb_dev_norms2(ctx, queries_d, nq, f, qn2.ptr));
+    if (!norms2_d) {
+        ASB_TRY(xn2.init(ctx, (size_t)n));
+        ASB_TRY(asb_dev_norms2(ctx, items_d, n, f, xn2.ptr));
+        norms2_d = xn2.ptr;
+    }
+    // the fused pass ranks by the GEMM-form distance (|q|^2 + |x|^2 - 2 q.x, absolute error ~1e-13 on d^2, i.e. up
+    // to ~3e-7 on a distance near zero): take 4 spare candidates, then rescore exactly
+    int64_t kc = k + 4;
+    if (kc > n) kc = n;
+    SearchArgs A{};
+    A.items = items_d;
+    A.lambdas = lambdas_d;
+    A.norms2 = norms2_d;
+    A.queries = queries_d;
+    A.lambda_q = lambda_q_d;
+    A.qnorms2 = qn2.ptr;
+    A.self_idx = nullptr;
+    A.n = n;
+    A.nq = nq;
+    A.f = (int)f;
+    A.k = (int)kc;
+    A.alpha = w_lambda;
+    A.w_dir = w_dirichlet;
+    A.status = status_d;
+    ASB_TRY(cs.init(ctx, (size_t)nq * kc));
+    ASB_TRY(ci.init(ctx, (size_t)nq * kc));
+    ASB_TRY(cc.init(ctx, (size_t)nq));
+    ASB_TRY(run_search(ctx, MODE_ENERGY, A, index_offset, ci.ptr, cs.ptr, cc.ptr));
+    const int wpb = 4;
+    energy_rescore_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        items_d, lambdas_d, (int)f, queries_d, lambda_q_d, (long long)nq, (int)kc, (int)k, (long long)index_offset,
+        w_lambda, w_dirichlet, (const long long *)ci.ptr, (const long long *)cc.ptr, (long long *)idx_d, score_d,
+        (long long *)count_d);
+    return asb_check_launch(ctx, "energy_rescore_kernel");
 }
 
 int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, const int64_t *sample_d, int64_t s,

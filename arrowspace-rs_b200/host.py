@@ -97,6 +97,7 @@ ABI_SYMBOLS = {
     "asb_prepare_query_lambdas": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, C.c_int32, _D, _P]),
     "asb_search_lambda_aware_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _I64, _P, _P,
                                                 _P]),
+    "asb_search_energy_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _D, _I64, _P, _P, _P]),
     "asb_search_lambda_aware_hybrid_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P]),
     "asb_range_search": (C.c_int, [_P, _P, _I64, _D, _D, _I64, _P, _P, _I64, C.POINTER(_I64)]),
     "asb_topk_merge": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
@@ -311,6 +312,25 @@ class Context:
                                                           _ptr(queries), _ptr(lambda_q), nq, int(k), float(alpha),
                                                           int(index_offset), _ptr(idx), _ptr(score), _ptr(count)))
         return idx, score, count
+
+    def search_energy_batch(self, items, lambdas, queries, lambda_q, k: int, w_lambda: float, w_dirichlet: float,
+                            norms2=None, index_offset: int = 0):
+        """``EnergyMaps::search_energy`` (src/energymaps.rs:368-407) for a batch of queries: (index, -energy),
+        best first.  Returns (idx[nq,k], score[nq,k], count[nq])."""
+        n, f = _shape2(items)
+        nq = _shape2(queries)[0]
+        idx = np.full((nq, max(k, 1)), -1, dtype=np.int64)
+        score = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        count = np.zeros(nq, dtype=np.int64)
+        keep = [_as_f64_matrix(items) if not _is_device(items) else items,
+                np.ascontiguousarray(lambdas, dtype=np.float64) if not _is_device(lambdas) else lambdas,
+                _as_f64_matrix(queries) if not _is_device(queries) else queries,
+                np.ascontiguousarray(lambda_q, dtype=np.float64) if not _is_device(lambda_q) else lambda_q]
+        self.check(self.lib.asb_search_energy_batch(self.handle, _ptr(keep[0]), _ptr(keep[1]),
+                                                    _ptr(norms2) if norms2 is not None else None, n, f, _ptr(keep[2]),
+                                                    _ptr(keep[3]), nq, int(k), float(w_lambda), float(w_dirichlet),
+                                                    int(index_offset), _ptr(idx), _ptr(score), _ptr(count)))
+        return idx[:, :k], score[:, :k], count
 
     def search_lambda_aware_hybrid_batch(self, items, lambdas, queries, lambda_q, k: int, alpha: float, norms2=None):
         items = _as_f64_matrix(items)
@@ -625,6 +645,19 @@ class ArrowSpace:
         idx, score, count = self.ctx.search_lambda_aware_hybrid_batch(
             items, lambdas, q, np.array([query.lambda_], dtype=np.float64), k, alpha, norms2=norms2)
         return [(int(idx[0][r]), float(score[0][r])) for r in range(int(count[0]))]
+
+    def search_energy(self, query, gl_energy: GraphLaplacian, k: int, w_lambda: float,
+                      w_dirichlet: float) -> List[Tuple[int, float]]:
+        """``EnergyMaps::search_energy`` (src/energymaps.rs:368-407): lambda_q from ``prepare_query_item`` on
+        ``gl_energy`` (:885), then (index, -energy) for the k items of least projected energy.  Spaces with a JL
+        projection or spectral signals take other branches of the reference's score (:858-882) -- unsupported."""
+        if self.projection_matrix is not None or self.signals is not None:
+            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "search_energy: projection / signals branches are not built")
+        q = np.ascontiguousarray(query.item if isinstance(query, ArrowItem) else query, dtype=np.float64)
+        lq = self.prepare_query_item(q, gl_energy)
+        idx, score, count = self.ctx.search_energy_batch(self.data, self.lambdas, q.reshape(1, -1), np.array([lq]), k,
+                                                         w_lambda, w_dirichlet)
+        return [(int(idx[0, r]), float(score[0, r])) for r in range(int(count[0]))]
 
     def range_search(self, query: ArrowItem, gl: GraphLaplacian, eps: float) -> List[Tuple[int, float]]:
         """``ArrowSpace::range_search`` (src/core.rs:944-976): the query lambda is re-prepared when it is

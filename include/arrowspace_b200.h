@@ -180,6 +180,16 @@ int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const doubl
                                   int64_t *idx, double *score, int64_t *count);
 
 /* ---- "next" rows ---------------------------------------------------- */
+/* EnergyMaps::search_energy (src/energymaps.rs:368-407) with ProjectedEnergy::score
+ * (:838-895) for an index without projection and without spectral signals: per item
+ *   energy = w_lambda * |lambda_q - lambda_i| + w_dirichlet * min(d / (1 + d), 1),  d = |q - x_i|_2,
+ * results are (index, -energy), best (largest) first, ties -> lower index, truncated to k (<= 60).
+ * lambda_q comes from asb_prepare_query_lambdas (the reference recomputes it per item, :884).  A fused pass
+ * ranks k+4 candidates by the GEMM-form distance, a second pass rescores them in the reference's direct form. */
+int asb_search_energy_batch(asb_ctx *ctx, const double *items, const double *lambdas, const double *norms2, int64_t n,
+                            int64_t f, const double *queries, const double *lambda_q, int64_t nq, int64_t k,
+                            double w_lambda, double w_dirichlet, int64_t index_offset, int64_t *idx, double *score,
+                            int64_t *count);
 /* Replaces ArrowSpace::search_lambda_aware_hybrid (src/core.rs:802-928) for a batch: the union of
  * {cosine > 0.9999} (scored by cosine), the lambda-aware top-k (scored alpha*cos+(1-alpha)*lam
  * unless already present) and the semantic top-1, sorted by that score, truncated to k.  Built

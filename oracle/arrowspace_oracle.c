@@ -672,3 +672,48 @@ int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double e
     *count_out = c;
     return ASO_OK;
 }
+
+/* EnergyMaps::search_energy (src/energymaps.rs:368-407) scoring every item with ProjectedEnergy::score
+ * (:884-894) for an ArrowSpace without projection_matrix (project_vec is the identity, :858-864) and without
+ * signals (projected_dirichlet falls back to bounded_l2_energy, :866-882,:846-850).  The reference recomputes
+ * lambda_q per item (:885); it is the same number every time and is an input here.  Scores are -energy, sorted
+ * descending with a stable sort (:397; partial_cmp().unwrap_or(Equal): a NaN score has no defined place -- reported
+ * as ASO_ERR_NAN_SCORE), truncated to k (:398). */
+int aso_search_energy(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
+                      double lambda_q, int64_t k, double w_lambda, double w_dirichlet, int64_t *idx_out,
+                      double *score_out, int64_t *count_out) {
+    if (n <= 0 || f <= 0 || k < 0) return ASO_ERR_INVALID;
+    sc_t *res = (sc_t *)malloc((size_t)n * sizeof(sc_t));
+    sc_t *tmp = (sc_t *)malloc((size_t)n * sizeof(sc_t));
+    int has_nan = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *xr = items + i * f;
+        const double d_lambda = fabs(lambda_q - lambdas[i]); /* :887 */
+        double ss = 0.0;                                     /* l2_norm(vec_diff(q, x)), :841-843,:892 */
+        for (int64_t j = 0; j < f; ++j) {
+            const double df = q[j] - xr[j];
+            ss += df * df;
+        }
+        const double num = sqrt(ss);
+        const double d_dir = fmin(num / (1.0 + num), 1.0);   /* bounded_l2_energy, :847-850 */
+        const double e = w_lambda * d_lambda + w_dirichlet * d_dir; /* :894 */
+        if (e != e) has_nan = 1;
+        res[i].s = -e; /* :393 */
+        res[i].i = i;
+    }
+    int rc = ASO_OK;
+    if (has_nan) {
+        rc = ASO_ERR_NAN_SCORE;
+    } else {
+        merge_sort_desc(res, tmp, n);
+        int64_t cnt = k < n ? k : n;
+        for (int64_t r = 0; r < cnt; ++r) {
+            idx_out[r] = res[r].i;
+            score_out[r] = res[r].s;
+        }
+        *count_out = cnt;
+    }
+    free(res);
+    free(tmp);
+    return rc;
+}

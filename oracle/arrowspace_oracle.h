@@ -135,6 +135,10 @@ int aso_search_lambda_aware_batch(const double *items, const double *lambdas, in
 int aso_search_lambda_aware_hybrid(const double *items, const double *lambdas, int64_t n, int64_t f,
                                    const double *q, double lambda_q, int64_t k, double alpha,
                                    int64_t *idx_out, double *score_out, int64_t *count_out);
+/* src/energymaps.rs:368-407 + :838-895 (no projection, no signals): (index, -energy) best first */
+int aso_search_energy(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
+                      double lambda_q, int64_t k, double w_lambda, double w_dirichlet, int64_t *idx_out,
+                      double *score_out, int64_t *count_out);
 int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double eps, int64_t *idx_out,
                      double *dist_out, int64_t *count_out);
 

@@ -56,6 +56,7 @@ class Oracle:
         lib.aso_search_lambda_aware_batch.argtypes = [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P, C.c_int]
         lib.aso_search_lambda_aware_hybrid.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_range_search.argtypes = [_P, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
+        lib.aso_search_energy.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_num_threads.restype = C.c_int
         self.lib = lib
 
@@ -159,6 +160,18 @@ class Oracle:
         self._chk(self.lib.aso_spectral_signals(_p(lp), _p(li), _p(ld), f, C.byref(P), _p(ip), _p(ii), _p(dd),
                                                 C.byref(nnz)))
         return ip, ii[: nnz.value].copy(), dd[: nnz.value].copy()
+
+    def search_energy(self, items, lambdas, q, lambda_q, k, w_lambda, w_dirichlet):
+        items = np.ascontiguousarray(items, dtype=np.float64)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        n, f = items.shape
+        idx = np.full(max(k, 1), -1, dtype=np.int64)
+        sc = np.zeros(max(k, 1), dtype=np.float64)
+        cnt = _I64(0)
+        self._chk(self.lib.aso_search_energy(_p(items), _p(lambdas), n, f, _p(q), lambda_q, k, w_lambda, w_dirichlet,
+                                             _p(idx), _p(sc), C.byref(cnt)))
+        return [(int(idx[r]), float(sc[r])) for r in range(cnt.value)]
 
     def search_lambda_aware(self, items, lambdas, q, lambda_q, k, alpha):
         items = np.ascontiguousarray(items, dtype=np.float64)

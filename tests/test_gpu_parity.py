@@ -605,6 +605,49 @@ def test_spectral_signals_build(ctx, asb, oracle):
     assert plain.signals is None and plain.index_info().nnz_signals == 0
 
 
+@pytest.mark.parametrize("n,f,k", [(20_000, 128, 10), (5_000, 33, 60), (300, 384, 7), (5, 16, 10)])
+def test_search_energy_parity(ctx, asb, oracle, n, f, k):
+    """EnergyMaps::search_energy (SURVEY 8f rank 4; src/energymaps.rs:368-407, :838-895): (index, -energy) best
+    first.  Queries include exact copies of items (distance 0, where the GEMM-form pre-ranking is weakest)."""
+    x = asb.synth.protein_like(n, f, seed=9)
+    rng = np.random.default_rng(3)
+    lam = rng.uniform(0.05, 0.9, n)
+    nq = 12
+    queries = x[rng.integers(0, n, nq)] * rng.uniform(0.97, 1.03, (nq, 1))
+    queries[0] = x[min(3, n - 1)]                       # exact duplicate of an item
+    lq = rng.uniform(0.05, 0.9, nq)
+    lq[0] = lam[min(3, n - 1)]
+    idx, score, count = ctx.search_energy_batch(x, lam, queries, lq, k, 1.0, 0.5)
+    for qi in range(nq):
+        want = oracle.search_energy(x, lam, queries[qi], float(lq[qi]), k, 1.0, 0.5)
+        assert int(count[qi]) == len(want) == min(k, n)
+        wi = np.array([i for i, _ in want])
+        ws = np.array([s for _, s in want])
+        gi, gs = np.asarray(idx[qi, :len(want)]), np.asarray(score[qi, :len(want)])
+        assert np.allclose(gs, ws, rtol=0, atol=1e-12)
+        diff = gi != wi
+        if diff.any():                                  # ids may only differ inside score gaps < 1e-9
+            for r in np.nonzero(diff)[0]:
+                assert abs(ws[r] - ws[max(r - 1, 0)]) < 1e-9 or abs(ws[r] - ws[min(r + 1, len(ws) - 1)]) < 1e-9
+    assert idx[0, 0] == min(3, n - 1) and score[0, 0] == 0.0
+    # other weights, and the ArrowSpace mirror on a built index
+    idx2, score2, _ = ctx.search_energy_batch(x, lam, queries[:2], lq[:2], min(k, 5), 0.25, 2.0)
+    want2 = oracle.search_energy(x, lam, queries[1], float(lq[1]), min(k, 5), 0.25, 2.0)
+    assert [int(i) for i in idx2[1, :len(want2)]] == [i for i, _ in want2]
+
+
+def test_search_energy_on_built_space(ctx, asb, oracle):
+    x = asb.synth.protein_like(3_000, 64, seed=42)
+    aspace, gl = (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(0.5, 12, 4, 2.0, 0.25).with_seed(42)
+                  .with_inline_sampling(None).with_cluster_params(40, 1.5 * 64 * 0.0025 * 2).build(x))
+    q = x[17] * 1.01
+    lq = oracle.compute_taumode(q.reshape(1, -1), gl.csr, TAU_MEDIAN)[0]
+    want = oracle.search_energy(x, aspace.lambdas, q, float(lq), 8, 1.0, 0.5)
+    got = aspace.search_energy(q, gl, 8, 1.0, 0.5)
+    assert [i for i, _ in got] == [i for i, _ in want]
+    assert np.allclose([s for _, s in got], [s for _, s in want], rtol=0, atol=1e-12)
+
+
 def test_builder_defaults_give_degenerate_graph(ctx, asb):
     """Literal builder defaults (eps=1e-3) on generic data: empty graph -> lambda == 0 -> the search
     panics in the reference (core.rs:773-776); here ASB_ERR_ZERO_LAMBDA."""

@@ -274,3 +274,19 @@ def test_spectral_signals_is_the_laplacian_of_the_dense_laplacian(oracle, golden
         sig[r, cols] = got[2][got[0][r]:got[0][r + 1]]
     assert np.allclose(sig, sig.T, atol=1e-12)
     assert np.allclose(sig.sum(axis=1), 0.0, atol=1e-9)
+
+
+def test_search_energy_semantics(oracle):
+    """SURVEY 8f rank 4 (src/energymaps.rs:368-407, :838-895): energy = w_lambda |dlambda| + w_D min(d/(1+d), 1),
+    results are (index, -energy) best first, ties to the lower index, truncated to k."""
+    items = np.array([[0.0, 0.0], [3.0, 4.0], [0.0, 0.0], [1.0, 0.0]])
+    lambdas = np.array([0.5, 0.5, 0.5, 0.1])
+    q = np.array([0.0, 0.0])
+    got = oracle.search_energy(items, lambdas, q, 0.5, 3, 1.0, 0.5)
+    # item 0 and 2: energy 0 (tie -> 0 first); item 1: 0.5 * 5/6; item 3: 0.4 + 0.5 * 1/2
+    assert [i for i, _ in got] == [0, 2, 1]
+    assert got[0][1] == 0.0 and got[1][1] == 0.0
+    assert np.isclose(got[2][1], -0.5 * 5.0 / 6.0, rtol=0, atol=1e-15)
+    full = oracle.search_energy(items, lambdas, q, 0.5, 10, 1.0, 0.5)
+    assert len(full) == 4 and np.isclose(full[3][1], -(0.4 + 0.25), atol=1e-15)
+    assert oracle.search_energy(items, lambdas, q, 0.5, 0, 1.0, 0.5) == []
