@@ -583,6 +583,32 @@ int asb_range_search(asb_ctx *ctx, const double *lambdas, int64_t n, double lamb
     return asb_sync(ctx);
 }
 
+int64_t asb_jl_dimension(int64_t n_points, double epsilon) {  // compute_jl_dimension, src/reduction.rs:127-141
+    const double log_n = log((double)n_points);
+    const double eps_sq = pow(epsilon, 2.0);
+    const double v = ceil(8.0 * log_n / eps_sq);
+    int64_t jl = (v != v || v < 0.0) ? 0 : (v > 9.0e18 ? INT64_MAX : (int64_t)v);  // `as usize` saturates
+    return jl > 32 ? jl : 32;
+}
+
+int asb_project_matrix(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const double *projection, int64_t r,
+                       double *out) {
+    ASB_TRY(set_device(ctx));
+    if (!rows || !projection || !out) ASB_FAIL(ctx, ASB_ERR_INVALID, "project_matrix: null pointer");
+    if (n <= 0 || f <= 0 || r <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "project_matrix: bad sizes");
+    DevIn<double> x, g;
+    DevOut<double> y;
+    ASB_TRY(x.init(ctx, rows, (size_t)n * f));
+    ASB_TRY(g.init(ctx, projection, (size_t)f * r));
+    ASB_TRY(y.init(ctx, out, (size_t)n * r));
+    StageTimer t(ctx, "project");
+    int rc = asb_dev_project(ctx, x.ptr, n, f, g.ptr, r, y.ptr);
+    t.stop();
+    ASB_TRY(rc);
+    ASB_TRY(y.finish(ctx));
+    return asb_sync(ctx);
+}
+
 int asb_topk_merge(asb_ctx *ctx, const double *in_score, const int64_t *in_idx, int64_t parts, int64_t nq,
                    int64_t k, double *out_score, int64_t *out_idx, int64_t *out_count) {
     ASB_TRY(set_device(ctx));

@@ -244,6 +244,8 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
 int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, const GraphPlan &plan,
                     int tau_mode, double tau_value, double *lambdas_d, double *norms2_d,
                     double *stats_d /*3 doubles: min,max,sum or null*/, int *nonfinite_flag_d);
+int asb_dev_project(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, const double *proj_d, int64_t r,
+                    double *out_d);
 int asb_dev_search_energy(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,
                           int64_t n, int64_t f, const double *queries_d, const double *lambda_q_d, int64_t nq,
                           int64_t k, double w_lambda, double w_dirichlet, int64_t index_offset, int64_t *idx_d,

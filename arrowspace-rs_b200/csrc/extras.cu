@@ -109,3 +109,52 @@ int asb_dev_range_search(asb_ctx *ctx, const double *lambdas_d, int64_t n, doubl
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host offsets vector goes out of scope
     return ASB_OK;
 }
+
+// ---- JL projection with a materialised matrix -------------------------------------------
+// ImplicitProjection::project (src/reduction.rs:180-199) regenerates the F x r Gaussian matrix from its seed on
+// every call (ChaCha8 + StandardNormal, third-party); the host hands the matrix over instead, in the order the
+// reference draws it: G[j * r + k] is the sample used for (feature j, output k).  Every output is the reference's
+// own chain  y_k = (...((x_0 g_0k) s + (x_1 g_1k) s) + ...)  with s = 1 / sqrt(r), features in ascending order and
+// separately rounded operations, so the result is bit-identical.  One thread per output column, kRowsPerBlock rows
+// per CTA staged in shared memory; G (a few hundred kB) is served by L2.
+namespace {
+constexpr int kProjRows = 8;
+__global__ void __launch_bounds__(256) project_kernel(const double *__restrict__ rows, long long n, int f,
+                                                      const double *__restrict__ proj, int r, double scale,
+                                                      double *__restrict__ out) {
+    extern __shared__ double xs[];  // kProjRows x f
+    const long long row0 = (long long)blockIdx.x * kProjRows;
+    const int nrows = (int)((n - row0) < kProjRows ? (n - row0) : kProjRows);
+    for (int e = threadIdx.x; e < nrows * f; e += blockDim.x) xs[e] = rows[row0 * f + e];
+    __syncthreads();
+    for (int k = threadIdx.x; k < r; k += blockDim.x) {
+        double acc[kProjRows];
+#pragma unroll
+        for (int i = 0; i < kProjRows; ++i) acc[i] = 0.0;
+        for (int j = 0; j < f; ++j) {
+            const double g = proj[(size_t)j * r + k];
+#pragma unroll
+            for (int i = 0; i < kProjRows; ++i)
+                if (i < nrows) acc[i] = __dadd_rn(acc[i], __dmul_rn(__dmul_rn(xs[i * f + j], g), scale));  // :195
+        }
+#pragma unroll
+        for (int i = 0; i < kProjRows; ++i)
+            if (i < nrows) out[(row0 + i) * r + k] = acc[i];
+    }
+}
+}  // namespace
+
+int asb_dev_project(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, const double *proj_d, int64_t r,
+                    double *out_d) {
+    if (n <= 0 || f <= 0 || r <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "project: bad sizes");
+    const size_t smem = (size_t)kProjRows * f * sizeof(double);
+    if (smem > 200 * 1024) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "project: f=%lld too wide", (long long)f);
+    ASB_CUDA(ctx, cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double scale = 1.0 / sqrt((double)r);  // src/reduction.rs:184
+    {
+        KernelTimer kt(ctx, "project_kernel");
+        project_kernel<<<(unsigned)((n + kProjRows - 1) / kProjRows), 256, smem, ctx->stream>>>(
+            rows_d, (long long)n, (int)f, proj_d, (int)r, scale, out_d);
+    }
+    return asb_check_launch(ctx, "project_kernel");
+}

@@ -97,6 +97,8 @@ ABI_SYMBOLS = {
     "asb_prepare_query_lambdas": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, C.c_int32, _D, _P]),
     "asb_search_lambda_aware_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _I64, _P, _P,
                                                 _P]),
+    "asb_project_matrix": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P]),
+    "asb_jl_dimension": (C.c_int64, [_I64, _D]),
     "asb_search_energy_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _D, _I64, _P, _P, _P]),
     "asb_search_lambda_aware_hybrid_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P]),
     "asb_range_search": (C.c_int, [_P, _P, _I64, _D, _D, _I64, _P, _P, _I64, C.POINTER(_I64)]),
@@ -313,6 +315,24 @@ class Context:
                                                           int(index_offset), _ptr(idx), _ptr(score), _ptr(count)))
         return idx, score, count
 
+    def project_matrix(self, rows, projection):
+        """``project_matrix`` (src/reduction.rs:143-166) with the Gaussian matrix materialised by the caller:
+        ``projection`` is F x r, drawn in the reference's order (feature-major).  Returns n x r (bit-identical to
+        the reference's accumulation order)."""
+        rows = rows if _is_device(rows) else _as_f64_matrix(rows)
+        projection = projection if _is_device(projection) else _as_f64_matrix(projection)
+        n, f = _shape2(rows)
+        f2, r = _shape2(projection)
+        if f2 != f:
+            raise ArrowSpaceError(ASB_ERR_DIM, f"projection has {f2} rows, items have {f} features")
+        if _is_device(rows):
+            import torch
+            out = torch.empty((n, r), dtype=torch.float64, device=rows.device)
+        else:
+            out = np.empty((n, r), dtype=np.float64)
+        self.check(self.lib.asb_project_matrix(self.handle, _ptr(rows), n, f, _ptr(projection), r, _ptr(out)))
+        return out
+
     def search_energy_batch(self, items, lambdas, queries, lambda_q, k: int, w_lambda: float, w_dirichlet: float,
                             norms2=None, index_offset: int = 0):
         """``EnergyMaps::search_energy`` (src/energymaps.rs:368-407) for a batch of queries: (index, -energy),
@@ -463,6 +483,31 @@ class GraphLaplacian:
             for e in range(self.indptr[i], self.indptr[i + 1]):
                 m[i, self.indices[e]] = self.data[e]
         return m
+
+
+class ImplicitProjection:
+    """``ImplicitProjection`` (src/reduction.rs:168-199) with the matrix materialised: the reference keeps only a
+    seed and redraws the F x r Gaussians (ChaCha8 + StandardNormal) on every call; those generators are third-party,
+    so the caller supplies the matrix, drawn feature-major like the reference does."""
+
+    def __init__(self, matrix, ctx: Optional["Context"] = None):
+        self.matrix = _as_f64_matrix(matrix)
+        self.original_dim, self.reduced_dim = self.matrix.shape
+        self.ctx = ctx
+
+    def project(self, query) -> np.ndarray:  # :180-199
+        q = np.ascontiguousarray(query, dtype=np.float64).reshape(1, -1)[:, : self.original_dim]
+        return np.asarray((self.ctx or default_context()).project_matrix(q, self.matrix))[0]
+
+
+def project_matrix(data, projection: ImplicitProjection, ctx: Optional["Context"] = None):
+    """``project_matrix`` (src/reduction.rs:143-166)."""
+    return (ctx or projection.ctx or default_context()).project_matrix(data, projection.matrix)
+
+
+def compute_jl_dimension(n_points: int, epsilon: float) -> int:
+    """``compute_jl_dimension`` (src/reduction.rs:127-141)."""
+    return int(load_library().asb_jl_dimension(int(n_points), float(epsilon)))
 
 
 @dataclass

@@ -180,6 +180,17 @@ int asb_search_lambda_aware_batch(asb_ctx *ctx, const double *items, const doubl
                                   int64_t *idx, double *score, int64_t *count);
 
 /* ---- "next" rows ---------------------------------------------------- */
+/* JL random projection with a MATERIALISED matrix.  ImplicitProjection::project /
+ * project_matrix / project_query (src/reduction.rs:143-199, src/core.rs:509-529) regenerate the F x r Gaussian matrix
+ * from a seed on every call (ChaCha8 + StandardNormal, third-party generators); the host draws it once, in the
+ * reference's order (projection[j * r + k] = the sample for feature j, output k), and hands it over.
+ * out[i * r + k] = sum_j (rows[i,j] * projection[j,k]) * (1 / sqrt(r)), accumulated in the reference's order with
+ * separately rounded operations (bit-identical).  rows: n x f, out: n x r (host or device). */
+int asb_project_matrix(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const double *projection, int64_t r,
+                       double *out);
+/* compute_jl_dimension (src/reduction.rs:127-141): max(ceil(8 ln(n_points) / eps^2), 32) */
+int64_t asb_jl_dimension(int64_t n_points, double epsilon);
+
 /* EnergyMaps::search_energy (src/energymaps.rs:368-407) with ProjectedEnergy::score
  * (:838-895) for an index without projection and without spectral signals: per item
  *   energy = w_lambda * |lambda_q - lambda_i| + w_dirichlet * min(d / (1 + d), 1),  d = |q - x_i|_2,

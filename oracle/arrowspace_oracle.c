@@ -717,3 +717,28 @@ int aso_search_energy(const double *items, const double *lambdas, int64_t n, int
     free(tmp);
     return rc;
 }
+
+/* compute_jl_dimension, src/reduction.rs:127-141 */
+int64_t aso_jl_dimension(int64_t n_points, double epsilon) {
+    const double log_n = log((double)n_points);
+    const double eps_sq = pow(epsilon, 2.0);
+    const double v = ceil(8.0 * log_n / eps_sq);
+    int64_t jl = (v != v || v < 0.0) ? 0 : (v > 9.0e18 ? INT64_MAX : (int64_t)v); /* `as usize` saturates */
+    return jl > 32 ? jl : 32;
+}
+
+/* project_matrix -> ImplicitProjection::project per row, src/reduction.rs:143-166,180-199: for each feature (outer
+ * loop) and each output (inner loop) `*reduced += original * sample * scale`, samples drawn in that order. */
+int aso_project_matrix(const double *rows, int64_t n, int64_t f, const double *projection, int64_t r, double *out) {
+    if (!rows || !projection || !out || n <= 0 || f <= 0 || r <= 0) return ASO_ERR_INVALID;
+    const double scale = 1.0 / sqrt((double)r); /* :184 */
+    for (int64_t i = 0; i < n; ++i) {
+        double *y = out + i * r;
+        for (int64_t k = 0; k < r; ++k) y[k] = 0.0;
+        for (int64_t j = 0; j < f; ++j) {
+            const double original = rows[i * f + j];
+            for (int64_t k = 0; k < r; ++k) y[k] += original * projection[j * r + k] * scale; /* :195 */
+        }
+    }
+    return ASO_OK;
+}

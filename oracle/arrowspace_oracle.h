@@ -139,6 +139,10 @@ int aso_search_lambda_aware_hybrid(const double *items, const double *lambdas, i
 int aso_search_energy(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
                       double lambda_q, int64_t k, double w_lambda, double w_dirichlet, int64_t *idx_out,
                       double *score_out, int64_t *count_out);
+/* src/reduction.rs:127-141 and :143-199 with the Gaussian matrix materialised by the caller
+ * (projection[j * r + k] = the sample drawn for feature j, output k) */
+int64_t aso_jl_dimension(int64_t n_points, double epsilon);
+int aso_project_matrix(const double *rows, int64_t n, int64_t f, const double *projection, int64_t r, double *out);
 int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double eps, int64_t *idx_out,
                      double *dist_out, int64_t *count_out);
 

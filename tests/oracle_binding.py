@@ -56,6 +56,9 @@ class Oracle:
         lib.aso_search_lambda_aware_batch.argtypes = [_P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P, C.c_int]
         lib.aso_search_lambda_aware_hybrid.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_range_search.argtypes = [_P, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
+        lib.aso_jl_dimension.restype = _I64
+        lib.aso_jl_dimension.argtypes = [_I64, _D]
+        lib.aso_project_matrix.argtypes = [_P, _I64, _I64, _P, _I64, _P]
         lib.aso_search_energy.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_num_threads.restype = C.c_int
         self.lib = lib
@@ -160,6 +163,18 @@ class Oracle:
         self._chk(self.lib.aso_spectral_signals(_p(lp), _p(li), _p(ld), f, C.byref(P), _p(ip), _p(ii), _p(dd),
                                                 C.byref(nnz)))
         return ip, ii[: nnz.value].copy(), dd[: nnz.value].copy()
+
+    def jl_dimension(self, n_points, eps):
+        return int(self.lib.aso_jl_dimension(int(n_points), float(eps)))
+
+    def project_matrix(self, rows, projection):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        projection = np.ascontiguousarray(projection, dtype=np.float64)
+        n, f = rows.shape
+        r = projection.shape[1]
+        out = np.empty((n, r), dtype=np.float64)
+        self._chk(self.lib.aso_project_matrix(_p(rows), n, f, _p(projection), r, _p(out)))
+        return out
 
     def search_energy(self, items, lambdas, q, lambda_q, k, w_lambda, w_dirichlet):
         items = np.ascontiguousarray(items, dtype=np.float64)

@@ -648,6 +648,25 @@ def test_search_energy_on_built_space(ctx, asb, oracle):
     assert np.allclose([s for _, s in got], [s for _, s in want], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,f,r", [(3_001, 384, 91), (17, 24, 32), (1_000, 130, 300), (5, 7, 1)])
+def test_project_matrix_bit_exact(ctx, asb, oracle, n, f, r):
+    """JL projection with a materialised matrix (src/reduction.rs:143-199): same operations in the
+    same order as the reference -> bit-identical, from host and from device buffers."""
+    import torch
+    rng = np.random.default_rng(11)
+    x = asb.synth.protein_like(n, f, seed=3)
+    g = rng.normal(size=(f, r))
+    want = oracle.project_matrix(x, g)
+    got = ctx.project_matrix(x, g)
+    assert got.shape == (n, r)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    got_d = ctx.project_matrix(torch.from_numpy(x).cuda(), torch.from_numpy(g).cuda())
+    assert np.array_equal(got_d.cpu().numpy().view(np.uint64), want.view(np.uint64))
+    proj = asb.host.ImplicitProjection(g, ctx)
+    assert np.array_equal(proj.project(x[0]), want[0])
+    assert np.array_equal(np.asarray(asb.host.project_matrix(x[:3], proj)), want[:3])
+
+
 def test_builder_defaults_give_degenerate_graph(ctx, asb):
     """Literal builder defaults (eps=1e-3) on generic data: empty graph -> lambda == 0 -> the search
     panics in the reference (core.rs:773-776); here ASB_ERR_ZERO_LAMBDA."""

@@ -290,3 +290,23 @@ def test_search_energy_semantics(oracle):
     full = oracle.search_energy(items, lambdas, q, 0.5, 10, 1.0, 0.5)
     assert len(full) == 4 and np.isclose(full[3][1], -(0.4 + 0.25), atol=1e-15)
     assert oracle.search_energy(items, lambdas, q, 0.5, 0, 1.0, 0.5) == []
+
+
+def test_jl_dimension_and_projection(oracle, asb):
+    """SURVEY 8f rank 2 (src/reduction.rs:127-199; src/tests/test_reduction.rs: dimension formula, shape, scale)."""
+    import math
+    assert oracle.jl_dimension(1000, 0.1) == math.ceil(8 * math.log(1000) / 0.01)   # 5527
+    assert oracle.jl_dimension(10, 0.9) == 32                                         # floor of 32
+    assert asb.host.compute_jl_dimension(1000, 0.1) == oracle.jl_dimension(1000, 0.1)
+    assert asb.host.compute_jl_dimension(100, 0.5) == oracle.jl_dimension(100, 0.5)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(7, 20))
+    g = rng.normal(size=(20, 5))
+    y = oracle.project_matrix(x, g)
+    assert y.shape == (7, 5)
+    assert np.allclose(y, x @ g / math.sqrt(5), rtol=1e-13, atol=1e-13)
+    # the accumulation order is the reference's: features ascending, (x * g) * scale per term
+    acc = 0.0
+    for j in range(20):
+        acc += x[2, j] * g[j, 3] * (1.0 / math.sqrt(5))
+    assert y[2, 3] == acc
