@@ -1,23 +1,26 @@
-// cluster_f32p.cuh -- K2, fourth variant: the FP32-prefilter walk of cluster_f32.cuh, software-pipelined.
+// cluster_f32p.cuh -- K2, the default variant: the certified 32-row-block walk of cluster_f32.cuh, software-
+// pipelined, with the distances on the tensor cores.
 //
-// cluster_f32_kernel spends more than half of every 32-row block outside the distance tile: the
-// cluster barrier of the all-to-all, the in-order resolve (one warp, 23 idle) and the tail of the
-// updates (profiles/r01_cluster_phases.md).  This variant hides them behind the distance tile of
-// the NEXT block:
-//   * after the all-to-all of block b every thread only ARRIVES on the cluster barrier; warp 0 waits
-//     and resolves block b while all the other warps (and warp 0 once it is done) already compute the
-//     FP32 distances of block b+1 -- speculatively: block b+1 is assumed to start where block b ends,
-//     which holds whenever block b commits whole (virtually always once max_clusters is reached);
-//   * those distances are taken from centroids that are one to two blocks stale (and may be read
-//     while an owner warp is rewriting them: every element read is some version of that element, so
-//     the vector read is within the summed displacement of the outstanding updates of the vector the
-//     row will really meet).  The staleness enters the interval arithmetic as one more displacement
-//     term P = E(b-1) + E(b-2), the certified displacement bounds of the two preceding blocks, so a
+// cluster_f32_kernel spends more than half of every block outside the distance tile: the cluster barrier of the
+// all-to-all, the in-order resolve (one warp, 23 idle) and the tail of the updates
+// (profiles/r01_cluster_phases.md).  Here they overlap the distance tile of the NEXT block:
+//   * roles (16 warps x 128 registers): warp 0 = control (receive, resolve), warps 1-7 = distances, warps 8-15 =
+//     centroid updates, each on its own slice of the features (the update is element-wise);
+//   * while warp 0 resolves block b, the compute warps produce q = |c|^2 - 2<x,c> for block b+1 with mma.sync
+//     TF32 in 3xTF32 form -- speculatively: block b+1 is assumed to start where block b ends, which holds whenever
+//     block b commits whole (virtually always once max_clusters is reached).  The compute warp that finishes the
+//     block merges the per-tile arg-mins and sends the CTA's entries to all 16 CTAs with st.async +
+//     mbarrier::complete_tx (no cluster barrier; 4 exchange buffers by sequence number);
+//   * those distances see centroids that are up to two blocks stale and possibly torn (every element read is
+//     some version of that element, so the vector read is within the summed displacement of the outstanding
+//     updates of the vector the row will really meet).  The staleness enters the interval arithmetic as one more
+//     displacement term P = E(b-1) + E(b-2), the certified displacement bounds of the two preceding blocks, so a
 //     decision is still taken from fast distances only when it is CERTIFIED to equal the reference's;
-//   * a block that does not commit whole (uncertifiable row, new centroid) simply drops the
-//     speculative tile and the next block is computed from settled centroids (P = 0).
-// The FP64 centroids live in global memory (L2-resident; only their owner warp and the exact path
-// touch them), which frees the shared memory for an 8-group row ring and the two distance buffers.
+//   * a block that does not commit whole (uncertifiable row, new centroid) drops the speculative tile (its
+//     exchange is drained) and the next block is computed from settled centroids (P = 0); a row that cannot be
+//     certified goes through the reference-arithmetic FP64 path.
+// The FP64 centroids live in global memory (L2-resident; only the update warps and the exact path touch them),
+// which frees the shared memory for a 64-row ring of FP32 rows (bulk async copies) and the exchange buffers.
 // Outputs are bit-identical to the reference, like every other variant.
 #pragma once
 
@@ -43,29 +46,6 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned saddr, int rank) {
     unsigned r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
-}
-// bulk copy from this CTA's shared memory into a peer CTA's, completing the bytes on the peer's mbarrier:
-// data and signal travel together, no fence and no barrier round trip on the sender
-__device__ __forceinline__ void bulk_s2peer(unsigned rdst, unsigned src, unsigned bytes, unsigned rmbar) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     rdst),
-                 "r"(src), "r"(bytes), "r"(rmbar)
-                 : "memory");
-}
-
-
-// Row pitch (floats) of the FP32 rows / centroid shadows: the feature count padded to the 32-wide k-chunk of
-// the MMA tile plus 4 floats, so that the 8 threads of a quarter-warp (2 rows x 4 k-segments) hit 32
-// different banks with 16-byte loads.  Padding is zero and contributes nothing to the dot products.
-__host__ __device__ inline int f32p_pitch(int f) { return ((f + 31) & ~31) + 4; }
-
-// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col).  Operands are FP32 bit patterns (low 13 mantissa bits ignored).
-__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
-                                         unsigned b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 // 16-byte store into a peer CTA's shared memory that completes 16 tx-bytes on that CTA's mbarrier
 __device__ __forceinline__ void st_async_16(unsigned raddr, unsigned rmbar, unsigned a, unsigned b, unsigned c,
@@ -955,7 +935,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     __syncthreads();
     if (rank == 0 && tid == 0 && A.phase_times)
         for (int k = 0; k < 8; ++k) A.phase_times[k] = tphase[k];
-    if (rank == 0 && tid < 24 && A.phase_times) A.phase_times[8 + tid] = arr_hist[tid] * 1000000ll + (arr_hist[tid] ? arr_late[tid] / arr_hist[tid] : 0);
+    if (rank == 0 && tid < nw && tid < 24 && A.phase_times) A.phase_times[8 + tid] = arr_hist[tid] * 1000000ll + (arr_hist[tid] ? arr_late[tid] / arr_hist[tid] : 0);
 }
 
 size_t cluster_f32p_smem_bytes(int f, int slots, int maxk) {
