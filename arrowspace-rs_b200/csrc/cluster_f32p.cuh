@@ -47,6 +47,19 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned saddr, int rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// Row pitch (floats) of the FP32 rows / centroid shadows: the feature count padded to the 32-wide k-chunk of
+// the MMA tile plus 4 floats, so that the 8 threads of a quarter-warp (2 rows x 4 k-segments) hit 32
+// different banks with 16-byte loads.  Padding is zero and contributes nothing to the dot products.
+__host__ __device__ inline int f32p_pitch(int f) { return ((f + 31) & ~31) + 4; }
+
+// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col).  Operands are FP32 bit patterns (low 13 mantissa bits ignored).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                         unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 // 16-byte store into a peer CTA's shared memory that completes 16 tx-bytes on that CTA's mbarrier
 __device__ __forceinline__ void st_async_16(unsigned raddr, unsigned rmbar, unsigned a, unsigned b, unsigned c,
                                             unsigned d) {
