@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     // Warp roles.  Warp 0 is the control warp (arg-min, all-to-all, resolve): its chain of dependent
     // instructions is the critical path.  The tensor-core tile needs few warps (one per 8 centroids x 16 rows),
     // so the rest apply the centroid updates, each on its own slice of the features.
-    const int ncomp = (nw - 1) / 2;            // warps 1 .. ncomp compute distances in the pipelined steady state
+    // A full block has 2 work items per 8 centroids of this CTA: one compute warp per item where possible
+    // (7 of 16 warps for <= 28 centroids per CTA, up to 11 for more), the rest apply updates.
+    int ncomp = 2 * ((slots + 7) >> 3);        // warps 1 .. ncomp compute distances in the pipelined steady state
+    if (ncomp < (nw - 1) / 2) ncomp = (nw - 1) / 2;
+    if (ncomp > nw - 5) ncomp = nw - 5;
     const int first_apply = ncomp + 1;         // warps first_apply .. nw-1 apply updates
     const int napply = nw - first_apply;
     const bool is_compute = warp >= 1 && warp <= ncomp;
