@@ -56,6 +56,7 @@ struct ClusterArgs {
     const double *rows_n2;  // |fl32(row)|^2 in FP64 (pipelined kernel: distances via dot products)
     int tick_tid;           // thread of CTA 0 that owns the debug phase timers
     int tile_check;         // debug: compare every tensor-core distance with FP64 (pipelined kernel, no speculation)
+    int ring_groups;        // pipelined kernel: 8-row groups in the shared-memory row ring (8, 6 or 4)
 };
 
 struct __align__(16) Xch {
@@ -482,13 +483,17 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     for (int variant = first_variant; variant < 3 && !launched; ++variant) {
         for (int ncta : {16, 8, 4, 2, 1}) {
             const int slots = (int)((max_clusters + ncta - 1) / ncta);
+            int ring_groups = 8;  // pipelined kernel: shrink the row ring (less prefetch) before giving the variant up
             auto bytes = [&](bool in_smem) -> size_t {
-                if (variant == -2) return cluster_f32p_smem_bytes((int)f, slots, (int)max_clusters);
+                if (variant == -2) return cluster_f32p_smem_bytes((int)f, slots, (int)max_clusters, ring_groups);
                 if (variant == -1) return cluster_f32_smem_bytes((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 0) return cluster_block_smem_bytes<16>((int)f, slots, (int)max_clusters, in_smem);
                 if (variant == 1) return cluster_block_smem_bytes<8>((int)f, slots, (int)max_clusters, in_smem);
                 return cluster_smem_bytes((int)f, slots, in_smem);
             };
+            if (variant == -2)
+                while (ring_groups > 4 && bytes(false) > smem_cap) ring_groups -= 2;
+            A.ring_groups = ring_groups;
             const bool in_smem = variant != -2 && bytes(true) <= smem_cap;
             const size_t smem = bytes(in_smem);
             if (smem > smem_cap) continue;
@@ -576,6 +581,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         for (int k = 0; k < 48; ++k) ctx->kernel_ms[std::string("cluster_phase") + std::to_string(k)] = (double)ht[k];
     }
     ctx->kernel_ms["cluster_ncta"] = (double)launched;
+    ctx->kernel_ms["cluster_ring_groups"] = variant_used == -2 ? (double)A.ring_groups : 0.0;
     ctx->kernel_ms["cluster_blocks"] = (double)h[2];
     ctx->kernel_ms["cluster_variant"] = (double)variant_used;
     if (h[0] == 0) ASB_FAIL(ctx, ASB_ERR_NO_CLUSTERS, "No clusters created from data");  // clustering.rs:869-874

@@ -39,7 +39,8 @@ namespace {
     } while (0)
 
 constexpr int kXBuf = 4;       // all-to-all buffers: a peer CTA can run up to three exchanges ahead of the slowest reader
-constexpr int kPipeGroups = 8;  // ring = 8 groups of 8 rows: the block being read + the next one in flight
+constexpr int kPipeGroups = 8;  // ring = up to 8 groups of 8 rows (the block being read + the next one in flight);
+                                 // 6 or 4 groups when the centroid shadows need the shared memory (A.ring_groups)
 
 // shared::cta address -> the same location in CTA `rank` of the cluster (shared::cluster window)
 __device__ __forceinline__ unsigned mapa_u32(unsigned saddr, int rank) {
@@ -98,7 +99,7 @@ __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) 
 
 __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     constexpr int B = kB32;
-    constexpr int NG = kPipeGroups;
+    const int NG = A.ring_groups;  // 8, 6 or 4
     cg::cluster_group cluster = cg::this_cluster();
     const int ncta = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     GRow32 *G = reinterpret_cast<GRow32 *>(xch_exact + 32);                    // B
     Dec *dec_all = reinterpret_cast<Dec *>(G + B);                             // [2][B]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(dec_all + 2 * B);  // NG mbarriers
-    unsigned long long *xbar = full + NG;                                      // kXBuf: all-to-all landed (per buffer)
+    unsigned long long *xbar = full + kPipeGroups;                                      // kXBuf: all-to-all landed (per buffer)
     unsigned long long *cnt = xbar + kXBuf;                                    // maxk (replicated counts)
     double *disp = reinterpret_cast<double *>(cnt + maxk);                     // maxk
     double *wred_d = disp + maxk;                                              // 32
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     auto Pbuf = [&](int which) -> Xch32 * { return part_all + (size_t)which * (slots4 / 8) * B; };
 
     if (tid == 0) {
-        for (int s = 0; s < NG; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kPipeGroups; ++s) mbar_init(&full[s], 1);
         for (int k = 0; k < kXBuf; ++k) mbar_init(&xbar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         item_ctr[0] = item_ctr[1] = item_ctr[2] = item_ctr[3] = 0;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     auto need_groups = [&](long long ga, long long gb) {
         if (ga < ring_lo || ga > ring_hi) ring_lo = ring_hi = ga;  // rows were dropped from the ring: restart here
         for (long long g = ring_hi; g < gb; ++g) {
-            const int s = (int)(g % NG);
+            const int s = (int)((unsigned)g % (unsigned)NG);  // group indices fit 31 bits (n < 2^34 rows)
             if (fetcher) {
                 // one copy per slot in flight: the previous one has landed before the slot is reused
                 if (!((waited >> s) & 1u)) mbar_wait(&full[s], ((issued >> s) & 1u) ^ 1u);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
         __syncwarp();
     };
     auto wait_group = [&](long long g) {
-        const int s = (int)(g % NG);
+        const int s = (int)((unsigned)g % (unsigned)NG);
         if (!((waited >> s) & 1u)) {
             mbar_wait(&full[s], ((issued >> s) & 1u) ^ 1u);
             waited |= 1u << s;
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
             const int ga = 2 * mt, gb = (2 * mt + 1 < nrg) ? 2 * mt + 1 : 2 * mt;  // odd tail: group a twice
             wait_group(g0 + ga);
             wait_group(g0 + gb);
-            const float *xa = ring + (size_t)(((g0 + ga) % NG) * kGroup + g) * fp + 8 * t;
-            const float *xb = ring + (size_t)(((g0 + gb) % NG) * kGroup + g) * fp + 8 * t;
+            const float *xa = ring + (size_t)(((unsigned)(g0 + ga) % (unsigned)NG) * kGroup + g) * fp + 8 * t;
+            const float *xb = ring + (size_t)(((unsigned)(g0 + gb) % (unsigned)NG) * kGroup + g) * fp + 8 * t;
             const float *cb = c32(nt * 8 + g) + 8 * t;
             float cm[4][4], cc[4], cn4[4];
 #pragma unroll
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
                 if (A.tile_check && slot < my_n && grp < nrg && ri >= 0 && ri < nbk && q < INFINITY && delta > 0.0) {
                     // debug: the same quantity in FP64 from the very FP32 operands (centroids are settled: no
                     // speculation in this mode); worst |error| / delta over the run, in units of 1e-12
-                    const float *xrow = ring + (size_t)(((g0 + grp) % NG) * kGroup + g) * fp;
+                    const float *xrow = ring + (size_t)(((unsigned)(g0 + grp) % (unsigned)NG) * kGroup + g) * fp;
                     const float *crow = c32(slot);
                     double sc = 0.0, sx = 0.0;
                     for (int kk = 0; kk < f; ++kk) {
@@ -955,10 +956,10 @@ __global__ void __launch_bounds__(512, 1) cluster_f32p_kernel(ClusterArgs A) {
     if (rank == 0 && tid < nw && tid < 24 && A.phase_times) A.phase_times[8 + tid] = arr_hist[tid] * 1000000ll + (arr_hist[tid] ? arr_late[tid] / arr_hist[tid] : 0);
 }
 
-size_t cluster_f32p_smem_bytes(int f, int slots, int maxk) {
+size_t cluster_f32p_smem_bytes(int f, int slots, int maxk, int ring_groups) {
     const int slots8 = (slots + 7) & ~7;
     const int fp = f32p_pitch(f);
-    size_t b = (size_t)kPipeGroups * kGroup * fp * 4;  // ring (f32)
+    size_t b = (size_t)ring_groups * kGroup * fp * 4;  // ring (f32)
     b += (size_t)slots8 * fp * 4;                      // cent32
     b += (size_t)2 * slots8 * kB32 * 4;                // D (two buffers)
     b += (size_t)(kXBuf * 16 + 2 * (slots8 / 8)) * kB32 * sizeof(Xch32);  // xch, per-tile arg-mins

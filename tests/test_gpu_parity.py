@@ -417,6 +417,19 @@ def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rsc
     assert 2.0 in seen
 
 
+@pytest.mark.parametrize("n,f,maxk,ring", [(9_000, 384, 700, 6), (9_000, 384, 896, 4), (5_000, 128, 1500, 8)])
+def test_cluster_pipelined_with_short_row_ring(ctx, asb, oracle, n, f, maxk, ring):
+    """Large centroid counts (the 4- and 8-GPU runs use K = 634 / 896) leave less shared memory for the row ring of
+    the pipelined kernel: 6 or 4 groups instead of 8 (less prefetch, same bits)."""
+    x = asb.synth.protein_like(n, f, seed=13, n_blobs=256)
+    radius = 0.6 * 1.5 * f * 0.0025 * 2
+    want = oracle.cluster_incremental(x, maxk, radius)
+    got = ctx.cluster_incremental(x, maxk, radius)
+    assert ctx.kernel_ms("cluster_variant") == -2.0 and ctx.kernel_ms("cluster_ring_groups") == ring
+    _assert_cluster_equal(got, want)
+    assert want[0].shape[0] > 300          # enough centroids to fill several tiles per CTA
+
+
 @pytest.mark.parametrize("n,f,maxk", [(6_000, 384, 100), (4_000, 132, 64), (3_000, 33, 20)])
 def test_cluster_tensor_tile_error_model(ctx, asb, oracle, n, f, maxk):
     """The certified decisions of the pipelined kernel rest on an error bound for the 3xTF32 tensor-core
