@@ -637,8 +637,9 @@ int asb_topk_merge(asb_ctx *ctx, const double *in_score, const int64_t *in_idx, 
 void asb_index_destroy(asb_index *ix) {
     if (!ix) return;
     // Independent of the creating context (it may already be gone at interpreter shutdown):
-    // cudaFree synchronises with outstanding work on the memory and accepts stream-ordered
-    // allocations as well.
+    // cudaFree synchronises with outstanding work on the memory and accepts the stream-ordered
+    // (pooled) allocations asb_index_build makes -- they go back to the device's memory pool, so the
+    // next build does not pay the driver for them again.
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
     cudaFree(ix->items_owned);
@@ -705,21 +706,21 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
     if (asb_is_device_ptr(rows)) {
         ix->items = rows;
     } else {
-        ASB_CUDA(ctx, cudaMalloc((void **)&ix->items_owned, (size_t)n * f * sizeof(double)));
+        ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->items_owned, (size_t)n * f * sizeof(double), ctx->stream));
         ASB_CUDA(ctx, cudaMemcpyAsync(ix->items_owned, rows, (size_t)n * f * sizeof(double), cudaMemcpyHostToDevice,
                                       ctx->stream));
         ix->items = ix->items_owned;
     }
     const int64_t cap = asb_laplacian_max_nnz(f, gp.topk);
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->lambdas, (size_t)n * sizeof(double)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->norms2, (size_t)n * sizeof(double)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->centroids, (size_t)bp->max_clusters * f * sizeof(double)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->stats, 3 * sizeof(double)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->assign, (size_t)n * sizeof(int64_t)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->sizes, (size_t)bp->max_clusters * sizeof(unsigned long long)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->indptr, (size_t)(f + 1) * sizeof(int64_t)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->indices, (size_t)cap * sizeof(int64_t)));
-    ASB_CUDA(ctx, cudaMalloc((void **)&ix->data, (size_t)cap * sizeof(double)));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->lambdas, (size_t)n * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->norms2, (size_t)n * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->centroids, (size_t)bp->max_clusters * f * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->stats, 3 * sizeof(double), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->assign, (size_t)n * sizeof(int64_t), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->sizes, (size_t)bp->max_clusters * sizeof(unsigned long long), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->indptr, (size_t)(f + 1) * sizeof(int64_t), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->indices, (size_t)cap * sizeof(int64_t), ctx->stream));
+    ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->data, (size_t)cap * sizeof(double), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(ix->centroids, 0, (size_t)bp->max_clusters * f * sizeof(double), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(ix->sizes, 0, (size_t)bp->max_clusters * sizeof(unsigned long long), ctx->stream));
 
@@ -748,9 +749,9 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
             ASB_TRY(dense_d.init(ctx, (size_t)f * f));
             ASB_CUDA(ctx, cudaMemcpyAsync(dense_d.ptr, dense.data(), (size_t)f * f * sizeof(double), cudaMemcpyHostToDevice,
                                           ctx->stream));
-            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_indptr, (size_t)(f + 1) * sizeof(int64_t)));
-            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_indices, (size_t)cap * sizeof(int64_t)));
-            ASB_CUDA(ctx, cudaMalloc((void **)&ix->sig_data, (size_t)cap * sizeof(double)));
+            ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->sig_indptr, (size_t)(f + 1) * sizeof(int64_t), ctx->stream));
+            ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->sig_indices, (size_t)cap * sizeof(int64_t), ctx->stream));
+            ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->sig_data, (size_t)cap * sizeof(double), ctx->stream));
             int64_t snnz = 0;
             ASB_TRY(asb_dev_laplacian(ctx, dense_d.ptr, f, f, gp, ix->sig_indptr, ix->sig_indices, ix->sig_data, cap, &snnz));
             ix->sig_nnz = snnz;
