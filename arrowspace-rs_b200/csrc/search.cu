@@ -566,6 +566,8 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
     return ASB_OK;
 }
 
+#include "search_pf.cuh"
+
 int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,
                    int64_t n, int64_t f, const double *queries_d, const double *lambda_q_d, int64_t nq,
                    int64_t k, double alpha, int64_t index_offset, int64_t *idx_d, double *score_d,
@@ -608,6 +610,14 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
         ASB_CUDA(ctx, cudaMemcpy2DAsync(score_d, k * sizeof(double), ts.ptr, A.k * sizeof(double),
                                         A.k * sizeof(double), nq, cudaMemcpyDeviceToDevice, ctx->stream));
         return ASB_OK;
+    }
+    {
+        auto it = ctx->options.find("search_prefilter");
+        if (it != ctx->options.end() && it->second != 0.0) {
+            bool done = false;
+            ASB_TRY(run_search_pf(ctx, A, index_offset, idx_d, score_d, count_d, &done));
+            if (done) return ASB_OK;
+        }
     }
     return run_search(ctx, MODE_COSINE, A, index_offset, idx_d, score_d, count_d);
 }

@@ -1,0 +1,578 @@
+// search_pf.cuh -- K8 with a certified tensor-core prefilter (option "search_prefilter", included by search.cu).
+//
+// The FP64 tensor pipe (DMMA, 34 TFLOP/s measured) is the ceiling of the exact search kernel.  This path ranks
+// every (query, item) pair with a cheap score whose distance to the reference's FP64 score is BOUNDED, keeps the
+// pairs the bound cannot exclude from the top-k, and rescoring those few in the reference's own arithmetic:
+//
+//   1. pf_unit_rows_kernel   x^ = fl32(x / |x|) for items and queries (zero rows stay zero: cos = 0, core.rs:231-236).
+//   2. search_pf_kernel      cos~ = <q^, x^> on the tensor cores (mma.sync m16n8k8 TF32 in 3xTF32 form: hi*lo + lo*hi +
+//                            hi*hi, FP32 accumulate), 128 queries x 128 items per CTA tile, operands streamed in
+//                            32-feature chunks through a 3-stage cp.async ring that runs across tile boundaries;
+//                            s~ = alpha cos~ + (1 - alpha)(1 - min(|dlambda|, 1)) in FP64 (core.rs:135-165).
+//                            Per (CTA, query) a sorted list of the k best s~ of the slab gives a lower bound of the
+//                            k-th best approximate score A_k; the bounds of all slabs meet in gthr[q] (atomicMax).
+//                            A pair is EMITTED to the query's candidate list when s~ >= bound - 2E.
+//   3. pf_finish_kernel      A_k itself = the k-th largest s~ of the query's list (every member of the approximate
+//                            top-k was emitted); candidates below A_k - 2E are dropped, the rest are scored exactly as the
+//                            reference does (sequential, separately rounded sums: core.rs:214-236; oracle
+//                            aso_search_lambda_aware) and the best k by (score desc, index asc) are written.
+//
+// Why no top-k member is lost: |s~ - s| <= E for every pair (below).  k items have s~ >= A_k, hence true scores
+// >= A_k - E, hence the true k-th best S_k >= A_k - E.  A member of the true top-k (ties included) has s >= S_k, so
+// s~ >= S_k - E >= A_k - 2E >= bound - 2E for every bound <= A_k -- and every slab-local k-th best, at any time,
+// is such a bound.
+//
+// E = |alpha| E_cos + 1e-10, E_cos =
+//     2^-22                      FP32 rounding of q^ and x^ (2 * 2^-24 * sum|q^_j x^_j|, Cauchy-Schwarz: <= 1), doubled
+//   + 3 * 2^-20                  dropped lo*lo and the TF32 truncation of the lo operands
+//   + (9 * chain + 16) * 2^-23   accumulation: chain = 3 * fp / 8 MMAs into one FP32 accumulator, each within
+//                                9 * 2^-23 * max(|acc|, |a b|) <= 9 * 2^-23 of exact -- the tensor-core model of
+//                                cluster_f32p.cuh (aligned truncating adders), validated on B200 by its
+//                                cluster_check_tile option (worst observed error 0.05 of that bound);
+// times 1.1.  The exact kernel is the fallback for everything the bound does not cover: non-finite rows or norms
+// outside [1e-145, 1e145], a NaN score (the reference panics there: status from the exact kernel), k > 32, a
+// candidate list that overflows.  Results are therefore identical to the exact path by construction, and the
+// rescored values are bit-identical to the oracle's.
+#pragma once
+
+namespace {
+
+constexpr int PF_KC = 32;                  // features per chunk
+constexpr int PF_PITCH = PF_KC + 4;        // floats: quarter-warp 16-byte fragment loads hit 32 different banks
+constexpr int PF_STAGES = 3;
+constexpr int PF_STAGE_FLOATS = (TQ + TN) * PF_PITCH;
+constexpr int PF_SP = 136;                 // cos~ tile pitch (floats): conflict-free float2 stores and row scans
+constexpr int PF_FLAG_FALLBACK = 1, PF_FLAG_OVERFLOW = 2;
+constexpr int PF_MAXSEL = 1024;            // rescored candidates per query
+
+struct PfArgs {
+    const float *xf, *qf;   // n x fp, nq x fp unit rows
+    int fp;                 // f rounded up to 32 (zero padded)
+    const double *lambdas, *lambda_q;
+    long long n, nq;
+    int k;
+    double alpha, band;     // band = 2E
+    int nslabs;
+    long long tiles_per_slab;
+    unsigned long long *gthr;  // nq: order-preserving encoding of the best known lower bound of A_k
+    int *cand_cnt;             // nq
+    int *cand_idx;             // nq x cap (index inside the shard)
+    float *cand_s;             // nq x cap
+    int cap;
+    int *flags;
+    unsigned long long *diag;  // [0] candidates emitted, [1] candidates rescored
+    int *status;
+};
+
+__device__ __forceinline__ unsigned long long pf_enc(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double pf_dec(unsigned long long e) {
+    const unsigned long long b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ void pf_split(float x, unsigned &hi, unsigned &lo) {  // x = hi + lo, hi a TF32 number
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void pf_mma(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) pf_init_kernel(unsigned long long *gthr, int *cand_cnt, long long nq) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) {
+        gthr[q] = pf_enc(-INFINITY);
+        cand_cnt[q] = 0;
+    }
+}
+
+// One warp per row: out = fl32(row / sqrt(norm2)), zero padded to fp.
+__global__ void __launch_bounds__(256) pf_unit_rows_kernel(const double *__restrict__ rows, const double *__restrict__ norms2,
+                                                           long long n, int f, int fp, float *__restrict__ out,
+                                                           int *__restrict__ flags) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double n2 = norms2[r];
+    const bool ok = (n2 == 0.0) || (n2 >= 1e-290 && n2 <= 1e290);   // false for NaN / inf as well
+    if (!ok && lane == 0) atomicOr(flags, PF_FLAG_FALLBACK);
+    const double inv = (ok && n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+    const double *src = rows + r * (long long)f;
+    float *dst = out + r * (long long)fp;
+    for (int j = lane; j < fp; j += 32) dst[j] = (ok && j < f) ? (float)(src[j] * inv) : 0.0f;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *stages = reinterpret_cast<float *>(smem_raw);                    // PF_STAGES * PF_STAGE_FLOATS
+    float *S = stages + PF_STAGES * PF_STAGE_FLOATS;                        // TQ * PF_SP
+    double *list_s = reinterpret_cast<double *>(S + TQ * PF_SP);            // TQ * k, sorted descending
+    double *sm_lq = list_s + (size_t)TQ * A.k;                              // TQ
+    int *list_len = reinterpret_cast<int *>(sm_lq + TQ);                    // TQ
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const int k = A.k, fp = A.fp;
+    const long long q0 = (long long)blockIdx.x * TQ;
+    const long long ntiles_total = (A.n + TN - 1) / TN;
+    const long long t_begin = (long long)blockIdx.y * A.tiles_per_slab;
+    long long t_end = t_begin + A.tiles_per_slab;
+    if (t_end > ntiles_total) t_end = ntiles_total;
+
+    for (int q = tid; q < TQ; q += kThreads) {
+        const long long gq = q0 + q;
+        const bool ok = gq < A.nq;
+        const double lq = ok ? A.lambda_q[gq] : 1.0;
+        if (ok && blockIdx.y == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);  // core.rs:773-776
+        sm_lq[q] = lq;
+        list_len[q] = 0;
+    }
+    const int nchunks = fp / PF_KC;
+    const long long total = (t_end - t_begin) * nchunks;
+    if (total <= 0) return;
+
+    // copy descriptors: thread -> rows (tid / 8) + 64 m, 16-byte column (tid % 8) of the chunk, both operands
+    const int lr = tid >> 3, lc = (tid & 7) * 4;
+    const float *gqp[2];
+    bool okq[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const long long row = q0 + lr + 64 * m;
+        okq[m] = row < A.nq;
+        gqp[m] = A.qf + (okq[m] ? row : 0) * (long long)fp + lc;
+    }
+    long long is_tile = t_begin;  // tile / chunk of the next copy to issue
+    int is_c = 0, is_stage = 0;
+    auto issue = [&]() {
+        float *st = stages + is_stage * PF_STAGE_FLOATS;
+        const int k0 = is_c * PF_KC;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            cp_async16(st + (lr + 64 * m) * PF_PITCH + lc, gqp[m] + k0, okq[m] ? 16 : 0);
+            const long long row = is_tile * TN + lr + 64 * m;
+            const bool ok = row < A.n;
+            cp_async16(st + (TQ + lr + 64 * m) * PF_PITCH + lc, A.xf + (ok ? row : 0) * (long long)fp + lc + k0, ok ? 16 : 0);
+        }
+        if (++is_c == nchunks) {
+            is_c = 0;
+            ++is_tile;
+        }
+        if (++is_stage == PF_STAGES) is_stage = 0;
+    };
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[i][j][u] = 0.0f;
+
+    issue();
+    cp_async_commit();
+    if (total > 1) issue();
+    cp_async_commit();
+
+    bool saw_nan = false;
+    long long tile = t_begin;
+    int c = 0, stage = 0;
+    for (long long gc = 0; gc < total; ++gc) {
+        cp_async_wait<1>();  // every group but the newest has landed: chunk gc is in its stage
+        __syncthreads();     // ... for all threads, and the stage of chunk gc - 1 is free
+        if (gc + 2 < total) issue();
+        cp_async_commit();
+
+        const float *qa = stages + stage * PF_STAGE_FLOATS + (wm * 32 + g) * PF_PITCH + 8 * t;
+        const float *xb = stages + stage * PF_STAGE_FLOATS + (TQ + wn * 32 + g) * PF_PITCH + 8 * t;
+        // thread (g, t) holds features 8t .. 8t+7 of its rows; MMA k-step (h, m) pairs the values (2m, 2m+1) of
+        // the h-th 16-byte load -- A and B use the same feature-to-slot mapping, which is all a dot product needs
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float va[2][2][4], vb[4][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float4 p = *reinterpret_cast<const float4 *>(qa + (i * 16 + r * 8) * PF_PITCH + 4 * h);
+                    va[i][r][0] = p.x, va[i][r][1] = p.y, va[i][r][2] = p.z, va[i][r][3] = p.w;
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 p = *reinterpret_cast<const float4 *>(xb + (j * 8) * PF_PITCH + 4 * h);
+                vb[j][0] = p.x, vb[j][1] = p.y, vb[j][2] = p.z, vb[j][3] = p.w;
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    pf_split(va[i][0][2 * m], ah[i][0], al[i][0]);      // (row g,     slot t)
+                    pf_split(va[i][1][2 * m], ah[i][1], al[i][1]);      // (row g + 8, slot t)
+                    pf_split(va[i][0][2 * m + 1], ah[i][2], al[i][2]);  // (row g,     slot t + 4)
+                    pf_split(va[i][1][2 * m + 1], ah[i][3], al[i][3]);  // (row g + 8, slot t + 4)
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    pf_split(vb[j][2 * m], bh[j][0], bl[j][0]);          // (slot t,     item g)
+                    pf_split(vb[j][2 * m + 1], bh[j][1], bl[j][1]);      // (slot t + 4, item g)
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pf_mma(acc[i][j], ah[i], bl[j]);
+                        pf_mma(acc[i][j], al[i], bh[j]);
+                        pf_mma(acc[i][j], ah[i], bh[j]);
+                    }
+            }
+        }
+        if (++stage == PF_STAGES) stage = 0;
+        if (++c < nchunks) continue;
+        c = 0;
+
+        // ---- tile finished: cos~ -> S, then one warp per query scans its 128 scores
+        const long long i0 = tile * TN;
+        ++tile;
+        double lx[4];
+        bool vx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long gi = i0 + 32 * e + lane;
+            vx[e] = gi < A.n;
+            lx[e] = vx[e] ? A.lambdas[gi] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // c0:(row g, col 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+                const int row = wm * 32 + i * 16 + g, col = wn * 32 + j * 8 + 2 * t;
+                *reinterpret_cast<float2 *>(&S[row * PF_SP + col]) = make_float2(acc[i][j][0], acc[i][j][1]);
+                *reinterpret_cast<float2 *>(&S[(row + 8) * PF_SP + col]) = make_float2(acc[i][j][2], acc[i][j][3]);
+                acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
+            }
+        __syncthreads();
+        unsigned long long genc = pf_enc(-INFINITY);
+        if (lane < TQ / kWarps && q0 + warp * (TQ / kWarps) + lane < A.nq)
+            genc = __ldcg(&A.gthr[q0 + warp * (TQ / kWarps) + lane]);
+        for (int qq = 0; qq < TQ / kWarps; ++qq) {
+            const int q = warp * (TQ / kWarps) + qq;
+            const long long gq = q0 + q;
+            if (gq >= A.nq) break;
+            const double gb = pf_dec(__shfl_sync(0xffffffffu, genc, qq));  // bound published by any slab
+            const double lq = sm_lq[q];
+            double *lst = list_s + (size_t)q * k;
+            int len = list_len[q];
+            double kth = (len == k) ? lst[k - 1] : -INFINITY;
+            bool changed = false;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double cosv = (double)S[q * PF_SP + 32 * e + lane];
+                const double lam = 1.0 - fmin(fabs(lq - lx[e]), 1.0);      // core.rs:136-137
+                const double s = A.alpha * cosv + (1.0 - A.alpha) * lam;   // core.rs:165 (approximate cos)
+                const bool valid = vx[e];
+                if (valid && s != s) saw_nan = true;
+                // keep the slab's k best approximate scores (only values above every known bound matter)
+                unsigned mask = __ballot_sync(0xffffffffu, valid && s > fmax(kth, gb));
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const double cs = __shfl_sync(0xffffffffu, s, src);
+                    const double es = (lane < len) ? lst[lane] : 0.0;
+                    const int pos = __popc(__ballot_sync(0xffffffffu, lane < len && es >= cs));
+                    __syncwarp();
+                    if (lane >= pos && lane < len && lane + 1 < k) lst[lane + 1] = es;
+                    if (lane == 0 && pos < k) lst[pos] = cs;
+                    if (len < k) ++len;
+                    __syncwarp();
+                    changed = true;
+                    if (len == k) {
+                        kth = lst[k - 1];
+                        mask &= __ballot_sync(0xffffffffu, s > fmax(kth, gb));
+                    }
+                }
+                // emit what the bound cannot exclude
+                const double bound = fmax(kth, gb);
+                const unsigned em = __ballot_sync(0xffffffffu, valid && s >= bound - A.band);
+                if (em) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&A.cand_cnt[gq], __popc(em));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if ((em >> lane) & 1u) {
+                        const int p = base + __popc(em & ((1u << lane) - 1u));
+                        if (p < A.cap) {
+                            A.cand_idx[(size_t)gq * A.cap + p] = (int)(i0 + 32 * e + lane);
+                            A.cand_s[(size_t)gq * A.cap + p] = (float)s;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                list_len[q] = len;
+                if (changed && len == k) atomicMax(&A.gthr[gq], pf_enc(kth));
+            }
+        }
+    }
+    if (saw_nan) atomicOr(A.flags, PF_FLAG_FALLBACK);
+}
+
+// One block per query: drop the candidates below the final bound, score the rest in the reference's arithmetic
+// (src/core.rs:214-236, :135-165 -- sequential sums, products and sums rounded separately), select the best k by
+// (score desc, index asc) = the reference's stable descending sort (:785-786).
+__global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *__restrict__ items,
+                                                        const double *__restrict__ queries, int f, long long index_offset,
+                                                        double band_f, long long *__restrict__ idx_out,
+                                                        double *__restrict__ score_out, long long *__restrict__ count_out) {
+    __shared__ int sel_idx[PF_MAXSEL];
+    __shared__ double sel_s[PF_MAXSEL];
+    __shared__ int nsel;
+    __shared__ double red_s[4];
+    __shared__ int red_i[4];
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = A.k;
+    if (tid == 0) nsel = 0;
+    __syncthreads();
+    const int cnt = A.cand_cnt[q];
+    if (cnt > A.cap) {
+        if (tid == 0) atomicOr(A.flags, PF_FLAG_OVERFLOW);
+        return;
+    }
+    // Every item of the approximate top-k passed the emission test (its s~ >= A_k >= any bound), so the k-th largest
+    // s~ of the list IS A_k: a bisection over the order-preserving key of the stored floats finds it by counting.
+    const float *cs = A.cand_s + (size_t)q * A.cap;
+    double thr = pf_dec(A.gthr[q]) - band_f;
+    if (cnt >= k) {
+        unsigned key = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned probe = key | (1u << bit);
+            int local = 0;
+            for (int c = tid; c < cnt; c += 128) {
+                const unsigned b = __float_as_uint(cs[c]);
+                local += (((b >> 31) ? ~b : (b | 0x80000000u)) >= probe) ? 1 : 0;
+            }
+            for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+            if (lane == 0) red_i[warp] = local;
+            __syncthreads();
+            const int total = red_i[0] + red_i[1] + red_i[2] + red_i[3];
+            __syncthreads();
+            if (total >= k) key = probe;
+        }
+        const float akf = __uint_as_float((key >> 31) ? (key & 0x7fffffffu) : ~key);
+        thr = fmax(thr, (double)akf - band_f);
+    }
+    for (int c = tid; c < cnt; c += 128)
+        if ((double)A.cand_s[(size_t)q * A.cap + c] >= thr) {
+            const int p = atomicAdd(&nsel, 1);
+            if (p < PF_MAXSEL) sel_idx[p] = A.cand_idx[(size_t)q * A.cap + c];
+        }
+    __syncthreads();
+    const int m = nsel;
+    if (m > PF_MAXSEL) {
+        if (tid == 0) atomicOr(A.flags, PF_FLAG_OVERFLOW);
+        return;
+    }
+    if (tid == 0) {
+        atomicAdd(&A.diag[0], (unsigned long long)cnt);
+        atomicAdd(&A.diag[1], (unsigned long long)m);
+    }
+    const double *qr = queries + q * (long long)f;
+    const double lq = A.lambda_q[q];
+    for (int c = tid; c < m; c += 128) {
+        const int li = sel_idx[c];
+        const double *x = items + (long long)li * f;
+        double nq2 = 0.0, nx2 = 0.0, dot = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < f; ++j) {
+            const double qv = qr[j], xv = x[j];
+            nq2 = __dadd_rn(nq2, __dmul_rn(qv, qv));
+            nx2 = __dadd_rn(nx2, __dmul_rn(xv, xv));
+            dot = __dadd_rn(dot, __dmul_rn(qv, xv));
+        }
+        const double denom = __dmul_rn(sqrt(nq2), sqrt(nx2));       // core.rs:230
+        const double cosv = denom > 0.0 ? dot / denom : 0.0;        // :231-236
+        const double lam = 1.0 - fmin(fabs(lq - A.lambdas[li]), 1.0);  // :136-137
+        const double s = __dadd_rn(__dmul_rn(A.alpha, cosv), __dmul_rn(1.0 - A.alpha, lam));  // :165
+        if (s != s) atomicOr(A.status, STATUS_NAN);
+        sel_s[c] = s;
+    }
+    __syncthreads();
+    double last_s = INFINITY;
+    int last_i = -1, taken = 0;
+    for (int r = 0; r < k; ++r) {
+        double bs = -INFINITY;
+        int bi = -1;
+        for (int c = tid; c < m; c += 128) {
+            const double s = sel_s[c];
+            const int ii = sel_idx[c];
+            const bool after = (s < last_s) || (s == last_s && ii > last_i);
+            if (!after) continue;
+            if (bi < 0 || s > bs || (s == bs && ii < bi)) {
+                bs = s;
+                bi = ii;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+                bs = os;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            red_s[warp] = bs;
+            red_i[warp] = bi;
+        }
+        __syncthreads();
+        bs = red_s[0];
+        bi = red_i[0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+            const double os = red_s[w];
+            const int oi = red_i[w];
+            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
+                bs = os;
+                bi = oi;
+            }
+        }
+        __syncthreads();
+        if (bi < 0) break;
+        if (tid == 0) {
+            score_out[q * k + r] = bs;
+            idx_out[q * k + r] = (long long)bi + index_offset;
+        }
+        last_s = bs;
+        last_i = bi;
+        ++taken;
+    }
+    if (tid == 0) {
+        for (int r = taken; r < k; ++r) {
+            score_out[q * k + r] = -INFINITY;
+            idx_out[q * k + r] = -1;
+        }
+        if (count_out) count_out[q] = taken;
+    }
+}
+
+size_t pf_smem_bytes(int k) {
+    return (size_t)PF_STAGES * PF_STAGE_FLOATS * 4 + (size_t)TQ * PF_SP * 4 + (size_t)TQ * k * 8 + (size_t)TQ * 8 +
+           (size_t)TQ * 4 + 16;
+}
+
+}  // namespace
+
+// Tries the prefilter path; *done = true when idx/score/count hold the final answer.  *done = false (with ASB_OK)
+// means "not applicable / not certain": the caller runs the exact kernel, which then decides everything.
+static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_offset, int64_t *idx_d, double *score_d,
+                         int64_t *count_d, bool *done) {
+    *done = false;
+    ctx->kernel_ms["search_pf_used"] = 0.0;
+    const int k = SA.k, f = SA.f;
+    const long long n = SA.n, nq = SA.nq;
+    if (k < 1 || k > 32 || n < 1024 || n > 0x7fffff00ll || !(fabs(SA.alpha) <= 1e6)) return ASB_OK;
+    const int fp = (f + 31) & ~31;
+    const long long qtiles = (nq + TQ - 1) / TQ, ntiles = (n + TN - 1) / TN;
+    long long want = ((long long)ctx->sm_count * 8 + qtiles - 1) / qtiles;
+    const long long max_slabs = (ntiles + 3) / 4;
+    if (want > max_slabs) want = max_slabs;
+    if (want > 64) want = 64;  // few, long slabs: a slab's own k-th best is the bound its first tiles are held to
+    if (want < 1) want = 1;
+    const long long tps = (ntiles + want - 1) / want;
+    const int nslabs = (int)((ntiles + tps - 1) / tps);
+    // candidate capacity: a stream of m items passes a running k-th best about k ln(m / k) times
+    const double slab_items = (double)tps * TN;
+    double conc = (double)ctx->sm_count / (double)qtiles + 2.0;
+    if (conc > nslabs) conc = nslabs;
+    const double est = k * (log(fmax((double)n / k, 2.0)) + 2.0) + conc * k * (log(fmax(slab_items / k, 2.0)) + 2.0);
+    int cap = 512;
+    while (cap < 4.0 * est && cap < 16384) cap *= 2;
+    if ((double)nq * cap * 8.0 > 2e9) return ASB_OK;
+    const size_t smem = pf_smem_bytes(k);
+    if (smem > 227 * 1024) return ASB_OK;
+
+    const double chain = 3.0 * fp / 8.0;
+    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+    const double E = fabs(SA.alpha) * e_cos + 1e-10;
+    const double band = 2.0 * E;
+    const double band_f = band + 1.1920928955078125e-7 * (fabs(SA.alpha) + fabs(1.0 - SA.alpha) + 1.0);  // cand_s is a float
+
+    DevTmp<float> xf, qf, cand_s;
+    DevTmp<int> cand_cnt, cand_idx, flags;
+    DevTmp<unsigned long long> gthr, diag;
+    // a failed allocation only means "use the exact kernel"
+    if (xf.init(ctx, (size_t)n * fp) != ASB_OK || qf.init(ctx, (size_t)nq * fp) != ASB_OK ||
+        cand_s.init(ctx, (size_t)nq * cap) != ASB_OK || cand_idx.init(ctx, (size_t)nq * cap) != ASB_OK) {
+        cudaGetLastError();
+        return ASB_OK;
+    }
+    ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 1));
+    ASB_TRY(gthr.init(ctx, (size_t)nq));
+    ASB_TRY(diag.init(ctx, 2));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(diag.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    pf_init_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(gthr.ptr, cand_cnt.ptr, nq);
+    ASB_TRY(asb_check_launch(ctx, "pf_init_kernel"));
+    {
+        KernelTimer kt(ctx, "search_pf_prep");
+        pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, flags.ptr);
+        pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr, flags.ptr);
+    }
+    ASB_TRY(asb_check_launch(ctx, "pf_unit_rows_kernel"));
+    ctx->launches++;
+
+    PfArgs A{};
+    A.xf = xf.ptr;
+    A.qf = qf.ptr;
+    A.fp = fp;
+    A.lambdas = SA.lambdas;
+    A.lambda_q = SA.lambda_q;
+    A.n = n;
+    A.nq = nq;
+    A.k = k;
+    A.alpha = SA.alpha;
+    A.band = band;
+    A.nslabs = nslabs;
+    A.tiles_per_slab = tps;
+    A.gthr = gthr.ptr;
+    A.cand_cnt = cand_cnt.ptr;
+    A.cand_idx = cand_idx.ptr;
+    A.cand_s = cand_s.ptr;
+    A.cap = cap;
+    A.flags = flags.ptr;
+    A.diag = diag.ptr;
+    A.status = SA.status;
+    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelTimer kt(ctx, "search_pf_kernel");
+        search_pf_kernel<<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
+    }
+    ASB_TRY(asb_check_launch(ctx, "search_pf_kernel"));
+    {
+        KernelTimer kt(ctx, "search_pf_finish");
+        pf_finish_kernel<<<(unsigned)nq, 128, 0, ctx->stream>>>(A, SA.items, SA.queries, f, index_offset, band_f,
+                                                                (long long *)idx_d, score_d, (long long *)count_d);
+    }
+    ASB_TRY(asb_check_launch(ctx, "pf_finish_kernel"));
+    int hflags = 0;
+    unsigned long long hdiag[2] = {0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hflags, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(hdiag, diag.ptr, sizeof(hdiag), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->kernel_ms["search_pf_flags"] = (double)hflags;
+    ctx->kernel_ms["search_pf_cap"] = (double)cap;
+    ctx->kernel_ms["search_pf_slabs"] = (double)nslabs;
+    ctx->kernel_ms["search_pf_band"] = band;
+    ctx->kernel_ms["search_pf_candidates"] = (double)hdiag[0];
+    ctx->kernel_ms["search_pf_rescored"] = (double)hdiag[1];
+    if (hflags != 0) return ASB_OK;  // the exact kernel decides (and reports NaN scores the way the reference does)
+    ctx->kernel_ms["search_pf_used"] = 1.0;
+    *done = true;
+    return ASB_OK;
+}
