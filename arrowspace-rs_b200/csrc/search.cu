@@ -573,6 +573,7 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
                    int64_t k, double alpha, int64_t index_offset, int64_t *idx_d, double *score_d,
                    int64_t *count_d, int *status_d) {
     if (n <= 0 || f <= 0 || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search: empty input");
+    ctx->kernel_ms["search_pf_used"] = 0.0;
     DevTmp<double> qn2, xn2;
     ASB_TRY(qn2.init(ctx, (size_t)nq));
     ASB_TRY(asb_dev_norms2(ctx, queries_d, nq, f, qn2.ptr));
@@ -612,8 +613,8 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
         return ASB_OK;
     }
     {
-        auto it = ctx->options.find("search_prefilter");
-        if (it != ctx->options.end() && it->second != 0.0) {
+        auto it = ctx->options.find("search_prefilter");  // default on; 0 = always the exact FP64 kernel
+        if (it == ctx->options.end() || it->second != 0.0) {
             bool done = false;
             ASB_TRY(run_search_pf(ctx, A, index_offset, idx_d, score_d, count_d, &done));
             if (done) return ASB_OK;

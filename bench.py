@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--queries", dest="nq", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exact-search", action="store_true",
+                    help="search with the exact FP64 DMMA kernel only (option search_prefilter = 0)")
     return ap.parse_args()
 
 
@@ -242,7 +244,11 @@ def run_b200(args):
                 .with_cluster_params(maxk, radius))
 
     compute = asb.parallel.GpuCompute(ctx)
-    kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": []}
+    if args.exact_search:
+        ctx.set_option("search_prefilter", 0)
+    kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": [],
+                  "search_pf_kernel": [], "search_pf_prep": [], "search_pf_finish": []}
+    pf_diag = {}
     stage_acc = {"twonn": [], "cluster": [], "laplacian": [], "taumode": [], "search": []}
 
     def twonn():
@@ -284,8 +290,17 @@ def run_b200(args):
             torch.cuda.synchronize()
             result = (idx, score, index)
         if record:
+            pf_used = ctx.kernel_ms("search_pf_used") == 1.0
             for kname in kernel_acc:
+                if kname.startswith("search_pf") and not pf_used:
+                    continue      # the exact kernel answered (option off, or the prefilter fell back)
+                if kname == "search_kernel" and pf_used:
+                    continue
                 kernel_acc[kname].append(ctx.kernel_ms(kname))
+            if pf_used:
+                for kname in ("search_pf_candidates", "search_pf_rescored", "search_pf_cap", "search_pf_slabs",
+                              "search_pf_band"):
+                    pf_diag[kname] = ctx.kernel_ms(kname)
         return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), result
 
     def barrier():
@@ -397,6 +412,24 @@ def run_b200(args):
                                     "frac": ach / dmma_peak, "ms": kms["search_kernel"], "traffic": None,
                                     "peak_source": "FP64 DMMA m8n8k4 micro-benchmark on this pool "
                                                    "(profiles/r01_fp64_peak.json); DFMA peak %.1f" % dfma_peak}
+    if kms["search_pf_kernel"] > 0:
+        # certified prefilter (csrc/search_pf.cuh): the same 2 Q N F algorithmic flops, executed as 3 TF32 MMAs per
+        # product (3xTF32) on the mma.sync tensor path; peak = the mma.sync TF32 rate measured on this pool by
+        # tools/mma_peak.cu (0.5 m16n8k8 MMA / clk / SM at the boost clock the clocks line reports)
+        fl = 2.0 * nq * n * f
+        ach = fl / (kms["search_pf_kernel"] * 1e-3) / 1e12
+        tf32_peak = 148 * 0.5 * 2048 * 1.965e9 / 1e12
+        kernels["search_pf_kernel"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                                       "frac": ach / tf32_peak, "ms": kms["search_pf_kernel"], "traffic": None,
+                                       "executed_frac": 3.0 * ach / tf32_peak,
+                                       "peak_source": "mma.sync TF32 m16n8k8 micro-benchmark on this pool (tools/mma_peak.cu, "
+                                                      "DESIGN.md section 4): 0.5 MMA/clk/SM = 298 TFLOP/s; the kernel issues 3 "
+                                                      "MMAs per algorithmic product (3xTF32), executed_frac counts those",
+                                       "vs_fp64_dmma_peak": ach / dmma_peak,
+                                       "prep_ms": kms["search_pf_prep"], "finish_ms": kms["search_pf_finish"],
+                                       "candidates_per_query": pf_diag.get("search_pf_candidates", 0.0) / max(nq, 1),
+                                       "rescored_per_query": pf_diag.get("search_pf_rescored", 0.0) / max(nq, 1),
+                                       "band": pf_diag.get("search_pf_band"), "slabs": pf_diag.get("search_pf_slabs")}
     if kms["twonn_kernel"] > 0:
         fl = 2.0 * 500 * n * f
         ach = fl / (kms["twonn_kernel"] * 1e-3) / 1e12
@@ -427,8 +460,10 @@ def run_b200(args):
     if roofline is not None:
         # HBM peaks come from MEASURED_PEAKS.json (or the profiling guide's fallback); that file has no FP64 entry,
         # so FP64 tensor-bound kernels are held against the DMMA rate measured on this pool by tools/fp64_peak.cu
-        roofline["peak_kind"] = peak_src if roofline["bound"] == "hbm" else \
-            "measured on this pool by tools/fp64_peak.cu (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure"
+        roofline["peak_kind"] = peak_src if roofline["bound"] == "hbm" else (
+            "mma.sync TF32 rate measured on this pool by tools/mma_peak.cu; MEASURED_PEAKS.json's bf16 figure is a "
+            "tcgen05 cuBLAS number, not the ceiling of an mma.sync kernel" if dominant == "search_pf_kernel" else
+            "measured on this pool by tools/fp64_peak.cu (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure")
 
     line = {
         "metric": "lambda_tau_build_items_per_s", "value": items_per_s, "unit": "items/s", "n_gpus": world,

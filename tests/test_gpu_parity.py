@@ -298,7 +298,9 @@ def test_topk_merge_matches_single_shard(ctx, asb, oracle):
         parts_s.append(s)
         parts_i.append(i)
     ms, mi, mc = ctx.topk_merge(np.stack(parts_s), np.stack(parts_i), len(parts_s), 20, k)
-    assert np.array_equal(mi, np.asarray(full[0])) and np.array_equal(ms, np.asarray(full[1]))
+    # shards below the prefilter's minimum size are scored by the exact DMMA kernel, the full set by the rescoring
+    # pass (reference summation order): same ids, scores equal to the last few bits
+    assert np.array_equal(mi, np.asarray(full[0])) and np.allclose(ms, np.asarray(full[1]), rtol=0, atol=1e-14)
     assert mc.tolist() == [k] * 20
 
 

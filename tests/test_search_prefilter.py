@@ -5,18 +5,14 @@ arithmetic (sequential, separately rounded sums), so ids must be identical and s
 (``aso_search_lambda_aware``), ties included.  Inputs the error bound does not cover must come out of the exact
 kernel unchanged (fallback), with the reference's error behaviour.
 
-The option is OFF by default in this round: the path was written after the round's GPU budget was spent and has
-not run on hardware yet.  ``ASB_TEST_PREFILTER=1 pytest -m gpu tests/test_search_prefilter.py`` runs it."""
-import os
-
+The option is on by default (validated on B200: gpurun_out/pf_validate2.log, profiles/r01_prefilter.md); the
+fixture sets it explicitly and ``search_prefilter = 0`` selects the exact FP64 kernel."""
 import numpy as np
 import pytest
 
 from oracle_binding import TAU_MEDIAN
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ASB_TEST_PREFILTER") != "1",
-                                 reason="search_prefilter is opt-in until validated on a B200 (ASB_TEST_PREFILTER=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
@@ -25,7 +21,7 @@ def pctx(ctx):
     try:
         yield ctx
     finally:
-        ctx.set_option("search_prefilter", 0)
+        ctx.set_option("search_prefilter", 1)
 
 
 def _case(asb, oracle, n, f, nq, seed=42):
@@ -135,6 +131,7 @@ def test_prefilter_through_the_index_handle(pctx, asb, oracle):
     assert pctx.kernel_ms("search_pf_used") == 1.0
     pctx.set_option("search_prefilter", 0)
     idx0, score0, count0, _ = aspace.search_batch(queries, 10, 0.7)
+    assert pctx.kernel_ms("search_pf_used") == 0.0 and pctx.kernel_ms("search_kernel") > 0   # the exact kernel ran
     assert np.array_equal(np.asarray(idx), np.asarray(idx0))
     assert np.allclose(np.asarray(score), np.asarray(score0), rtol=0, atol=1e-12)
     want = oracle.search_lambda_aware_batch(x, np.asarray(aspace.lambdas), queries, np.asarray(lq), 10, 0.7)
