@@ -111,7 +111,15 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *   "cluster_no_pipeline", "cluster_no_f32", "cluster_rowwise" (0|1)  shorthands for -1, 0 and 2;
  *   "cluster_phase_times" (0|1), "cluster_tick_tid" (t)  per-block cycle probes, read back with
  *                                 asb_last_kernel_ms(ctx, "cluster_phaseN");
- *   "taumode_generic" (0|1)       use the generic CSR kernel even for a symmetric graph. */
+ *   "taumode_generic" (0|1)       use the generic CSR kernel even for a symmetric graph;
+ *   "search_prefilter" (1|0)      1 (default): asb_search_lambda_aware_batch / asb_index_search rank all pairs with a
+ *                                 certified 3xTF32 tensor-core score and compute only the pairs the error bound cannot
+ *                                 exclude from the top-k in the reference's FP64 arithmetic (k <= 32, n >= 1024; any
+ *                                 input the bound does not cover falls back); 0: the exact FP64 DMMA kernel scores every
+ *                                 pair.  Same ids either way; scores agree to the last few bits (both within 1e-12 of
+ *                                 the reference, the prefilter path bit-identical to a sequential evaluation).
+ * Read-only diagnostics through asb_last_kernel_ms: "search_pf_used", "search_pf_flags", "search_pf_candidates",
+ * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */
 int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
 
 /* ---- stage 1: clustering ------------------------------------------------------------ */

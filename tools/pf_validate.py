@@ -1,4 +1,4 @@
-"""One process (one torch import): tools/pf_diag.py at the C3 shape, then the gated prefilter tests."""
+"""One process (one torch import): tools/pf_diag.py at the C3 shape, then the prefilter tests."""
 import os
 import sys
 from pathlib import Path
@@ -6,7 +6,6 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tools"))
-os.environ["ASB_TEST_PREFILTER"] = "1"
 
 import pf_diag
 

@@ -1,5 +1,7 @@
 """Runs ONE stage of the path at a moderate size so that `ncu` can capture its kernel quickly.
-    python tools/profile_driver.py taumode|search|cluster|twonn|laplacian [n] [f] [nq]"""
+    python tools/profile_driver.py taumode|search|search_exact|cluster|twonn|laplacian [n] [f] [nq]
+`search` runs the default path (certified TF32 prefilter + exact rescoring, search_pf_kernel), `search_exact` the
+FP64 DMMA kernel (search_prefilter = 0)."""
 import sys
 from pathlib import Path
 
@@ -35,14 +37,21 @@ elif stage == "taumode":
     for _ in range(3):
         lam, n2, st = ctx.compute_taumode(xd, csr, asb.TauMode.Median, want_norms=True)
     print("taumode_ms", ctx.kernel_ms("taumode_kernel"), "GB/s", n * (8 * f + 16) / ctx.kernel_ms("taumode_kernel") / 1e6)
-elif stage == "search":
+elif stage in ("search", "search_exact"):
     lam, n2, st = ctx.compute_taumode(xd, csr, asb.TauMode.Median, want_norms=True)
     q = torch.from_numpy(asb.synth.rows_at(asb.synth.query_indices(n, nq, 43), f, 42) * 1.02).cuda()
     lq = ctx.prepare_query_lambdas(q, csr, asb.TauMode.Median)
+    ctx.set_option("search_prefilter", 0 if stage == "search_exact" else 1)
     for _ in range(3):
         ctx.search_lambda_aware_batch(xd, lam, q, lq, 10, 0.7, norms2=n2)
-    ms = ctx.kernel_ms("search_kernel")
-    print("search_ms", ms, "TFLOP/s", 2.0 * nq * n * f / ms / 1e9)
+    if ctx.kernel_ms("search_pf_used") == 1.0:
+        ms = ctx.kernel_ms("search_pf_kernel")
+        print("search_pf_ms", ms, "effective TFLOP/s", 2.0 * nq * n * f / ms / 1e9, "prep_ms", ctx.kernel_ms("search_pf_prep"),
+              "finish_ms", ctx.kernel_ms("search_pf_finish"), "candidates/query", ctx.kernel_ms("search_pf_candidates") / nq,
+              "rescored/query", ctx.kernel_ms("search_pf_rescored") / nq)
+    else:
+        ms = ctx.kernel_ms("search_kernel")
+        print("search_ms", ms, "TFLOP/s", 2.0 * nq * n * f / ms / 1e9, "pf_flags", ctx.kernel_ms("search_pf_flags"))
 elif stage == "twonn":
     si = torch.from_numpy(asb.heuristics.sample_indices(n, 500, 129)).cuda()
     for _ in range(3):
