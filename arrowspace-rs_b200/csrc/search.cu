@@ -496,22 +496,30 @@ size_t search_smem_bytes(int k, int kc) {
     return b + 16;
 }
 
-template <int MODE>
-int launch_search(asb_ctx *ctx, SearchArgs &A, int *nslabs_out) {
-    const long long qtiles = (A.nq + TQ - 1) / TQ;
-    const long long ntiles = (A.n + TN - 1) / TN;
-    // enough (query tile, slab) units for ~8 waves over the SMs, each slab >= 4 tiles
-    long long want = ((long long)ctx->sm_count * 8 + qtiles - 1) / qtiles;
+// Slab split of the item tiles.  A (query tile, slab) unit is one CTA and the CTAs run in waves of sm_count, so
+// the time is ~ ceil(units / sm_count) * tiles_per_slab: pick the slab count that minimises it (a single unit
+// spilling into an extra wave costs a whole slab time: 79 query tiles x 15 slabs = 8 waves + 1 CTA), each slab
+// at least 4 tiles, fewer slabs preferred among near-equal costs (shorter merges, tighter prefilter bounds).
+void pick_slabs(int sm_count, long long qtiles, long long ntiles, long long limit, int *nslabs_out, long long *tps_out) {
     long long max_slabs = (ntiles + 3) / 4;
-    if (want > max_slabs) want = max_slabs;
-    if (want < 1) want = 1;
-    if (want > 4096) want = 4096;
-    long long tps = (ntiles + want - 1) / want;
-    int nslabs = (int)((ntiles + tps - 1) / tps);
-    A.nslabs = nslabs;
-    A.tiles_per_slab = tps;
-    *nslabs_out = nslabs;
-    return ASB_OK;
+    if (max_slabs > limit) max_slabs = limit;
+    if (max_slabs < 1) max_slabs = 1;
+    double best_cost = 0.0;
+    long long best_tps = ntiles > 0 ? ntiles : 1;
+    int best_ns = 1;
+    for (long long ns = 1; ns <= max_slabs; ++ns) {
+        const long long tps = (ntiles + ns - 1) / ns;
+        const long long real_ns = (ntiles + tps - 1) / tps;
+        const long long waves = (qtiles * real_ns + sm_count - 1) / sm_count;
+        const double cost = (double)waves * (double)(tps + 1) * (1.0 + 5e-4 * (double)real_ns);
+        if (ns == 1 || cost < best_cost) {
+            best_cost = cost;
+            best_tps = tps;
+            best_ns = (int)real_ns;
+        }
+    }
+    *nslabs_out = best_ns;
+    *tps_out = best_tps;
 }
 
 }  // namespace
@@ -522,7 +530,8 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
     if (k < 1 || k > 64) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: k=%d outside 1..64", k);
     if (A.n > 0x7fffff00ll) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: shard larger than 2^31 items");
     int nslabs = 1;
-    launch_search<MODE_COSINE>(ctx, A, &nslabs);  // the slab split does not depend on the mode
+    pick_slabs(ctx->sm_count, (A.nq + TQ - 1) / TQ, (A.n + TN - 1) / TN, 4096, &nslabs, &A.tiles_per_slab);
+    A.nslabs = nslabs;
     DevTmp<double> part_s;
     DevTmp<int> part_i;
     ASB_TRY(part_s.init(ctx, (size_t)nslabs * A.nq * k));

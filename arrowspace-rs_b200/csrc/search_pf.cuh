@@ -478,13 +478,10 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     if (k < 1 || k > 32 || n < 1024 || n > 0x7fffff00ll || !(fabs(SA.alpha) <= 1e6)) return ASB_OK;
     const int fp = (f + 31) & ~31;
     const long long qtiles = (nq + TQ - 1) / TQ, ntiles = (n + TN - 1) / TN;
-    long long want = ((long long)ctx->sm_count * 8 + qtiles - 1) / qtiles;
-    const long long max_slabs = (ntiles + 3) / 4;
-    if (want > max_slabs) want = max_slabs;
-    if (want > 64) want = 64;  // few, long slabs: a slab's own k-th best is the bound its first tiles are held to
-    if (want < 1) want = 1;
-    const long long tps = (ntiles + want - 1) / want;
-    const int nslabs = (int)((ntiles + tps - 1) / tps);
+    // few, long slabs: a slab's own k-th best is the bound its first tiles are held to
+    int nslabs = 1;
+    long long tps = ntiles;
+    pick_slabs(ctx->sm_count, qtiles, ntiles, 64, &nslabs, &tps);
     // candidate capacity: a stream of m items passes a running k-th best about k ln(m / k) times
     const double slab_items = (double)tps * TN;
     double conc = (double)ctx->sm_count / (double)qtiles + 2.0;
