@@ -733,3 +733,14 @@ int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in
         (long long *)out_idx_d, (long long *)out_count_d);
     return asb_check_launch(ctx, "topk_merge_kernel");
 }
+
+int asb_search_slab_plan(int sm_count, int64_t nq, int64_t n, int64_t max_slabs, int64_t *nslabs,
+                         int64_t *tiles_per_slab) {
+    if (sm_count < 1 || nq < 1 || n < 1 || max_slabs < 1 || !nslabs || !tiles_per_slab) return ASB_ERR_INVALID;
+    int ns = 1;
+    long long tps = 1;
+    pick_slabs(sm_count, (nq + TQ - 1) / TQ, (n + TN - 1) / TN, max_slabs, &ns, &tps);
+    *nslabs = ns;
+    *tiles_per_slab = tps;
+    return ASB_OK;
+}

@@ -99,6 +99,7 @@ ABI_SYMBOLS = {
                                                 _P]),
     "asb_project_matrix": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P]),
     "asb_jl_dimension": (C.c_int64, [_I64, _D]),
+    "asb_search_slab_plan": (C.c_int, [C.c_int, _I64, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
     "asb_search_energy_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _D, _I64, _P, _P, _P]),
     "asb_search_lambda_aware_hybrid_batch": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _D, _P, _P, _P]),
     "asb_range_search": (C.c_int, [_P, _P, _I64, _D, _D, _I64, _P, _P, _I64, C.POINTER(_I64)]),
@@ -136,6 +137,15 @@ def load_library(build: bool = True) -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def search_slab_plan(sm_count: int, nq: int, n: int, max_slabs: int = 4096) -> Tuple[int, int]:
+    """(nslabs, tiles_per_slab) the search kernels use for nq queries x n items (host arithmetic only)."""
+    ns, tps = _I64(0), _I64(0)
+    rc = load_library().asb_search_slab_plan(int(sm_count), int(nq), int(n), int(max_slabs), C.byref(ns), C.byref(tps))
+    if rc != 0:
+        raise ArrowSpaceError(rc, "search_slab_plan: bad sizes")
+    return int(ns.value), int(tps.value)
 
 
 def _ptr(a) -> int:

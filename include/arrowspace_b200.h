@@ -121,6 +121,12 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  * Read-only diagnostics through asb_last_kernel_ms: "search_pf_used", "search_pf_flags", "search_pf_candidates",
  * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */
 int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
+/* The slab split the search kernels use for nq queries x n items on a device with sm_count SMs (pure host
+ * arithmetic, no device needed): a (128-query tile, slab) pair is one CTA and CTAs run in waves of sm_count, so the
+ * split minimises ceil(units / sm_count) * tiles_per_slab.  max_slabs: 4096 for the exact kernel, 64 for the
+ * prefilter.  nslabs * tiles_per_slab covers ceil(n / 128) item tiles. */
+int asb_search_slab_plan(int sm_count, int64_t nq, int64_t n, int64_t max_slabs, int64_t *nslabs,
+                         int64_t *tiles_per_slab);
 
 /* ---- stage 1: clustering ------------------------------------------------------------ */
 /* Two-NN scan: replaces the distance pass of estimate_intrinsic_dimension

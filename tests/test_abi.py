@@ -89,3 +89,27 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_gpu(asb):
         pytest.skip("GPU present")
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+def test_search_slab_plan_covers_and_fills_waves(asb):
+    """Launch plan of the search kernels (host arithmetic behind asb_search_slab_plan): the slabs cover every item
+    tile, respect the limits, and never cost more waves x tiles than the fixed "8 waves" split they replaced."""
+    import math
+    sm = 148
+    for n, nq in [(1_000_000, 10_000), (1_250_000, 10_000), (200_000, 2048), (100_000, 1000), (10_000, 100),
+                  (1_000_000, 128), (5_001, 33), (129, 5), (64, 3), (1, 1), (10_000_000, 10_000), (123_457, 777)]:
+        ntiles, qtiles = -(-n // 128), -(-nq // 128)
+        for limit in (64, 4096):
+            ns, tps = asb.host.search_slab_plan(sm, nq, n, limit)
+            assert 1 <= ns <= limit and tps >= 1
+            assert ns * tps >= ntiles and (ns - 1) * tps < ntiles          # covers, no empty slab
+            assert tps >= min(4, ntiles) or ns == 1                         # slabs of at least 4 tiles
+            cost = math.ceil(qtiles * ns / sm) * tps
+            want = min(max(-(-sm * 8 // qtiles), 1), max((ntiles + 3) // 4, 1), limit)   # the old split
+            tps_old = -(-ntiles // want)
+            cost_old = math.ceil(qtiles * (-(-ntiles // tps_old)) / sm) * tps_old
+            assert cost <= cost_old + 1, (n, nq, limit, ns, tps, cost, cost_old)
+    ns, tps = asb.host.search_slab_plan(sm, 10_000, 1_000_000, 4096)      # C3: 7 full waves instead of 8 + 1 CTA
+    assert (ns, tps) == (13, 601)
+    with pytest.raises(asb.ArrowSpaceError):
+        asb.host.search_slab_plan(0, 1, 1, 1)
