@@ -398,7 +398,7 @@ size_t cluster_smem_bytes(int f, int slots, bool cent_in_smem) {
 
 }  // namespace
 
-int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
+int asb_dev_cluster_seq(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
                     double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host,
                     int64_t init_k) {
     if (n <= 0 || f <= 0 || max_clusters <= 0)

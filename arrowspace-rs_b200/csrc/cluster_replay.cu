@@ -1,0 +1,286 @@
+// cluster_replay.cu -- K2, option "cluster_replay" (off by default: written after the round's GPU budget was spent,
+// validated so far only by its CPU prototype tools/replay_proto.py, which reproduces the oracle's walk bit for bit).
+//
+// The walk of run_incremental_clustering_with_sampling (src/clustering.rs:547-928) is sequential because row r sees
+// the centroids all earlier rows left behind.  Once the centroids have settled, almost every row's decision can be
+// PROVEN without walking:
+//   1. guess: b(r) = nearest centroid of the chunk-start snapshot S0 and the distance to the runner-up, for all rows
+//      of a chunk at once (dense contraction with a fused 2-min: the Two-NN kernel, asb_dev_top2_l2);
+//   2. chains: given the guess, every centroid only sees its own rows, in row order -- K independent sequential
+//      chains (one warp each).  A chain evaluates the row's distance to the centroid's CURRENT state, classifies it
+//      (d^2 <= radius: running-mean update c += (x - c) / k, :747-751, the reference's element-wise IEEE operations;
+//      <= 1.5 radius: count only, :767-781; else dropped) and tracks the centroid's net displacement |c - S0|;
+//   3. certification: row r is proven when  d(x_r, c_b at r)  <  d(x_r, runner-up in S0) - max displacement of any
+//      centroid in the chunk - rounding slack: no other centroid can be nearer at row r's time, so the walk picks b.
+//      If every row of the chunk is proven, then by induction over the rows (row r depends only on rows < r) the
+//      guess IS the walk's assignment and the chain results are the walk's centroids, bit for bit.
+// A chunk with a single unproven row -- or a row that would open a new centroid, or a d^2 within 1e-9 radius of a
+// threshold (the chains sum in a different order than the reference) -- is thrown away and walked by the sequential
+// kernel from the same start state (asb_dev_cluster_seq with init_k: the resume entry the multi-GPU hand-off uses).
+// Two consecutive failures end the attempts.  On the C3 bench data every chunk after a 16k-row prefix is proven
+// (tools/replay_proto.py single 200000 384: min margin 0.15 against a displacement of 0.06 -> 0.006).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) replay_keys_kernel(const int64_t *__restrict__ top2_idx, int m, int *__restrict__ keys,
+                                                          int *__restrict__ vals) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) {
+        keys[r] = (int)top2_idx[2 * (size_t)r];
+        vals[r] = r;
+    }
+}
+
+// seg_off[c] = first position of centroid c in the sorted key list (seg_off[K] = m)
+__global__ void __launch_bounds__(256) replay_offsets_kernel(const int *__restrict__ keys_sorted, int m, int K,
+                                                             int *__restrict__ seg_off) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > K) return;
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys_sorted[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    seg_off[c] = lo;
+}
+
+__global__ void __launch_bounds__(256) replay_max_kernel(const double *__restrict__ v, int n, unsigned long long *__restrict__ out_bits) {
+    double mx = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mx = fmax(mx, v[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(out_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+// One warp per centroid: its rows of the chunk, in row order.
+__global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restrict__ rows, int f,
+                                                           const int *__restrict__ seg_off, const int *__restrict__ seg_rows,
+                                                           int K, int saturated, double radius, double *cent,
+                                                           const double *__restrict__ cent0, unsigned long long *sizes,
+                                                           long long *__restrict__ assign, double *__restrict__ dcur,
+                                                           unsigned long long *maxdisp_bits, int *fail) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= K) return;
+    const int beg = seg_off[c], end = seg_off[c + 1];
+    if (beg == end) return;
+    double *cc = cent + (size_t)c * f;
+    const double *c0 = cent0 + (size_t)c * f;
+    unsigned long long cnt = sizes[c];
+    const double guard = 1e-9 * radius;
+    double dmax2 = 0.0;
+    bool bad = false;
+    for (int i = beg; i < end; ++i) {
+        const int r = seg_rows[i];
+        const double *x = rows + (size_t)r * f;
+        double acc = 0.0;
+        for (int j = lane; j < f; j += 32) {
+            const double d = x[j] - cc[j];
+            acc = fma(d, d, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double d2 = acc;   // accurate to ~1e-15 relative, NOT the reference's summation order: guard band below
+        if (!(d2 == d2) || fabs(d2 - radius) <= guard || fabs(d2 - 1.5 * radius) <= guard ||
+            (!saturated && fabs(d2 - 0.5 * radius) <= guard))
+            bad = true;
+        int cls;
+        if (!saturated && d2 > 0.5 * radius) {   // the walk would open a new centroid here (:672): not replayable
+            cls = 3;
+            bad = true;
+        } else if (d2 <= radius) {
+            cls = 0;
+        } else if (d2 <= 1.5 * radius) {
+            cls = 1;
+        } else {
+            cls = 2;
+        }
+        if (lane == 0) {
+            dcur[r] = sqrt(d2);
+            assign[r] = cls == 2 ? -1ll : (long long)c;
+        }
+        if (cls == 0) {
+            cnt += 1;
+            const double k = (double)cnt;
+            double dsp = 0.0;
+            for (int j = lane; j < f; j += 32) {
+                const double cj = cc[j];
+                const double nj = __dadd_rn(cj, __ddiv_rn(__dsub_rn(x[j], cj), k));   // clustering.rs:747-751
+                cc[j] = nj;
+                const double e = nj - c0[j];
+                dsp = fma(e, e, dsp);
+            }
+            for (int o = 16; o > 0; o >>= 1) dsp += __shfl_xor_sync(0xffffffffu, dsp, o);
+            dmax2 = fmax(dmax2, dsp);
+        } else if (cls == 1) {
+            cnt += 1;
+        }
+    }
+    if (lane == 0) {
+        sizes[c] = cnt;
+        const double dm = sqrt(dmax2) * (1.0 + 1e-12);
+        if (dm == dm) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(dm));
+        else bad = true;
+        if (bad) atomicOr(fail, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) replay_certify_kernel(const double *__restrict__ dcur, const double *__restrict__ top2_dist,
+                                                             const long long *__restrict__ top2_cnt,
+                                                             const double *__restrict__ qn2, const unsigned long long *cn2max_bits,
+                                                             const unsigned long long *maxdisp_bits, int f, int m, int *fail) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const double cn2max = __longlong_as_double((long long)*cn2max_bits);
+    const double maxdisp = __longlong_as_double((long long)*maxdisp_bits);
+    // GEMM-form squared distance |q|^2 + |c|^2 - 2 q.c from the FP64 tensor pipe: absolute error below e2
+    const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
+    const double s = top2_dist[2 * (size_t)r + 1];
+    const double lower = sqrt(fmax(s * s - e2, 0.0)) - maxdisp;
+    if (top2_cnt[r] < 2 || !(dcur[r] < lower)) atomicOr(fail, 2);
+}
+
+struct ReplayWs {
+    DevTmp<double> qn2, xn2, dist, dcur, cent_tmp;
+    DevTmp<int64_t> idx, cnt, minus1;
+    DevTmp<int> keys, vals, keys_s, vals_s, seg_off, flags;
+    DevTmp<unsigned long long> sizes_tmp, scal;   // scal[0] = max |c|^2 bits, scal[1] = max displacement bits
+    DevTmp<unsigned char> cub_tmp;
+    size_t cub_bytes = 0;
+    int cap_m = 0, cap_k = 0;
+};
+
+int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
+    w.cap_m = m;
+    w.cap_k = K;
+    ASB_TRY(w.qn2.init(ctx, (size_t)m));
+    ASB_TRY(w.xn2.init(ctx, (size_t)K));
+    ASB_TRY(w.dist.init(ctx, (size_t)m * 2));
+    ASB_TRY(w.dcur.init(ctx, (size_t)m));
+    ASB_TRY(w.cent_tmp.init(ctx, (size_t)K * f));
+    ASB_TRY(w.idx.init(ctx, (size_t)m * 2));
+    ASB_TRY(w.cnt.init(ctx, (size_t)m));
+    ASB_TRY(w.minus1.init(ctx, (size_t)m));
+    ASB_TRY(w.keys.init(ctx, (size_t)m));
+    ASB_TRY(w.vals.init(ctx, (size_t)m));
+    ASB_TRY(w.keys_s.init(ctx, (size_t)m));
+    ASB_TRY(w.vals_s.init(ctx, (size_t)m));
+    ASB_TRY(w.seg_off.init(ctx, (size_t)K + 1));
+    ASB_TRY(w.flags.init(ctx, 2));
+    ASB_TRY(w.sizes_tmp.init(ctx, (size_t)K));
+    ASB_TRY(w.scal.init(ctx, 2));
+    ASB_CUDA(ctx, cudaMemsetAsync(w.minus1.ptr, 0xff, (size_t)m * sizeof(int64_t), ctx->stream));
+    w.cub_bytes = 0;
+    ASB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.keys.ptr, w.keys_s.ptr, w.vals.ptr, w.vals_s.ptr, m,
+                                                  0, 32, ctx->stream));
+    ASB_TRY(w.cub_tmp.init(ctx, w.cub_bytes));
+    return ASB_OK;
+}
+
+// One chunk.  *ok = 1: centroids / sizes / assign hold the walk's state after the chunk; 0: nothing was touched
+// except assign (the caller's sequential walk rewrites it).
+int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, int saturated, double radius,
+                 double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int *ok) {
+    *ok = 0;
+    ASB_CUDA(ctx, cudaMemsetAsync(w.flags.ptr, 0, 2 * sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    ASB_TRY(asb_dev_norms2(ctx, rows_d, m, f, w.qn2.ptr));
+    ASB_TRY(asb_dev_norms2(ctx, centroids_d, K, f, w.xn2.ptr));
+    replay_max_kernel<<<1, 256, 0, ctx->stream>>>(w.xn2.ptr, K, w.scal.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_max_kernel"));
+    ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, centroids_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
+                            w.cnt.ptr, w.flags.ptr + 1));
+    replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.idx.ptr, m, w.keys.ptr, w.vals.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_keys_kernel"));
+    int bits = 1;
+    while ((1ll << bits) < K) ++bits;
+    ASB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(w.cub_tmp.ptr, w.cub_bytes, w.keys.ptr, w.keys_s.ptr, w.vals.ptr,
+                                                  w.vals_s.ptr, m, 0, bits, ctx->stream));   // stable: rows stay ascending
+    ctx->launches++;
+    replay_offsets_kernel<<<(K + 1 + 255) / 256, 256, 0, ctx->stream>>>(w.keys_s.ptr, m, K, w.seg_off.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_offsets_kernel"));
+    ASB_CUDA(ctx, cudaMemcpyAsync(w.cent_tmp.ptr, centroids_d, (size_t)K * f * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(w.sizes_tmp.ptr, sizes_d, (size_t)K * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        KernelTimer kt(ctx, "cluster_chain_kernel");
+        replay_chain_kernel<<<(K + 3) / 4, 128, 0, ctx->stream>>>(rows_d, f, w.seg_off.ptr, w.vals_s.ptr, K, saturated, radius,
+                                                                 w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr,
+                                                                 (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);
+    }
+    ASB_TRY(asb_check_launch(ctx, "replay_chain_kernel"));
+    replay_certify_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.dcur.ptr, w.dist.ptr, (const long long *)w.cnt.ptr,
+                                                                    w.qn2.ptr, w.scal.ptr, w.scal.ptr + 1, f, m, w.flags.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_certify_kernel"));
+    int hflags[2] = {0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hflags[0] != 0 || hflags[1] != 0) return ASB_OK;
+    ASB_CUDA(ctx, cudaMemcpyAsync(centroids_d, w.cent_tmp.ptr, (size_t)K * f * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(sizes_d, w.sizes_tmp.ptr, (size_t)K * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    *ok = 1;
+    return ASB_OK;
+}
+
+double opt_or(asb_ctx *ctx, const char *key, double dflt) {
+    auto it = ctx->options.find(key);
+    return it == ctx->options.end() ? dflt : it->second;
+}
+
+}  // namespace
+
+int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
+                    double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host,
+                    int64_t init_k) {
+    const int64_t prefix = (int64_t)opt_or(ctx, "cluster_replay_prefix", 16384.0);
+    const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 32768.0);
+    const bool replay = opt_or(ctx, "cluster_replay", 0.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk <= (1 << 24) &&
+                        n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
+    ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
+    ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;
+    ctx->kernel_ms["cluster_replay_rows"] = 0.0;
+    if (!replay)
+        return asb_dev_cluster_seq(ctx, rows_d, n, f, max_clusters, radius, centroids_d, assign_d, sizes_d, x_out_host, init_k);
+
+    int64_t x = init_k;
+    ASB_TRY(asb_dev_cluster_seq(ctx, rows_d, prefix, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, init_k));
+    ReplayWs w;
+    bool ws_ready = false;
+    int fails = 0, tried = 0, proven = 0;
+    int64_t rows_replayed = 0;
+    int64_t lo = prefix;
+    while (lo < n) {
+        int64_t hi = lo + chunk < n ? lo + chunk : n;
+        int ok = 0;
+        if (fails < 2 && x >= 2) {
+            if (!ws_ready || w.cap_k < x) {
+                ASB_TRY(replay_ws_init(ctx, w, (int)chunk, (int)(x > max_clusters ? x : max_clusters), (int)f));
+                ws_ready = true;
+            }
+            ++tried;
+            ASB_TRY(replay_chunk(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
+                                 centroids_d, assign_d + lo, sizes_d, &ok));
+        }
+        if (ok) {
+            fails = 0;
+            ++proven;
+            rows_replayed += hi - lo;
+        } else {
+            ++fails;
+            if (fails >= 2) hi = n;   // this input does not settle: walk the rest in one go
+            const int64_t x_before = x;
+            ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, hi - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
+                                        sizes_d, &x, x_before));
+        }
+        lo = hi;
+    }
+    *x_out_host = x;
+    ctx->kernel_ms["cluster_replay_chunks"] = (double)tried;
+    ctx->kernel_ms["cluster_replay_chunks_ok"] = (double)proven;
+    ctx->kernel_ms["cluster_replay_rows"] = (double)rows_replayed;
+    return ASB_OK;
+}

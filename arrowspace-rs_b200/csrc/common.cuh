@@ -260,6 +260,16 @@ int asb_dev_norms2(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, dou
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters,
                     double radius, double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d,
                     int64_t *x_out_host, int64_t init_k = 0);
+// the walk itself (cluster.cu); asb_dev_cluster (cluster_replay.cu) = this, or -- option "cluster_replay" -- a
+// sequential prefix followed by certified parallel replay of row chunks with this kernel as the per-chunk fallback
+int asb_dev_cluster_seq(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters,
+                        double radius, double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d,
+                        int64_t *x_out_host, int64_t init_k = 0);
+// nearest and second nearest of `k_items` rows (centroids) for each of m query rows: ids and Euclidean distances
+// (GEMM form on the FP64 tensor pipe, the Two-NN kernel); idx_d int64[m*2], dist_d f64[m*2] ascending
+int asb_dev_top2_l2(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const double *items_d, int64_t k_items,
+                    const double *qn2_d, const double *xn2_d, const int64_t *minus1_d, int64_t *idx_d, double *dist_d,
+                    int64_t *cnt_d, int *status_d);
 int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_t f,
                       const asb_graph_params &gp, int64_t *indptr_d, int64_t *indices_d, double *data_d,
                       int64_t capacity, int64_t *nnz_host);

@@ -525,7 +525,7 @@ void pick_slabs(int sm_count, long long qtiles, long long ntiles, long long limi
 }  // namespace
 
 static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_offset, int64_t *idx_d,
-                      double *score_d, int64_t *count_d) {
+                      double *score_d, int64_t *count_d, const char *timer_name = nullptr) {
     const int k = A.k;
     if (k < 1 || k > 64) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: k=%d outside 1..64", k);
     if (A.n > 0x7fffff00ll) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search: shard larger than 2^31 items");
@@ -556,7 +556,8 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
         }                                                                                                      \
     } while (0)
     {
-        KernelTimer kt(ctx, mode == MODE_COSINE ? "search_kernel" : (mode == MODE_ENERGY ? "energy_kernel" : "twonn_kernel"));
+        KernelTimer kt(ctx, timer_name ? timer_name
+                                       : (mode == MODE_COSINE ? "search_kernel" : (mode == MODE_ENERGY ? "energy_kernel" : "twonn_kernel")));
         if (mode == MODE_COSINE) {
             if (vec) LAUNCH(MODE_COSINE, true); else LAUNCH(MODE_COSINE, false);
         } else if (mode == MODE_ENERGY) {
@@ -722,6 +723,25 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
         rows_d, (long long)n, (int)f, (const long long *)sample_d, (const long long *)ci.ptr, ncand, (long long)s,
         d1_d, d2_d);
     return asb_check_launch(ctx, "twonn_rescore_kernel");
+}
+
+int asb_dev_top2_l2(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const double *items_d, int64_t k_items,
+                    const double *qn2_d, const double *xn2_d, const int64_t *minus1_d, int64_t *idx_d, double *dist_d,
+                    int64_t *cnt_d, int *status_d) {
+    if (m < 1 || f < 1 || k_items < 2) ASB_FAIL(ctx, ASB_ERR_INVALID, "top2: m=%lld k_items=%lld", (long long)m, (long long)k_items);
+    SearchArgs A{};
+    A.items = items_d;
+    A.norms2 = xn2_d;
+    A.queries = q_d;
+    A.qnorms2 = qn2_d;
+    A.self_idx = (const long long *)minus1_d;   // -1 everywhere: no row is excluded
+    A.n = k_items;
+    A.nq = m;
+    A.f = (int)f;
+    A.k = 2;
+    A.alpha = 0.0;
+    A.status = status_d;
+    return run_search(ctx, MODE_L2, A, 0, idx_d, dist_d, cnt_d, "cluster_top2_kernel");
 }
 
 int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in_idx_d, int64_t parts, int64_t nq,

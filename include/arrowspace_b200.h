@@ -118,7 +118,16 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 input the bound does not cover falls back); 0: the exact FP64 DMMA kernel scores every
  *                                 pair.  Same ids either way; scores agree to the last few bits (both within 1e-12 of
  *                                 the reference, the prefilter path bit-identical to a sequential evaluation).
- * Read-only diagnostics through asb_last_kernel_ms: "search_pf_used", "search_pf_flags", "search_pf_candidates",
+ *   "cluster_replay" (0|1)        0 (default): the clustering walk runs on the sequential kernel.  1 (experimental, not
+ *                                 yet run on hardware): after a sequential prefix ("cluster_replay_prefix" rows,
+ *                                 default 16384) chunks of "cluster_replay_chunk" rows (default 32768) are replayed in
+ *                                 parallel -- nearest / runner-up centroid of the chunk-start snapshot for all rows at
+ *                                 once, one sequential chain per centroid, every row's decision proven from the
+ *                                 centroids' net displacement -- and a chunk with a single unproven row is walked by
+ *                                 the sequential kernel instead.  Same bits either way (csrc/cluster_replay.cu,
+ *                                 tools/replay_proto.py).
+ * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
+ * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
  * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */
 int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
 /* The slab split the search kernels use for nq queries x n items on a device with sm_count SMs (pure host

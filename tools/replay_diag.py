@@ -1,0 +1,56 @@
+"""Sequential clustering kernel vs certified parallel replay (option cluster_replay) on device-resident rows.
+
+    python tools/replay_diag.py [n] [f] [prefix] [chunk]        (defaults: 1_000_000 384 16384 32768)
+
+Rows come from synth.protein_like (the bench data), max_clusters / radius from the bench's own rule.  Prints the wall
+time of both paths (CUDA events around the C-ABI call), how many chunks were proven, and whether centroids,
+assignments and sizes are identical.  A timing / agreement probe; tests/test_cluster_replay.py is the parity test."""
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import numpy as np
+import torch
+
+import arrowspace_b200 as asb
+
+
+def main():
+    a = [int(v) for v in sys.argv[1:]]
+    n, f, prefix, chunk = a + [1_000_000, 384, 16_384, 32_768][len(a):]
+    ctx = asb.Context(0)
+    x = asb.synth.protein_like(n, f, seed=42)
+    _, kmax = asb.heuristics.step1_bounds(n, f, f)
+    radius = asb.heuristics.pilot_radius(x[: min(n, 50_000)], kmax, asb.heuristics.CLUSTERING_SEED)
+    xd = torch.from_numpy(x).cuda()
+    out = {"n": n, "f": f, "max_clusters": int(kmax), "radius": radius, "prefix": prefix, "chunk": chunk}
+    res = {}
+    for name, opt in (("sequential", 0), ("replay", 1)):
+        ctx.set_option("cluster_replay", opt)
+        ctx.set_option("cluster_replay_prefix", prefix)
+        ctx.set_option("cluster_replay_chunk", chunk)
+        for _ in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cent, asg, sizes = ctx.cluster_incremental(xd, kmax, radius)
+            e1.record()
+            torch.cuda.synchronize()
+        res[name] = (np.asarray(cent), asg.cpu().numpy() if hasattr(asg, "cpu") else np.asarray(asg), np.asarray(sizes))
+        out[name] = {"call_ms": e0.elapsed_time(e1), "clusters": int(len(res[name][0])),
+                     "chunks": ctx.kernel_ms("cluster_replay_chunks"), "chunks_ok": ctx.kernel_ms("cluster_replay_chunks_ok"),
+                     "rows_replayed": ctx.kernel_ms("cluster_replay_rows"),
+                     "top2_kernel_ms_last": ctx.kernel_ms("cluster_top2_kernel"),
+                     "chain_kernel_ms_last": ctx.kernel_ms("cluster_chain_kernel")}
+    s, r = res["sequential"], res["replay"]
+    out["centroids_bit_identical"] = bool(s[0].shape == r[0].shape and np.array_equal(
+        np.ascontiguousarray(s[0]).view(np.uint64), np.ascontiguousarray(r[0]).view(np.uint64)))
+    out["assignments_equal"] = bool(np.array_equal(s[1], r[1]))
+    out["sizes_equal"] = bool(np.array_equal(s[2], r[2]))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
