@@ -12,6 +12,7 @@
 //      <= 1.5 radius: count only, :767-781; else dropped) and tracks the centroid's net displacement |c - S0|;
 //   3. certification: row r is proven when  d(x_r, c_b at r)  <  d(x_r, runner-up in S0) - max displacement of any
 //      centroid in the chunk - rounding slack: no other centroid can be nearer at row r's time, so the walk picks b.
+//      (A row farther than sqrt(1.5 radius) from every centroid is dropped whoever is nearest: proven as well.)
 //      If every row of the chunk is proven, then by induction over the rows (row r depends only on rows < r) the
 //      guess IS the walk's assignment and the chain results are the walk's centroids, bit for bit.
 // A chunk with a single unproven row -- or a row that would open a new centroid, or a d^2 within 1e-9 radius of a
@@ -72,9 +73,14 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
     const double guard = 1e-9 * radius;
     double dmax2 = 0.0;
     bool bad = false;
+    const int lines = (f * 8 + 127) / 128;   // 128-byte lines per row
     for (int i = beg; i < end; ++i) {
         const int r = seg_rows[i];
         const double *x = rows + (size_t)r * f;
+        if (i + 2 < end) {   // the chain is latency bound: pull the row after next towards the SM while this one is applied
+            const char *nx = reinterpret_cast<const char *>(rows + (size_t)seg_rows[i + 2] * f);
+            for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+        }
         double acc = 0.0;
         for (int j = lane; j < f; j += 32) {
             const double d = x[j] - cc[j];
@@ -129,7 +135,9 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
 __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__restrict__ dcur, const double *__restrict__ top2_dist,
                                                              const long long *__restrict__ top2_cnt,
                                                              const double *__restrict__ qn2, const unsigned long long *cn2max_bits,
-                                                             const unsigned long long *maxdisp_bits, int f, int m, int *fail) {
+                                                             const unsigned long long *maxdisp_bits,
+                                                             const long long *__restrict__ assign, double radius, int f,
+                                                             int m, int *fail) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const double cn2max = __longlong_as_double((long long)*cn2max_bits);
@@ -138,7 +146,12 @@ __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__res
     const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
     const double s = top2_dist[2 * (size_t)r + 1];
     const double lower = sqrt(fmax(s * s - e2, 0.0)) - maxdisp;
-    if (top2_cnt[r] < 2 || !(dcur[r] < lower)) atomicOr(fail, 2);
+    // A row farther than sqrt(1.5 radius) from EVERY centroid at its own time is dropped whichever centroid is the
+    // nearest (no update, no count, assignment None: clustering.rs:759-815) -- e.g. a blob no centroid was opened for.
+    const double b = top2_dist[2 * (size_t)r];
+    const double lb = fmax(sqrt(fmax(b * b - e2, 0.0)) - maxdisp, 0.0);
+    const bool dropped_anyway = lb * lb > 1.5 * radius * (1.0 + 1e-9) && assign[r] == -1;
+    if (top2_cnt[r] < 2 || !(dcur[r] < lower || dropped_anyway)) atomicOr(fail, 2);
 }
 
 struct ReplayWs {
@@ -212,7 +225,8 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
     }
     ASB_TRY(asb_check_launch(ctx, "replay_chain_kernel"));
     replay_certify_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.dcur.ptr, w.dist.ptr, (const long long *)w.cnt.ptr,
-                                                                    w.qn2.ptr, w.scal.ptr, w.scal.ptr + 1, f, m, w.flags.ptr);
+                                                                    w.qn2.ptr, w.scal.ptr, w.scal.ptr + 1,
+                                                                    (const long long *)assign_d, radius, f, m, w.flags.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_certify_kernel"));
     int hflags[2] = {0, 0};
     ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));

@@ -145,12 +145,132 @@ def single_sweep_chunk(X, C0, cnt0, radius, kmax):
                     borderline += 1
         C[j], cnt[j] = c, k
     margin = second - max_disp - slack - db               # > 0: certified
+    # a row farther than sqrt(1.5 radius) from EVERY centroid at its own time is dropped whichever centroid is the
+    # nearest (no update, no count, assignment None: clustering.rs:759-815) -- e.g. a blob no centroid was opened for
+    best = np.sqrt(part[:, 0])
+    far = np.maximum(best - max_disp - slack, 0.0) ** 2 > 1.5 * radius * (1.0 + 1e-9)
+    margin = np.where(far & (cls == 2), np.inf, margin)
     ok = bool((margin > 0).all()) and not (cls == 3).any() and borderline == 0
     info = {"ok": ok, "uncertified": int((margin <= 0).sum()), "creates": int((cls == 3).sum()),
+            "dropped_whoever_is_nearest": int((far & (cls == 2)).sum()),
             "max_net_displacement": max_disp, "min_margin": float(margin.min()),
             "median_margin": float(np.median(margin)), "active_centroids": int(len(np.unique(A[cls == 0]))),
             "longest_chain": int(np.bincount(A, minlength=K).max())}
     return ok, np.where(cls == 2, -1, A), C, cnt, info
+
+
+def grouped_sweep_chunk(X, C0, cnt0, radius, kmax, delta_p, T=4):
+    """Single sweep with CANDIDATE SETS: robust to centroids that contest the same rows.  delta_p is an a-priori bound
+    on every centroid's net displacement inside the chunk (checked afterwards).  A row's nearest centroid at its own
+    time is one of the snapshot's top-T whose snapshot distance is within 2 delta_p of the best (everything farther
+    cannot overtake).  Centroids that share a row's candidate set are merged into a group (union-find); each group is
+    ONE sequential chain over its rows, evaluating the few candidates exactly; groups are independent.  Fails when a
+    candidate set is not closed inside the top-T, when a centroid moves farther than delta_p, on a near-tie between
+    candidates, on a creation or on a threshold within the guard band."""
+    m, K = len(X), len(C0)
+    T = min(T, K)
+    x2 = np.einsum("ij,ij->i", X, X)
+    c2 = np.einsum("ij,ij->i", C0, C0)
+    D0 = np.maximum(x2[:, None] + c2[None, :] - 2.0 * (X @ C0.T), 0.0)
+    top = np.argsort(D0, axis=1, kind="stable")[:, :T]
+    d0 = np.sqrt(np.take_along_axis(D0, top, axis=1))
+    slack = 1e-6 * (np.sqrt(x2).max() + np.sqrt(c2).max())
+    within = d0 <= d0[:, :1] + 2.0 * delta_p + slack            # candidate mask (column 0 always true)
+    far = np.maximum(d0[:, 0] - delta_p - slack, 0.0) ** 2 > 1.5 * radius * (1.0 + 1e-9)   # dropped whoever is nearest
+    within[far, 1:] = False
+    info = {"delta_p": delta_p, "dropped_whoever_is_nearest": int(far.sum())}
+    if T < K and within[:, T - 1].any():
+        info.update(ok=False, reason="candidate set not closed inside the top-T", rows=int(within[:, T - 1].sum()))
+        return False, None, None, None, info
+    parent = list(range(K))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    multi = np.nonzero(within.sum(1) > 1)[0]
+    for r in multi:
+        a = find(int(top[r, 0]))
+        for i in range(1, T):
+            if within[r, i]:
+                b = find(int(top[r, i]))
+                if a != b:
+                    parent[b] = a
+    label = np.array([find(j) for j in range(K)])
+    row_group = label[top[:, 0]]
+    C, cnt = C0.copy(), cnt0.copy()
+    asg = np.empty(m, dtype=np.int64)
+    max_disp, bad = 0.0, 0
+    for g in np.unique(row_group):                               # groups are independent chains
+        for r in np.nonzero(row_group == g)[0]:
+            cands = top[r][within[r]]
+            dd = C[cands] - X[r]
+            dc2 = np.einsum("ij,ij->i", dd, dd)
+            order = np.argsort(dc2, kind="stable")
+            if len(cands) > 1 and dc2[order[1]] - dc2[order[0]] <= 1e-9 * radius:
+                bad += 1                                         # near tie: the reference's summation order decides
+            j, d2 = int(cands[order[0]]), float(dc2[order[0]])
+            if any(abs(d2 - t) < 1e-9 * radius for t in (0.5 * radius, radius, 1.5 * radius)):
+                bad += 1
+            if K < kmax and d2 > 0.5 * radius:
+                bad += 1
+                asg[r] = -2
+            elif d2 <= radius:
+                cnt[j] += 1.0
+                C[j] += (X[r] - C[j]) / cnt[j]
+                dn = C[j] - C0[j]
+                max_disp = max(max_disp, float(np.sqrt(dn @ dn)))
+                asg[r] = j
+            elif d2 <= 1.5 * radius:
+                cnt[j] += 1.0
+                asg[r] = j
+            else:
+                asg[r] = -1
+    ok = bool(bad == 0 and max_disp <= delta_p)
+    sizes = np.bincount(label, minlength=K)
+    info.update(ok=ok, bad=bad, max_net_displacement=max_disp, multi_candidate_rows=int(len(multi)),
+                groups=int(len(np.unique(label))), largest_group=int(sizes.max()),
+                longest_group_chain=int(np.bincount(row_group, minlength=K).max()))
+    return ok, asg, C, cnt, info
+
+
+def main_grouped(n, f, kmax_arg, chunk, first):
+    o = Oracle()
+    x = asb.synth.protein_like(n, f, seed=42)
+    kmax = kmax_arg if kmax_arg > 0 else asb.heuristics.step1_bounds(n, f, f)[1]
+    radius = asb.heuristics.pilot_radius(x[: min(n, 50_000)], kmax, asb.heuristics.CLUSTERING_SEED)
+    cent, asg, sizes = o.cluster_incremental(x, kmax, radius)
+    C, a0, cnt = o.cluster_incremental(x[:first], kmax, radius)
+    cnt = cnt.astype(np.float64)
+    got, infos, lo = [a0], [], first
+    delta_p = 0.05 * np.sqrt(radius)
+    while lo < n:
+        hi = min(lo + chunk, n)
+        for attempt in range(2):
+            ok, a, C2, cnt2, info = grouped_sweep_chunk(x[lo:hi], C, cnt, radius, kmax, delta_p)
+            info["rows"] = [lo, hi]
+            infos.append(info)
+            if ok or "max_net_displacement" not in info or info.get("bad", 0):
+                break
+            delta_p = 2.0 * info["max_net_displacement"]          # moved farther than predicted: widen once
+        if ok:
+            C, cnt = C2, cnt2
+            got.append(a)
+            delta_p = max(1.5 * info["max_net_displacement"], 1e-6)
+        else:
+            got.append(asg[lo:hi])
+            C, _, cntn = o.cluster_incremental(x[:hi], kmax, radius)
+            cnt = cntn.astype(np.float64)
+        lo = hi
+    got = np.concatenate(got)
+    out = {"mode": "grouped", "n": n, "f": f, "max_clusters": int(kmax), "clusters": int(len(cent)), "radius": radius,
+           "sequential_prefix_rows": first, "chunk": chunk, "attempts": len(infos),
+           "chunks_ok": int(sum(i["ok"] for i in infos)),
+           "assignments_equal": bool(np.array_equal(got, asg)),
+           "centroids_bit_identical": bool(C.shape == cent.shape and np.array_equal(C.view(np.uint64), cent.view(np.uint64))),
+           "counts_equal": bool(np.array_equal(cnt.astype(np.uint64), sizes)), "per_attempt": infos}
+    print(json.dumps(out))
 
 
 def main_single(n, f, chunk, first):
@@ -195,6 +315,9 @@ def main_single(n, f, chunk, first):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "grouped":
+        a = [int(v) for v in sys.argv[2:]]
+        return main_grouped(*(a + [60_000, 384, 200, 8_192, 12_288][len(a):]))
     if len(sys.argv) > 1 and sys.argv[1] == "single":
         a = [int(v) for v in sys.argv[2:]]
         return main_single(*(a + [200_000, 384, 32_768, 16_384][len(a):]))
