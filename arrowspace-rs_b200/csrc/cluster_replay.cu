@@ -18,7 +18,7 @@
 // A chunk with a single unproven row -- or a row that would open a new centroid, or a d^2 within 1e-9 radius of a
 // threshold (the chains sum in a different order than the reference) -- is thrown away and walked by the sequential
 // kernel from the same start state (asb_dev_cluster_seq with init_k: the resume entry the multi-GPU hand-off uses).
-// Two consecutive failures end the attempts.  On the C3 bench data every chunk after a 16k-row prefix is proven
+// Every further failure in a row doubles the stretch walked sequentially before the next attempt.  On the C3 bench data every chunk after a 16k-row prefix is proven
 // (tools/replay_proto.py single 200000 384: min margin 0.15 against a displacement of 0.06 -> 0.006).
 #include <cub/cub.cuh>
 
@@ -270,7 +270,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     while (lo < n) {
         int64_t hi = lo + chunk < n ? lo + chunk : n;
         int ok = 0;
-        if (fails < 2 && x >= 2) {
+        if (x >= 2) {
             if (!ws_ready || w.cap_k < x) {
                 ASB_TRY(replay_ws_init(ctx, w, (int)chunk, (int)(x > max_clusters ? x : max_clusters), (int)f));
                 ws_ready = true;
@@ -284,8 +284,11 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             ++proven;
             rows_replayed += hi - lo;
         } else {
+            // not provable (yet): walk sequentially, and twice as far after every further failure in a row -- data that
+            // never settles costs O(log(n / chunk)) wasted attempts, data that settles late is picked up when it does
             ++fails;
-            if (fails >= 2) hi = n;   // this input does not settle: walk the rest in one go
+            const int64_t span = chunk << (fails - 1 < 12 ? fails - 1 : 12);
+            hi = lo + span < n ? lo + span : n;
             const int64_t x_before = x;
             ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, hi - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
                                         sizes_d, &x, x_before));

@@ -62,7 +62,7 @@ def test_replay_proves_the_settled_chunks_of_the_bench_data(rctx, asb, oracle):
 
 def test_replay_gives_up_on_unsettled_data(rctx, asb, oracle):
     """Uniform noise never settles (every row is about as far from every centroid): chunks fail certification, the
-    sequential kernel walks them, two failures in a row end the attempts -- and the outputs are still the walk's."""
+    sequential kernel walks them -- twice as far after every failure in a row -- and the outputs are still the walk's."""
     rng = np.random.default_rng(5)
     n, f = 50_000, 64
     x = rng.random((n, f))
@@ -72,7 +72,7 @@ def test_replay_gives_up_on_unsettled_data(rctx, asb, oracle):
     rctx.set_option("cluster_replay_chunk", 8_192)
     got = rctx.cluster_incremental(x, kmax, radius)
     _same_walk(got, want)
-    assert rctx.kernel_ms("cluster_replay_chunks") <= 2 + rctx.kernel_ms("cluster_replay_chunks_ok") * 2
+    assert rctx.kernel_ms("cluster_replay_chunks_ok") == 0 and 1 <= rctx.kernel_ms("cluster_replay_chunks") <= 4
 
 
 def test_replay_through_the_builder_and_resume(rctx, asb, oracle):
