@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--queries", dest="nq", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cluster-replay", action="store_true",
+                    help="experimental: certified parallel replay of the clustering walk (option cluster_replay = 1)")
     ap.add_argument("--exact-search", action="store_true",
                     help="search with the exact FP64 DMMA kernel only (option search_prefilter = 0)")
     return ap.parse_args()
@@ -246,6 +248,8 @@ def run_b200(args):
     compute = asb.parallel.GpuCompute(ctx)
     if args.exact_search:
         ctx.set_option("search_prefilter", 0)
+    if args.cluster_replay:
+        ctx.set_option("cluster_replay", 1)
     kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": [],
                   "search_pf_kernel": [], "search_pf_prep": [], "search_pf_finish": []}
     pf_diag = {}
@@ -477,6 +481,8 @@ def run_b200(args):
                    "nnz_laplacian": info_nnz, "data_gen_s": t_gen},
         "search_qps": qps, "build_ms": build_ms_mean, "search_ms": search_ms_mean,
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_acc.items() if v},
+        "cluster_replay": ({"chunks": ctx.kernel_ms("cluster_replay_chunks"), "proven": ctx.kernel_ms("cluster_replay_chunks_ok"),
+                            "rows": ctx.kernel_ms("cluster_replay_rows")} if args.cluster_replay else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
 
