@@ -252,7 +252,9 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
                     int64_t init_k) {
     const int64_t prefix = (int64_t)opt_or(ctx, "cluster_replay_prefix", 16384.0);
     const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 32768.0);
-    const bool replay = opt_or(ctx, "cluster_replay", 0.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk <= (1 << 24) &&
+    int64_t chunk_max = (int64_t)opt_or(ctx, "cluster_replay_chunk_max", 262144.0);
+    if (chunk_max < chunk) chunk_max = chunk;
+    const bool replay = opt_or(ctx, "cluster_replay", 0.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
                         n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
     ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;
@@ -267,12 +269,14 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     int fails = 0, tried = 0, proven = 0;
     int64_t rows_replayed = 0;
     int64_t lo = prefix;
+    int64_t cur = chunk;   // rows per attempt: doubles after every proven chunk (one snapshot holds for longer and
+                           // longer stretches as the centroids settle), back to `chunk` after a failure
     while (lo < n) {
-        int64_t hi = lo + chunk < n ? lo + chunk : n;
+        int64_t hi = lo + cur < n ? lo + cur : n;
         int ok = 0;
         if (x >= 2) {
-            if (!ws_ready || w.cap_k < x) {
-                ASB_TRY(replay_ws_init(ctx, w, (int)chunk, (int)(x > max_clusters ? x : max_clusters), (int)f));
+            if (!ws_ready || w.cap_k < x || w.cap_m < hi - lo) {
+                ASB_TRY(replay_ws_init(ctx, w, (int)cur, (int)(x > max_clusters ? x : max_clusters), (int)f));
                 ws_ready = true;
             }
             ++tried;
@@ -283,12 +287,14 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             fails = 0;
             ++proven;
             rows_replayed += hi - lo;
+            cur = cur * 2 < chunk_max ? cur * 2 : chunk_max;
         } else {
             // not provable (yet): walk sequentially, and twice as far after every further failure in a row -- data that
             // never settles costs O(log(n / chunk)) wasted attempts, data that settles late is picked up when it does
             ++fails;
             const int64_t span = chunk << (fails - 1 < 12 ? fails - 1 : 12);
             hi = lo + span < n ? lo + span : n;
+            cur = chunk;
             const int64_t x_before = x;
             ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, hi - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
                                         sizes_d, &x, x_before));
