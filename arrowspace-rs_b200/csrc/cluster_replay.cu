@@ -1,5 +1,5 @@
 // cluster_replay.cu -- K2, option "cluster_replay" (off by default: written after the round's GPU budget was spent,
-// validated so far only by its CPU prototype tools/replay_proto.py, which reproduces the oracle's walk bit for bit).
+// validated so far only by its CPU prototype tests/replay_proto.py, which reproduces the oracle's walk bit for bit).
 //
 // The walk of run_incremental_clustering_with_sampling (src/clustering.rs:547-928) is sequential because row r sees
 // the centroids all earlier rows left behind.  Once the centroids have settled, almost every row's decision can be
@@ -19,7 +19,7 @@
 // threshold (the chains sum in a different order than the reference) -- is thrown away and walked by the sequential
 // kernel from the same start state (asb_dev_cluster_seq with init_k: the resume entry the multi-GPU hand-off uses).
 // Every further failure in a row doubles the stretch walked sequentially before the next attempt.  On the C3 bench data every chunk after a 16k-row prefix is proven
-// (tools/replay_proto.py single 200000 384: min margin 0.15 against a displacement of 0.06 -> 0.006).
+// (tests/replay_proto.py single 200000 384: min margin 0.15 against a displacement of 0.06 -> 0.006).
 #include <cub/cub.cuh>
 
 #include "common.cuh"

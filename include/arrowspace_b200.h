@@ -126,7 +126,7 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 once, one sequential chain per centroid, every row's decision proven from the
  *                                 centroids' net displacement -- and a chunk with a single unproven row is walked by
  *                                 the sequential kernel instead.  Same bits either way (csrc/cluster_replay.cu,
- *                                 tools/replay_proto.py).
+ *                                 tests/replay_proto.py).
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
  * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
  * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */

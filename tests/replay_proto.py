@@ -18,7 +18,7 @@ The walk is sequential because row r sees the centroids every earlier row left b
 This script replays the saturated part of a walk that way (numpy; updates follow the guess A, decisions are re-derived
 row by row against the guessed trajectories -- exactly what a parallel implementation would see) and reports sweeps per
 chunk, the share of rows that needed exact competitor distances, and whether assignments / centroids / counts match
-the oracle's sequential walk bit for bit.   python tools/replay_proto.py [n] [f] [chunk]
+the oracle's sequential walk bit for bit.   python tests/replay_proto.py [n] [f] [chunk]
 """
 import json
 import sys
@@ -32,7 +32,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 import arrowspace_b200 as asb  # noqa: E402  (synthetic data + the host heuristics only; no GPU code is touched)
-from oracle_binding import Oracle  # noqa: E402  (this is a tool, not product code)
+from oracle_binding import Oracle  # noqa: E402  (test infrastructure: lives under tests/ because it runs the oracle)
 
 
 def replay_chunk(X, C0, cnt0, radius, stats):

@@ -2,7 +2,7 @@
 
 Whatever the replay proves or fails to prove, the outputs must be the walk's: centroids bit-identical, assignments
 and sizes identical (src/clustering.rs:547-928, deterministic branch).  The algorithm is pinned on the CPU by
-``tools/replay_proto.py`` (numpy restatement, bit-identical to the oracle); the CUDA path was written after round 1's
+``tests/replay_proto.py`` (numpy restatement, bit-identical to the oracle); the CUDA path was written after round 1's
 GPU budget was spent, so the option is off by default and these tests are opt-in until they have passed on a B200:
 ``ASB_TEST_CLUSTER_REPLAY=1 pytest -m gpu tests/test_cluster_replay.py``."""
 import os

@@ -1,12 +1,12 @@
 """CPU pin of the certified parallel replay of the clustering walk (csrc/cluster_replay.cu restated in numpy by
-tools/replay_proto.py): whatever is proven must be the oracle's walk bit for bit, and settled data must be provable."""
+tests/replay_proto.py): whatever is proven must be the oracle's walk bit for bit, and settled data must be provable."""
 import sys
 from pathlib import Path
 
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "tools"))
+sys.path.insert(0, str(ROOT / "tests"))
 
 
 def _walk_with_replay(asb, oracle, x, kmax, radius, prefix, chunk):
