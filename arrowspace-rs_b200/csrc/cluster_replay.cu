@@ -18,8 +18,10 @@
 // A chunk with a single unproven row -- or a row that would open a new centroid, or a d^2 within 1e-9 radius of a
 // threshold (the chains sum in a different order than the reference) -- is thrown away and walked by the sequential
 // kernel from the same start state (asb_dev_cluster_seq with init_k: the resume entry the multi-GPU hand-off uses).
-// Every further failure in a row doubles the stretch walked sequentially before the next attempt.  On the C3 bench data every chunk after a 16k-row prefix is proven
-// (tests/replay_proto.py single 200000 384: min margin 0.15 against a displacement of 0.06 -> 0.006).
+// Every further failure in a row doubles the stretch walked sequentially before the next attempt; every proven chunk
+// doubles the next attempt (1024 rows after a 2048-row sequential prefix by default, up to 262144 rows).  On the C3
+// bench data everything after row 2048 is proven that way, and one snapshot taken after 16k rows proves a single
+// 184k-row chunk (tests/replay_proto.py: min margin 0.14 against a net displacement of 0.066).
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -250,8 +252,8 @@ double opt_or(asb_ctx *ctx, const char *key, double dflt) {
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
                     double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host,
                     int64_t init_k) {
-    const int64_t prefix = (int64_t)opt_or(ctx, "cluster_replay_prefix", 16384.0);
-    const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 32768.0);
+    const int64_t prefix = (int64_t)opt_or(ctx, "cluster_replay_prefix", 2048.0);
+    const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 1024.0);
     int64_t chunk_max = (int64_t)opt_or(ctx, "cluster_replay_chunk_max", 262144.0);
     if (chunk_max < chunk) chunk_max = chunk;
     const bool replay = opt_or(ctx, "cluster_replay", 0.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&

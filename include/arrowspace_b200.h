@@ -120,7 +120,7 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 the reference, the prefilter path bit-identical to a sequential evaluation).
  *   "cluster_replay" (0|1)        0 (default): the clustering walk runs on the sequential kernel.  1 (experimental, not
  *                                 yet run on hardware): after a sequential prefix ("cluster_replay_prefix" rows,
- *                                 default 16384) chunks of "cluster_replay_chunk" rows (default 32768, doubling after every proven
+ *                                 default 2048) chunks of "cluster_replay_chunk" rows (default 1024, doubling after every proven
  *                                 chunk up to "cluster_replay_chunk_max", default 262144) are replayed in
  *                                 parallel -- nearest / runner-up centroid of the chunk-start snapshot for all rows at
  *                                 once, one sequential chain per centroid, every row's decision proven from the

@@ -21,7 +21,7 @@ def rctx(ctx):
     try:
         yield ctx
     finally:
-        for key, val in (("cluster_replay", 0), ("cluster_replay_prefix", 16384), ("cluster_replay_chunk", 32768),
+        for key, val in (("cluster_replay", 0), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
                          ("cluster_replay_chunk_max", 262144)):
             ctx.set_option(key, val)
 
@@ -58,7 +58,7 @@ def test_replay_proves_the_settled_chunks_of_the_bench_data(rctx, asb, oracle):
     got = rctx.cluster_incremental(x, kmax, radius)
     _same_walk(got, want)
     tried, ok = rctx.kernel_ms("cluster_replay_chunks"), rctx.kernel_ms("cluster_replay_chunks_ok")
-    assert tried == ok == 3 and rctx.kernel_ms("cluster_replay_rows") == n - 16_384     # 32 k, 64 k, the last 5 k rows
+    assert tried == ok == 7 and rctx.kernel_ms("cluster_replay_rows") == n - 2_048      # 1 k, 2 k, ... 64 k, the rest
 
 
 def test_replay_gives_up_on_unsettled_data(rctx, asb, oracle):

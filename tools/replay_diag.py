@@ -1,6 +1,6 @@
 """Sequential clustering kernel vs certified parallel replay (option cluster_replay) on device-resident rows.
 
-    python tools/replay_diag.py [n] [f] [prefix] [chunk]        (defaults: 1_000_000 384 16384 32768)
+    python tools/replay_diag.py [n] [f] [prefix] [chunk]        (defaults: 1_000_000 384 2048 1024)
 
 Rows come from synth.protein_like (the bench data), max_clusters / radius from the bench's own rule.  Prints the wall
 time of both paths (CUDA events around the C-ABI call), how many chunks were proven, and whether centroids,
@@ -19,7 +19,7 @@ import arrowspace_b200 as asb
 
 def main():
     a = [int(v) for v in sys.argv[1:]]
-    n, f, prefix, chunk = a + [1_000_000, 384, 16_384, 32_768][len(a):]
+    n, f, prefix, chunk = a + [1_000_000, 384, 2_048, 1_024][len(a):]
     ctx = asb.Context(0)
     x = asb.synth.protein_like(n, f, seed=42)
     _, kmax = asb.heuristics.step1_bounds(n, f, f)
