@@ -134,6 +134,123 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
     }
 }
 
+// RN(a / b) from y = RN(1 / b) with two FMA correction steps (Markstein; the same routine the sequential kernel uses,
+// cluster_f32p.cuh): correctly rounded for an integer divisor below 2^52 as long as nothing under- or overflows --
+// operands outside [1e-280, 1e280] (and non-finite ones) take the library division.
+__device__ __forceinline__ double replay_div_by_count(double a, double b, double y) {
+    const double aa = fabs(a);
+    if (!(aa >= 1e-280 && aa <= 1e280)) return a == 0.0 ? a / b : __ddiv_rn(a, b);
+    const double q0 = __dmul_rn(a, y);
+    const double q1 = __fma_rn(__fma_rn(-q0, b, a), y, q0);
+    return __fma_rn(__fma_rn(-q1, b, a), y, q1);
+}
+
+// The same chain with the centroid, its snapshot and the NEXT row held in registers (f <= 32 NPL): the loads of row
+// i + 1 are in flight while row i is applied, so a chain step costs its arithmetic, not a memory round trip.
+template <int NPL>
+__global__ void __launch_bounds__(128) replay_chain_reg_kernel(const double *__restrict__ rows, int f,
+                                                               const int *__restrict__ seg_off,
+                                                               const int *__restrict__ seg_rows, int K, int saturated,
+                                                               double radius, double *__restrict__ cent,
+                                                               const double *__restrict__ cent0, unsigned long long *sizes,
+                                                               long long *__restrict__ assign, double *__restrict__ dcur,
+                                                               unsigned long long *maxdisp_bits, int *fail) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= K) return;
+    const int beg = seg_off[c], end = seg_off[c + 1];
+    if (beg == end) return;
+    double cr[NPL], s0[NPL], xn[NPL];
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int j = lane + 32 * u;
+        cr[u] = s0[u] = j < f ? cent0[(size_t)c * f + j] : 0.0;   // padding lanes hold zeros everywhere: no effect
+    }
+    int r_next = seg_rows[beg];
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int j = lane + 32 * u;
+        xn[u] = j < f ? rows[(size_t)r_next * f + j] : 0.0;
+    }
+    unsigned long long cnt = sizes[c];
+    const double guard = 1e-9 * radius;
+    const int lines = (f * 8 + 127) / 128;
+    double dmax2 = 0.0;
+    bool bad = false;
+    for (int i = beg; i < end; ++i) {
+        const int r = r_next;
+        double x[NPL];
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) x[u] = xn[u];
+        if (i + 1 < end) {
+            r_next = seg_rows[i + 1];
+#pragma unroll
+            for (int u = 0; u < NPL; ++u) {
+                const int j = lane + 32 * u;
+                xn[u] = j < f ? rows[(size_t)r_next * f + j] : 0.0;
+            }
+        }
+        if (i + 4 < end) {
+            const char *nx = reinterpret_cast<const char *>(rows + (size_t)seg_rows[i + 4] * f);
+            for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const double d = x[u] - cr[u];
+            acc = fma(d, d, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double d2 = acc;
+        if (!(d2 == d2) || fabs(d2 - radius) <= guard || fabs(d2 - 1.5 * radius) <= guard ||
+            (!saturated && fabs(d2 - 0.5 * radius) <= guard))
+            bad = true;
+        int cls;
+        if (!saturated && d2 > 0.5 * radius) {
+            cls = 3;
+            bad = true;
+        } else if (d2 <= radius) {
+            cls = 0;
+        } else if (d2 <= 1.5 * radius) {
+            cls = 1;
+        } else {
+            cls = 2;
+        }
+        if (lane == 0) {
+            dcur[r] = sqrt(d2);
+            assign[r] = cls == 2 ? -1ll : (long long)c;
+        }
+        if (cls == 0) {
+            cnt += 1;
+            const double k = (double)cnt;
+            const double y = __drcp_rn(k);
+            double dsp = 0.0;
+#pragma unroll
+            for (int u = 0; u < NPL; ++u) {
+                cr[u] = __dadd_rn(cr[u], replay_div_by_count(__dsub_rn(x[u], cr[u]), k, y));   // clustering.rs:747-751
+                const double e = cr[u] - s0[u];
+                dsp = fma(e, e, dsp);
+            }
+            for (int o = 16; o > 0; o >>= 1) dsp += __shfl_xor_sync(0xffffffffu, dsp, o);
+            dmax2 = fmax(dmax2, dsp);
+        } else if (cls == 1) {
+            cnt += 1;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int j = lane + 32 * u;
+        if (j < f) cent[(size_t)c * f + j] = cr[u];
+    }
+    if (lane == 0) {
+        sizes[c] = cnt;
+        const double dm = sqrt(dmax2) * (1.0 + 1e-12);
+        if (dm == dm) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(dm));
+        else bad = true;
+        if (bad) atomicOr(fail, 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__restrict__ dcur, const double *__restrict__ top2_dist,
                                                              const long long *__restrict__ top2_cnt,
                                                              const double *__restrict__ qn2, const unsigned long long *cn2max_bits,
@@ -154,6 +271,11 @@ __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__res
     const double lb = fmax(sqrt(fmax(b * b - e2, 0.0)) - maxdisp, 0.0);
     const bool dropped_anyway = lb * lb > 1.5 * radius * (1.0 + 1e-9) && assign[r] == -1;
     if (top2_cnt[r] < 2 || !(dcur[r] < lower || dropped_anyway)) atomicOr(fail, 2);
+}
+
+double opt_or(asb_ctx *ctx, const char *key, double dflt) {
+    auto it = ctx->options.find(key);
+    return it == ctx->options.end() ? dflt : it->second;
 }
 
 struct ReplayWs {
@@ -221,9 +343,17 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     {
         KernelTimer kt(ctx, "cluster_chain_kernel");
-        replay_chain_kernel<<<(K + 3) / 4, 128, 0, ctx->stream>>>(rows_d, f, w.seg_off.ptr, w.vals_s.ptr, K, saturated, radius,
-                                                                 w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr,
-                                                                 (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);
+        const bool generic = f > 512 || opt_or(ctx, "cluster_replay_generic_chain", 0.0) != 0.0;
+#define ASB_CHAIN_ARGS                                                                                                  \
+    rows_d, f, w.seg_off.ptr, w.vals_s.ptr, K, saturated, radius, w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr,          \
+        (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr
+        const unsigned grid = (unsigned)((K + 3) / 4);
+        if (generic) replay_chain_kernel<<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+        else if (f <= 128) replay_chain_reg_kernel<4><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+        else if (f <= 256) replay_chain_reg_kernel<8><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+        else if (f <= 384) replay_chain_reg_kernel<12><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+        else replay_chain_reg_kernel<16><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+#undef ASB_CHAIN_ARGS
     }
     ASB_TRY(asb_check_launch(ctx, "replay_chain_kernel"));
     replay_certify_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.dcur.ptr, w.dist.ptr, (const long long *)w.cnt.ptr,
@@ -240,11 +370,6 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
                                   cudaMemcpyDeviceToDevice, ctx->stream));
     *ok = 1;
     return ASB_OK;
-}
-
-double opt_or(asb_ctx *ctx, const char *key, double dflt) {
-    auto it = ctx->options.find(key);
-    return it == ctx->options.end() ? dflt : it->second;
 }
 
 }  // namespace

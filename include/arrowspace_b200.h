@@ -125,7 +125,9 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 parallel -- nearest / runner-up centroid of the chunk-start snapshot for all rows at
  *                                 once, one sequential chain per centroid, every row's decision proven from the
  *                                 centroids' net displacement -- and a chunk with a single unproven row is walked by
- *                                 the sequential kernel instead.  Same bits either way (csrc/cluster_replay.cu,
+ *                                 the sequential kernel instead ("cluster_replay_generic_chain" = 1 selects the chain
+ *                                 kernel that keeps the centroid in memory instead of registers).  Same bits either
+ *                                 way (csrc/cluster_replay.cu,
  *                                 tests/replay_proto.py).
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
  * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",

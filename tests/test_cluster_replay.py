@@ -22,7 +22,7 @@ def rctx(ctx):
         yield ctx
     finally:
         for key, val in (("cluster_replay", 0), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
-                         ("cluster_replay_chunk_max", 262144)):
+                         ("cluster_replay_chunk_max", 262144), ("cluster_replay_generic_chain", 0)):
             ctx.set_option(key, val)
 
 
@@ -36,7 +36,8 @@ def _same_walk(got, want):
 
 
 @pytest.mark.parametrize("n,f,prefix,chunk", [(60_000, 384, 16_384, 32_768), (40_000, 128, 4_096, 8_192),
-                                              (30_000, 25, 2_048, 4_096), (20_001, 384, 1_024, 1_000)])
+                                              (30_000, 25, 2_048, 4_096), (20_001, 384, 1_024, 1_000),
+                                              (12_000, 200, 2_048, 1_024), (9_000, 520, 2_048, 1_024)])
 def test_replay_reproduces_the_walk(rctx, asb, oracle, n, f, prefix, chunk):
     x = asb.synth.protein_like(n, f, seed=42)
     _, kmax = asb.heuristics.step1_bounds(n, f, f)
@@ -47,6 +48,8 @@ def test_replay_reproduces_the_walk(rctx, asb, oracle, n, f, prefix, chunk):
     got = rctx.cluster_incremental(x, kmax, radius)
     _same_walk(got, want)
     assert rctx.kernel_ms("cluster_replay_chunks") >= 1
+    rctx.set_option("cluster_replay_generic_chain", 1)      # the memory-resident chain kernel (any f) gives the same bits
+    _same_walk(rctx.cluster_incremental(x, kmax, radius), want)
 
 
 def test_replay_proves_the_settled_chunks_of_the_bench_data(rctx, asb, oracle):
