@@ -28,12 +28,13 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) replay_keys_kernel(const int64_t *__restrict__ top2_idx, int m, int *__restrict__ keys,
-                                                          int *__restrict__ vals) {
+__global__ void __launch_bounds__(256) replay_keys_kernel(const int64_t *__restrict__ top2_idx, int m, int K,
+                                                          int *__restrict__ keys, int *__restrict__ vals) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < m) {
-        keys[r] = (int)top2_idx[2 * (size_t)r];
-        vals[r] = r;
+        const int64_t b = top2_idx[2 * (size_t)r];
+        keys[r] = (b >= 0 && b < K) ? (int)b : K;   // a row without a nearest centroid (NaN row) goes to bucket K: no chain
+        vals[r] = r;                                 // touches it, the certification fails on its missing candidates
     }
 }
 
@@ -328,10 +329,10 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
     ASB_TRY(asb_check_launch(ctx, "replay_max_kernel"));
     ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, centroids_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
                             w.cnt.ptr, w.flags.ptr + 1));
-    replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.idx.ptr, m, w.keys.ptr, w.vals.ptr);
+    replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.idx.ptr, m, K, w.keys.ptr, w.vals.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_keys_kernel"));
     int bits = 1;
-    while ((1ll << bits) < K) ++bits;
+    while ((1ll << bits) < (long long)K + 1) ++bits;
     ASB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(w.cub_tmp.ptr, w.cub_bytes, w.keys.ptr, w.keys_s.ptr, w.vals.ptr,
                                                   w.vals_s.ptr, m, 0, bits, ctx->stream));   // stable: rows stay ascending
     ctx->launches++;
