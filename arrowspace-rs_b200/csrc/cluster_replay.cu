@@ -279,6 +279,18 @@ double opt_or(asb_ctx *ctx, const char *key, double dflt) {
     return it == ctx->options.end() ? dflt : it->second;
 }
 
+// elapsed time of the most recent launch bracketed by KernelTimer(name); the stream must be idle
+double ktimer_ms(asb_ctx *ctx, const char *name) {
+    auto it = ctx->ktimers.find(name);
+    if (it == ctx->ktimers.end() || !it->second.a || !it->second.b) return 0.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(it->second.b) != cudaSuccess || cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0;
+    }
+    return ms;
+}
+
 struct ReplayWs {
     DevTmp<double> qn2, xn2, dist, dcur, cent_tmp;
     DevTmp<int64_t> idx, cnt, minus1;
@@ -391,7 +403,9 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
         return asb_dev_cluster_seq(ctx, rows_d, n, f, max_clusters, radius, centroids_d, assign_d, sizes_d, x_out_host, init_k);
 
     int64_t x = init_k;
+    double ms_seq = 0.0, ms_top2 = 0.0, ms_chain = 0.0;   // device time per part, summed over the chunks
     ASB_TRY(asb_dev_cluster_seq(ctx, rows_d, prefix, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, init_k));
+    ms_seq += ktimer_ms(ctx, "cluster_kernel");
     ReplayWs w;
     bool ws_ready = false;
     int fails = 0, tried = 0, proven = 0;
@@ -410,6 +424,8 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             ++tried;
             ASB_TRY(replay_chunk(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
                                  centroids_d, assign_d + lo, sizes_d, &ok));
+            ms_top2 += ktimer_ms(ctx, "cluster_top2_kernel");
+            ms_chain += ktimer_ms(ctx, "cluster_chain_kernel");
         }
         if (ok) {
             fails = 0;
@@ -426,6 +442,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             const int64_t x_before = x;
             ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, hi - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
                                         sizes_d, &x, x_before));
+            ms_seq += ktimer_ms(ctx, "cluster_kernel");
         }
         lo = hi;
     }
@@ -433,5 +450,8 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ctx->kernel_ms["cluster_replay_chunks"] = (double)tried;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = (double)proven;
     ctx->kernel_ms["cluster_replay_rows"] = (double)rows_replayed;
+    ctx->kernel_ms["cluster_replay_seq_ms"] = ms_seq;
+    ctx->kernel_ms["cluster_replay_top2_ms"] = ms_top2;
+    ctx->kernel_ms["cluster_replay_chain_ms"] = ms_chain;
     return ASB_OK;
 }

@@ -482,7 +482,10 @@ def run_b200(args):
         "search_qps": qps, "build_ms": build_ms_mean, "search_ms": search_ms_mean,
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_acc.items() if v},
         "cluster_replay": ({"chunks": ctx.kernel_ms("cluster_replay_chunks"), "proven": ctx.kernel_ms("cluster_replay_chunks_ok"),
-                            "rows": ctx.kernel_ms("cluster_replay_rows")} if args.cluster_replay else None),
+                            "rows": ctx.kernel_ms("cluster_replay_rows"), "sequential_ms": ctx.kernel_ms("cluster_replay_seq_ms"),
+                            "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
+                            "note": "kernels.cluster_kernel.ms is the LAST sequential launch only when the replay is on"}
+                           if args.cluster_replay else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
 

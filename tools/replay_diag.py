@@ -42,8 +42,8 @@ def main():
         out[name] = {"call_ms": e0.elapsed_time(e1), "clusters": int(len(res[name][0])),
                      "chunks": ctx.kernel_ms("cluster_replay_chunks"), "chunks_ok": ctx.kernel_ms("cluster_replay_chunks_ok"),
                      "rows_replayed": ctx.kernel_ms("cluster_replay_rows"),
-                     "top2_kernel_ms_last": ctx.kernel_ms("cluster_top2_kernel"),
-                     "chain_kernel_ms_last": ctx.kernel_ms("cluster_chain_kernel")}
+                     "sequential_ms": ctx.kernel_ms("cluster_replay_seq_ms") if opt else ctx.kernel_ms("cluster_kernel"),
+                     "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms")}
     s, r = res["sequential"], res["replay"]
     out["centroids_bit_identical"] = bool(s[0].shape == r[0].shape and np.array_equal(
         np.ascontiguousarray(s[0]).view(np.uint64), np.ascontiguousarray(r[0]).view(np.uint64)))
