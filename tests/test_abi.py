@@ -113,3 +113,24 @@ def test_search_slab_plan_covers_and_fills_waves(asb):
     assert (ns, tps) == (13, 601)
     with pytest.raises(asb.ArrowSpaceError):
         asb.host.search_slab_plan(0, 1, 1, 1)
+
+
+def test_rust_sys_crate_covers_header():
+    """integration/arrowspace-b200-sys (the thin extern "C" FFI crate north_star asks for; not compilable here: no
+    Rust toolchain in the image) declares every symbol, status code and struct field of the header."""
+    lib_rs = (ROOT / "integration" / "arrowspace-b200-sys" / "src" / "lib.rs").read_text()
+    hdr = (ROOT / "include" / "arrowspace_b200.h").read_text()
+    declared = _declared_symbols()
+    rust_fns = sorted(set(re.findall(r"pub fn (asb_[a-z0-9_]+)\s*\(", lib_rs)))
+    assert rust_fns == declared
+    for name, val in re.findall(r"#define (ASB_[A-Z_]+) (\d+)", hdr):
+        assert re.search(rf"pub const {name}: (c_int|i32) = {val};", lib_rs), name
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_structs = {name: b for b, name in re.findall(r"typedef struct \{([^}]*)\} (\w+);", body)}
+    for struct in ("asb_graph_params", "asb_build_params", "asb_index_info"):
+        c_body = c_structs[struct]
+        c_fields = [f.strip() for decl in c_body.split(";") if decl.strip()
+                    for f in re.sub(r"^\s*[a-z_0-9]+\s+", "", decl.strip()).split(",")]
+        r_body = re.search(r"pub struct " + struct + r" \{(.*?)\n\}", lib_rs, flags=re.S).group(1)
+        r_fields = re.findall(r"pub ([a-z_0-9]+):", r_body)
+        assert r_fields == c_fields, (struct, r_fields, c_fields)
