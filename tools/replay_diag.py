@@ -2,7 +2,7 @@
 
     python tools/replay_diag.py [n] [f] [prefix] [chunk]        (defaults: 1_000_000 384 2048 1024)
 
-Rows come from synth.protein_like (the bench data), max_clusters / radius from the bench's own rule.  Prints the wall
+Rows have the bench data's shape (drawn on the GPU), max_clusters / radius come from the bench's own rule.  Prints the wall
 time of both paths (CUDA events around the C-ABI call), how many chunks were proven, and whether centroids,
 assignments and sizes are identical.  A timing / agreement probe; tests/test_cluster_replay.py is the parity test."""
 import json
@@ -21,10 +21,16 @@ def main():
     a = [int(v) for v in sys.argv[1:]]
     n, f, prefix, chunk = a + [1_000_000, 384, 2_048, 1_024][len(a):]
     ctx = asb.Context(0)
-    x = asb.synth.protein_like(n, f, seed=42)
+    # the bench data's shape (64 non-negative blobs + 0.05 noise) drawn on the GPU: synth.protein_like takes ~26 s of
+    # host time at 1M x 384, which a gpurun call pays for in box minutes
+    g = torch.Generator(device="cuda").manual_seed(42)
+    centres = torch.rand((64, f), dtype=torch.float64, device="cuda", generator=g)
+    lab = torch.randint(0, 64, (n,), device="cuda", generator=g)
+    xd = centres[lab]
+    xd += 0.05 * torch.randn((n, f), dtype=torch.float64, device="cuda", generator=g)
+    xd.clamp_(min=0.0)
     _, kmax = asb.heuristics.step1_bounds(n, f, f)
-    radius = asb.heuristics.pilot_radius(x[: min(n, 50_000)], kmax, asb.heuristics.CLUSTERING_SEED)
-    xd = torch.from_numpy(x).cuda()
+    radius = asb.heuristics.pilot_radius(xd[: min(n, 50_000)].cpu().numpy(), kmax, asb.heuristics.CLUSTERING_SEED)
     out = {"n": n, "f": f, "max_clusters": int(kmax), "radius": radius, "prefix": prefix, "chunk": chunk}
     res = {}
     for name, opt in (("sequential", 0), ("replay", 1)):
