@@ -37,6 +37,10 @@ class Context {
     void check(int rc) const {
         if (rc != ASB_OK) throw Panic(rc, asb_last_error(ctx_));
     }
+    /// switches listed in arrowspace_b200.h ("search_prefilter", "cluster_replay", ...); results never depend on them
+    void set_option(const char *key, double value) { check(asb_ctx_set_option(ctx_, key, value)); }
+    /// device time / diagnostics of the most recent call ("search_pf_kernel", "search_pf_used", "cluster_kernel", ...)
+    double kernel_ms(const char *which) const { return asb_last_kernel_ms(ctx_, which); }
 
   private:
     asb_ctx *ctx_ = nullptr;
