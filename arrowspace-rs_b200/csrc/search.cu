@@ -717,6 +717,29 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
     A.k = ncand;
     A.alpha = 0.0;
     A.status = status.ptr;
+    ctx->kernel_ms["twonn_pf_used"] = 0.0;
+    {
+        auto it = ctx->options.find("twonn_prefilter");   // opt-in: certified TF32 ranking + direct-form distances
+        if (it != ctx->options.end() && it->second != 0.0 && n - 1 >= 2) {
+            DevTmp<double> dist;
+            DevTmp<int64_t> pi, pc;
+            ASB_TRY(dist.init(ctx, (size_t)s * 2));
+            ASB_TRY(pi.init(ctx, (size_t)s * 2));
+            ASB_TRY(pc.init(ctx, (size_t)s));
+            bool done = false;
+            ASB_TRY(run_search_pf_l2(ctx, rows_d, n, (int)f, q.ptr, s, xn2.ptr, qn2.ptr, (const long long *)sample_d, 2, pi.ptr,
+                                     dist.ptr, pc.ptr, &done));
+            if (done) {
+                ASB_CUDA(ctx, cudaMemcpy2DAsync(d1_d, sizeof(double), dist.ptr, 2 * sizeof(double), sizeof(double), s,
+                                                cudaMemcpyDeviceToDevice, ctx->stream));
+                ASB_CUDA(ctx, cudaMemcpy2DAsync(d2_d, sizeof(double), dist.ptr + 1, 2 * sizeof(double), sizeof(double), s,
+                                                cudaMemcpyDeviceToDevice, ctx->stream));
+                ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the temporaries die with this scope
+                ctx->kernel_ms["twonn_pf_used"] = 1.0;
+                return ASB_OK;
+            }
+        }
+    }
     ASB_TRY(run_search(ctx, MODE_L2, A, 0, ci.ptr, cs.ptr, cc.ptr));
     const int wpb = 4;
     twonn_rescore_kernel<<<(unsigned)((s + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
@@ -729,6 +752,14 @@ int asb_dev_top2_l2(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const
                     const double *qn2_d, const double *xn2_d, const int64_t *minus1_d, int64_t *idx_d, double *dist_d,
                     int64_t *cnt_d, int *status_d) {
     if (m < 1 || f < 1 || k_items < 2) ASB_FAIL(ctx, ASB_ERR_INVALID, "top2: m=%lld k_items=%lld", (long long)m, (long long)k_items);
+    {
+        auto it = ctx->options.find("cluster_replay_tf32");   // opt-in: certified TF32 ranking + direct-form distances
+        if (it != ctx->options.end() && it->second != 0.0 && k_items >= 3) {
+            bool done = false;
+            ASB_TRY(run_search_pf_l2(ctx, items_d, k_items, (int)f, q_d, m, xn2_d, qn2_d, nullptr, 2, idx_d, dist_d, cnt_d, &done));
+            if (done) return ASB_OK;
+        }
+    }
     SearchArgs A{};
     A.items = items_d;
     A.norms2 = xn2_d;

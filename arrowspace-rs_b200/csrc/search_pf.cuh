@@ -44,6 +44,8 @@ constexpr int PF_STAGE_FLOATS = (TQ + TN) * PF_PITCH;
 constexpr int PF_SP = 136;                 // cos~ tile pitch (floats): conflict-free float2 stores and row scans
 constexpr int PF_FLAG_FALLBACK = 1, PF_FLAG_OVERFLOW = 2;
 constexpr int PF_MAXSEL = 1024;            // rescored candidates per query
+constexpr int PF_COSINE = 0;               // score = alpha cos + (1 - alpha) lambda proximity (search_lambda_aware)
+constexpr int PF_L2 = 1;                   // score = -|q - x|^2 (nearest neighbours: Two-NN scan, replay top-2); opt-in
 
 struct PfArgs {
     const float *xf, *qf;   // n x fp, nq x fp unit rows
@@ -62,6 +64,12 @@ struct PfArgs {
     int *flags;
     unsigned long long *diag;  // [0] candidates emitted, [1] candidates rescored
     int *status;
+    // PF_L2 only: s~ = -(|q|^2 + |x|^2 - 2 |q| |x| cos~), |s~ - s| <= 2 |q| |x| E_cos + rounding
+    const double *qn2, *xn2;                 // squared norms
+    const double *qnrm, *xnrm;               // norms
+    const long long *self_idx;               // per query: item index to leave out (clustering.rs:123), or null
+    const unsigned long long *xn2max_bits;   // device scalar: bits of max |x|^2
+    double band_rel, band_abs;               // band(q) = band_rel |q| max|x| + band_abs (|q|^2 + max|x|^2)
 };
 
 __device__ __forceinline__ unsigned long long pf_enc(double d) {
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(256) pf_init_kernel(unsigned long long *gthr, 
 // One warp per row: out = fl32(row / sqrt(norm2)), zero padded to fp.
 __global__ void __launch_bounds__(256) pf_unit_rows_kernel(const double *__restrict__ rows, const double *__restrict__ norms2,
                                                            long long n, int f, int fp, float *__restrict__ out,
-                                                           int *__restrict__ flags) {
+                                                           int *__restrict__ flags, double *__restrict__ norm_out = nullptr) {
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n) return;
@@ -102,11 +110,13 @@ __global__ void __launch_bounds__(256) pf_unit_rows_kernel(const double *__restr
     const bool ok = (n2 == 0.0) || (n2 >= 1e-290 && n2 <= 1e290);   // false for NaN / inf as well
     if (!ok && lane == 0) atomicOr(flags, PF_FLAG_FALLBACK);
     const double inv = (ok && n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+    if (norm_out && lane == 0) norm_out[r] = ok ? sqrt(n2) : 0.0;
     const double *src = rows + r * (long long)f;
     float *dst = out + r * (long long)fp;
     for (int j = lane; j < fp; j += 32) dst[j] = (ok && j < f) ? (float)(src[j] * inv) : 0.0f;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *stages = reinterpret_cast<float *>(smem_raw);                    // PF_STAGES * PF_STAGE_FLOATS
@@ -114,6 +124,9 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
     double *list_s = reinterpret_cast<double *>(S + TQ * PF_SP);            // TQ * k, sorted descending
     double *sm_lq = list_s + (size_t)TQ * A.k;                              // TQ
     int *list_len = reinterpret_cast<int *>(sm_lq + TQ);                    // TQ
+    double *sm_nq = reinterpret_cast<double *>(list_len + TQ);              // TQ   (PF_L2: |q|; sm_lq holds |q|^2)
+    double *sm_band = sm_nq + TQ;                                           // TQ   (PF_L2)
+    long long *sm_self = reinterpret_cast<long long *>(sm_band + TQ);       // TQ   (PF_L2)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp >> 2, wn = warp & 3;
@@ -128,9 +141,18 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
     for (int q = tid; q < TQ; q += kThreads) {
         const long long gq = q0 + q;
         const bool ok = gq < A.nq;
-        const double lq = ok ? A.lambda_q[gq] : 1.0;
-        if (ok && blockIdx.y == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);  // core.rs:773-776
-        sm_lq[q] = lq;
+        if constexpr (MODE == PF_COSINE) {
+            const double lq = ok ? A.lambda_q[gq] : 1.0;
+            if (ok && blockIdx.y == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);  // core.rs:773-776
+            sm_lq[q] = lq;
+        } else {
+            const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
+            const double q2 = ok ? A.qn2[gq] : 0.0, qn = ok ? A.qnrm[gq] : 0.0;
+            sm_lq[q] = q2;
+            sm_nq[q] = qn;
+            sm_band[q] = A.band_rel * qn * sqrt(xmax2) + A.band_abs * (q2 + xmax2);
+            sm_self[q] = (ok && A.self_idx) ? A.self_idx[gq] : -1ll;
+        }
         list_len[q] = 0;
     }
     const int nchunks = fp / PF_KC;
@@ -239,13 +261,18 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
         // ---- tile finished: cos~ -> S, then one warp per query scans its 128 scores
         const long long i0 = tile * TN;
         ++tile;
-        double lx[4];
+        double lx[4], lxn[MODE == PF_L2 ? 4 : 1];
         bool vx[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const long long gi = i0 + 32 * e + lane;
             vx[e] = gi < A.n;
-            lx[e] = vx[e] ? A.lambdas[gi] : 0.0;
+            if constexpr (MODE == PF_COSINE) {
+                lx[e] = vx[e] ? A.lambdas[gi] : 0.0;
+            } else {
+                lx[e] = vx[e] ? A.xn2[gi] : 0.0;
+                lxn[e] = vx[e] ? A.xnrm[gi] : 0.0;
+            }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -273,9 +300,15 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const double cosv = (double)S[q * PF_SP + 32 * e + lane];
-                const double lam = 1.0 - fmin(fabs(lq - lx[e]), 1.0);      // core.rs:136-137
-                const double s = A.alpha * cosv + (1.0 - A.alpha) * lam;   // core.rs:165 (approximate cos)
-                const bool valid = vx[e];
+                double s;
+                bool valid = vx[e];
+                if constexpr (MODE == PF_COSINE) {
+                    const double lam = 1.0 - fmin(fabs(lq - lx[e]), 1.0);      // core.rs:136-137
+                    s = A.alpha * cosv + (1.0 - A.alpha) * lam;                // core.rs:165 (approximate cos)
+                } else {
+                    s = -(lq + lx[e] - 2.0 * sm_nq[q] * lxn[e] * cosv);        // -|q - x|^2 from the approximate cos
+                    valid = valid && (i0 + 32 * e + lane) != sm_self[q];
+                }
                 if (valid && s != s) saw_nan = true;
                 // keep the slab's k best approximate scores (only values above every known bound matter)
                 unsigned mask = __ballot_sync(0xffffffffu, valid && s > fmax(kth, gb));
@@ -298,7 +331,8 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
                 }
                 // emit what the bound cannot exclude
                 const double bound = fmax(kth, gb);
-                const unsigned em = __ballot_sync(0xffffffffu, valid && s >= bound - A.band);
+                const double band = MODE == PF_COSINE ? A.band : sm_band[q];
+                const unsigned em = __ballot_sync(0xffffffffu, valid && s >= bound - band);
                 if (em) {
                     int base = 0;
                     if (lane == 0) base = atomicAdd(&A.cand_cnt[gq], __popc(em));
@@ -324,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
 // One block per query: drop the candidates below the final bound, score the rest in the reference's arithmetic
 // (src/core.rs:214-236, :135-165 -- sequential sums, products and sums rounded separately), select the best k by
 // (score desc, index asc) = the reference's stable descending sort (:785-786).
+template <int MODE>
 __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *__restrict__ items,
                                                         const double *__restrict__ queries, int f, long long index_offset,
                                                         double band_f, long long *__restrict__ idx_out,
@@ -346,6 +381,11 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     // Every item of the approximate top-k passed the emission test (its s~ >= A_k >= any bound), so the k-th largest
     // s~ of the list IS A_k: a bisection over the order-preserving key of the stored floats finds it by counting.
     const float *cs = A.cand_s + (size_t)q * A.cap;
+    if constexpr (MODE == PF_L2) {   // per-query band; the stored floats round |s~| <= 2 (|q|^2 + max|x|^2)
+        const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
+        const double q2 = A.qn2[q];
+        band_f = A.band_rel * A.qnrm[q] * sqrt(xmax2) + A.band_abs * (q2 + xmax2) + 2.5e-7 * (q2 + xmax2);
+    }
     double thr = pf_dec(A.gthr[q]) - band_f;
     if (cnt >= k) {
         unsigned key = 0;
@@ -382,6 +422,20 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
         atomicAdd(&A.diag[1], (unsigned long long)m);
     }
     const double *qr = queries + q * (long long)f;
+    if constexpr (MODE == PF_L2) {
+        // reference arithmetic of the distance scan (src/clustering.rs:125-130): df = a - b, acc += df * df in feature
+        // order, products and sums rounded separately; ranked by -acc, reported as sqrt(acc)
+        for (int c = tid; c < m; c += 128) {
+            const double *x = items + (long long)sel_idx[c] * f;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < f; ++j) {
+                const double df = __dsub_rn(qr[j], x[j]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            sel_s[c] = (acc == acc) ? -acc : -INFINITY;
+        }
+    } else {
     const double lq = A.lambda_q[q];
     for (int c = tid; c < m; c += 128) {
         const int li = sel_idx[c];
@@ -400,6 +454,7 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
         const double s = __dadd_rn(__dmul_rn(A.alpha, cosv), __dmul_rn(1.0 - A.alpha, lam));  // :165
         if (s != s) atomicOr(A.status, STATUS_NAN);
         sel_s[c] = s;
+    }
     }
     __syncthreads();
     double last_s = INFINITY;
@@ -444,7 +499,7 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
         __syncthreads();
         if (bi < 0) break;
         if (tid == 0) {
-            score_out[q * k + r] = bs;
+            score_out[q * k + r] = MODE == PF_L2 ? sqrt(fmax(-bs, 0.0)) : bs;
             idx_out[q * k + r] = (long long)bi + index_offset;
         }
         last_s = bs;
@@ -453,16 +508,23 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     }
     if (tid == 0) {
         for (int r = taken; r < k; ++r) {
-            score_out[q * k + r] = -INFINITY;
+            score_out[q * k + r] = MODE == PF_L2 ? INFINITY : -INFINITY;
             idx_out[q * k + r] = -1;
         }
         if (count_out) count_out[q] = taken;
     }
 }
 
-size_t pf_smem_bytes(int k) {
+__global__ void __launch_bounds__(256) pf_max_kernel(const double *__restrict__ v, long long n, unsigned long long *__restrict__ out_bits) {
+    double mx = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) mx = fmax(mx, v[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx == mx) atomicMax(out_bits, (unsigned long long)__double_as_longlong(mx));   // >= 0: bits order
+}
+
+size_t pf_smem_bytes(int k, int mode = PF_COSINE) {
     return (size_t)PF_STAGES * PF_STAGE_FLOATS * 4 + (size_t)TQ * PF_SP * 4 + (size_t)TQ * k * 8 + (size_t)TQ * 8 +
-           (size_t)TQ * 4 + 16;
+           (size_t)TQ * 4 + 16 + (mode == PF_L2 ? (size_t)TQ * 24 : 0);
 }
 
 }  // namespace
@@ -545,15 +607,15 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     A.flags = flags.ptr;
     A.diag = diag.ptr;
     A.status = SA.status;
-    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         KernelTimer kt(ctx, "search_pf_kernel");
-        search_pf_kernel<<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
+        search_pf_kernel<PF_COSINE><<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
     }
     ASB_TRY(asb_check_launch(ctx, "search_pf_kernel"));
     {
         KernelTimer kt(ctx, "search_pf_finish");
-        pf_finish_kernel<<<(unsigned)nq, 128, 0, ctx->stream>>>(A, SA.items, SA.queries, f, index_offset, band_f,
+        pf_finish_kernel<PF_COSINE><<<(unsigned)nq, 128, 0, ctx->stream>>>(A, SA.items, SA.queries, f, index_offset, band_f,
                                                                 (long long *)idx_d, score_d, (long long *)count_d);
     }
     ASB_TRY(asb_check_launch(ctx, "pf_finish_kernel"));
@@ -570,6 +632,108 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     ctx->kernel_ms["search_pf_rescored"] = (double)hdiag[1];
     if (hflags != 0) return ASB_OK;  // the exact kernel decides (and reports NaN scores the way the reference does)
     ctx->kernel_ms["search_pf_used"] = 1.0;
+    *done = true;
+    return ASB_OK;
+}
+
+// The same scheme for nearest neighbours in Euclidean distance (PF_L2; options "twonn_prefilter" and
+// "cluster_replay_tf32", both off by default -- written after the round's GPU budget was spent): the k nearest items of
+// every query, ids and distances, the distances computed in the reference's direct form (sequential, separately
+// rounded: src/clustering.rs:125-130) for the candidates the certified score cannot exclude.  self_idx (or null) names
+// one item per query to leave out.  *done = false: the caller uses the exact FP64 kernel.
+static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, int f, const double *queries_d, long long nq,
+                            const double *xn2_d, const double *qn2_d, const long long *self_idx_d, int k,
+                            int64_t *idx_d, double *dist_d, int64_t *count_d, bool *done) {
+    *done = false;
+    if (k < 1 || k > 32 || n < (long long)k + 1 || n > 0x7fffff00ll || nq < 1) return ASB_OK;
+    const int fp = (f + 31) & ~31;
+    const long long qtiles = (nq + TQ - 1) / TQ, ntiles = (n + TN - 1) / TN;
+    int nslabs = 1;
+    long long tps = ntiles;
+    pick_slabs(ctx->sm_count, qtiles, ntiles, 64, &nslabs, &tps);
+    const double slab_items = (double)tps * TN;
+    double conc = (double)ctx->sm_count / (double)qtiles + 2.0;
+    if (conc > nslabs) conc = nslabs;
+    const double est = k * (log(fmax((double)n / k, 2.0)) + 2.0) + conc * k * (log(fmax(slab_items / k, 2.0)) + 2.0);
+    int cap = 64;
+    while (cap < 4.0 * est && cap < 16384) cap *= 2;
+    while (cap / 2 >= n && cap > 64) cap /= 2;            // never more candidates than items
+    if ((double)nq * cap * 8.0 > 2e9) return ASB_OK;
+    const size_t smem = pf_smem_bytes(k, PF_L2);
+    if (smem > 227 * 1024) return ASB_OK;
+    const double chain = 3.0 * fp / 8.0;
+    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+
+    DevTmp<float> xf, qf, cand_s;
+    DevTmp<double> xnrm, qnrm;
+    DevTmp<int> cand_cnt, cand_idx, flags, status;
+    DevTmp<unsigned long long> gthr, diag, xmax;
+    if (xf.init(ctx, (size_t)n * fp) != ASB_OK || qf.init(ctx, (size_t)nq * fp) != ASB_OK ||
+        cand_s.init(ctx, (size_t)nq * cap) != ASB_OK || cand_idx.init(ctx, (size_t)nq * cap) != ASB_OK) {
+        cudaGetLastError();
+        return ASB_OK;
+    }
+    ASB_TRY(xnrm.init(ctx, (size_t)n));
+    ASB_TRY(qnrm.init(ctx, (size_t)nq));
+    ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 1));
+    ASB_TRY(status.init(ctx, 1));
+    ASB_TRY(gthr.init(ctx, (size_t)nq));
+    ASB_TRY(diag.init(ctx, 2));
+    ASB_TRY(xmax.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(diag.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(xmax.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    pf_init_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(gthr.ptr, cand_cnt.ptr, nq);
+    ASB_TRY(asb_check_launch(ctx, "pf_init_kernel"));
+    pf_max_kernel<<<64, 256, 0, ctx->stream>>>(xn2_d, n, xmax.ptr);
+    ASB_TRY(asb_check_launch(ctx, "pf_max_kernel"));
+    pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, flags.ptr, xnrm.ptr);
+    pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, flags.ptr, qnrm.ptr);
+    ASB_TRY(asb_check_launch(ctx, "pf_unit_rows_kernel"));
+    ctx->launches++;
+
+    PfArgs A{};
+    A.xf = xf.ptr;
+    A.qf = qf.ptr;
+    A.fp = fp;
+    A.n = n;
+    A.nq = nq;
+    A.k = k;
+    A.nslabs = nslabs;
+    A.tiles_per_slab = tps;
+    A.gthr = gthr.ptr;
+    A.cand_cnt = cand_cnt.ptr;
+    A.cand_idx = cand_idx.ptr;
+    A.cand_s = cand_s.ptr;
+    A.cap = cap;
+    A.flags = flags.ptr;
+    A.diag = diag.ptr;
+    A.status = status.ptr;
+    A.qn2 = qn2_d;
+    A.xn2 = xn2_d;
+    A.qnrm = qnrm.ptr;
+    A.xnrm = xnrm.ptr;
+    A.self_idx = self_idx_d;
+    A.xn2max_bits = xmax.ptr;
+    // |s~ - s| <= E(q) = 2 |q| max|x| E_cos + 1e-13 (|q|^2 + max|x|^2)  (norm rounding, the reference's own sum);  band = 2 E
+    A.band_rel = 4.0 * e_cos * (1.0 + 1e-6);
+    A.band_abs = 2e-13;
+    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelTimer kt(ctx, "l2_pf_kernel");
+        search_pf_kernel<PF_L2><<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
+    }
+    ASB_TRY(asb_check_launch(ctx, "search_pf_kernel<L2>"));
+    pf_finish_kernel<PF_L2><<<(unsigned)nq, 128, 0, ctx->stream>>>(A, items_d, queries_d, f, 0, 0.0, (long long *)idx_d, dist_d,
+                                                                  (long long *)count_d);
+    ASB_TRY(asb_check_launch(ctx, "pf_finish_kernel<L2>"));
+    int hflags = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hflags, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->kernel_ms["l2_pf_flags"] = (double)hflags;
+    if (hflags != 0) return ASB_OK;
     *done = true;
     return ASB_OK;
 }

@@ -129,6 +129,11 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 kernel that keeps the centroid in memory instead of registers).  Same bits either
  *                                 way (csrc/cluster_replay.cu,
  *                                 tests/replay_proto.py).
+ *   "twonn_prefilter", "cluster_replay_tf32" (0|1)  experimental, not yet run on hardware: the Two-NN scan / the
+ *                                 replay's nearest-and-runner-up pass ranked by the certified 3xTF32 score of the
+ *                                 search prefilter (score -|q - x|^2) with the surviving distances evaluated in the
+ *                                 reference's direct form (bit-identical to a sequential evaluation) instead of the
+ *                                 FP64 tensor kernel.
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
  * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
  * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */

@@ -22,7 +22,8 @@ def rctx(ctx):
         yield ctx
     finally:
         for key, val in (("cluster_replay", 0), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
-                         ("cluster_replay_chunk_max", 262144), ("cluster_replay_generic_chain", 0)):
+                         ("cluster_replay_chunk_max", 262144), ("cluster_replay_generic_chain", 0),
+                         ("cluster_replay_tf32", 0), ("twonn_prefilter", 0)):
             ctx.set_option(key, val)
 
 
@@ -103,3 +104,32 @@ def test_replay_through_the_builder_and_resume(rctx, asb, oracle):
         k, part = rctx.cluster_incremental_resume(np.ascontiguousarray(x[a:b]), maxk, radius, cent, sizes, k)
         parts.append(part)
     _same_walk((cent[:k], np.concatenate(parts), sizes[:k]), want)
+
+
+def test_replay_with_the_tf32_ranking(rctx, asb, oracle):
+    """cluster_replay_tf32: nearest / runner-up of the snapshot from the certified TF32 ranking with direct-form
+    distances (search_pf.cuh, PF_L2) instead of the FP64 tensor kernel -- same bits."""
+    n, f = 60_000, 384
+    x = asb.synth.protein_like(n, f, seed=42)
+    kmax, radius = 384, asb.heuristics.pilot_radius(x[:50_000], 384, asb.heuristics.CLUSTERING_SEED)
+    want = oracle.cluster_incremental(x, kmax, radius)
+    rctx.set_option("cluster_replay_tf32", 1)
+    _same_walk(rctx.cluster_incremental(x, kmax, radius), want)
+    assert rctx.kernel_ms("cluster_replay_chunks_ok") >= 1 and rctx.kernel_ms("l2_pf_flags") == 0
+
+
+@pytest.mark.parametrize("n,f", [(20_000, 128), (5_001, 384), (3_000, 25)])
+def test_twonn_with_the_tf32_ranking(rctx, asb, oracle, n, f):
+    """twonn_prefilter: the Two-NN scan (src/clustering.rs:118-145) ranked by the certified TF32 score, the two nearest
+    distances evaluated in the reference's direct form -- bit-identical to the oracle (the FP64 kernel path is held to
+    1e-9)."""
+    x = asb.synth.protein_like(n, f, seed=42)
+    x[7] = x[3]                                              # an exact duplicate: d1 = 0 for both
+    sample = asb.heuristics.sample_indices(n, 500, 129)
+    sample[:2] = (3, 7)
+    wd1, wd2 = oracle.twonn_distances(x, sample)
+    rctx.set_option("twonn_prefilter", 1)
+    d1, d2 = rctx.twonn_distances(x, sample)
+    assert rctx.kernel_ms("twonn_pf_used") == 1.0
+    assert np.array_equal(np.asarray(d1), wd1) and np.array_equal(np.asarray(d2), wd2)
+    assert d1[0] == 0.0 and d1[1] == 0.0
