@@ -1,6 +1,6 @@
 """Sequential clustering kernel vs certified parallel replay (option cluster_replay) on device-resident rows.
 
-    python tools/replay_diag.py [n] [f] [prefix] [chunk]        (defaults: 1_000_000 384 2048 1024)
+    python tools/replay_diag.py [n] [f] [prefix] [chunk] [tf32]  (defaults: 1_000_000 384 2048 1024 0)
 
 Rows have the bench data's shape (drawn on the GPU), max_clusters / radius come from the bench's own rule.  Prints the wall
 time of both paths (CUDA events around the C-ABI call), how many chunks were proven, and whether centroids,
@@ -19,7 +19,7 @@ import arrowspace_b200 as asb
 
 def main():
     a = [int(v) for v in sys.argv[1:]]
-    n, f, prefix, chunk = a + [1_000_000, 384, 2_048, 1_024][len(a):]
+    n, f, prefix, chunk, tf32 = a + [1_000_000, 384, 2_048, 1_024, 0][len(a):]
     ctx = asb.Context(0)
     # the bench data's shape (64 non-negative blobs + 0.05 noise) drawn on the GPU: synth.protein_like takes ~26 s of
     # host time at 1M x 384, which a gpurun call pays for in box minutes
@@ -31,10 +31,11 @@ def main():
     xd.clamp_(min=0.0)
     _, kmax = asb.heuristics.step1_bounds(n, f, f)
     radius = asb.heuristics.pilot_radius(xd[: min(n, 50_000)].cpu().numpy(), kmax, asb.heuristics.CLUSTERING_SEED)
-    out = {"n": n, "f": f, "max_clusters": int(kmax), "radius": radius, "prefix": prefix, "chunk": chunk}
+    out = {"n": n, "f": f, "max_clusters": int(kmax), "radius": radius, "prefix": prefix, "chunk": chunk, "tf32": tf32}
     res = {}
     for name, opt in (("sequential", 0), ("replay", 1)):
         ctx.set_option("cluster_replay", opt)
+        ctx.set_option("cluster_replay_tf32", tf32 if opt else 0)   # nearest / runner-up pass on the certified TF32 ranking
         ctx.set_option("cluster_replay_prefix", prefix)
         ctx.set_option("cluster_replay_chunk", chunk)
         for _ in range(2):
