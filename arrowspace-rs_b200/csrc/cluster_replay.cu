@@ -1,5 +1,5 @@
-// cluster_replay.cu -- K2, option "cluster_replay" (off by default: written after the round's GPU budget was spent,
-// validated so far only by its CPU prototype tests/replay_proto.py, which reproduces the oracle's walk bit for bit).
+// cluster_replay.cu -- K2, option "cluster_replay" (default 1; validated on B200 in round 2: bit-identical to the oracle's
+// walk on every test shape and at 1M x 384, profiles/r02_replay_first_run.json; CPU prototype tests/replay_proto.py).
 //
 // The walk of run_incremental_clustering_with_sampling (src/clustering.rs:547-928) is sequential because row r sees
 // the centroids all earlier rows left behind.  Once the centroids have settled, almost every row's decision can be
@@ -394,7 +394,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 1024.0);
     int64_t chunk_max = (int64_t)opt_or(ctx, "cluster_replay_chunk_max", 262144.0);
     if (chunk_max < chunk) chunk_max = chunk;
-    const bool replay = opt_or(ctx, "cluster_replay", 0.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
+    const bool replay = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
                         n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
     ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;

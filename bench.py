@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--queries", dest="nq", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cluster-replay", action="store_true",
-                    help="experimental: certified parallel replay of the clustering walk (option cluster_replay = 1)")
+    ap.add_argument("--no-cluster-replay", action="store_true",
+                    help="walk every row on the sequential clustering kernel (option cluster_replay = 0; the default is "
+                         "the certified parallel replay, same bits)")
     ap.add_argument("--exact-search", action="store_true",
                     help="search with the exact FP64 DMMA kernel only (option search_prefilter = 0)")
     return ap.parse_args()
@@ -248,8 +249,8 @@ def run_b200(args):
     compute = asb.parallel.GpuCompute(ctx)
     if args.exact_search:
         ctx.set_option("search_prefilter", 0)
-    if args.cluster_replay:
-        ctx.set_option("cluster_replay", 1)
+    if args.no_cluster_replay:
+        ctx.set_option("cluster_replay", 0)
     kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": [],
                   "search_pf_kernel": [], "search_pf_prep": [], "search_pf_finish": []}
     pf_diag = {}
@@ -485,7 +486,7 @@ def run_b200(args):
                             "rows": ctx.kernel_ms("cluster_replay_rows"), "sequential_ms": ctx.kernel_ms("cluster_replay_seq_ms"),
                             "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
                             "note": "kernels.cluster_kernel.ms is the LAST sequential launch only when the replay is on"}
-                           if args.cluster_replay else None),
+                           if not args.no_cluster_replay else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
 

@@ -118,8 +118,8 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 input the bound does not cover falls back); 0: the exact FP64 DMMA kernel scores every
  *                                 pair.  Same ids either way; scores agree to the last few bits (both within 1e-12 of
  *                                 the reference, the prefilter path bit-identical to a sequential evaluation).
- *   "cluster_replay" (0|1)        0 (default): the clustering walk runs on the sequential kernel.  1 (experimental, not
- *                                 yet run on hardware): after a sequential prefix ("cluster_replay_prefix" rows,
+ *   "cluster_replay" (1|0)        0: the whole clustering walk runs on the sequential kernel.  1 (default): after a
+ *                                 sequential prefix ("cluster_replay_prefix" rows,
  *                                 default 2048) chunks of "cluster_replay_chunk" rows (default 1024, doubling after every proven
  *                                 chunk up to "cluster_replay_chunk_max", default 262144) are replayed in
  *                                 parallel -- nearest / runner-up centroid of the chunk-start snapshot for all rows at

@@ -2,17 +2,12 @@
 
 Whatever the replay proves or fails to prove, the outputs must be the walk's: centroids bit-identical, assignments
 and sizes identical (src/clustering.rs:547-928, deterministic branch).  The algorithm is pinned on the CPU by
-``tests/replay_proto.py`` (numpy restatement, bit-identical to the oracle); the CUDA path was written after round 1's
-GPU budget was spent, so the option is off by default and these tests are opt-in until they have passed on a B200:
-``ASB_TEST_CLUSTER_REPLAY=1 pytest -m gpu tests/test_cluster_replay.py``."""
-import os
-
+``tests/replay_proto.py`` (numpy restatement, bit-identical to the oracle).  The option is on by default since round 2
+(first B200 run: profiles/r02_replay_first_run.json); the fixture still sets it explicitly and restores the defaults."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ASB_TEST_CLUSTER_REPLAY") != "1",
-                                 reason="cluster_replay is opt-in until validated on a B200 (ASB_TEST_CLUSTER_REPLAY=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture()
@@ -21,7 +16,7 @@ def rctx(ctx):
     try:
         yield ctx
     finally:
-        for key, val in (("cluster_replay", 0), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
+        for key, val in (("cluster_replay", 1), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
                          ("cluster_replay_chunk_max", 262144), ("cluster_replay_generic_chain", 0),
                          ("cluster_replay_tf32", 0), ("twonn_prefilter", 0)):
             ctx.set_option(key, val)

@@ -381,38 +381,55 @@ def _assert_cluster_equal(got, want):
 
 @pytest.mark.parametrize("n,f,maxk,rscale", [(5_000, 64, 40, 1.0), (20_000, 128, 100, 1.0), (3_000, 384, 316, 0.6),
                                              (2_000, 33, 7, 1.0), (4_000, 130, 1001, 0.2), (500, 24, 3, 3.0)])
-def test_cluster_parity(ctx, asb, oracle, n, f, maxk, rscale):
+@pytest.mark.parametrize("replay", [1, 0])
+def test_cluster_parity(ctx, asb, oracle, n, f, maxk, rscale, replay):
+    """replay = 1: the default path (sequential prefix + certified parallel replay, csrc/cluster_replay.cu);
+    replay = 0: the sequential kernel walks every row."""
     x = asb.synth.protein_like(n, f, seed=21)
     radius = rscale * 1.5 * f * 0.0025 * 2
     want = oracle.cluster_incremental(x, maxk, radius)
-    got = ctx.cluster_incremental(x, maxk, radius)
+    ctx.set_option("cluster_replay", replay)
+    try:
+        got = ctx.cluster_incremental(x, maxk, radius)
+    finally:
+        ctx.set_option("cluster_replay", 1)
     _assert_cluster_equal(got, want)
     assert (want[1] >= 0).sum() > 0
 
 
+@pytest.fixture()
+def seqctx(ctx):
+    """The sequential clustering kernels on their own (the tests below select and inspect kernel variants)."""
+    ctx.set_option("cluster_replay", 0)
+    try:
+        yield ctx
+    finally:
+        ctx.set_option("cluster_replay", 1)
+
+
 @pytest.mark.parametrize("n,f,maxk,rscale", [(60_000, 64, 100, 1.0), (30_000, 128, 316, 0.8), (8_000, 770, 64, 1.0),
                                              (5_000, 33, 40, 0.7), (12_000, 384, 449, 1.0), (6_000, 768, 1001, 1.0)])
-def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rscale):
+def test_cluster_parity_long_runs_all_variants(seqctx, asb, oracle, n, f, maxk, rscale):
     """Long walks exercise the blocked kernel's interval certification (counts grow, displacements
     shrink, blocks get longer); the row-wise kernel must give the same bits."""
     x = asb.synth.protein_like(n, f, seed=77)
     radius = rscale * 1.5 * f * 0.0025 * 2
     want = oracle.cluster_incremental(x, maxk, radius)
-    got = ctx.cluster_incremental(x, maxk, radius)
+    got = seqctx.cluster_incremental(x, maxk, radius)
     _assert_cluster_equal(got, want)
-    blocks = ctx.kernel_ms("cluster_blocks")
+    blocks = seqctx.kernel_ms("cluster_blocks")
     assert 0 < blocks <= n
     # -2: pipelined FP32-prefilter kernel (default), -1: FP32-prefilter kernel, 0/1: FP64 blocked kernel
     # (16 / 8 rows per barrier), 2: row-wise kernel.
     # A variant that does not fit shared memory for this shape falls through to the next one.
-    seen = {ctx.kernel_ms("cluster_variant")}
+    seen = {seqctx.kernel_ms("cluster_variant")}
     for first in (-1, 0, 1, 2):
-        ctx.set_option("cluster_first_variant", first)
+        seqctx.set_option("cluster_first_variant", first)
         try:
-            got = ctx.cluster_incremental(x, maxk, radius)
-            used = ctx.kernel_ms("cluster_variant")
+            got = seqctx.cluster_incremental(x, maxk, radius)
+            used = seqctx.kernel_ms("cluster_variant")
         finally:
-            ctx.set_option("cluster_first_variant", -9)
+            seqctx.set_option("cluster_first_variant", -9)
         assert used >= first
         seen.add(used)
         _assert_cluster_equal(got, want)
@@ -420,20 +437,20 @@ def test_cluster_parity_long_runs_all_variants(ctx, asb, oracle, n, f, maxk, rsc
 
 
 @pytest.mark.parametrize("n,f,maxk,ring", [(9_000, 384, 700, 6), (9_000, 384, 896, 4), (5_000, 128, 1500, 8)])
-def test_cluster_pipelined_with_short_row_ring(ctx, asb, oracle, n, f, maxk, ring):
+def test_cluster_pipelined_with_short_row_ring(seqctx, asb, oracle, n, f, maxk, ring):
     """Large centroid counts (the 4- and 8-GPU runs use K = 634 / 896) leave less shared memory for the row ring of
     the pipelined kernel: 6 or 4 groups instead of 8 (less prefetch, same bits)."""
     x = asb.synth.protein_like(n, f, seed=13, n_blobs=256)
     radius = 0.6 * 1.5 * f * 0.0025 * 2
     want = oracle.cluster_incremental(x, maxk, radius)
-    got = ctx.cluster_incremental(x, maxk, radius)
-    assert ctx.kernel_ms("cluster_variant") == -2.0 and ctx.kernel_ms("cluster_ring_groups") == ring
+    got = seqctx.cluster_incremental(x, maxk, radius)
+    assert seqctx.kernel_ms("cluster_variant") == -2.0 and seqctx.kernel_ms("cluster_ring_groups") == ring
     _assert_cluster_equal(got, want)
     assert want[0].shape[0] > 300          # enough centroids to fill several tiles per CTA
 
 
 @pytest.mark.parametrize("n,f,maxk", [(6_000, 384, 100), (4_000, 132, 64), (3_000, 33, 20)])
-def test_cluster_tensor_tile_error_model(ctx, asb, oracle, n, f, maxk):
+def test_cluster_tensor_tile_error_model(seqctx, asb, oracle, n, f, maxk):
     """The certified decisions of the pipelined kernel rest on an error bound for the 3xTF32 tensor-core
     distances (exact products, truncating accumulation -- an assumption about the hardware).
     `cluster_check_tile` recomputes every distance of the walk in FP64 from the same FP32 operands and
@@ -441,14 +458,14 @@ def test_cluster_tensor_tile_error_model(ctx, asb, oracle, n, f, maxk):
     x = asb.synth.protein_like(n, f, seed=5)
     radius = 1.5 * f * 0.0025 * 2
     want = oracle.cluster_incremental(x, maxk, radius)
-    ctx.set_option("cluster_check_tile", 1)
+    seqctx.set_option("cluster_check_tile", 1)
     try:
-        got = ctx.cluster_incremental(x, maxk, radius)
-        assert ctx.kernel_ms("cluster_variant") == -2.0
-        worst = ctx.kernel_ms("cluster_phase47") * 1e-12
+        got = seqctx.cluster_incremental(x, maxk, radius)
+        assert seqctx.kernel_ms("cluster_variant") == -2.0
+        worst = seqctx.kernel_ms("cluster_phase47") * 1e-12
     finally:
-        ctx.set_option("cluster_check_tile", 0)
-        ctx.set_option("cluster_phase_times", 0)
+        seqctx.set_option("cluster_check_tile", 0)
+        seqctx.set_option("cluster_phase_times", 0)
     _assert_cluster_equal(got, want)
     assert 0.0 < worst < 0.25, worst
 
@@ -468,7 +485,7 @@ def test_cluster_resume_equals_single_walk(ctx, asb, oracle):
     _assert_cluster_equal((cent[:k], np.concatenate(asg), sizes[:k]), want)
 
 
-def test_cluster_exact_path_and_ties(ctx, asb, oracle):
+def test_cluster_exact_path_and_ties(seqctx, asb, oracle):
     """Integer-valued data makes many distances tie exactly -> the certified fast path must hand
     those rows to the reference-arithmetic path; forcing that path for ALL rows gives the same
     result."""
@@ -476,17 +493,17 @@ def test_cluster_exact_path_and_ties(ctx, asb, oracle):
     x = np.ascontiguousarray(rng.randint(0, 3, size=(3000, 16)).astype(np.float64))
     for radius in (2.0, 4.0, 7.0):
         want = oracle.cluster_incremental(x, 24, radius)
-        got = ctx.cluster_incremental(x, 24, radius)
+        got = seqctx.cluster_incremental(x, 24, radius)
         _assert_cluster_equal(got, want)
-    assert ctx.kernel_ms("cluster_exact_rows") > 0
+    assert seqctx.kernel_ms("cluster_exact_rows") > 0
     y = asb.synth.protein_like(3_000, 64, seed=22)
     want = oracle.cluster_incremental(y, 30, 0.5)
-    ctx.set_option("cluster_force_exact", 1)
+    seqctx.set_option("cluster_force_exact", 1)
     try:
-        got = ctx.cluster_incremental(y, 30, 0.5)
-        assert ctx.kernel_ms("cluster_exact_rows") == 3_000 - 1
+        got = seqctx.cluster_incremental(y, 30, 0.5)
+        assert seqctx.kernel_ms("cluster_exact_rows") == 3_000 - 1
     finally:
-        ctx.set_option("cluster_force_exact", 0)
+        seqctx.set_option("cluster_force_exact", 0)
     _assert_cluster_equal(got, want)
 
 
