@@ -135,121 +135,306 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
     }
 }
 
-// RN(a / b) from y = RN(1 / b) with two FMA correction steps (Markstein; the same routine the sequential kernel uses,
-// cluster_f32p.cuh): correctly rounded for an integer divisor below 2^52 as long as nothing under- or overflows --
-// operands outside [1e-280, 1e280] (and non-finite ones) take the library division.
-__device__ __forceinline__ double replay_div_by_count(double a, double b, double y) {
-    const double aa = fabs(a);
-    if (!(aa >= 1e-280 && aa <= 1e280)) return a == 0.0 ? a / b : __ddiv_rn(a, b);
-    const double q0 = __dmul_rn(a, y);
-    const double q1 = __fma_rn(__fma_rn(-q0, b, a), y, q0);
-    return __fma_rn(__fma_rn(-q1, b, a), y, q1);
+// ---- the chain kernel proper -----------------------------------------------------------------------------------
+// A chain is ONE dependent sequence: the longest chain of a chunk is the chunk's critical path (17.8k steps per 1M rows
+// on the bench data), so the cost of a step is all that counts, and a lone warp pays ~4 cycles per instruction.  The
+// first register-resident version spent 500 warp-instructions per step (ncu: profiles/r02_chain_v2_*), most of them on
+// the distance |x - c|^2 and the displacement |c - S0|^2 with their cross-lane reductions; the second one (features
+// split over four warps, no distance in the common step) 150, but stalled on its own global loads (index -> address
+// -> row, and scoreboard slots shared between the load generations in flight: profiles/r02_chain_v3_*).  This version
+//   * splits the FEATURES of a chain over 4 consumer warps (the update c += (x - c) / k is element-wise): each lane owns
+//     ceil(f / 128) elements, centroid and snapshot in registers;
+//   * streams the rows through a shared-memory ring filled by a fifth, producer warp with 1-D bulk async copies
+//     (cp.async.bulk = the TMA engine, SASS UBLKCP) that complete on per-slot mbarriers: a slot = kRG rows + their
+//     metadata, kRingSlots slots in flight, "full" / "empty" barriers both ways -- a consumer step reads shared memory
+//     only, its address arithmetic is immediate offsets;
+//   * does NOT compute the distance in the common step.  The nearest-centroid pass already delivered the distance d0
+//     of the row to the SNAPSHOT of its centroid (certified to +-e: dlo <= true <= dhi), and the chain knows a bound B
+//     on how far its centroid has moved since, so  |x - c_now|  lies in  [dlo - B, dhi + B]: when (dhi + B)^2 is safely
+//     below the radius the row is an update, when (dlo - B)^2 is safely above 1.5 radius it is dropped -- no reduction,
+//     no communication between the warps (all four evaluate the same scalars, bit for bit).  Anything else -- and any
+//     row whose bound dhi + B would not certify against the runner-up's distance under the displacement the previous
+//     chunk saw (`disp_hint`) -- takes the exact step: |x - c|^2 reduced across lanes and warps (shared memory, one
+//     named barrier), classified with the guard band;
+//   * keeps B rigorous and cheap: every update moves the centroid by |x - c| / k <= (dhi + B) / k, which is added to B;
+//     every `interval` steps (1 while the count is small, k / 256 up to 16 later: the bound may grow by about 0.5 %
+//     of the row distance between two exact values) B is reset to the exact |c - S0| (one reduction + one barrier);
+//   * divides branch-free: reciprocal + two FMA corrections for every element (Markstein; div_by_count of the
+//     sequential kernel, correctly rounded for an integer divisor), an exponent-field test on the integer pipe sends the
+//     step to the careful variant (library division for the affected elements) when an element is zero, denormal-small,
+//     huge or not finite; the reciprocal of the next count is computed while the current update is in flight.
+// The certification kernel receives an UPPER BOUND of the row's distance to its centroid at the row's own time
+// (dhi + B, or the exact value from the exact step).
+constexpr int kChainWarps = 4;    // consumer warps; warp kChainWarps is the producer
+constexpr int kRingSlots = 4;
+
+struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
+    double dlo, dhi;              // certified bounds of the row's distance to the snapshot of its nearest centroid
+    double slo;                   // certified lower bound of its distance to the runner-up's snapshot
+    int row, pad;
+};
+
+struct ChainShared {
+    double part[2][kChainWarps];
+    int stop[2];
+    unsigned long long full[kRingSlots], empty[kRingSlots];
+};
+
+__device__ __forceinline__ unsigned rp_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rp_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void rp_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rp_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rp_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rp_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RP_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RP_DONE;\n\t"
+        "bra RP_WAIT_LOOP;\n\t"
+        "RP_DONE:\n\t}" ::"r"(rp_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void rp_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     rp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(rp_smem_u32(bar))
+                 : "memory");
 }
 
-// The same chain with the centroid, its snapshot and the NEXT row held in registers (f <= 32 NPL): the loads of row
-// i + 1 are in flight while row i is applied, so a chain step costs its arithmetic, not a memory round trip.
-template <int NPL>
-__global__ void __launch_bounds__(128) replay_chain_reg_kernel(const double *__restrict__ rows, int f,
-                                                               const int *__restrict__ seg_off,
-                                                               const int *__restrict__ seg_rows, int K, int saturated,
-                                                               double radius, double *__restrict__ cent,
-                                                               const double *__restrict__ cent0, unsigned long long *sizes,
-                                                               long long *__restrict__ assign, double *__restrict__ dcur,
-                                                               unsigned long long *maxdisp_bits, int *fail) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c >= K) return;
+// shared memory: ring[kRingSlots][RG][fpad] doubles, then meta[kRingSlots][RG]; fpad = 128 NPW
+template <int NPW, int RG>
+__global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kernel(
+    const double *__restrict__ rows, int f, const int *__restrict__ seg_off, const SegMeta *__restrict__ seg_meta, int K,
+    int saturated, double radius, double disp_hint, double *__restrict__ cent, const double *__restrict__ cent0,
+    unsigned long long *sizes, long long *__restrict__ assign, double *__restrict__ dub, unsigned long long *maxdisp_bits,
+    int *fail) {
+    extern __shared__ __align__(128) unsigned char rp_smem[];
+    __shared__ ChainShared sh;
+    constexpr int FP = 128 * NPW;
+    double *ring = reinterpret_cast<double *>(rp_smem);
+    SegMeta *metas = reinterpret_cast<SegMeta *>(rp_smem + (size_t)kRingSlots * RG * FP * sizeof(double));
+    const int c = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int beg = seg_off[c], end = seg_off[c + 1];
     if (beg == end) return;
-    double cr[NPL], s0[NPL], xn[NPL];
-#pragma unroll
-    for (int u = 0; u < NPL; ++u) {
-        const int j = lane + 32 * u;
-        cr[u] = s0[u] = j < f ? cent0[(size_t)c * f + j] : 0.0;   // padding lanes hold zeros everywhere: no effect
+    const int ngroups = (end - beg + RG - 1) / RG;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRingSlots; ++s) {
+            rp_mbar_init(&sh.full[s], 1);
+            rp_mbar_init(&sh.empty[s], kChainWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    int r_next = seg_rows[beg];
-#pragma unroll
-    for (int u = 0; u < NPL; ++u) {
-        const int j = lane + 32 * u;
-        xn[u] = j < f ? rows[(size_t)r_next * f + j] : 0.0;
-    }
-    unsigned long long cnt = sizes[c];
-    const double guard = 1e-9 * radius;
-    const int lines = (f * 8 + 127) / 128;
-    double dmax2 = 0.0;
-    bool bad = false;
-    for (int i = beg; i < end; ++i) {
-        const int r = r_next;
-        double x[NPL];
-#pragma unroll
-        for (int u = 0; u < NPL; ++u) x[u] = xn[u];
-        if (i + 1 < end) {
-            r_next = seg_rows[i + 1];
-#pragma unroll
-            for (int u = 0; u < NPL; ++u) {
-                const int j = lane + 32 * u;
-                xn[u] = j < f ? rows[(size_t)r_next * f + j] : 0.0;
+    __syncthreads();
+
+    if (warp == kChainWarps) {
+        // ---- producer: one slot = RG rows + their metadata
+        for (int g = 0; g < ngroups; ++g) {
+            const int slot = g % kRingSlots;
+            if (g >= kRingSlots) rp_mbar_wait(&sh.empty[slot], ((g / kRingSlots) - 1) & 1);
+            const int pos = beg + g * RG;
+            const int nr = end - pos < RG ? end - pos : RG;
+            if (lane == 0) rp_mbar_expect_tx(&sh.full[slot], (unsigned)(nr * (f * 8 + (int)sizeof(SegMeta))));
+            __syncwarp();
+            if (lane < nr) {
+                const int r = seg_meta[pos + lane].row;
+                rp_bulk_g2s(ring + ((size_t)slot * RG + lane) * FP, rows + (size_t)r * f, (unsigned)(f * 8), &sh.full[slot]);
             }
+            if (lane == 0) rp_bulk_g2s(metas + slot * RG, seg_meta + pos, (unsigned)(nr * sizeof(SegMeta)), &sh.full[slot]);
         }
-        if (i + 4 < end) {
-            const char *nx = reinterpret_cast<const char *>(rows + (size_t)seg_rows[i + 4] * f);
-            for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
-        }
-        double acc = 0.0;
+        return;
+    }
+
+    // ---- consumers.  Element u of this lane = feature 128 u + 32 warp + lane
+    const int j0 = 32 * warp + lane;
+    const bool last_valid = 128 * (NPW - 1) + j0 < f;   // NPW = ceil(f / 128): only the last element can be padding
+    double cr[NPW], s0[NPW];
 #pragma unroll
-        for (int u = 0; u < NPL; ++u) {
-            const double d = x[u] - cr[u];
-            acc = fma(d, d, acc);
-        }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const double d2 = acc;
-        if (!(d2 == d2) || fabs(d2 - radius) <= guard || fabs(d2 - 1.5 * radius) <= guard ||
-            (!saturated && fabs(d2 - 0.5 * radius) <= guard))
-            bad = true;
-        int cls;
-        if (!saturated && d2 > 0.5 * radius) {
-            cls = 3;
-            bad = true;
-        } else if (d2 <= radius) {
+    for (int u = 0; u < NPW; ++u) {
+        const bool v = u < NPW - 1 || last_valid;
+        cr[u] = s0[u] = v ? cent0[(size_t)c * f + 128 * u + j0] : 0.0;   // padding holds zeros everywhere: no effect
+    }
+    double kd = (double)sizes[c];
+    double y_next = __drcp_rn(kd + 1.0);
+    double B = 0.0, dmax = 0.0;
+    int since = 0, par = 0;
+    bool bad = false, go = true;
+    const double guard = 1e-9 * radius;
+    const double thr_upd = (saturated ? radius : 0.5 * radius) * (1.0 - 1e-9);   // (dhi + B)^2 below: an update for sure
+    const double thr_drop = 1.5 * radius * (1.0 + 1e-9);                         // (dlo - B)^2 above: dropped for sure
+
+    // all four warps reduce `v` to the same bits: butterfly inside the warp, fixed-order sum of the four partials
+    auto block_sum = [&](double v, bool want_stop) -> double {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh.part[par][warp] = v;
+        if (want_stop && threadIdx.x == 0) sh.stop[par] = *(volatile int *)fail;
+        asm volatile("bar.sync 1, %0;" ::"n"(kChainWarps * 32) : "memory");
+        const double t = (sh.part[par][0] + sh.part[par][1]) + (sh.part[par][2] + sh.part[par][3]);
+        if (want_stop && sh.stop[par] != 0) go = false;   // the chunk is lost already: stop early
+        par ^= 1;
+        return t;
+    };
+
+    auto step = [&](const double(&X)[NPW], const SegMeta &mt) {
+        const double hi = mt.dhi + B, lo = mt.dlo - B;
+        const double hi2 = hi * hi;
+        int cls;                  // 0 update, 1 count only, 2 dropped
+        double d_up = hi;         // what the certification sees: an upper bound of |x - c_now|
+        double a[NPW];
+#pragma unroll
+        for (int u = 0; u < NPW; ++u) a[u] = __dsub_rn(X[u], cr[u]);   // clustering.rs:749 (and the diff of :917)
+        if (hi2 < thr_upd && hi + disp_hint < mt.slo) {
             cls = 0;
-        } else if (d2 <= 1.5 * radius) {
-            cls = 1;
+        } else if (saturated && lo > 0.0 && lo * lo > thr_drop) {
+            cls = 2;   // (while centroids can still be opened a far row opens one, :672: the exact step below says so)
         } else {
-            cls = 2;
-        }
-        if (lane == 0) {
-            dcur[r] = sqrt(d2);
-            assign[r] = cls == 2 ? -1ll : (long long)c;
+            double p = 0.0;
+#pragma unroll
+            for (int u = 0; u < NPW; ++u) p = fma(a[u], a[u], p);
+            const double d2 = block_sum(p, false);   // ~1e-15 relative, NOT the reference's summation order: guard band
+            if (!(d2 == d2) || fabs(d2 - radius) <= guard || fabs(d2 - 1.5 * radius) <= guard ||
+                (!saturated && fabs(d2 - 0.5 * radius) <= guard))
+                bad = true;
+            if (!saturated && d2 > 0.5 * radius) {   // the walk would open a new centroid here (:672): not replayable
+                bad = true;
+                go = false;
+                return;
+            }
+            cls = d2 <= radius ? 0 : (d2 <= 1.5 * radius ? 1 : 2);
+            d_up = fmin(hi, sqrt(d2) * (1.0 + 1e-12));
         }
         if (cls == 0) {
-            cnt += 1;
-            const double k = (double)cnt;
-            const double y = __drcp_rn(k);
-            double dsp = 0.0;
+            kd += 1.0;
+            const double y = y_next;
+            bool slow = false;
 #pragma unroll
-            for (int u = 0; u < NPL; ++u) {
-                cr[u] = __dadd_rn(cr[u], replay_div_by_count(__dsub_rn(x[u], cr[u]), k, y));   // clustering.rs:747-751
-                const double e = cr[u] - s0[u];
-                dsp = fma(e, e, dsp);
+            for (int u = 0; u < NPW; ++u) {
+                const unsigned h = (unsigned)__double2hiint(a[u]) & 0x7fffffffu;   // |a| in [~1e-280, ~1e280]?
+                const bool out = h - 0x05d00000u > 0x74200000u;
+                slow |= (u < NPW - 1) ? out : (out && last_valid);
             }
-            for (int o = 16; o > 0; o >>= 1) dsp += __shfl_xor_sync(0xffffffffu, dsp, o);
-            dmax2 = fmax(dmax2, dsp);
+            if (!__any_sync(0xffffffffu, slow)) {
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) {
+                    const double q0 = __dmul_rn(a[u], y);
+                    const double q1 = __fma_rn(__fma_rn(-q0, kd, a[u]), y, q0);
+                    cr[u] = __dadd_rn(cr[u], __fma_rn(__fma_rn(-q1, kd, a[u]), y, q1));   // clustering.rs:747-751
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) {
+                    const unsigned h = (unsigned)__double2hiint(a[u]) & 0x7fffffffu;
+                    double q;
+                    if (h - 0x05d00000u > 0x74200000u) {
+                        q = a[u] == 0.0 ? a[u] / kd : __ddiv_rn(a[u], kd);
+                    } else {
+                        const double q0 = __dmul_rn(a[u], y);
+                        const double q1 = __fma_rn(__fma_rn(-q0, kd, a[u]), y, q0);
+                        q = __fma_rn(__fma_rn(-q1, kd, a[u]), y, q1);
+                    }
+                    cr[u] = __dadd_rn(cr[u], q);
+                }
+            }
+            B = fma(hi * y, 1.0 + 1e-9, B);   // the centroid moved by |x - c| / k <= hi / k
+            dmax = fmax(dmax, B);
+            y_next = __drcp_rn(kd + 1.0);
+            ++since;
+            const int interval = kd < 512.0 ? 1 : (kd < 4096.0 ? (int)(kd * (1.0 / 256.0)) : 16);
+            if (since >= interval) {   // B back to the exact displacement
+                double p = 0.0;
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) {
+                    const double e = cr[u] - s0[u];
+                    p = fma(e, e, p);
+                }
+                const double t = block_sum(p, true);
+                const double nb = sqrt(t) * (1.0 + 1e-12);
+                if (!(nb == nb) || !(nb <= 1e300)) bad = true;
+                else B = fmin(B, nb);
+                since = 0;
+            }
         } else if (cls == 1) {
-            cnt += 1;
+            kd += 1.0;
+            y_next = __drcp_rn(kd + 1.0);
         }
+        if (threadIdx.x == 0) {
+            assign[mt.row] = cls == 2 ? -1ll : (long long)c;
+            dub[mt.row] = d_up;
+        }
+    };
+
+    int done = 0;   // rows applied
+    for (int g = 0; g < ngroups; ++g) {
+        const int slot = g % kRingSlots;
+        rp_mbar_wait(&sh.full[slot], (g / kRingSlots) & 1);
+        const int nr = end - (beg + g * RG) < RG ? end - (beg + g * RG) : RG;
+        if (go) {
+            double X[RG][NPW];
+            SegMeta mt[RG];
+#pragma unroll
+            for (int t = 0; t < RG; ++t) {
+                const double *src = ring + ((size_t)slot * RG + t) * FP + j0;
+#pragma unroll
+                for (int u = 0; u < NPW; ++u) X[t][u] = (u < NPW - 1 || last_valid) ? src[128 * u] : 0.0;
+                mt[t] = metas[slot * RG + t];
+            }
+#pragma unroll
+            for (int t = 0; t < RG; ++t)
+                if (t < nr && go) {
+                    step(X[t], mt[t]);
+                    if (go) ++done;
+                }
+        }
+        __syncwarp();
+        if (lane == 0) rp_mbar_arrive(&sh.empty[slot]);   // (a lost chain keeps draining its ring: the producer must finish)
     }
 #pragma unroll
-    for (int u = 0; u < NPL; ++u) {
-        const int j = lane + 32 * u;
-        if (j < f) cent[(size_t)c * f + j] = cr[u];
-    }
-    if (lane == 0) {
-        sizes[c] = cnt;
-        const double dm = sqrt(dmax2) * (1.0 + 1e-12);
+    for (int u = 0; u < NPW; ++u)
+        if (u < NPW - 1 || last_valid) cent[(size_t)c * f + 128 * u + j0] = cr[u];
+    if (threadIdx.x == 0) {
+        sizes[c] = (unsigned long long)kd;
+        const double dm = dmax * (1.0 + 1e-12);
         if (dm == dm) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(dm));
         else bad = true;
-        if (bad) atomicOr(fail, 1);
+        if (bad || !go || done < end - beg) atomicOr(fail, 1);
     }
+}
+
+// per sorted position: the row, certified bounds [dlo, dhi] of its distance to the SNAPSHOT of its nearest centroid and
+// a certified lower bound of its distance to the runner-up (GEMM-form squared distance |q|^2 + |c|^2 - 2 q.c from the
+// FP64 tensor pipe: absolute error below e2, the bound the certification kernel uses)
+__global__ void __launch_bounds__(256) replay_bounds_kernel(const int *__restrict__ rows_sorted, int m, int f,
+                                                            const double *__restrict__ top2_dist,
+                                                            const long long *__restrict__ top2_cnt,
+                                                            const double *__restrict__ qn2,
+                                                            const unsigned long long *cn2max_bits,
+                                                            SegMeta *__restrict__ meta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int r = rows_sorted[i];
+    const double cn2max = __longlong_as_double((long long)*cn2max_bits);
+    const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
+    const double d0 = top2_dist[2 * (size_t)r], d1 = top2_dist[2 * (size_t)r + 1];
+    SegMeta mt;
+    mt.dlo = sqrt(fmax(d0 * d0 - e2, 0.0)) * (1.0 - 1e-15);
+    mt.dhi = sqrt(d0 * d0 + e2) * (1.0 + 1e-15);
+    mt.slo = top2_cnt[r] >= 2 ? sqrt(fmax(d1 * d1 - e2, 0.0)) * (1.0 - 1e-15) : 0.0;
+    if (!(mt.dhi == mt.dhi) || !(mt.dlo == mt.dlo) || !(mt.slo == mt.slo)) {   // no usable distance: exact steps only
+        mt.dlo = 0.0;
+        mt.dhi = 1e300;
+        mt.slo = 0.0;
+    }
+    mt.row = r;
+    mt.pad = 0;
+    meta[i] = mt;
 }
 
 __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__restrict__ dcur, const double *__restrict__ top2_dist,
@@ -271,7 +456,53 @@ __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__res
     const double b = top2_dist[2 * (size_t)r];
     const double lb = fmax(sqrt(fmax(b * b - e2, 0.0)) - maxdisp, 0.0);
     const bool dropped_anyway = lb * lb > 1.5 * radius * (1.0 + 1e-9) && assign[r] == -1;
+    // dcur: the row's distance to its centroid at the row's own time, or an upper bound of it
     if (top2_cnt[r] < 2 || !(dcur[r] < lower || dropped_anyway)) atomicOr(fail, 2);
+}
+
+// ---- the creator run at the start of a fresh walk --------------------------------------------------------------
+// While every row opens a new centroid (len < max_clusters and d^2 > radius / 2 to everything opened so far,
+// clustering.rs:672) the centroids ARE the rows, nothing is averaged, and the decisions of the first P rows follow
+// from their pairwise distances alone: row r opens a centroid iff no earlier row lies within radius / 2 of it.  One
+// parallel pass evaluates all pairs in the reference's arithmetic (sequential separately rounded (a - b)^2 sums,
+// :917-921) and returns the first row that does NOT open one; the walk proper starts there with rows 0 .. G-1 as
+// centroids of size 1.  On the bench data that is the whole growth phase (384 centroids in the first 384 rows), which
+// costs the sequential kernel 7 ms because every new centroid ends one of its blocks.
+constexpr int kGrowTile = 16, kGrowChunk = 32;
+__global__ void __launch_bounds__(kGrowTile *kGrowTile) growth_pairs_kernel(const double *__restrict__ rows, int p, int f,
+                                                                            double half_radius, int *first_noncreator) {
+    if (blockIdx.x > blockIdx.y) return;   // pairs (r, r') with r' < r only: tile column <= tile row
+    __shared__ double sa[kGrowTile][kGrowChunk + 1], sb[kGrowTile][kGrowChunk + 1];
+    const int tx = threadIdx.x % kGrowTile, ty = threadIdx.x / kGrowTile;
+    const int r = blockIdx.y * kGrowTile + ty, q = blockIdx.x * kGrowTile + tx;
+    double d2 = 0.0;
+    for (int j0 = 0; j0 < f; j0 += kGrowChunk) {
+        for (int e = threadIdx.x; e < kGrowTile * kGrowChunk; e += kGrowTile * kGrowTile) {
+            const int rr = e / kGrowChunk, jj = e % kGrowChunk;
+            const int ra = blockIdx.y * kGrowTile + rr, rb = blockIdx.x * kGrowTile + rr;
+            sa[rr][jj] = (ra < p && j0 + jj < f) ? rows[(size_t)ra * f + j0 + jj] : 0.0;
+            sb[rr][jj] = (rb < p && j0 + jj < f) ? rows[(size_t)rb * f + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+        const int lim = f - j0 < kGrowChunk ? f - j0 : kGrowChunk;
+        for (int jj = 0; jj < lim; ++jj) {
+            const double diff = __dsub_rn(sa[ty][jj], sb[tx][jj]);
+            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+        }
+        __syncthreads();
+    }
+    // d2 > radius * 0.5 opens a centroid; NaN compares false both ways: a NaN distance is never the nearest (:922) and
+    // a row with only NaN distances sees d2 = +inf, so it opens one -- "not within half_radius" in every case
+    if (r < p && q < r && d2 <= half_radius) atomicMin(first_noncreator, r);
+}
+
+__global__ void __launch_bounds__(256) growth_fill_kernel(int g, unsigned long long *__restrict__ sizes,
+                                                          long long *__restrict__ assign) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < g) {
+        sizes[c] = 1ull;
+        assign[c] = c;
+    }
 }
 
 double opt_or(asb_ctx *ctx, const char *key, double dflt) {
@@ -297,8 +528,10 @@ struct ReplayWs {
     DevTmp<int> keys, vals, keys_s, vals_s, seg_off, flags;
     DevTmp<unsigned long long> sizes_tmp, scal;   // scal[0] = max |c|^2 bits, scal[1] = max displacement bits
     DevTmp<unsigned char> cub_tmp;
+    DevTmp<SegMeta> meta;
     size_t cub_bytes = 0;
     int cap_m = 0, cap_k = 0;
+    double last_disp = INFINITY;   // largest centroid displacement of the previous (proven) chunk
 };
 
 int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
@@ -317,6 +550,7 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     ASB_TRY(w.keys_s.init(ctx, (size_t)m));
     ASB_TRY(w.vals_s.init(ctx, (size_t)m));
     ASB_TRY(w.seg_off.init(ctx, (size_t)K + 1));
+    ASB_TRY(w.meta.init(ctx, (size_t)m));
     ASB_TRY(w.flags.init(ctx, 2));
     ASB_TRY(w.sizes_tmp.init(ctx, (size_t)K));
     ASB_TRY(w.scal.init(ctx, 2));
@@ -354,18 +588,42 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
                                   ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(w.sizes_tmp.ptr, sizes_d, (size_t)K * sizeof(unsigned long long),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    replay_bounds_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.vals_s.ptr, m, f, w.dist.ptr, (const long long *)w.cnt.ptr,
+                                                                   w.qn2.ptr, w.scal.ptr, w.meta.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_bounds_kernel"));
     {
         KernelTimer kt(ctx, "cluster_chain_kernel");
-        const bool generic = f > 512 || opt_or(ctx, "cluster_replay_generic_chain", 0.0) != 0.0;
+        // the ring kernel needs 16-byte aligned rows of a multiple of 16 bytes (bulk copies) and f <= 1024
+        const bool generic = f > 1024 || (f & 1) || (((uintptr_t)rows_d) & 15) ||
+                             opt_or(ctx, "cluster_replay_generic_chain", 0.0) != 0.0;
+        const double hint = 2.0 * w.last_disp;   // the displacement the previous chunk saw, doubled (inf at first)
 #define ASB_CHAIN_ARGS                                                                                                  \
-    rows_d, f, w.seg_off.ptr, w.vals_s.ptr, K, saturated, radius, w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr,          \
-        (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr
-        const unsigned grid = (unsigned)((K + 3) / 4);
-        if (generic) replay_chain_kernel<<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
-        else if (f <= 128) replay_chain_reg_kernel<4><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
-        else if (f <= 256) replay_chain_reg_kernel<8><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
-        else if (f <= 384) replay_chain_reg_kernel<12><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
-        else replay_chain_reg_kernel<16><<<grid, 128, 0, ctx->stream>>>(ASB_CHAIN_ARGS);
+    K, saturated, radius, w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, \
+        w.flags.ptr
+#define ASB_CHAIN_TMA(NPW, RG)                                                                                         \
+    {                                                                                                                   \
+        const size_t smem = (size_t)kRingSlots * RG * (128 * NPW * sizeof(double) + sizeof(SegMeta));                   \
+        ASB_CUDA(ctx, cudaFuncSetAttribute(replay_chain_tma_kernel<NPW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem));                                                                 \
+        replay_chain_tma_kernel<NPW, RG><<<(unsigned)K, (kChainWarps + 1) * 32, smem, ctx->stream>>>(                   \
+            rows_d, f, w.seg_off.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, centroids_d,             \
+            w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);                          \
+    }
+        if (generic)
+            replay_chain_kernel<<<(unsigned)((K + 3) / 4), 128, 0, ctx->stream>>>(rows_d, f, w.seg_off.ptr, w.vals_s.ptr,
+                                                                                  ASB_CHAIN_ARGS);
+        else
+            switch ((f + 127) / 128) {
+                case 1: ASB_CHAIN_TMA(1, 4) break;
+                case 2: ASB_CHAIN_TMA(2, 4) break;
+                case 3: ASB_CHAIN_TMA(3, 4) break;
+                case 4: ASB_CHAIN_TMA(4, 4) break;
+                case 5: ASB_CHAIN_TMA(5, 2) break;
+                case 6: ASB_CHAIN_TMA(6, 2) break;
+                case 7: ASB_CHAIN_TMA(7, 2) break;
+                default: ASB_CHAIN_TMA(8, 2) break;
+            }
+#undef ASB_CHAIN_TMA
 #undef ASB_CHAIN_ARGS
     }
     ASB_TRY(asb_check_launch(ctx, "replay_chain_kernel"));
@@ -374,9 +632,15 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
                                                                     (const long long *)assign_d, radius, f, m, w.flags.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_certify_kernel"));
     int hflags[2] = {0, 0};
+    unsigned long long hdisp = 0;
     ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hdisp, w.scal.ptr + 1, sizeof(hdisp), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (hflags[0] != 0 || hflags[1] != 0) return ASB_OK;
+    if (hflags[0] != 0 || hflags[1] != 0) {
+        w.last_disp = INFINITY;   // the next attempt follows a sequential stretch: no estimate
+        return ASB_OK;
+    }
+    memcpy(&w.last_disp, &hdisp, sizeof(double));
     ASB_CUDA(ctx, cudaMemcpyAsync(centroids_d, w.cent_tmp.ptr, (size_t)K * f * sizeof(double), cudaMemcpyDeviceToDevice,
                                   ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(sizes_d, w.sizes_tmp.ptr, (size_t)K * sizeof(unsigned long long),
@@ -386,6 +650,35 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
 }
 
 }  // namespace
+
+// rows 0 .. g-1 of a fresh walk that each open a centroid (see growth_pairs_kernel); *g_out = 0 when not applicable
+static int growth_run(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
+                      double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *g_out) {
+    *g_out = 0;
+    int64_t p = n < max_clusters ? n : max_clusters;
+    if (p > 2048) p = 2048;
+    if (p < 8 || !(radius == radius)) return ASB_OK;
+    DevTmp<int> first;
+    ASB_TRY(first.init(ctx, 1));
+    const int big = (int)p;
+    ASB_CUDA(ctx, cudaMemcpyAsync(first.ptr, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned t = (unsigned)((p + kGrowTile - 1) / kGrowTile);
+    {
+        KernelTimer kt(ctx, "cluster_growth_kernel");
+        growth_pairs_kernel<<<dim3(t, t), kGrowTile * kGrowTile, 0, ctx->stream>>>(rows_d, (int)p, (int)f, radius * 0.5,
+                                                                                   first.ptr);
+    }
+    ASB_TRY(asb_check_launch(ctx, "growth_pairs_kernel"));
+    int g = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&g, first.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (g < 2) return ASB_OK;
+    ASB_CUDA(ctx, cudaMemcpyAsync(centroids_d, rows_d, (size_t)g * f * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    growth_fill_kernel<<<(g + 255) / 256, 256, 0, ctx->stream>>>(g, sizes_d, (long long *)assign_d);
+    ASB_TRY(asb_check_launch(ctx, "growth_fill_kernel"));
+    *g_out = g;
+    return ASB_OK;
+}
 
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters, double radius,
                     double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int64_t *x_out_host,
@@ -399,26 +692,38 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;
     ctx->kernel_ms["cluster_replay_rows"] = 0.0;
-    if (!replay)
+    ctx->kernel_ms["cluster_growth_rows"] = 0.0;
+    if (n <= 0 || f <= 0 || max_clusters <= 0 || init_k < 0 || init_k > max_clusters || !replay)
         return asb_dev_cluster_seq(ctx, rows_d, n, f, max_clusters, radius, centroids_d, assign_d, sizes_d, x_out_host, init_k);
 
     int64_t x = init_k;
     double ms_seq = 0.0, ms_top2 = 0.0, ms_chain = 0.0;   // device time per part, summed over the chunks
-    ASB_TRY(asb_dev_cluster_seq(ctx, rows_d, prefix, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, init_k));
-    ms_seq += ktimer_ms(ctx, "cluster_kernel");
+    int64_t lo = 0;
+    if (init_k == 0 && opt_or(ctx, "cluster_growth_run", 1.0) != 0.0) {
+        ASB_TRY(growth_run(ctx, rows_d, n, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &lo));
+        x = lo;
+        ctx->kernel_ms["cluster_growth_rows"] = (double)lo;
+    }
+    if (lo < prefix) {
+        const int64_t x_before = x;
+        ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, prefix - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
+                                    sizes_d, &x, x_before));
+        ms_seq += ktimer_ms(ctx, "cluster_kernel");
+        lo = prefix;
+    }
     ReplayWs w;
     bool ws_ready = false;
     int fails = 0, tried = 0, proven = 0;
     int64_t rows_replayed = 0;
-    int64_t lo = prefix;
     int64_t cur = chunk;   // rows per attempt: doubles after every proven chunk (one snapshot holds for longer and
                            // longer stretches as the centroids settle), back to `chunk` after a failure
     while (lo < n) {
         int64_t hi = lo + cur < n ? lo + cur : n;
         int ok = 0;
         if (x >= 2) {
-            if (!ws_ready || w.cap_k < x || w.cap_m < hi - lo) {
-                ASB_TRY(replay_ws_init(ctx, w, (int)cur, (int)(x > max_clusters ? x : max_clusters), (int)f));
+            if (!ws_ready) {   // sized once for the largest chunk this call can attempt
+                const int64_t cap = chunk_max < n - prefix ? chunk_max : n - prefix;
+                ASB_TRY(replay_ws_init(ctx, w, (int)(cap > cur ? cap : cur), (int)max_clusters, (int)f));
                 ws_ready = true;
             }
             ++tried;

@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cluster-replay", action="store_true",
                     help="walk every row on the sequential clustering kernel (option cluster_replay = 0; the default is "
                          "the certified parallel replay, same bits)")
+    ap.add_argument("--ref-full", action="store_true",
+                    help="with --impl reference: run the WHOLE workload once on the host cores instead of a bounded sample")
     ap.add_argument("--exact-search", action="store_true",
                     help="search with the exact FP64 DMMA kernel only (option search_prefilter = 0)")
     return ap.parse_args()
@@ -136,59 +138,113 @@ def cluster_inputs(n_global: int, f: int, sample_rows: np.ndarray):
 
 
 # ----------------------------------------------------------------------------- reference arm
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port_times(o, x, queries, maxk, radius, n_build, n_search, cores):
+    """One pass of the oracle port over a sample: per-stage wall times (s).  Every stage of the reference path is
+    linear in the row count except the feature Laplacian (fixed: F nodes), so each stage is timed on its own and the
+    caller scales stage by stage instead of scaling the sum."""
+    from oracle_binding import TAU_MEDIAN
+    t = {}
+    t0 = time.perf_counter()
+    o.twonn_distances(x[:n_build], asb_heur().sample_indices(n_build, 500, 129))
+    t["twonn"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cent, asg, sizes = o.cluster_incremental(x[:n_build], maxk, radius)      # sequential in the deterministic mode
+    t["cluster"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    csr = o.feature_laplacian(cent, **GRAPH)
+    t["laplacian"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lam_b = o.compute_taumode(x[:n_build], csr, TAU_MEDIAN)
+    t["taumode"] = time.perf_counter() - t0
+    lam = lam_b if n_search == n_build else o.compute_taumode(x[:n_search], csr, TAU_MEDIAN)
+    lq = o.compute_taumode(queries, csr, TAU_MEDIAN)
+    t0 = time.perf_counter()
+    o.search_lambda_aware_batch(x[:n_search], lam, queries, lq, TOPK, ALPHA)
+    t["search"] = time.perf_counter() - t0
+    t["n_clusters"] = int(len(cent))
+    return t
+
+
+def asb_heur():
+    import arrowspace_b200 as asb
+    return asb.heuristics
+
+
+def cpu_port_model(t, n_build, n_search, nq_sample, n_full):
+    """Full-size figures from the sample's stage times: row-linear stages x (n_full / sample rows), Laplacian as is."""
+    sb = n_full / n_build
+    build_s = (t["twonn"] + t["cluster"] + t["taumode"]) * sb + t["laplacian"]
+    qps = (nq_sample / t["search"]) * (n_search / n_full)
+    return build_s, n_full / build_s, qps
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be
-    compiled here -- DESIGN.md) on the box's host cores, each step a bounded sample of the workload."""
+    """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be compiled here --
+    DESIGN.md) on the box's host cores, each step a bounded sample of the workload; `--ref-full` runs the whole
+    workload once instead (minutes; the record that checks the sample's extrapolation is kept under profiles/)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import arrowspace_b200 as asb
-    from oracle_binding import Oracle, TAU_MEDIAN
+    from oracle_binding import Oracle
     o = Oracle()
-    cores = o.num_threads()
+    # a launcher may have exported OMP_NUM_THREADS=1 (torch.distributed.run does): the baseline uses every host core
+    cores = o.set_num_threads(host_threads())
     n, f = args.n, args.f
-    n_s = min(n, 20_000)            # rows of the build sample
-    n_items_search = min(n, 200_000)
-    q_s = max(cores, 16)
+    full = bool(args.ref_full)
+    n_s = n if full else min(n, 20_000)            # rows of the build sample
+    n_items_search = n if full else min(n, 200_000)
+    q_s = max(cores, 16) * (4 if full else 1)
     x = asb.synth.protein_like(n_items_search, f, seed=DATA_SEED)
     maxk, radius = cluster_inputs(n * args.gpus, f, x[: min(len(x), 50_000)])
     queries = asb.synth.rows_at(asb.synth.query_indices(n_items_search, q_s, QUERY_SEED), f, DATA_SEED) * 1.02
-    si = asb.heuristics.sample_indices(n_s, 500, 129)
-    build_t, search_t = [], []
-    for step in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        o.twonn_distances(x[:n_s], si)
-        cent, asg, sizes = o.cluster_incremental(x[:n_s], maxk, radius)
-        csr = o.feature_laplacian(cent, **GRAPH)
-        lam_s = o.compute_taumode(x[:n_s], csr, TAU_MEDIAN)
-        t1 = time.perf_counter()
-        lam = o.compute_taumode(x, csr, TAU_MEDIAN)
-        lq = o.compute_taumode(queries, csr, TAU_MEDIAN)
-        t2 = time.perf_counter()
-        o.search_lambda_aware_batch(x, lam, queries, lq, TOPK, ALPHA)
-        t3 = time.perf_counter()
-        if step >= args.warmup:
-            build_t.append(t1 - t0)
-            search_t.append(t3 - t2)
-    bt, st = float(np.mean(build_t)), float(np.mean(search_t))
-    items_s = n_s / bt
-    # search cost is linear in N: QPS at the full N = measured QPS x (sample items / N)
-    qps = (q_s / st) * (n_items_search / n)
-    sample = (f"build: first {n_s} rows of the {n}x{f} workload (Two-NN 500 samples + sequential clustering + Laplacian "
-              f"+ taumode); search: {q_s} queries x {n_items_search} items, QPS scaled by {n_items_search}/{n}")
+    steps, warm = (1, 0) if full else (args.steps, args.warmup)
+    acc = []
+    for step in range(warm + steps):
+        t = cpu_port_times(o, x, queries, maxk, radius, n_s, n_items_search, cores)
+        if step >= warm:
+            acc.append(t)
+    t = {k: float(np.mean([a[k] for a in acc])) for k in acc[0]}
+    build_s, items_s, qps = cpu_port_model(t, n_s, n_items_search, q_s, n)
+    sample = (f"build: {'all' if full else 'first'} {n_s} rows of the {n}x{f} workload, stage by stage (Two-NN 500 samples, "
+              f"sequential clustering, taumode scaled by {n}/{n_s}; feature Laplacian unscaled); search: {q_s} queries x "
+              f"{n_items_search} items, QPS scaled by {n_items_search}/{n}")
     line = {
         "impl": "reference", "metric": "lambda_tau_build_items_per_s", "value": items_s, "unit": "items/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": (bt + st) * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": (build_s + args.nq / qps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n}x{f} lambda-tau build + {args.nq}-query lambda-aware search k={TOPK} (bounded sample)",
+        "config": {"workload": f"{n}x{f} lambda-tau build + {args.nq}-query lambda-aware search k={TOPK}"
+                               + ("" if full else " (bounded sample, stage-wise linear model)"),
                    "max_clusters": maxk, "radius": radius, "graph": GRAPH, "taumode": "Median", "alpha": ALPHA},
-        "search_qps": qps,
+        "search_qps": qps, "same_config": full, "extrapolated": not full,
         "cpu_baseline": {"value": items_s, "unit": "items/s", "cores": cores, "kind": "port", "sample": sample,
-                         "search_qps": qps},
+                         "search_qps": qps, "stage_s_on_sample": t, "omp_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                         "full_size_check": full_size_record()},
         "e2e": {"value": items_s, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+def full_size_record():
+    """The one full-size run of the oracle port kept under profiles/ (`bench.py --impl reference --ref-full`): what the
+    bounded sample's stage-wise model is checked against."""
+    p = ROOT / "profiles" / "r02_reference_full_1m.json"
+    if not p.exists():
+        return None
+    try:
+        d = json.loads(p.read_text())
+        return {"items_per_s": d["value"], "search_qps": d["search_qps"], "cores": d["cpu_baseline"]["cores"],
+                "file": "profiles/r02_reference_full_1m.json"}
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------- B200 arm
@@ -492,29 +548,20 @@ def run_b200(args):
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
-        from oracle_binding import Oracle, TAU_MEDIAN
+        from oracle_binding import Oracle
         o = Oracle()
-        cores = o.num_threads()
+        cores = o.set_num_threads(host_threads())
         n_s = min(n, 20_000)
         n_items_search = min(n, 200_000)
         q_s = max(cores, 16)
-        xs = rows_h.numpy()
-        t0 = time.perf_counter()
-        o.twonn_distances(xs[:n_s], asb.heuristics.sample_indices(n_s, 500, 129))
-        cent, asg, sizes = o.cluster_incremental(xs[:n_s], maxk, radius)
-        csr = o.feature_laplacian(cent, **GRAPH)
-        lam_s = o.compute_taumode(xs[:n_s], csr, TAU_MEDIAN)
-        t1 = time.perf_counter()
-        lam = o.compute_taumode(xs[:n_items_search], csr, TAU_MEDIAN)
-        lq = o.compute_taumode(queries_h.numpy()[:q_s], csr, TAU_MEDIAN)
-        t2 = time.perf_counter()
-        o.search_lambda_aware_batch(xs[:n_items_search], lam, queries_h.numpy()[:q_s], lq, TOPK, ALPHA)
-        t3 = time.perf_counter()
+        t = cpu_port_times(o, rows_h.numpy(), queries_h.numpy()[:q_s], maxk, radius, n_s, n_items_search, cores)
+        build_s, items_s, cqps = cpu_port_model(t, n_s, n_items_search, q_s, n)
         line["cpu_baseline"] = {
-            "value": n_s / (t1 - t0), "unit": "items/s", "cores": cores, "kind": "port",
-            "sample": f"build on the first {n_s} rows (clustering is sequential in the reference's deterministic "
-                      f"mode); search {q_s} queries x {n_items_search} items scaled to N={n}",
-            "search_qps": (q_s / (t3 - t2)) * (n_items_search / n), "build_s": t1 - t0, "search_s": t3 - t2}
+            "value": items_s, "unit": "items/s", "cores": cores, "kind": "port",
+            "sample": f"build on the first {n_s} rows, stage by stage (row-linear stages scaled by {n}/{n_s}, Laplacian "
+                      f"unscaled; clustering is sequential in the reference's deterministic mode); search {q_s} queries x "
+                      f"{n_items_search} items scaled to N={n}",
+            "search_qps": cqps, "stage_s_on_sample": t, "build_s_model": build_s, "full_size_check": full_size_record()}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

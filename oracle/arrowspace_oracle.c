@@ -38,6 +38,18 @@ int aso_num_threads(void) {
 #endif
 }
 
+/* the OpenMP team size of every later call with threads <= 0 (a launcher may have exported OMP_NUM_THREADS=1:
+ * torch.distributed.run does); returns the size now in effect */
+int aso_set_num_threads(int threads) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+    return omp_get_max_threads();
+#else
+    (void)threads;
+    return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------ taumode */
 
 static int cmp_f64_asc(const void *a, const void *b) {

@@ -147,6 +147,7 @@ int aso_range_search(const double *lambdas, int64_t n, double lambda_q, double e
                      double *dist_out, int64_t *count_out);
 
 int aso_num_threads(void);
+int aso_set_num_threads(int threads);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,8 @@ class Oracle:
         lib.aso_project_matrix.argtypes = [_P, _I64, _I64, _P, _I64, _P]
         lib.aso_search_energy.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
         lib.aso_num_threads.restype = C.c_int
+        lib.aso_set_num_threads.restype = C.c_int
+        lib.aso_set_num_threads.argtypes = [C.c_int]
         self.lib = lib
 
     @staticmethod
@@ -70,6 +72,10 @@ class Oracle:
 
     def num_threads(self) -> int:
         return int(self.lib.aso_num_threads())
+
+    def set_num_threads(self, threads: int) -> int:
+        """OpenMP team size of every later call (overrides an inherited OMP_NUM_THREADS); returns the size in effect."""
+        return int(self.lib.aso_set_num_threads(int(threads)))
 
     def select_tau(self, x, mode, value=0.0) -> float:
         x = np.ascontiguousarray(x, dtype=np.float64)

