@@ -529,6 +529,8 @@ size_t pf_smem_bytes(int k, int mode = PF_COSINE) {
 
 }  // namespace
 
+#include "search_umma.cuh"   // the same tile on tcgen05 / TMA / TMEM (needs PfArgs and the helpers above)
+
 // Tries the prefilter path; *done = true when idx/score/count hold the final answer.  *done = false (with ASB_OK)
 // means "not applicable / not certain": the caller runs the exact kernel, which then decides everything.
 static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_offset, int64_t *idx_d, double *score_d,
@@ -561,7 +563,7 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     const double band = 2.0 * E;
     const double band_f = band + 1.1920928955078125e-7 * (fabs(SA.alpha) + fabs(1.0 - SA.alpha) + 1.0);  // cand_s is a float
 
-    DevTmp<float> xf, qf, cand_s;
+    DevTmp<float> xf, qf, xlo, qlo, cand_s;
     DevTmp<int> cand_cnt, cand_idx, flags;
     DevTmp<unsigned long long> gthr, diag;
     // a failed allocation only means "use the exact kernel"
@@ -569,6 +571,21 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
         cand_s.init(ctx, (size_t)nq * cap) != ASB_OK || cand_idx.init(ctx, (size_t)nq * cap) != ASB_OK) {
         cudaGetLastError();
         return ASB_OK;
+    }
+    // Blackwell tensor pipe (search_umma.cuh): needs the lo planes and four TMA descriptors; anything missing falls
+    // back to the mma.sync tile above -- same certificate, same lists
+    UmMaps maps;
+    bool umma = um_wanted(ctx) && um_smem_bytes(k, PF_COSINE) <= 227 * 1024;
+    if (umma && (xlo.init(ctx, (size_t)n * fp) != ASB_OK || qlo.init(ctx, (size_t)nq * fp) != ASB_OK)) {
+        cudaGetLastError();
+        umma = false;
+    }
+    if (umma)
+        umma = um_make_map(&maps.qhi, qf.ptr, nq, fp, UM_TQ) && um_make_map(&maps.qlo, qlo.ptr, nq, fp, UM_TQ) &&
+               um_make_map(&maps.xhi, xf.ptr, n, fp, UM_TN) && um_make_map(&maps.xlo, xlo.ptr, n, fp, UM_TN);
+    if (umma) {
+        const long long utiles = (n + UM_TN - 1) / UM_TN;
+        pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, utiles, 64, &nslabs, &tps);
     }
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
     ASB_TRY(flags.init(ctx, 1));
@@ -580,8 +597,15 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     ASB_TRY(asb_check_launch(ctx, "pf_init_kernel"));
     {
         KernelTimer kt(ctx, "search_pf_prep");
-        pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, flags.ptr);
-        pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr, flags.ptr);
+        if (umma) {
+            um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, xlo.ptr,
+                                                                                  flags.ptr, nullptr);
+            um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr,
+                                                                                   qlo.ptr, flags.ptr, nullptr);
+        } else {
+            pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, flags.ptr);
+            pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr, flags.ptr);
+        }
     }
     ASB_TRY(asb_check_launch(ctx, "pf_unit_rows_kernel"));
     ctx->launches++;
@@ -607,8 +631,14 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     A.flags = flags.ptr;
     A.diag = diag.ptr;
     A.status = SA.status;
-    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
+    ctx->kernel_ms["search_pf_umma"] = umma ? 1.0 : 0.0;
+    if (umma) {
+        const size_t usmem = um_smem_bytes(k, PF_COSINE);
+        ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+        KernelTimer kt(ctx, "search_pf_kernel");
+        search_umma_kernel<PF_COSINE><<<dim3((unsigned)((nq + UM_TQ - 1) / UM_TQ), (unsigned)nslabs), UM_THREADS, usmem, ctx->stream>>>(maps, A);
+    } else {
+        ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(ctx, "search_pf_kernel");
         search_pf_kernel<PF_COSINE><<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
     }
@@ -664,7 +694,7 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     const double chain = 3.0 * fp / 8.0;
     const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
 
-    DevTmp<float> xf, qf, cand_s;
+    DevTmp<float> xf, qf, xlo, qlo, cand_s;
     DevTmp<double> xnrm, qnrm;
     DevTmp<int> cand_cnt, cand_idx, flags, status;
     DevTmp<unsigned long long> gthr, diag, xmax;
@@ -673,6 +703,16 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
         cudaGetLastError();
         return ASB_OK;
     }
+    UmMaps maps;
+    bool umma = um_wanted(ctx) && um_smem_bytes(k, PF_L2) <= 227 * 1024;
+    if (umma && (xlo.init(ctx, (size_t)n * fp) != ASB_OK || qlo.init(ctx, (size_t)nq * fp) != ASB_OK)) {
+        cudaGetLastError();
+        umma = false;
+    }
+    if (umma)
+        umma = um_make_map(&maps.qhi, qf.ptr, nq, fp, UM_TQ) && um_make_map(&maps.qlo, qlo.ptr, nq, fp, UM_TQ) &&
+               um_make_map(&maps.xhi, xf.ptr, n, fp, UM_TN) && um_make_map(&maps.xlo, xlo.ptr, n, fp, UM_TN);
+    if (umma) pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, (n + UM_TN - 1) / UM_TN, 64, &nslabs, &tps);
     ASB_TRY(xnrm.init(ctx, (size_t)n));
     ASB_TRY(qnrm.init(ctx, (size_t)nq));
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
@@ -689,8 +729,15 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     ASB_TRY(asb_check_launch(ctx, "pf_init_kernel"));
     pf_max_kernel<<<64, 256, 0, ctx->stream>>>(xn2_d, n, xmax.ptr);
     ASB_TRY(asb_check_launch(ctx, "pf_max_kernel"));
-    pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, flags.ptr, xnrm.ptr);
-    pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, flags.ptr, qnrm.ptr);
+    if (umma) {
+        um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr,
+                                                                              xnrm.ptr);
+        um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr,
+                                                                               flags.ptr, qnrm.ptr);
+    } else {
+        pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, flags.ptr, xnrm.ptr);
+        pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, flags.ptr, qnrm.ptr);
+    }
     ASB_TRY(asb_check_launch(ctx, "pf_unit_rows_kernel"));
     ctx->launches++;
 
@@ -720,8 +767,13 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     // |s~ - s| <= E(q) = 2 |q| max|x| E_cos + 1e-13 (|q|^2 + max|x|^2)  (norm rounding, the reference's own sum);  band = 2 E
     A.band_rel = 4.0 * e_cos * (1.0 + 1e-6);
     A.band_abs = 2e-13;
-    ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
+    if (umma) {
+        const size_t usmem = um_smem_bytes(k, PF_L2);
+        ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+        KernelTimer kt(ctx, "l2_pf_kernel");
+        search_umma_kernel<PF_L2><<<dim3((unsigned)((nq + UM_TQ - 1) / UM_TQ), (unsigned)nslabs), UM_THREADS, usmem, ctx->stream>>>(maps, A);
+    } else {
+        ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(ctx, "l2_pf_kernel");
         search_pf_kernel<PF_L2><<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
     }

@@ -1,0 +1,353 @@
+// search_umma.cuh -- the certified prefilter tile of search_pf.cuh on Blackwell's own tensor pipe (included by search.cu).
+//
+// Same scheme, same certificate, same candidate lists and the same finishing kernel as search_pf.cuh (read its header
+// first); only the contraction cos~ = <q^, x^> moves from mma.sync + cp.async to
+//   * tcgen05.mma kind::tf32 (SASS UTCHMMA...), cta_group::1, M = 128 queries x N = 256 items x K = 8 per instruction,
+//     3xTF32 as three instructions per K-step into ONE accumulator: hi*lo + lo*hi + hi*hi;
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) from four planes prepared once per call -- q^ / x^
+//     split into hi = the TF32 truncation (exactly representable, so the tensor core's own operand conversion has
+//     nothing to drop) and lo = fl32(x^) - hi -- as K-major 128-byte-swizzled boxes of 32 features: 96 KB per stage
+//     (2 x 16 KB query boxes, 2 x 32 KB item boxes), UM_STAGES stages on full / empty mbarriers;
+//   * accumulators in tensor memory: 2 x 256 columns, so the tile t + 1 is multiplied while the epilogue warps read tile
+//     t back with tcgen05.ld (SASS LDTM): warp-specialised -- one TMA thread, one MMA thread, four epilogue warps that
+//     each own 32 TMEM lanes = 32 queries, ONE THREAD PER QUERY: the blended score, the slab's k best (a sorted list
+//     per query in shared memory) and the emission test are thread-local, no shuffles, no block barriers.
+// Error model: the bound E of search_pf.cuh assumes exact products and a truncating aligned accumulation of at most
+// 9 * 2^-23 per instruction; tools/umma_probe.cu measured this data path at K = 384 (144 instructions into one
+// accumulator): worst |error| 9.7e-6 of sum|a||b| against the bound's 1.56e-4 (profiles/r02_umma_probe.log) -- the
+// same 0.06 the mma.sync path shows, so E is kept unchanged.
+#pragma once
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+
+namespace {
+
+constexpr int UM_TQ = 128, UM_TN = 256, UM_KC = 32, UM_STAGES = 2;
+constexpr int UM_A_BYTES = UM_TQ * UM_KC * 4;                      // 16 KB: one query plane box
+constexpr int UM_B_BYTES = UM_TN * UM_KC * 4;                      // 32 KB: one item plane box
+constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES;    // hi + lo of both operands
+constexpr int UM_THREADS = 256;                                    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..7 epilogue
+
+struct UmBarriers {
+    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2];
+    unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned um_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void um_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(um_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void um_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(um_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void um_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(um_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void um_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "UM_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra UM_DONE;\n\t"
+        "bra UM_WAIT_LOOP;\n\t"
+        "UM_DONE:\n\t}" ::"r"(um_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void um_tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            um_smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(um_smem_u32(bar))
+        : "memory");
+}
+// K-major operand plane, 128-byte swizzle: rows of 128 bytes, 8-row atoms 1024 bytes apart (the layout TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B; descriptor fields as cute/arch/mma_sm100_desc.hpp, validated by tools/umma_probe.cu)
+__device__ __forceinline__ unsigned long long um_desc(unsigned saddr) {
+    unsigned long long d = (unsigned long long)((saddr >> 4) & 0x3fff);
+    d |= 1ull << 16;                          // leading byte offset (unused for this layout)
+    d |= (unsigned long long)(1024 >> 4) << 32;   // stride byte offset: one 8-row atom
+    d |= 1ull << 46;                          // descriptor version (Blackwell)
+    d |= 2ull << 61;                          // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void um_mma_tf32(unsigned tmem_c, unsigned long long da, unsigned long long db, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void um_commit(unsigned long long *bar) {   // arrives when every MMA issued so far is done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(um_smem_u32(bar)) : "memory");
+}
+
+// One warp per row: hi = TF32 truncation of fl32(row / |row|), lo = fl32(row / |row|) - hi (exact), zero padded to fp.
+__global__ void __launch_bounds__(256) um_split_rows_kernel(const double *__restrict__ rows, const double *__restrict__ norms2,
+                                                            long long n, int f, int fp, float *__restrict__ hi,
+                                                            float *__restrict__ lo, int *__restrict__ flags,
+                                                            double *__restrict__ norm_out) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double n2 = norms2[r];
+    const bool ok = (n2 == 0.0) || (n2 >= 1e-290 && n2 <= 1e290);   // false for NaN / inf as well
+    if (!ok && lane == 0) atomicOr(flags, PF_FLAG_FALLBACK);
+    const double inv = (ok && n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+    if (norm_out && lane == 0) norm_out[r] = ok ? sqrt(n2) : 0.0;
+    const double *src = rows + r * (long long)f;
+    for (int j = lane; j < fp; j += 32) {
+        const float v = (ok && j < f) ? (float)(src[j] * inv) : 0.0f;
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[r * (long long)fp + j] = h;
+        lo[r * (long long)fp + j] = v - h;
+    }
+}
+
+struct UmMaps {
+    CUtensorMap qhi, qlo, xhi, xlo;
+};
+
+// shared memory: [UM_STAGES][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned), then per accumulator buffer the item-side
+// epilogue inputs (2 x 256 doubles each), then the per-query sorted lists (float, rounded down: still lower bounds)
+template <int MODE>
+__global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid_constant__ UmMaps maps, PfArgs A) {
+    extern __shared__ __align__(1024) unsigned char um_smem[];
+    __shared__ UmBarriers bars;
+    // the swizzled boxes need 1024-byte alignment; the launch reserves the slack (um_smem_bytes)
+    unsigned char *stages = um_smem + ((1024u - (um_smem_u32(um_smem) & 1023u)) & 1023u);
+    double *ep_x0 = reinterpret_cast<double *>(stages + (size_t)UM_STAGES * UM_STAGE_BYTES);   // [2][UM_TN]: lambda / |x|^2
+    double *ep_x1 = ep_x0 + 2 * UM_TN;                                                           // [2][UM_TN]: |x| (PF_L2)
+    float *lists = reinterpret_cast<float *>(ep_x1 + (MODE == PF_L2 ? 2 * UM_TN : 0));           // [UM_TQ][k]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = A.k, fp = A.fp;
+    const long long q0 = (long long)blockIdx.x * UM_TQ;
+    const long long ntiles_total = (A.n + UM_TN - 1) / UM_TN;
+    const long long t_begin = (long long)blockIdx.y * A.tiles_per_slab;
+    long long t_end = t_begin + A.tiles_per_slab;
+    if (t_end > ntiles_total) t_end = ntiles_total;
+    const int ntile = (int)(t_end > t_begin ? t_end - t_begin : 0);
+    const int nchunks = fp / UM_KC;
+    if (ntile == 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) {
+            um_mbar_init(&bars.full[s], 1);
+            um_mbar_init(&bars.empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            um_mbar_init(&bars.tfull[b], 1);
+            um_mbar_init(&bars.tempty[b], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(&bars.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = bars.tmem_base;
+
+    if (warp == 0) {
+        // ---- TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int t = 0; t < ntile; ++t) {
+                const int row_x = (int)((t_begin + t) * UM_TN);
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % UM_STAGES;
+                    if (it >= UM_STAGES) um_mbar_wait(&bars.empty[s], ((it / UM_STAGES) - 1) & 1);
+                    unsigned char *st = stages + (size_t)s * UM_STAGE_BYTES;
+                    um_mbar_expect_tx(&bars.full[s], UM_STAGE_BYTES);
+                    um_tma_2d(st, &maps.qhi, c * UM_KC, (int)q0, &bars.full[s]);
+                    um_tma_2d(st + UM_A_BYTES, &maps.qlo, c * UM_KC, (int)q0, &bars.full[s]);
+                    um_tma_2d(st + 2 * UM_A_BYTES, &maps.xhi, c * UM_KC, row_x, &bars.full[s]);
+                    um_tma_2d(st + 2 * UM_A_BYTES + UM_B_BYTES, &maps.xlo, c * UM_KC, row_x, &bars.full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: D[128 x 256] (+)= A[128 x 8] B[256 x 8]^T, three instructions per K-step
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(UM_TN >> 3) << 17) | ((unsigned)(UM_TQ >> 4) << 24);
+            int it = 0;
+            for (int t = 0; t < ntile; ++t) {
+                const int b = t & 1;
+                if (t >= 2) um_mbar_wait(&bars.tempty[b], ((t >> 1) - 1) & 1);   // the epilogue has drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned tmem_c = tmem_base + (unsigned)(b * UM_TN);
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % UM_STAGES;
+                    um_mbar_wait(&bars.full[s], (it / UM_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned sa = um_smem_u32(stages + (size_t)s * UM_STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < UM_KC / 8; ++j) {
+                        const unsigned long long dah = um_desc(sa + 32 * j), dal = um_desc(sa + UM_A_BYTES + 32 * j);
+                        const unsigned long long dbh = um_desc(sa + 2 * UM_A_BYTES + 32 * j);
+                        const unsigned long long dbl = um_desc(sa + 2 * UM_A_BYTES + UM_B_BYTES + 32 * j);
+                        um_mma_tf32(tmem_c, dah, dbl, idesc, (c | j) ? 1u : 0u);
+                        um_mma_tf32(tmem_c, dal, dbh, idesc, 1u);
+                        um_mma_tf32(tmem_c, dah, dbh, idesc, 1u);
+                    }
+                    um_commit(&bars.empty[s]);   // the stage is free once these instructions have read it
+                }
+                um_commit(&bars.tfull[b]);       // the accumulator is complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: thread e = query q0 + e = TMEM lane e
+        const int e = tid - 128, ew = warp - 4;
+        const long long gq = q0 + e;
+        const bool okq = gq < A.nq;
+        double lq = 1.0, qn = 0.0, qband = A.band;
+        long long self = -1;
+        if constexpr (MODE == PF_COSINE) {
+            lq = okq ? A.lambda_q[gq] : 1.0;
+            if (okq && blockIdx.y == 0 && lq == 0.0) atomicOr(A.status, STATUS_ZERO_LAMBDA);   // core.rs:773-776
+        } else {
+            const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
+            lq = okq ? A.qn2[gq] : 0.0;
+            qn = okq ? A.qnrm[gq] : 0.0;
+            qband = A.band_rel * qn * sqrt(xmax2) + A.band_abs * (lq + xmax2);
+            self = (okq && A.self_idx) ? A.self_idx[gq] : -1ll;
+        }
+        float *lst = lists + (size_t)e * k;
+        int len = 0;
+        double kth = -INFINITY;
+        bool saw_nan = false;
+        const double beta = 1.0 - A.alpha;
+        for (int t = 0; t < ntile; ++t) {
+            const int b = t & 1;
+            const long long i0 = (t_begin + t) * UM_TN;
+            // item-side inputs of this tile (two items per thread); the buffer was last read two tiles ago
+            for (int c = e; c < UM_TN; c += 128) {
+                const long long gi = i0 + c;
+                if constexpr (MODE == PF_COSINE) {
+                    ep_x0[b * UM_TN + c] = gi < A.n ? A.lambdas[gi] : 0.0;
+                } else {
+                    ep_x0[b * UM_TN + c] = gi < A.n ? A.xn2[gi] : 0.0;
+                    ep_x1[b * UM_TN + c] = gi < A.n ? A.xnrm[gi] : 0.0;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const double gb = okq ? pf_dec(__ldcg(&A.gthr[gq])) : -INFINITY;   // bound published by any slab
+            um_mbar_wait(&bars.tfull[b], (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long nvalid = A.n - i0;   // columns below this index are real items
+            bool changed = false;
+            double bound = fmax(kth, gb);
+#pragma unroll 1
+            for (int c0 = 0; c0 < UM_TN; c0 += 32) {
+                unsigned v[32];
+                const unsigned taddr = tmem_base + ((unsigned)(ew * 32) << 16) + (unsigned)(b * UM_TN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!okq || c0 >= nvalid) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    const double cosv = (double)__uint_as_float(v[j]);
+                    double s;
+                    bool valid = c < nvalid;
+                    if constexpr (MODE == PF_COSINE) {
+                        const double lam = 1.0 - fmin(fabs(lq - ep_x0[b * UM_TN + c]), 1.0);   // core.rs:136-137
+                        s = A.alpha * cosv + beta * lam;                                       // core.rs:165 (approximate cos)
+                    } else {
+                        s = -(lq + ep_x0[b * UM_TN + c] - 2.0 * qn * ep_x1[b * UM_TN + c] * cosv);   // -|q - x|^2
+                        valid = valid && (i0 + c) != self;
+                    }
+                    if (valid && s != s) saw_nan = true;
+                    if (valid && s >= bound - qband) {
+                        if (s > bound) {
+                            // keep the slab's k best approximate scores: sorted descending, stored rounded DOWN
+                            const float sf = __double2float_rd(s);
+                            int pos = len < k ? len : k - 1;
+                            while (pos > 0 && lst[pos - 1] < sf) {
+                                lst[pos] = lst[pos - 1];
+                                --pos;
+                            }
+                            lst[pos] = sf;
+                            if (len < k) ++len;
+                            if (len == k) {
+                                kth = (double)lst[k - 1];
+                                bound = fmax(kth, gb);
+                                changed = true;
+                            }
+                        }
+                        // emit what the bound cannot exclude
+                        const int p = atomicAdd(&A.cand_cnt[gq], 1);
+                        if (p < A.cap) {
+                            A.cand_idx[(size_t)gq * A.cap + p] = (int)(i0 + c);
+                            A.cand_s[(size_t)gq * A.cap + p] = (float)s;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            um_mbar_arrive(&bars.tempty[b]);
+            if (changed && okq) atomicMax(&A.gthr[gq], pf_enc(kth));
+        }
+        if (saw_nan) atomicOr(A.flags, PF_FLAG_FALLBACK);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+size_t um_smem_bytes(int k, int mode) {
+    return (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)(mode == PF_L2 ? 4 : 2) * UM_TN * 8 + (size_t)UM_TQ * k * 4 + 1024;
+}
+
+typedef CUresult (*um_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+um_encode_fn um_encoder() {
+    static um_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<um_encode_fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// rows x fp fp32 plane, boxes of UM_KC features x box_rows rows, 128-byte swizzle, out-of-range rows read as zeros
+bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, int box_rows) {
+    um_encode_fn enc = um_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)fp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)fp * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)UM_KC, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// option "search_umma" (default 1): 0 keeps the mma.sync tile of search_pf.cuh
+bool um_wanted(asb_ctx *ctx) {
+    auto it = ctx->options.find("search_umma");
+    return it == ctx->options.end() || it->second != 0.0;
+}
+
+}  // namespace

@@ -188,6 +188,7 @@ class Context:
             raise ArrowSpaceError(rc, "asb_ctx_create failed: no usable B200 (sm_100) device / CUDA runtime; "
                                       "this library has no CPU fallback")
         self.handle = h
+        self._options = {}
         self.device = device
 
     def close(self):
@@ -215,6 +216,11 @@ class Context:
 
     def set_option(self, key: str, value: float) -> None:
         self.check(self.lib.asb_ctx_set_option(self.handle, key.encode(), float(value)))
+        self._options[key] = float(value)
+
+    def get_option(self, key: str, default: float = 0.0) -> float:
+        """The value last set through :meth:`set_option` (the library's default is the caller's to state)."""
+        return self._options.get(key, float(default))
 
     # ---- thin wrappers over the stage entry points -------------------------------------------
     def twonn_distances(self, rows, sample_idx) -> Tuple[np.ndarray, np.ndarray]:

@@ -65,7 +65,11 @@ def test_c2_100k_x_384_full(ctx, asb, oracle):
     _assert_lambda_close(lq, lq_want)
     _assert_topk_equal(idx, score, count, *want)
     assert np.array_equal(np.asarray(idx), want[0])                         # this path is held to identical ids ...
-    assert np.array_equal(np.asarray(score).view(np.uint64), want[1].view(np.uint64))   # ... and bit-identical scores
+    # ... and, fed the SAME lambdas as the oracle (the index's own agree to 1e-9, not to the bit), bit-identical scores
+    got = ctx.search_lambda_aware_batch(x, lam, queries, lq_want, 10, 0.7)
+    assert ctx.kernel_ms("search_pf_used") == 1.0
+    assert np.array_equal(np.asarray(got[0]), want[0])
+    assert np.array_equal(np.asarray(got[1]).view(np.uint64), want[1].view(np.uint64))
 
 
 def test_c3_1m_x_384_cluster_bits_all_lambdas_64_queries(ctx, asb, oracle):

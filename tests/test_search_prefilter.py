@@ -15,13 +15,17 @@ from oracle_binding import TAU_MEDIAN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def pctx(ctx):
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "mma_sync"])
+def pctx(ctx, request):
+    """Both instantiations of the prefilter tile: search_umma = 1 (default: tcgen05.mma + TMA + TMEM, csrc/search_umma.cuh)
+    and 0 (mma.sync + cp.async, csrc/search_pf.cuh) -- same certificate, same candidate lists, same finishing kernel."""
     ctx.set_option("search_prefilter", 1)
+    ctx.set_option("search_umma", request.param)
     try:
         yield ctx
     finally:
         ctx.set_option("search_prefilter", 1)
+        ctx.set_option("search_umma", 1)
 
 
 def _case(asb, oracle, n, f, nq, seed=42):
@@ -58,6 +62,7 @@ def test_prefilter_matches_oracle_bitwise(pctx, asb, oracle, n, f, nq, k, alpha)
     used = pctx.kernel_ms("search_pf_used")
     flags = pctx.kernel_ms("search_pf_flags")
     if used == 1.0:
+        assert pctx.kernel_ms("search_pf_umma") == pctx.get_option("search_umma", 1.0)   # the requested tile ran
         _bit_equal(got, want, k)
         assert pctx.kernel_ms("search_pf_rescored") >= nq * min(k, n)
     else:   # overflow -> exact kernel: the usual parity bar
