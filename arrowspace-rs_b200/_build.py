@@ -18,7 +18,7 @@ LIB_PATH = PKG_DIR / "libarrowspace_b200.so"
 ORACLE_DIR = ROOT / "oracle"
 ORACLE_LIB = ORACLE_DIR / "libarrowspace_oracle.so"
 
-CUDA_SOURCES = ["api.cu", "taumode.cu", "search.cu", "laplacian.cu", "cluster.cu", "cluster_replay.cu", "extras.cu"]
+CUDA_SOURCES = ["api.cu", "taumode.cu", "search.cu", "laplacian.cu", "cluster.cu", "cluster_replay.cu", "extras.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -2,7 +2,7 @@
 // entry points and the device-resident index (ArrowSpaceBuilder::build, src/builder.rs:249-455).
 #include <algorithm>
 
-#include "common.cuh"
+#include "comm.cuh"
 
 #define ASB_VERSION_STRING "arrowspace_b200 0.1.0 (sm_100a)"
 
@@ -27,7 +27,17 @@ struct asb_index {
     double tau_value = 0.0;
     double h_stats[3] = {0, 0, 0};
     double ms_cluster = 0, ms_laplacian = 0, ms_taumode = 0, ms_total = 0;
+    int64_t shard_offset = 0, n_global = 0;   // row-sharded build: global index of the first local row, global row count
 };
+
+// {min, max, sum} <-> {min, -max, sum}: one MIN all-reduce covers the first two
+__global__ void stats_pack_kernel(const double *in, double *out, int /*unused*/) {
+    if (threadIdx.x == 0) {
+        out[0] = in[0];
+        out[1] = -in[1];
+        out[2] = in[2];
+    }
+}
 
 extern "C" {
 
@@ -667,13 +677,18 @@ void asb_index_destroy(asb_index *ix) {
     delete ix;
 }
 
-int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const asb_build_params *bp,
-                    asb_index **out) {
+}  // extern "C"
+
+// stages 1-3 over the local rows; comm == nullptr (or one rank): the whole dataset is local
+static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, int64_t n, int64_t f, int64_t shard_offset,
+                            int64_t n_global, const asb_build_params *bp, asb_index **out) {
     ASB_TRY(set_device(ctx));
     if (!rows || !bp || !out) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: null pointer");
     *out = nullptr;
-    if (n <= 0) ASB_FAIL(ctx, ASB_ERR_EMPTY, "items cannot be empty");  // src/core.rs:416
-    if (n <= 1) ASB_FAIL(ctx, ASB_ERR_EMPTY, "cannot create a arrowspace of one arrow only");  // :417-420
+    const bool sharded = comm && comm->nranks > 1;
+    if (n_global <= 0) ASB_FAIL(ctx, ASB_ERR_EMPTY, "items cannot be empty");  // src/core.rs:416
+    if (n_global <= 1) ASB_FAIL(ctx, ASB_ERR_EMPTY, "cannot create a arrowspace of one arrow only");  // :417-420
+    if (n <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: a shard needs at least one row");
     if (f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: f<=0");
     if (bp->max_clusters <= 0 || !(bp->radius >= 0.0))
         ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: max_clusters/radius must come from the host heuristic");
@@ -687,6 +702,8 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
     ix->stream = ctx->stream;
     ix->n = n;
     ix->f = f;
+    ix->shard_offset = shard_offset;
+    ix->n_global = n_global;
     ix->max_clusters = bp->max_clusters;
     ix->radius = bp->radius;
     ix->tau_mode = bp->tau_mode;
@@ -727,12 +744,38 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
     // stage 1: clustering (src/eigenmaps.rs:224-232)
     cudaEventRecord(e0, ctx->stream);
     int64_t x = 0;
-    ASB_TRY(asb_dev_cluster(ctx, ix->items, n, f, bp->max_clusters, bp->radius, ix->centroids, ix->assign, ix->sizes, &x));
+    if (sharded)
+        ASB_TRY(asb_dev_cluster_sharded(ctx, comm, ix->items, n, f, bp->max_clusters, bp->radius, ix->centroids, ix->assign,
+                                        ix->sizes, &x));
+    else
+        ASB_TRY(asb_dev_cluster(ctx, ix->items, n, f, bp->max_clusters, bp->radius, ix->centroids, ix->assign, ix->sizes, &x));
     ix->x = x;
     cudaEventRecord(e1, ctx->stream);
-    // stage 2: feature Laplacian (src/eigenmaps.rs:313-323); assert clustered.shape().0 <= n_items holds
+    // stage 2: feature Laplacian (src/eigenmaps.rs:313-323); assert clustered.shape().0 <= n_items holds.  Row-sharded:
+    // rank 0 builds it once, the CSR is broadcast (a few hundred kB) -- every rank ends with the same bytes
     int64_t nnz = 0;
-    ASB_TRY(asb_dev_laplacian(ctx, ix->centroids, x, f, gp, ix->indptr, ix->indices, ix->data, cap, &nnz));
+    if (!sharded || comm->rank == 0) {
+        int rc_lap = asb_dev_laplacian(ctx, ix->centroids, x, f, gp, ix->indptr, ix->indices, ix->data, cap, &nnz);
+        if (!sharded) ASB_TRY(rc_lap);
+        else if (rc_lap != ASB_OK) nnz = -(int64_t)rc_lap;   // the status travels with the broadcast: no rank hangs
+    }
+    if (sharded) {
+        DevTmp<long long> hdr;
+        ASB_TRY(hdr.init(ctx, 1));
+        long long h_nnz = nnz;
+        ASB_CUDA(ctx, cudaMemcpyAsync(hdr.ptr, &h_nnz, 8, cudaMemcpyHostToDevice, ctx->stream));
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, hdr.ptr, 8, 0));
+        ASB_CUDA(ctx, cudaMemcpyAsync(&h_nnz, hdr.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_nnz < 0) {
+            if (comm->rank != 0) ctx->last_error = "feature Laplacian failed on rank 0";
+            return (int)(-h_nnz);
+        }
+        nnz = h_nnz;
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->indptr, (size_t)(f + 1) * sizeof(int64_t), 0));
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->indices, (size_t)nnz * sizeof(int64_t), 0));
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->data, (size_t)nnz * sizeof(double), 0));
+    }
     ix->nnz = nnz;
     {
         std::vector<int64_t> hp, hi;
@@ -767,6 +810,16 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
     ASB_TRY(asb_dev_taumode(ctx, ix->items, n, f, bp->spectral ? ix->plan_sig : ix->plan, bp->tau_mode, bp->tau_value,
                             ix->lambdas, ix->norms2, ix->stats, nullptr));
     cudaEventRecord(e3, ctx->stream);
+    if (sharded) {   // global lambda statistics (src/eigenmaps.rs:372-382): min, max, sum over all shards
+        DevTmp<double> st;
+        ASB_TRY(st.init(ctx, 3));
+        stats_pack_kernel<<<1, 32, 0, ctx->stream>>>(ix->stats, st.ptr, 0);
+        ASB_TRY(asb_comm_allreduce_f64(ctx, comm, st.ptr, 2, ASB_RED_MIN));      // {min, -max}
+        ASB_TRY(asb_comm_allreduce_f64(ctx, comm, st.ptr + 2, 1, ASB_RED_SUM));
+        stats_pack_kernel<<<1, 32, 0, ctx->stream>>>(st.ptr, ix->stats, 1);
+        ASB_TRY(asb_check_launch(ctx, "stats_pack_kernel"));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // st dies with this scope
+    }
     ASB_CUDA(ctx, cudaMemcpyAsync(ix->h_stats, ix->stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -781,6 +834,19 @@ int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, cons
     guard.p = nullptr;
     *out = ix;
     return ASB_OK;
+}
+
+extern "C" {
+
+int asb_index_build(asb_ctx *ctx, const double *rows, int64_t n, int64_t f, const asb_build_params *bp,
+                    asb_index **out) {
+    return index_build_impl(ctx, nullptr, rows, n, f, 0, n, bp, out);
+}
+
+int asb_index_build_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_local, int64_t n_local, int64_t f,
+                            int64_t shard_offset, int64_t n_global, const asb_build_params *bp, asb_index **out) {
+    if (!ctx || !comm) return ASB_ERR_INVALID;
+    return index_build_impl(ctx, comm, rows_local, n_local, f, shard_offset, n_global, bp, out);
 }
 
 int asb_index_info_get(const asb_index *ix, asb_index_info *info) {
@@ -905,5 +971,116 @@ int asb_index_search_lambda_aware(asb_ctx *ctx, const asb_index *ix, const doubl
     return asb_search_lambda_aware_batch(ctx, ix->items, ix->lambdas, ix->norms2, ix->n, ix->f, queries, lambda_q, nq,
                                          k, alpha, 0, idx, score, count);
 }
+
+
+// ---- row-sharded entry points ("multi-GPU variants taking an ncclComm_t + shard offset") -------------------
+
+/* EigenMaps::search over a row-sharded index: local top-k with global indices, all-gather of the per-shard lists
+ * (Q x k x 16 B per rank), k-way merge by (score desc, global index asc) = the order of the reference's stable sort
+ * (src/core.rs:785).  Every rank returns the merged result. */
+int asb_index_search_sharded(asb_ctx *ctx, asb_comm *comm, const asb_index *ix, const double *queries, int64_t nq, int64_t k,
+                             double alpha, int64_t *idx, double *score, int64_t *count, double *lambda_q_out) {
+    ASB_TRY(set_device(ctx));
+    if (!comm || !ix || !queries || !idx || !score) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search_sharded: null pointer");
+    if (nq <= 0 || k < 1) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search_sharded: bad sizes");
+    const int64_t f = ix->f;
+    const int R = comm->nranks;
+    DevIn<double> q;
+    DevTmp<double> lq, ls, gs;
+    DevTmp<int> flags;
+    DevTmp<int64_t> li, lc, gi, cnt_tmp;
+    DevOut<int64_t> oi, oc;
+    DevOut<double> os;
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lq.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 2));
+    ASB_TRY(ls.init(ctx, (size_t)nq * k));
+    ASB_TRY(li.init(ctx, (size_t)nq * k));
+    ASB_TRY(lc.init(ctx, (size_t)nq));
+    ASB_TRY(gs.init(ctx, (size_t)R * nq * k));
+    ASB_TRY(gi.init(ctx, (size_t)R * nq * k));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, 2 * sizeof(int), ctx->stream));
+    ASB_TRY(asb_dev_taumode(ctx, q.ptr, nq, f, ix->plan, ix->tau_mode, ix->tau_value, lq.ptr, nullptr, nullptr, flags.ptr));
+    // every collective is reached by every rank: an error on one rank is agreed on first
+    DevTmp<long long> agree;
+    ASB_TRY(agree.init(ctx, 1));
+    int h[2] = {0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(h, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    long long bad = h[0] ? ASB_ERR_NONFINITE_QUERY : 0;
+    int rc = ASB_OK;
+    if (!bad) {
+        rc = asb_dev_search(ctx, ix->items, ix->lambdas, ix->norms2, ix->n, f, q.ptr, lq.ptr, nq, k, alpha, ix->shard_offset,
+                            li.ptr, ls.ptr, lc.ptr, flags.ptr + 1);
+        if (rc == ASB_OK) {
+            ASB_CUDA(ctx, cudaMemcpyAsync(h + 1, flags.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            rc = search_status_to_rc(ctx, h[1]);
+        }
+        bad = rc;
+    }
+    ASB_CUDA(ctx, cudaMemcpyAsync(agree.ptr, &bad, 8, cudaMemcpyHostToDevice, ctx->stream));
+    ASB_TRY(asb_comm_allreduce_i64(ctx, comm, agree.ptr, 1, ASB_RED_MAX));
+    long long worst = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&worst, agree.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (worst != 0) {
+        if (bad == 0) ctx->last_error = "another rank failed in index_search_sharded";
+        else if (bad == ASB_ERR_NONFINITE_QUERY)
+            ctx->last_error = "Query item contains invalid values (NaN or infinity). All values must be finite.";
+        return (int)(bad ? bad : worst);
+    }
+    if (lambda_q_out) ASB_TRY(copy_out(ctx, lambda_q_out, lq.ptr, (size_t)nq * sizeof(double)));
+    // unused tail slots of a short shard: idx = -1 (the merge skips them)
+    ASB_TRY(asb_dev_mark_tail(ctx, li.ptr, lc.ptr, nq, k));
+    ASB_TRY(asb_comm_allgather_bytes(ctx, comm, ls.ptr, gs.ptr, (size_t)nq * k * sizeof(double)));
+    ASB_TRY(asb_comm_allgather_bytes(ctx, comm, li.ptr, gi.ptr, (size_t)nq * k * sizeof(int64_t)));
+    ASB_TRY(oi.init(ctx, idx, (size_t)nq * k));
+    ASB_TRY(os.init(ctx, score, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, count, count ? (size_t)nq : 0));
+    ASB_TRY(asb_dev_topk_merge(ctx, gs.ptr, gi.ptr, R, nq, k, os.ptr, oi.ptr, count ? oc.ptr : cnt_tmp.ptr));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
+
+/* The Two-NN scan over a row-sharded dataset (src/clustering.rs:118-145): sample_idx are GLOBAL row
+ * indices (the same list on every rank).  The sample rows are assembled on every rank (all-reduce of a gather buffer:
+ * each entry is non-zero on exactly one rank), every rank scans its own shard, the per-shard two nearest distances
+ * are all-gathered and merged.  d1 / d2 (f64[s]) are returned on every rank. */
+int asb_twonn_distances_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_local, int64_t n_local, int64_t f,
+                                int64_t shard_offset, const int64_t *sample_idx, int64_t s, double *d1, double *d2) {
+    ASB_TRY(set_device(ctx));
+    if (!comm || !rows_local || !sample_idx || !d1 || !d2) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn_sharded: null pointer");
+    if (n_local < 1 || f <= 0 || s <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn_sharded: bad sizes");
+    const int R = comm->nranks;
+    DevIn<double> rows;
+    DevIn<int64_t> samp;
+    DevTmp<double> q, part, all;
+    DevTmp<int64_t> self;
+    DevOut<double> o1, o2;
+    ASB_TRY(rows.init(ctx, rows_local, (size_t)n_local * f));
+    ASB_TRY(samp.init(ctx, sample_idx, (size_t)s));
+    ASB_TRY(q.init(ctx, (size_t)s * f));
+    ASB_TRY(self.init(ctx, (size_t)s));
+    ASB_TRY(part.init(ctx, (size_t)2 * s));
+    ASB_TRY(all.init(ctx, (size_t)R * 2 * s));
+    ASB_TRY(o1.init(ctx, d1, (size_t)s));
+    ASB_TRY(o2.init(ctx, d2, (size_t)s));
+    StageTimer t(ctx, "twonn");
+    ASB_TRY(asb_dev_twonn_gather(ctx, rows.ptr, n_local, f, shard_offset, samp.ptr, s, q.ptr, self.ptr));
+    ASB_TRY(asb_comm_allreduce_f64(ctx, comm, q.ptr, (size_t)s * f, ASB_RED_SUM));
+    ASB_TRY(asb_dev_twonn_queries(ctx, q.ptr, self.ptr, s, rows.ptr, n_local, f, part.ptr, part.ptr + s));
+    ASB_TRY(asb_comm_allgather_bytes(ctx, comm, part.ptr, all.ptr, (size_t)2 * s * sizeof(double)));
+    ASB_TRY(asb_dev_twonn_merge(ctx, all.ptr, R, s, o1.ptr, o2.ptr));
+    t.stop();
+    ASB_TRY(o1.finish(ctx));
+    ASB_TRY(o2.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int64_t asb_index_shard_offset(const asb_index *ix) { return ix ? ix->shard_offset : 0; }
 
 }  // extern "C"

@@ -24,7 +24,7 @@
 // 184k-row chunk (tests/replay_proto.py: min margin 0.14 against a net displacement of 0.066).
 #include <cub/cub.cuh>
 
-#include "common.cuh"
+#include "comm.cuh"
 
 namespace {
 
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) replay_max_kernel(const double *__restric
 __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restrict__ rows, int f,
                                                            const int *__restrict__ seg_off, const int *__restrict__ seg_rows,
                                                            int K, int saturated, double radius, double *cent,
-                                                           const double *__restrict__ cent0, unsigned long long *sizes,
+                                                           const double *__restrict__ cent0,
+                                                           const double *__restrict__ disp0, unsigned long long *sizes,
                                                            long long *__restrict__ assign, double *__restrict__ dcur,
                                                            unsigned long long *maxdisp_bits, int *fail) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
     const double *c0 = cent0 + (size_t)c * f;
     unsigned long long cnt = sizes[c];
     const double guard = 1e-9 * radius;
-    double dmax2 = 0.0;
+    double dmax2 = disp0 ? disp0[c] * disp0[c] * (1.0 + 1e-12) : 0.0;
     bool bad = false;
     const int lines = (f * 8 + 127) / 128;   // 128-byte lines per row
     for (int i = beg; i < end; ++i) {
@@ -213,8 +214,10 @@ template <int NPW, int RG>
 __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kernel(
     const double *__restrict__ rows, int f, const int *__restrict__ seg_off, const SegMeta *__restrict__ seg_meta, int K,
     int saturated, double radius, double disp_hint, double *__restrict__ cent, const double *__restrict__ cent0,
-    unsigned long long *sizes, long long *__restrict__ assign, double *__restrict__ dub, unsigned long long *maxdisp_bits,
-    int *fail) {
+    const double *__restrict__ disp0, unsigned long long *sizes, long long *__restrict__ assign, double *__restrict__ dub,
+    unsigned long long *maxdisp_bits, int *fail) {
+    // cent: the state the chains start from (in) and leave behind (out); cent0: the snapshot the rows were ranked
+    // against; disp0 (or null when the two coincide): |cent - cent0| per centroid on entry
     extern __shared__ __align__(128) unsigned char rp_smem[];
     __shared__ ChainShared sh;
     constexpr int FP = 128 * NPW;
@@ -259,11 +262,12 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
 #pragma unroll
     for (int u = 0; u < NPW; ++u) {
         const bool v = u < NPW - 1 || last_valid;
-        cr[u] = s0[u] = v ? cent0[(size_t)c * f + 128 * u + j0] : 0.0;   // padding holds zeros everywhere: no effect
+        s0[u] = v ? cent0[(size_t)c * f + 128 * u + j0] : 0.0;   // padding holds zeros everywhere: no effect
+        cr[u] = v ? cent[(size_t)c * f + 128 * u + j0] : 0.0;
     }
     double kd = (double)sizes[c];
     double y_next = __drcp_rn(kd + 1.0);
-    double B = 0.0, dmax = 0.0;
+    double B = disp0 ? disp0[c] : 0.0, dmax = B;
     int since = 0, par = 0;
     bool bad = false, go = true;
     const double guard = 1e-9 * radius;
@@ -505,6 +509,28 @@ __global__ void __launch_bounds__(256) growth_fill_kernel(int g, unsigned long l
     }
 }
 
+// |start_c - snap_c| per centroid (rounded up), and its maximum: the displacement the chains of a chunk start with when
+// the rows were ranked against an OLDER snapshot than the state they are applied to (row-sharded build)
+__global__ void __launch_bounds__(128) replay_disp0_kernel(const double *__restrict__ start, const double *__restrict__ snap,
+                                                           int K, int f, double *__restrict__ disp0,
+                                                           unsigned long long *maxdisp_bits, int *fail) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= K) return;
+    double acc = 0.0;
+    for (int j = lane; j < f; j += 32) {
+        const double e = start[(size_t)c * f + j] - snap[(size_t)c * f + j];
+        acc = fma(e, e, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const double d = sqrt(acc) * (1.0 + 1e-12);
+        disp0[c] = d;
+        if (d == d && d <= 1e300) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(d));
+        else atomicOr(fail, 1);
+    }
+}
+
 double opt_or(asb_ctx *ctx, const char *key, double dflt) {
     auto it = ctx->options.find(key);
     return it == ctx->options.end() ? dflt : it->second;
@@ -523,7 +549,7 @@ double ktimer_ms(asb_ctx *ctx, const char *name) {
 }
 
 struct ReplayWs {
-    DevTmp<double> qn2, xn2, dist, dcur, cent_tmp;
+    DevTmp<double> qn2, xn2, dist, dcur, cent_tmp, disp0;
     DevTmp<int64_t> idx, cnt, minus1;
     DevTmp<int> keys, vals, keys_s, vals_s, seg_off, flags;
     DevTmp<unsigned long long> sizes_tmp, scal;   // scal[0] = max |c|^2 bits, scal[1] = max displacement bits
@@ -542,6 +568,7 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     ASB_TRY(w.dist.init(ctx, (size_t)m * 2));
     ASB_TRY(w.dcur.init(ctx, (size_t)m));
     ASB_TRY(w.cent_tmp.init(ctx, (size_t)K * f));
+    ASB_TRY(w.disp0.init(ctx, (size_t)K));
     ASB_TRY(w.idx.init(ctx, (size_t)m * 2));
     ASB_TRY(w.cnt.init(ctx, (size_t)m));
     ASB_TRY(w.minus1.init(ctx, (size_t)m));
@@ -562,18 +589,16 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     return ASB_OK;
 }
 
-// One chunk.  *ok = 1: centroids / sizes / assign hold the walk's state after the chunk; 0: nothing was touched
-// except assign (the caller's sequential walk rewrites it).
-int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, int saturated, double radius,
-                 double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int *ok) {
-    *ok = 0;
+// Everything of a chunk that depends only on the SNAPSHOT the rows are ranked against: nearest / runner-up centroid of
+// every row, the rows sorted by nearest centroid, the per-position metadata.
+int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, const double *snap_d) {
     ASB_CUDA(ctx, cudaMemsetAsync(w.flags.ptr, 0, 2 * sizeof(int), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
     ASB_TRY(asb_dev_norms2(ctx, rows_d, m, f, w.qn2.ptr));
-    ASB_TRY(asb_dev_norms2(ctx, centroids_d, K, f, w.xn2.ptr));
+    ASB_TRY(asb_dev_norms2(ctx, snap_d, K, f, w.xn2.ptr));
     replay_max_kernel<<<1, 256, 0, ctx->stream>>>(w.xn2.ptr, K, w.scal.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_max_kernel"));
-    ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, centroids_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
+    ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, snap_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
                             w.cnt.ptr, w.flags.ptr + 1));
     replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.idx.ptr, m, K, w.keys.ptr, w.vals.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_keys_kernel"));
@@ -584,13 +609,30 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
     ctx->launches++;
     replay_offsets_kernel<<<(K + 1 + 255) / 256, 256, 0, ctx->stream>>>(w.keys_s.ptr, m, K, w.seg_off.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_offsets_kernel"));
+    replay_bounds_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.vals_s.ptr, m, f, w.dist.ptr, (const long long *)w.cnt.ptr,
+                                                                   w.qn2.ptr, w.scal.ptr, w.meta.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_bounds_kernel"));
+    return ASB_OK;
+}
+
+// The chains and the certification of a prepared chunk, from the state in centroids_d / sizes_d (snap_d == centroids_d
+// on one GPU; an older snapshot in the row-sharded build: the chains then start with the displacement |start - snap|).
+// *ok = 1: centroids / sizes / assign hold the walk's state after the chunk; 0: nothing was touched except assign (the
+// caller's sequential walk rewrites it).
+int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, int saturated, double radius,
+               const double *snap_d, double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d, int *ok) {
+    *ok = 0;
     ASB_CUDA(ctx, cudaMemcpyAsync(w.cent_tmp.ptr, centroids_d, (size_t)K * f * sizeof(double), cudaMemcpyDeviceToDevice,
                                   ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(w.sizes_tmp.ptr, sizes_d, (size_t)K * sizeof(unsigned long long),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
-    replay_bounds_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.vals_s.ptr, m, f, w.dist.ptr, (const long long *)w.cnt.ptr,
-                                                                   w.qn2.ptr, w.scal.ptr, w.meta.ptr);
-    ASB_TRY(asb_check_launch(ctx, "replay_bounds_kernel"));
+    const double *disp0 = nullptr;
+    if (snap_d != centroids_d) {
+        replay_disp0_kernel<<<(unsigned)((K + 3) / 4), 128, 0, ctx->stream>>>(centroids_d, snap_d, K, f, w.disp0.ptr,
+                                                                             w.scal.ptr + 1, w.flags.ptr);
+        ASB_TRY(asb_check_launch(ctx, "replay_disp0_kernel"));
+        disp0 = w.disp0.ptr;
+    }
     {
         KernelTimer kt(ctx, "cluster_chain_kernel");
         // the ring kernel needs 16-byte aligned rows of a multiple of 16 bytes (bulk copies) and f <= 1024
@@ -598,15 +640,15 @@ int replay_chunk(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, 
                              opt_or(ctx, "cluster_replay_generic_chain", 0.0) != 0.0;
         const double hint = 2.0 * w.last_disp;   // the displacement the previous chunk saw, doubled (inf at first)
 #define ASB_CHAIN_ARGS                                                                                                  \
-    K, saturated, radius, w.cent_tmp.ptr, centroids_d, w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, \
-        w.flags.ptr
+    K, saturated, radius, w.cent_tmp.ptr, snap_d, disp0, w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr,           \
+        w.scal.ptr + 1, w.flags.ptr
 #define ASB_CHAIN_TMA(NPW, RG)                                                                                         \
     {                                                                                                                   \
         const size_t smem = (size_t)kRingSlots * RG * (128 * NPW * sizeof(double) + sizeof(SegMeta));                   \
         ASB_CUDA(ctx, cudaFuncSetAttribute(replay_chain_tma_kernel<NPW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                                 \
         replay_chain_tma_kernel<NPW, RG><<<(unsigned)K, (kChainWarps + 1) * 32, smem, ctx->stream>>>(                   \
-            rows_d, f, w.seg_off.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, centroids_d,             \
+            rows_d, f, w.seg_off.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, snap_d, disp0,           \
             w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);                          \
     }
         if (generic)
@@ -727,8 +769,9 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
                 ws_ready = true;
             }
             ++tried;
-            ASB_TRY(replay_chunk(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
-                                 centroids_d, assign_d + lo, sizes_d, &ok));
+            ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, centroids_d));
+            ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
+                               centroids_d, centroids_d, assign_d + lo, sizes_d, &ok));
             ms_top2 += ktimer_ms(ctx, "cluster_top2_kernel");
             ms_chain += ktimer_ms(ctx, "cluster_chain_kernel");
         }
@@ -758,5 +801,101 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ctx->kernel_ms["cluster_replay_seq_ms"] = ms_seq;
     ctx->kernel_ms["cluster_replay_top2_ms"] = ms_top2;
     ctx->kernel_ms["cluster_replay_chain_ms"] = ms_chain;
+    return ASB_OK;
+}
+
+// ---- row-sharded walk (one process per GPU, shard g = global rows [offset_g, offset_g + n_g) in rank order) --
+// The walk is order dependent, so the K x F state still travels down the ranks -- but only the CHAINS are serial.  Rank 0
+// walks the head of its shard and broadcasts that state P as the common snapshot; every later rank ranks ALL its rows
+// against P (nearest / runner-up: the expensive contraction) while rank 0 is still finishing its shard; when the state
+// C arrives from the rank before, the chains start from C with the displacement |C - P| already on their books, and the
+// certification holds every row to the same proof as on one GPU.  A shard that cannot be proven against the stale
+// snapshot (or that receives a state still opening centroids) falls back to the single-GPU algorithm from the
+// received state -- the bits are the walk's either way, as asb_cluster_incremental_resume already guarantees.
+// The packed state is [x : int64][sizes : uint64 x max_clusters][centroids : f64 x max_clusters x f].
+namespace {
+size_t shard_state_bytes(int64_t max_clusters, int64_t f) { return 8 + (size_t)max_clusters * 8 + (size_t)max_clusters * f * 8; }
+
+int shard_pack(asb_ctx *ctx, unsigned char *pack_d, int64_t x, const double *cent_d, const unsigned long long *sizes_d,
+               int64_t max_clusters, int64_t f) {
+    ASB_CUDA(ctx, cudaMemcpyAsync(pack_d, &x, 8, cudaMemcpyHostToDevice, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(pack_d + 8, sizes_d, (size_t)max_clusters * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(pack_d + 8 + (size_t)max_clusters * 8, cent_d, (size_t)max_clusters * f * 8,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // &x is a stack address
+    return ASB_OK;
+}
+int shard_unpack(asb_ctx *ctx, const unsigned char *pack_d, int64_t *x, double *cent_d, unsigned long long *sizes_d,
+                 int64_t max_clusters, int64_t f) {
+    ASB_CUDA(ctx, cudaMemcpyAsync(x, pack_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sizes_d)
+        ASB_CUDA(ctx, cudaMemcpyAsync(sizes_d, pack_d + 8, (size_t)max_clusters * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(cent_d, pack_d + 8 + (size_t)max_clusters * 8, (size_t)max_clusters * f * 8,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+}  // namespace
+
+int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, int64_t n_local, int64_t f,
+                            int64_t max_clusters, double radius, double *centroids_d, int64_t *assign_d,
+                            unsigned long long *sizes_d, int64_t *x_out_host) {
+    if (!comm || comm->nranks == 1)
+        return asb_dev_cluster(ctx, rows_d, n_local, f, max_clusters, radius, centroids_d, assign_d, sizes_d, x_out_host, 0);
+    const int R = comm->nranks, r = comm->rank;
+    if (f <= 0 || max_clusters <= 0 || n_local < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster_sharded: bad sizes");
+    const size_t sb = shard_state_bytes(max_clusters, f);
+    DevTmp<unsigned char> pack;
+    DevTmp<double> snap;
+    ASB_TRY(pack.init(ctx, sb));
+    ASB_TRY(snap.init(ctx, (size_t)max_clusters * f));
+    ctx->kernel_ms["cluster_shard_speculative"] = 0.0;   // 1: this shard's rows were proven against the common snapshot
+    ctx->kernel_ms["cluster_shard_fallback"] = 0.0;      // 1: ... were not, and the shard was re-ranked from the fresh state
+    int64_t x = 0;
+    if (r == 0) {
+        int64_t head = (int64_t)opt_or(ctx, "cluster_shard_snapshot_rows", 262144.0);
+        if (head > n_local) head = n_local;
+        if (head > 0)
+            ASB_TRY(asb_dev_cluster(ctx, rows_d, head, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, 0));
+        ASB_TRY(shard_pack(ctx, pack.ptr, x, centroids_d, sizes_d, max_clusters, f));
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, 0));
+        if (n_local > head) {
+            const int64_t x_before = x;
+            ASB_TRY(asb_dev_cluster(ctx, rows_d + head * f, n_local - head, f, max_clusters, radius, centroids_d,
+                                    assign_d + head, sizes_d, &x, x_before));
+        }
+    } else {
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, 0));
+        int64_t x_snap = 0;
+        ASB_TRY(shard_unpack(ctx, pack.ptr, &x_snap, snap.ptr, nullptr, max_clusters, f));
+        // speculative ranking against the common snapshot, in parallel with the ranks still walking
+        ReplayWs w;
+        const bool speculate = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && opt_or(ctx, "cluster_shard_speculate", 1.0) != 0.0 &&
+                               x_snap == max_clusters && x_snap >= 2 && n_local >= 1024 && n_local <= (1 << 24) &&
+                               max_clusters * f <= (1ll << 27);
+        if (speculate) {
+            ASB_TRY(replay_ws_init(ctx, w, (int)n_local, (int)max_clusters, (int)f));
+            ASB_TRY(replay_prepare(ctx, w, rows_d, (int)n_local, (int)f, (int)x_snap, snap.ptr));
+        }
+        ASB_TRY(asb_comm_recv_bytes(ctx, comm, pack.ptr, sb, r - 1));
+        ASB_TRY(shard_unpack(ctx, pack.ptr, &x, centroids_d, sizes_d, max_clusters, f));
+        int ok = 0;
+        if (speculate && x == x_snap) {
+            w.last_disp = INFINITY;   // no hint: rows with thin margins take the exact step
+            ASB_TRY(replay_run(ctx, w, rows_d, (int)n_local, (int)f, (int)x, 1, radius, snap.ptr, centroids_d, assign_d,
+                               sizes_d, &ok));
+            ctx->kernel_ms["cluster_shard_speculative"] = ok ? 1.0 : 0.0;
+            ctx->kernel_ms["cluster_shard_fallback"] = ok ? 0.0 : 1.0;
+        }
+        if (!ok && n_local > 0) {
+            const int64_t x_before = x;
+            ASB_TRY(asb_dev_cluster(ctx, rows_d, n_local, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, x_before));
+        }
+    }
+    ASB_TRY(shard_pack(ctx, pack.ptr, x, centroids_d, sizes_d, max_clusters, f));
+    if (r < R - 1) ASB_TRY(asb_comm_send_bytes(ctx, comm, pack.ptr, sb, r + 1));
+    ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, R - 1));
+    ASB_TRY(shard_unpack(ctx, pack.ptr, &x, centroids_d, sizes_d, max_clusters, f));
+    *x_out_host = x;
     return ASB_OK;
 }

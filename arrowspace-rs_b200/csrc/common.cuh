@@ -256,6 +256,8 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
                    int64_t *count_d, int *status_d);
 int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, const int64_t *sample_d,
                   int64_t s, double *d1_d, double *d2_d);
+int asb_dev_twonn_queries(asb_ctx *ctx, const double *q_rows_d, const int64_t *self_d, int64_t s, const double *rows_d,
+                          int64_t n, int64_t f, double *d1_d, double *d2_d);
 int asb_dev_norms2(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, double *norms2_d);
 int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int64_t max_clusters,
                     double radius, double *centroids_d, int64_t *assign_d, unsigned long long *sizes_d,
@@ -278,3 +280,7 @@ int asb_dev_range_search(asb_ctx *ctx, const double *lambdas_d, int64_t n, doubl
                          int64_t *count_host);
 int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in_idx_d, int64_t parts,
                        int64_t nq, int64_t k, double *out_score_d, int64_t *out_idx_d, int64_t *out_count_d);
+int asb_dev_mark_tail(asb_ctx *ctx, int64_t *idx_d, const int64_t *cnt_d, int64_t nq, int64_t k);
+int asb_dev_twonn_gather(asb_ctx *ctx, const double *rows_d, int64_t n_local, int64_t f, int64_t offset,
+                         const int64_t *sample_d, int64_t s, double *q_d, int64_t *self_d);
+int asb_dev_twonn_merge(asb_ctx *ctx, const double *all_d, int parts, int64_t s, double *d1_d, double *d2_d);

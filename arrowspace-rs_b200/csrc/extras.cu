@@ -158,3 +158,61 @@ int asb_dev_project(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, co
     }
     return asb_check_launch(ctx, "project_kernel");
 }
+
+// ---- helpers of the row-sharded entry points (api.cu) ------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) mark_tail_kernel(long long *__restrict__ idx, const long long *__restrict__ cnt,
+                                                        long long nq, int k) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * k) return;
+    const long long q = t / k;
+    if ((t - q * k) >= cnt[q]) idx[t] = -1;
+}
+// sample t: the row (when this shard owns it, zeros otherwise) and its local index (or -1)
+__global__ void __launch_bounds__(128) twonn_gather_kernel(const double *__restrict__ rows, long long n_local, int f,
+                                                           long long offset, const long long *__restrict__ sample,
+                                                           long long s, double *__restrict__ q, long long *__restrict__ self) {
+    const long long t = blockIdx.x;
+    if (t >= s) return;
+    const long long g = sample[t] - offset;
+    const bool mine = g >= 0 && g < n_local;
+    for (int j = threadIdx.x; j < f; j += blockDim.x) q[t * f + j] = mine ? rows[g * f + j] : 0.0;
+    if (threadIdx.x == 0) self[t] = mine ? g : -1;
+}
+// two smallest of the 2 R per-shard distances of every sample
+__global__ void __launch_bounds__(256) twonn_merge_kernel(const double *__restrict__ all, int parts, long long s,
+                                                          double *__restrict__ d1, double *__restrict__ d2) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s) return;
+    double m1 = INFINITY, m2 = INFINITY;
+    for (int p = 0; p < parts; ++p)
+        for (int w = 0; w < 2; ++w) {
+            const double d = all[(size_t)p * 2 * s + (size_t)w * s + t];
+            if (d < m1) {
+                m2 = m1;
+                m1 = d;
+            } else if (d < m2) {
+                m2 = d;
+            }
+        }
+    d1[t] = m1;
+    d2[t] = m2;
+}
+}  // namespace
+
+int asb_dev_mark_tail(asb_ctx *ctx, int64_t *idx_d, const int64_t *cnt_d, int64_t nq, int64_t k) {
+    mark_tail_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, ctx->stream>>>((long long *)idx_d, (const long long *)cnt_d,
+                                                                              (long long)nq, (int)k);
+    return asb_check_launch(ctx, "mark_tail_kernel");
+}
+int asb_dev_twonn_gather(asb_ctx *ctx, const double *rows_d, int64_t n_local, int64_t f, int64_t offset,
+                         const int64_t *sample_d, int64_t s, double *q_d, int64_t *self_d) {
+    twonn_gather_kernel<<<(unsigned)s, 128, 0, ctx->stream>>>(rows_d, (long long)n_local, (int)f, (long long)offset,
+                                                              (const long long *)sample_d, (long long)s, q_d,
+                                                              (long long *)self_d);
+    return asb_check_launch(ctx, "twonn_gather_kernel");
+}
+int asb_dev_twonn_merge(asb_ctx *ctx, const double *all_d, int parts, int64_t s, double *d1_d, double *d2_d) {
+    twonn_merge_kernel<<<(unsigned)((s + 255) / 256), 256, 0, ctx->stream>>>(all_d, parts, (long long)s, d1_d, d2_d);
+    return asb_check_launch(ctx, "twonn_merge_kernel");
+}

@@ -395,14 +395,14 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const double *__restric
 // Two-NN rescoring: exact direct-form distances for the 4 GEMM-form candidates of each sample
 // (src/clustering.rs:125-130), two smallest -> d1, d2.  One warp per sample.
 __global__ void __launch_bounds__(128) twonn_rescore_kernel(const double *__restrict__ rows, long long n, int f,
-                                                            const long long *__restrict__ sample,
+                                                            const double *__restrict__ qrows,
                                                             const long long *__restrict__ cand_idx, int ncand,
                                                             long long s, double *__restrict__ d1,
                                                             double *__restrict__ d2) {
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= s) return;
-    const double *ri = rows + sample[w] * (long long)f;
+    const double *ri = qrows + w * (long long)f;   // the sample row itself (it may live on another GPU's shard)
     double m1 = INFINITY, m2 = INFINITY;
     for (int c = 0; c < ncand; ++c) {
         const long long j = cand_idx[w * ncand + c];
@@ -683,18 +683,8 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
                   double *d1_d, double *d2_d) {
     if (n < 2 || f <= 0 || s <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn: n=%lld s=%lld", (long long)n, (long long)s);
     // gather the sample rows (they are the "queries" of the contraction)
-    DevTmp<double> q, qn2, xn2, cs;
-    DevTmp<int64_t> ci, cc;
-    DevTmp<int> status;
+    DevTmp<double> q;
     ASB_TRY(q.init(ctx, (size_t)s * f));
-    ASB_TRY(qn2.init(ctx, (size_t)s));
-    ASB_TRY(xn2.init(ctx, (size_t)n));
-    const int ncand = (int)(n - 1 < 4 ? n - 1 : 4);
-    ASB_TRY(cs.init(ctx, (size_t)s * ncand));
-    ASB_TRY(ci.init(ctx, (size_t)s * ncand));
-    ASB_TRY(cc.init(ctx, (size_t)s));
-    ASB_TRY(status.init(ctx, 1));
-    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
     std::vector<int64_t> hs((size_t)s);
     ASB_CUDA(ctx, cudaMemcpyAsync(hs.data(), sample_d, s * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -703,6 +693,29 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
         ASB_CUDA(ctx, cudaMemcpyAsync(q.ptr + t * f, rows_d + hs[t] * f, f * sizeof(double),
                                       cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    return asb_dev_twonn_queries(ctx, q.ptr, sample_d, s, rows_d, n, f, d1_d, d2_d);
+}
+
+// The scan proper: for each of s query rows the two smallest Euclidean distances to the n rows, the row self_d[t] (an
+// index into rows, or -1: the sample lives elsewhere) left out.  Fewer than two admissible rows leave +inf.
+int asb_dev_twonn_queries(asb_ctx *ctx, const double *q_rows_d, const int64_t *self_d, int64_t s, const double *rows_d,
+                          int64_t n, int64_t f, double *d1_d, double *d2_d) {
+    if (n < 1 || f <= 0 || s <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "twonn: n=%lld s=%lld", (long long)n, (long long)s);
+    DevTmp<double> qn2, xn2, cs;
+    DevTmp<int64_t> ci, cc;
+    DevTmp<int> status;
+    struct QView {
+        const double *ptr;
+    } q{q_rows_d};
+    const int64_t *sample_d = self_d;
+    ASB_TRY(qn2.init(ctx, (size_t)s));
+    ASB_TRY(xn2.init(ctx, (size_t)n));
+    const int ncand = (int)(n < 4 ? n : 4);
+    ASB_TRY(cs.init(ctx, (size_t)s * ncand));
+    ASB_TRY(ci.init(ctx, (size_t)s * ncand));
+    ASB_TRY(cc.init(ctx, (size_t)s));
+    ASB_TRY(status.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(status.ptr, 0, sizeof(int), ctx->stream));
     ASB_TRY(asb_dev_norms2(ctx, q.ptr, s, f, qn2.ptr));
     ASB_TRY(asb_dev_norms2(ctx, rows_d, n, f, xn2.ptr));
     SearchArgs A{};
@@ -743,8 +756,7 @@ int asb_dev_twonn(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, cons
     ASB_TRY(run_search(ctx, MODE_L2, A, 0, ci.ptr, cs.ptr, cc.ptr));
     const int wpb = 4;
     twonn_rescore_kernel<<<(unsigned)((s + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-        rows_d, (long long)n, (int)f, (const long long *)sample_d, (const long long *)ci.ptr, ncand, (long long)s,
-        d1_d, d2_d);
+        rows_d, (long long)n, (int)f, q.ptr, (const long long *)ci.ptr, ncand, (long long)s, d1_d, d2_d);
     return asb_check_launch(ctx, "twonn_rescore_kernel");
 }
 

@@ -580,9 +580,7 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
         cudaGetLastError();
         umma = false;
     }
-    if (umma)
-        umma = um_make_map(&maps.qhi, qf.ptr, nq, fp, UM_TQ) && um_make_map(&maps.qlo, qlo.ptr, nq, fp, UM_TQ) &&
-               um_make_map(&maps.xhi, xf.ptr, n, fp, UM_TN) && um_make_map(&maps.xlo, xlo.ptr, n, fp, UM_TN);
+    if (umma) umma = um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp);
     if (umma) {
         const long long utiles = (n + UM_TN - 1) / UM_TN;
         pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, utiles, 64, &nslabs, &tps);
@@ -633,10 +631,7 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     A.status = SA.status;
     ctx->kernel_ms["search_pf_umma"] = umma ? 1.0 : 0.0;
     if (umma) {
-        const size_t usmem = um_smem_bytes(k, PF_COSINE);
-        ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-        KernelTimer kt(ctx, "search_pf_kernel");
-        search_umma_kernel<PF_COSINE><<<dim3((unsigned)((nq + UM_TQ - 1) / UM_TQ), (unsigned)nslabs), UM_THREADS, usmem, ctx->stream>>>(maps, A);
+        ASB_TRY(um_launch<PF_COSINE>(ctx, maps, A, nslabs, "search_pf_kernel"));
     } else {
         ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(ctx, "search_pf_kernel");
@@ -709,9 +704,7 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
         cudaGetLastError();
         umma = false;
     }
-    if (umma)
-        umma = um_make_map(&maps.qhi, qf.ptr, nq, fp, UM_TQ) && um_make_map(&maps.qlo, qlo.ptr, nq, fp, UM_TQ) &&
-               um_make_map(&maps.xhi, xf.ptr, n, fp, UM_TN) && um_make_map(&maps.xlo, xlo.ptr, n, fp, UM_TN);
+    if (umma) umma = um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp);
     if (umma) pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, (n + UM_TN - 1) / UM_TN, 64, &nslabs, &tps);
     ASB_TRY(xnrm.init(ctx, (size_t)n));
     ASB_TRY(qnrm.init(ctx, (size_t)nq));
@@ -768,10 +761,7 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     A.band_rel = 4.0 * e_cos * (1.0 + 1e-6);
     A.band_abs = 2e-13;
     if (umma) {
-        const size_t usmem = um_smem_bytes(k, PF_L2);
-        ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-        KernelTimer kt(ctx, "l2_pf_kernel");
-        search_umma_kernel<PF_L2><<<dim3((unsigned)((nq + UM_TQ - 1) / UM_TQ), (unsigned)nslabs), UM_THREADS, usmem, ctx->stream>>>(maps, A);
+        ASB_TRY(um_launch<PF_L2>(ctx, maps, A, nslabs, "l2_pf_kernel"));
     } else {
         ASB_CUDA(ctx, cudaFuncSetAttribute(search_pf_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt(ctx, "l2_pf_kernel");

@@ -22,14 +22,25 @@
 
 namespace {
 
-constexpr int UM_TQ = 128, UM_TN = 256, UM_KC = 32, UM_STAGES = 2;
-constexpr int UM_A_BYTES = UM_TQ * UM_KC * 4;                      // 16 KB: one query plane box
-constexpr int UM_B_BYTES = UM_TN * UM_KC * 4;                      // 32 KB: one item plane box
-constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES;    // hi + lo of both operands
+constexpr int UM_TQ = 128, UM_TN = 256;
 constexpr int UM_THREADS = 256;                                    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..7 epilogue
+constexpr int UM_RING_BYTES = 192 * 1024;                          // operand ring: UM_RING_BYTES / stage bytes stages
+constexpr int UM_MAX_STAGES = 4;
+// features per stage KC = 32 (128-byte rows, SWIZZLE_128B, 96 KB stages, 2 in the ring) or 16 (64-byte rows, SWIZZLE_64B,
+// 48 KB stages, 4 in the ring: three loads in flight while one stage is multiplied -- a 96 KB stage alone cannot keep
+// 64 B/clk of operand traffic in flight across the L2 latency, profiles/r02_umma_v1_summary.csv: tensor pipe 21 %)
+template <int KC>
+struct UmCfg {
+    static constexpr int A_BYTES = UM_TQ * KC * 4;                 // one query plane box
+    static constexpr int B_BYTES = UM_TN * KC * 4;                 // one item plane box
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi + lo of both operands
+    static constexpr int STAGES = UM_RING_BYTES / STAGE_BYTES;
+    static constexpr int ROW_BYTES = KC * 4;
+    static constexpr unsigned long long LAYOUT = KC == 32 ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
+};
 
 struct UmBarriers {
-    unsigned long long full[UM_STAGES], empty[UM_STAGES], tfull[2], tempty[2];
+    unsigned long long full[UM_MAX_STAGES], empty[UM_MAX_STAGES], tfull[2], tempty[2];
     unsigned tmem_base;
 };
 
@@ -61,14 +72,16 @@ __device__ __forceinline__ void um_tma_2d(void *dst, const CUtensorMap *map, int
         "l"(map), "r"(c0), "r"(c1), "r"(um_smem_u32(bar))
         : "memory");
 }
-// K-major operand plane, 128-byte swizzle: rows of 128 bytes, 8-row atoms 1024 bytes apart (the layout TMA writes with
-// CU_TENSOR_MAP_SWIZZLE_128B; descriptor fields as cute/arch/mma_sm100_desc.hpp, validated by tools/umma_probe.cu)
+// K-major operand plane, rows of ROW_BYTES (one swizzle span), 8-row atoms 8 ROW_BYTES apart -- the layout TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B / _64B (canonical layouts of cute/atom/mma_traits_sm100.hpp: Swizzle<3,4,3> / <2,4,3> o
+// ((8,n),2):((8 | 4,SBO),1) in 16-byte units; descriptor fields as cute/arch/mma_sm100_desc.hpp; tools/umma_probe.cu)
+template <int KC>
 __device__ __forceinline__ unsigned long long um_desc(unsigned saddr) {
     unsigned long long d = (unsigned long long)((saddr >> 4) & 0x3fff);
-    d |= 1ull << 16;                          // leading byte offset (unused for this layout)
-    d |= (unsigned long long)(1024 >> 4) << 32;   // stride byte offset: one 8-row atom
-    d |= 1ull << 46;                          // descriptor version (Blackwell)
-    d |= 2ull << 61;                          // SWIZZLE_128B
+    d |= 1ull << 16;                                                   // leading byte offset (unused for these layouts)
+    d |= (unsigned long long)((8 * UmCfg<KC>::ROW_BYTES) >> 4) << 32;  // stride byte offset: one 8-row atom
+    d |= 1ull << 46;                                                   // descriptor version (Blackwell)
+    d |= UmCfg<KC>::LAYOUT << 61;
     return d;
 }
 __device__ __forceinline__ void um_mma_tf32(unsigned tmem_c, unsigned long long da, unsigned long long db, unsigned idesc,
@@ -78,6 +91,29 @@ __device__ __forceinline__ void um_mma_tf32(unsigned tmem_c, unsigned long long 
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_c),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
+}
+// the same box delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in mask
+__device__ __forceinline__ void um_tma_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar,
+                                             unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+        "[%4], %5;" ::"r"(um_smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(um_smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void um_commit_mc(unsigned long long *bar, unsigned short mask) {   // ... in every CTA of mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     um_smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned um_cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void um_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void um_commit(unsigned long long *bar) {   // arrives when every MMA issued so far is done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(um_smem_u32(bar)) : "memory");
@@ -111,15 +147,23 @@ struct UmMaps {
 
 // shared memory: [UM_STAGES][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned), then per accumulator buffer the item-side
 // epilogue inputs (2 x 256 doubles each), then the per-query sorted lists (float, rounded down: still lower bounds)
-template <int MODE>
+// CL = CTAs per cluster (1, 2 or 4; consecutive query tiles of one slab): they walk the same item tiles in step, so
+// every item box is fetched from L2 ONCE per cluster and multicast into all CL shared memories -- rank c fetches piece c
+// of the 2 planes x 256 rows (CL = 2: one plane each; CL = 4: half a plane each).  A stage may only be refilled when
+// every CTA of the cluster has multiplied it: the MMA threads commit their "stage free" signal to all CL empty barriers.
+template <int MODE, int UM_KC, int CL>
 __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid_constant__ UmMaps maps, PfArgs A) {
+    constexpr int UM_A_BYTES = UmCfg<UM_KC>::A_BYTES, UM_B_BYTES = UmCfg<UM_KC>::B_BYTES;
+    constexpr int UM_STAGE_BYTES = UmCfg<UM_KC>::STAGE_BYTES, UM_STAGES = UmCfg<UM_KC>::STAGES;
     extern __shared__ __align__(1024) unsigned char um_smem[];
     __shared__ UmBarriers bars;
     // the swizzled boxes need 1024-byte alignment; the launch reserves the slack (um_smem_bytes)
     unsigned char *stages = um_smem + ((1024u - (um_smem_u32(um_smem) & 1023u)) & 1023u);
     double *ep_x0 = reinterpret_cast<double *>(stages + (size_t)UM_STAGES * UM_STAGE_BYTES);   // [2][UM_TN]: lambda / |x|^2
     double *ep_x1 = ep_x0 + 2 * UM_TN;                                                           // [2][UM_TN]: |x| (PF_L2)
-    float *lists = reinterpret_cast<float *>(ep_x1 + (MODE == PF_L2 ? 2 * UM_TN : 0));           // [UM_TQ][k]
+    float *ep_f0 = reinterpret_cast<float *>(ep_x1 + (MODE == PF_L2 ? 2 * UM_TN : 0));           // FP32 copies of both
+    float *ep_f1 = ep_f0 + 2 * UM_TN;
+    float *lists = ep_f1 + (MODE == PF_L2 ? 2 * UM_TN : 0);                                      // [UM_TQ][k]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = A.k, fp = A.fp;
@@ -132,10 +176,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     const int nchunks = fp / UM_KC;
     if (ntile == 0) return;
 
+    const unsigned crank = CL > 1 ? um_cluster_ctarank() : 0u;
+    constexpr unsigned short kAllCtas = (unsigned short)((1u << CL) - 1u);
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
             um_mbar_init(&bars.full[s], 1);
-            um_mbar_init(&bars.empty[s], 1);
+            um_mbar_init(&bars.empty[s], CL);
         }
         for (int b = 0; b < 2; ++b) {
             um_mbar_init(&bars.tfull[b], 1);
@@ -149,6 +195,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) um_cluster_sync();   // every CTA's barriers exist before a peer multicasts to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = bars.tmem_base;
 
@@ -165,8 +212,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     um_mbar_expect_tx(&bars.full[s], UM_STAGE_BYTES);
                     um_tma_2d(st, &maps.qhi, c * UM_KC, (int)q0, &bars.full[s]);
                     um_tma_2d(st + UM_A_BYTES, &maps.qlo, c * UM_KC, (int)q0, &bars.full[s]);
-                    um_tma_2d(st + 2 * UM_A_BYTES, &maps.xhi, c * UM_KC, row_x, &bars.full[s]);
-                    um_tma_2d(st + 2 * UM_A_BYTES + UM_B_BYTES, &maps.xlo, c * UM_KC, row_x, &bars.full[s]);
+                    if constexpr (CL == 1) {
+                        um_tma_2d(st + 2 * UM_A_BYTES, &maps.xhi, c * UM_KC, row_x, &bars.full[s]);
+                        um_tma_2d(st + 2 * UM_A_BYTES + UM_B_BYTES, &maps.xlo, c * UM_KC, row_x, &bars.full[s]);
+                    } else if constexpr (CL == 2) {   // rank 0: the hi plane, rank 1: the lo plane
+                        um_tma_2d_mc(st + 2 * UM_A_BYTES + crank * UM_B_BYTES, crank == 0 ? &maps.xhi : &maps.xlo, c * UM_KC,
+                                     row_x, &bars.full[s], kAllCtas);
+                    } else {                          // rank 0 / 1: halves of the hi plane, rank 2 / 3: of the lo plane
+                        um_tma_2d_mc(st + 2 * UM_A_BYTES + (crank >> 1) * UM_B_BYTES + (crank & 1) * (UM_B_BYTES / 2),
+                                     (crank >> 1) == 0 ? &maps.xhi : &maps.xlo, c * UM_KC, row_x + (int)(crank & 1) * (UM_TN / 2),
+                                     &bars.full[s], kAllCtas);
+                    }
                 }
             }
         }
@@ -188,14 +244,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     const unsigned sa = um_smem_u32(stages + (size_t)s * UM_STAGE_BYTES);
 #pragma unroll
                     for (int j = 0; j < UM_KC / 8; ++j) {
-                        const unsigned long long dah = um_desc(sa + 32 * j), dal = um_desc(sa + UM_A_BYTES + 32 * j);
-                        const unsigned long long dbh = um_desc(sa + 2 * UM_A_BYTES + 32 * j);
-                        const unsigned long long dbl = um_desc(sa + 2 * UM_A_BYTES + UM_B_BYTES + 32 * j);
+                        const unsigned long long dah = um_desc<UM_KC>(sa + 32 * j), dal = um_desc<UM_KC>(sa + UM_A_BYTES + 32 * j);
+                        const unsigned long long dbh = um_desc<UM_KC>(sa + 2 * UM_A_BYTES + 32 * j);
+                        const unsigned long long dbl = um_desc<UM_KC>(sa + 2 * UM_A_BYTES + UM_B_BYTES + 32 * j);
                         um_mma_tf32(tmem_c, dah, dbl, idesc, (c | j) ? 1u : 0u);
                         um_mma_tf32(tmem_c, dal, dbh, idesc, 1u);
                         um_mma_tf32(tmem_c, dah, dbh, idesc, 1u);
                     }
-                    um_commit(&bars.empty[s]);   // the stage is free once these instructions have read it
+                    // the stage is free once these instructions have read it -- in every CTA that feeds it
+                    if constexpr (CL == 1) um_commit(&bars.empty[s]);
+                    else um_commit_mc(&bars.empty[s], kAllCtas);
                 }
                 um_commit(&bars.tfull[b]);       // the accumulator is complete
             }
@@ -222,6 +280,18 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         double kth = -INFINITY;
         bool saw_nan = false;
         const double beta = 1.0 - A.alpha;
+        // The hot loop is FP32: sf approximates the FP64 score s~ of search_pf.cuh to within fdelta (operands rounded to
+        // FP32, five FP32 operations on magnitudes bounded by smag), and only an element with sf >= thr_f = (bound - band
+        // - fdelta) rounded down -- or a NaN -- reaches the FP64 code below, which evaluates s~ exactly as the mma.sync
+        // kernel does and applies the SAME tests: sf < thr_f implies s~ < bound - band, so the lists, the published bounds
+        // and the emitted candidates are unchanged.  (The FP64 epilogue cost 4x the tile's MMAs: profiles/r02_umma_v1_*.)
+        const float lqf = (float)lq, qnf2 = (float)(2.0 * qn), alf = (float)A.alpha, bef = (float)beta;
+        // |sf - s~| <= fdelta, u = 2^-24 < 6e-8.  Cosine: the lambda term is clamped at |lq - lx| >= 1, so only |lx| <=
+        // |lq| + 1.1 matter: u (2 |alpha| + |beta| (3 (|lq| + 1.1) + 4)).  L2: u (3 (q2 + x2) + 8 |q| |x|) <= 7 u (q2 + max x2).
+        // A non-finite fdelta (absurd lambda / norm) makes thr_f -inf: every element takes the exact path.
+        double fdelta;
+        if constexpr (MODE == PF_COSINE) fdelta = 1.0e-7 * (2.0 * fabs(A.alpha) + fabs(beta) * (3.0 * fabs(lq) + 8.0)) + 1e-30;
+        else fdelta = 1.0e-6 * (lq + __longlong_as_double((long long)*A.xn2max_bits)) + 1e-300;
         for (int t = 0; t < ntile; ++t) {
             const int b = t & 1;
             const long long i0 = (t_begin + t) * UM_TN;
@@ -229,19 +299,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
             for (int c = e; c < UM_TN; c += 128) {
                 const long long gi = i0 + c;
                 if constexpr (MODE == PF_COSINE) {
-                    ep_x0[b * UM_TN + c] = gi < A.n ? A.lambdas[gi] : 0.0;
+                    const double v0 = gi < A.n ? A.lambdas[gi] : 0.0;
+                    ep_x0[b * UM_TN + c] = v0;
+                    ep_f0[b * UM_TN + c] = (float)v0;
                 } else {
-                    ep_x0[b * UM_TN + c] = gi < A.n ? A.xn2[gi] : 0.0;
-                    ep_x1[b * UM_TN + c] = gi < A.n ? A.xnrm[gi] : 0.0;
+                    const double v0 = gi < A.n ? A.xn2[gi] : 0.0, v1 = gi < A.n ? A.xnrm[gi] : 0.0;
+                    ep_x0[b * UM_TN + c] = v0;
+                    ep_x1[b * UM_TN + c] = v1;
+                    ep_f0[b * UM_TN + c] = (float)v0;
+                    ep_f1[b * UM_TN + c] = (float)v1;
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const double gb = okq ? pf_dec(__ldcg(&A.gthr[gq])) : -INFINITY;   // bound published by any slab
             um_mbar_wait(&bars.tfull[b], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long nvalid = A.n - i0;   // columns below this index are real items
+            const long long nvalid_ll = A.n - i0;   // columns below this index are real items
+            const int nvalid = nvalid_ll < UM_TN ? (int)nvalid_ll : UM_TN;
+            const long long self_rel_ll = self - i0;
+            const int self_rel = (self_rel_ll >= 0 && self_rel_ll < UM_TN) ? (int)self_rel_ll : -1;
             bool changed = false;
             double bound = fmax(kth, gb);
+            float thr_f = okq ? __double2float_rd(bound - qband - fdelta) : INFINITY;   // -inf while the list is filling
+            const float *f0 = ep_f0 + b * UM_TN, *f1 = ep_f1 + b * UM_TN;
 #pragma unroll 1
             for (int c0 = 0; c0 < UM_TN; c0 += 32) {
                 unsigned v[32];
@@ -259,7 +339,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int c = c0 + j;
-                    const double cosv = (double)__uint_as_float(v[j]);
+                    const float cosf = __uint_as_float(v[j]);
+                    float sf;
+                    if constexpr (MODE == PF_COSINE) sf = fmaf(alf, cosf, bef * (1.0f - fminf(fabsf(lqf - f0[c]), 1.0f)));
+                    else sf = fmaf(qnf2 * f1[c], cosf, -(lqf + f0[c]));
+                    if (sf < thr_f) continue;   // (a NaN falls through)
+                    // ---- rare: the exact FP64 evaluation and tests of search_pf.cuh
+                    const double cosv = (double)cosf;
                     double s;
                     bool valid = c < nvalid;
                     if constexpr (MODE == PF_COSINE) {
@@ -267,23 +353,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                         s = A.alpha * cosv + beta * lam;                                       // core.rs:165 (approximate cos)
                     } else {
                         s = -(lq + ep_x0[b * UM_TN + c] - 2.0 * qn * ep_x1[b * UM_TN + c] * cosv);   // -|q - x|^2
-                        valid = valid && (i0 + c) != self;
+                        valid = valid && c != self_rel;
                     }
                     if (valid && s != s) saw_nan = true;
                     if (valid && s >= bound - qband) {
                         if (s > bound) {
                             // keep the slab's k best approximate scores: sorted descending, stored rounded DOWN
-                            const float sf = __double2float_rd(s);
+                            const float sd = __double2float_rd(s);
                             int pos = len < k ? len : k - 1;
-                            while (pos > 0 && lst[pos - 1] < sf) {
+                            while (pos > 0 && lst[pos - 1] < sd) {
                                 lst[pos] = lst[pos - 1];
                                 --pos;
                             }
-                            lst[pos] = sf;
+                            lst[pos] = sd;
                             if (len < k) ++len;
                             if (len == k) {
                                 kth = (double)lst[k - 1];
                                 bound = fmax(kth, gb);
+                                thr_f = __double2float_rd(bound - qband - fdelta);
                                 changed = true;
                             }
                         }
@@ -304,11 +391,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) um_cluster_sync();   // no CTA leaves while a peer may still write its shared memory or barriers
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 size_t um_smem_bytes(int k, int mode) {
-    return (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)(mode == PF_L2 ? 4 : 2) * UM_TN * 8 + (size_t)UM_TQ * k * 4 + 1024;
+    return (size_t)UM_RING_BYTES + (size_t)(mode == PF_L2 ? 4 : 2) * UM_TN * 12 + (size_t)UM_TQ * k * 4 + 1024;
 }
 
 typedef CUresult (*um_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -331,16 +419,17 @@ um_encode_fn um_encoder() {
     return fn;
 }
 
-// rows x fp fp32 plane, boxes of UM_KC features x box_rows rows, 128-byte swizzle, out-of-range rows read as zeros
-bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, int box_rows) {
+// rows x fp fp32 plane, boxes of kc features x box_rows rows, swizzle span = box row, out-of-range rows read as zeros
+bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, int box_rows, int kc) {
     um_encode_fn enc = um_encoder();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)fp, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)fp * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)UM_KC, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -348,6 +437,66 @@ bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, i
 bool um_wanted(asb_ctx *ctx) {
     auto it = ctx->options.find("search_umma");
     return it == ctx->options.end() || it->second != 0.0;
+}
+// option "search_umma_kc": features per pipeline stage, 16 (default) or 32
+int um_kc(asb_ctx *ctx) {
+    auto it = ctx->options.find("search_umma_kc");
+    return (it != ctx->options.end() && it->second == 32.0) ? 32 : 16;
+}
+
+// option "search_umma_cluster": CTAs that share one multicast item stream, 1, 2 (default) or 4
+int um_cluster(asb_ctx *ctx, long long nq) {
+    auto it = ctx->options.find("search_umma_cluster");
+    int cl = it == ctx->options.end() ? 2 : (int)it->second;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    while (cl > 1 && (nq + UM_TQ - 1) / UM_TQ < cl) cl >>= 1;   // fewer query tiles than CTAs per cluster
+    return cl;
+}
+
+bool um_make_maps(asb_ctx *ctx, UmMaps *maps, const float *qhi, const float *qlo, long long nq, const float *xhi,
+                  const float *xlo, long long n, int fp) {
+    const int kc = um_kc(ctx);
+    const int xbox = um_cluster(ctx, nq) == 4 ? UM_TN / 2 : UM_TN;   // rows per item box (a CTA of 4 fetches half a plane)
+    return um_make_map(&maps->qhi, qhi, nq, fp, UM_TQ, kc) && um_make_map(&maps->qlo, qlo, nq, fp, UM_TQ, kc) &&
+           um_make_map(&maps->xhi, xhi, n, fp, xbox, kc) && um_make_map(&maps->xlo, xlo, n, fp, xbox, kc);
+}
+
+template <int MODE, int KC, int CL>
+int um_launch_one(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, size_t usmem) {
+    ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<MODE, KC, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+    const unsigned qtiles = (unsigned)((A.nq + UM_TQ - 1) / UM_TQ);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((qtiles + CL - 1) / CL * CL, (unsigned)nslabs);   // a padding CTA sees no query in range
+    cfg.blockDim = dim3(UM_THREADS);
+    cfg.dynamicSmemBytes = usmem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ASB_CUDA(ctx, cudaLaunchKernelEx(&cfg, search_umma_kernel<MODE, KC, CL>, maps, A));
+    return ASB_OK;
+}
+
+template <int MODE>
+int um_launch(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, const char *timer) {
+    const size_t usmem = um_smem_bytes(A.k, MODE);
+    const int kc = um_kc(ctx), cl = um_cluster(ctx, A.nq);
+    ctx->kernel_ms["search_umma_cluster"] = (double)cl;
+    KernelTimer kt(ctx, timer);
+#define ASB_UM_GO(KC, CL) return um_launch_one<MODE, KC, CL>(ctx, maps, A, nslabs, usmem)
+    if (kc == 32) {
+        if (cl == 4) ASB_UM_GO(32, 4);
+        if (cl == 2) ASB_UM_GO(32, 2);
+        ASB_UM_GO(32, 1);
+    }
+    if (cl == 4) ASB_UM_GO(16, 4);
+    if (cl == 2) ASB_UM_GO(16, 2);
+    ASB_UM_GO(16, 1);
+#undef ASB_UM_GO
 }
 
 }  // namespace

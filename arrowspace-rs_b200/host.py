@@ -115,6 +115,16 @@ ABI_SYMBOLS = {
     "asb_index_signals": (C.c_int, [_P, _P, _P, _P, _P]),
     "asb_index_search": (C.c_int, [_P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P]),
     "asb_index_search_lambda_aware": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _D, _P, _P, _P]),
+    "asb_comm_unique_id": (C.c_int, [_P, _P]),
+    "asb_comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "asb_comm_from_nccl": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "asb_comm_destroy": (None, [_P]),
+    "asb_comm_rank": (C.c_int, [_P]),
+    "asb_comm_size": (C.c_int, [_P]),
+    "asb_twonn_distances_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P, _P]),
+    "asb_index_build_sharded": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, C.POINTER(BuildParamsC), C.POINTER(_P)]),
+    "asb_index_shard_offset": (_I64, [_P]),
+    "asb_index_search_sharded": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -155,14 +165,37 @@ def _ptr(a) -> int:
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     if hasattr(a, "data_ptr"):
+        if getattr(a, "is_cuda", False):
+            # The library runs on its context's stream, which has no ordering against torch's streams: whatever torch
+            # still has in flight for this tensor must be complete before the pointer is handed over (header contract:
+            # device buffers are ready when the call is made).  Idle streams make this a no-op.
+            import torch
+            torch.cuda.current_stream(a.device).synchronize()
         return a.data_ptr()
     raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _check_tensor(t, what: str = "buffer"):
+    """A torch tensor crosses the C ABI as a raw pointer: it must already be what the kernels expect -- float64 (or the
+    integer type the argument names), contiguous, and when it lives on a GPU that GPU must be usable by the caller's
+    context (the library classifies pointers, it cannot see dtypes or strides)."""
+    import torch
+    if not t.is_contiguous():
+        raise ArrowSpaceError(ASB_ERR_INVALID, f"{what}: torch tensor must be contiguous (row-major)")
+    if t.dtype not in (torch.float64, torch.int64, torch.uint64):
+        raise ArrowSpaceError(ASB_ERR_INVALID, f"{what}: torch tensor must be float64 (got {t.dtype})")
+    return t
 
 
 def _as_f64_matrix(rows) -> np.ndarray:
     """Vec<Vec<f64>> -> contiguous row-major f64 (the one repack the shim does)."""
     if hasattr(rows, "data_ptr"):
-        return rows
+        import torch
+        if rows.dtype != torch.float64:
+            raise ArrowSpaceError(ASB_ERR_INVALID, f"rows: torch tensor must be float64 (got {rows.dtype})")
+        if rows.dim() != 2:
+            raise ArrowSpaceError(ASB_ERR_INVALID, "rows must be a 2-D matrix")
+        return _check_tensor(rows, "rows")
     a = np.ascontiguousarray(rows, dtype=np.float64)
     if a.ndim != 2:
         raise ArrowSpaceError(ASB_ERR_INVALID, "rows must be a 2-D matrix")
@@ -230,6 +263,17 @@ class Context:
         d1 = np.empty(len(si), dtype=np.float64)
         d2 = np.empty(len(si), dtype=np.float64)
         self.check(self.lib.asb_twonn_distances(self.handle, _ptr(rows), n, f, _ptr(si), len(si), _ptr(d1), _ptr(d2)))
+        return d1, d2
+
+    def twonn_distances_sharded(self, comm: "Comm", rows_local, shard_offset: int, sample_idx):
+        """``asb_twonn_distances_sharded``: ``sample_idx`` are GLOBAL row indices, the same on every rank."""
+        rows_local = _as_f64_matrix(rows_local)
+        n, f = _shape2(rows_local)
+        si = np.ascontiguousarray(sample_idx, dtype=np.int64)
+        d1 = np.empty(len(si), dtype=np.float64)
+        d2 = np.empty(len(si), dtype=np.float64)
+        self.check(self.lib.asb_twonn_distances_sharded(self.handle, comm.handle, _ptr(rows_local), n, f, int(shard_offset),
+                                                        _ptr(si), len(si), _ptr(d1), _ptr(d2)))
         return d1, d2
 
     def cluster_incremental(self, rows, max_clusters: int, radius: float):
@@ -410,6 +454,109 @@ class Context:
 
 
 _default_ctx: Optional[Context] = None
+
+
+class Comm:
+    """One rank of a row-sharded job (``asb_comm``; one process per GPU, NCCL over NVLink inside the library).
+
+    ``Comm.make_unique_id(ctx)`` on rank 0 returns the 128 bytes of an ``ncclUniqueId``; ship them to the other ranks by
+    any means (``torch.distributed.broadcast_object_list``, a file, MPI ...) and construct ``Comm(ctx, nranks, rank, id)``
+    everywhere.  Every ``*_sharded`` call is collective."""
+
+    def __init__(self, ctx: "Context", nranks: int, rank: int, unique_id: bytes):
+        self.ctx = ctx
+        h = _P()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        ctx.check(ctx.lib.asb_comm_init_rank(ctx.handle, buf, int(nranks), int(rank), C.byref(h)))
+        self.handle = h
+        self.rank, self.size = int(rank), int(nranks)
+
+    @staticmethod
+    def make_unique_id(ctx: "Context") -> bytes:
+        buf = C.create_string_buffer(128)
+        ctx.check(ctx.lib.asb_comm_unique_id(ctx.handle, buf))
+        return bytes(buf.raw)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.asb_comm_destroy(self.handle)
+            self.handle = None
+
+
+class ShardedIndex:
+    """``asb_index_build_sharded``: stages 1-3 of ``ArrowSpaceBuilder::build`` (src/builder.rs:249-455) over a row-sharded
+    dataset, every intermediate resident in HBM.  ``rows_local``: this rank's rows (torch CUDA tensor or host array),
+    global rows ``[shard_offset, shard_offset + n_local)``.  Results equal a single-GPU build of the concatenated rows:
+    centroids bit-identical, assignments / Laplacian identical, lambdas of the local rows."""
+
+    def __init__(self, ctx: "Context", comm: Comm, rows_local, shard_offset: int, n_global: int, params: BuildParamsC):
+        self.ctx, self.comm = ctx, comm
+        rows_local = _as_f64_matrix(rows_local)
+        self.rows = rows_local              # borrowed by the native index when it is a device tensor
+        n, f = _shape2(rows_local)
+        self.n_local, self.f, self.offset, self.n_global = n, f, int(shard_offset), int(n_global)
+        h = _P()
+        ctx.check(ctx.lib.asb_index_build_sharded(ctx.handle, comm.handle, _ptr(rows_local), n, f, int(shard_offset),
+                                                  int(n_global), C.byref(params), C.byref(h)))
+        self.handle = h
+        self.params = params
+
+    def info(self) -> IndexInfoC:
+        info = IndexInfoC()
+        self.ctx.check(self.ctx.lib.asb_index_info_get(self.handle, C.byref(info)))
+        return info
+
+    def lambdas(self) -> np.ndarray:
+        out = np.empty(self.n_local, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.asb_index_lambdas(self.ctx.handle, self.handle, _ptr(out)))
+        return out
+
+    def assignments(self) -> np.ndarray:
+        out = np.empty(self.n_local, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.asb_index_assignments(self.ctx.handle, self.handle, _ptr(out)))
+        return out
+
+    def centroids(self) -> np.ndarray:
+        x = int(self.info().n_clusters)
+        out = np.empty((x, self.f), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.asb_index_centroids(self.ctx.handle, self.handle, _ptr(out)))
+        return out
+
+    def cluster_sizes(self) -> np.ndarray:
+        out = np.empty(int(self.info().n_clusters), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.asb_index_cluster_sizes(self.ctx.handle, self.handle, _ptr(out)))
+        return out
+
+    def laplacian(self):
+        nnz = int(self.info().nnz)
+        ip, ii, dd = np.empty(self.f + 1, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.asb_index_laplacian(self.ctx.handle, self.handle, _ptr(ip), _ptr(ii), _ptr(dd)))
+        return ip, ii, dd
+
+    def search(self, queries, k: int, alpha: float):
+        """``EigenMaps::search`` for a batch over all shards: merged (idx, score, count, lambda_q) on every rank."""
+        queries = _as_f64_matrix(queries)
+        nq, fq = _shape2(queries)
+        if fq != self.f:
+            raise ArrowSpaceError(ASB_ERR_DIM, f"Query dimension {fq} doesn't match index original dimension {self.f}")
+        if _is_device(queries):
+            import torch
+            idx = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+            score = torch.empty((nq, k), dtype=torch.float64, device=queries.device)
+            count = torch.empty(nq, dtype=torch.int64, device=queries.device)
+            lq = torch.empty(nq, dtype=torch.float64, device=queries.device)
+        else:
+            idx, score = np.empty((nq, k), dtype=np.int64), np.empty((nq, k), dtype=np.float64)
+            count, lq = np.empty(nq, dtype=np.int64), np.empty(nq, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.asb_index_search_sharded(self.ctx.handle, self.comm.handle, self.handle, _ptr(queries), nq,
+                                                             int(k), float(alpha), _ptr(idx), _ptr(score), _ptr(count),
+                                                             _ptr(lq)))
+        return idx, score, count, lq
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.asb_index_destroy(self.handle)
+            self.handle = None
 
 
 def default_context() -> Context:

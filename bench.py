@@ -269,6 +269,13 @@ def run_b200(args):
     asb._build.build_cuda()
     stream = torch.cuda.current_stream().cuda_stream
     ctx = asb.Context(local_rank, stream=stream if stream else None)
+    comm = None
+    if world > 1:
+        # the data path's collectives run inside the C ABI on its own NCCL communicator (asb_comm_*): torch.distributed
+        # only ships the 128-byte ncclUniqueId and the timing reductions
+        box = [asb.host.Comm.make_unique_id(ctx) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = asb.host.Comm(ctx, world, rank, box[0])
 
     n, f, nq = args.n, args.f, args.nq
     n_global = n * world
@@ -290,7 +297,9 @@ def run_b200(args):
         radius = float(t.item())
     gp = asb.GraphParams(GRAPH["eps"], GRAPH["k"], GRAPH["topk"], GRAPH["p"], GRAPH["sigma"])
     tm = asb.TauMode.Median
-    sample_idx = torch.from_numpy(asb.heuristics.sample_indices(n, 500, 129)).to(dev)
+    # Two-NN samples: 500 rows of the GLOBAL dataset (at N > 1 the per-shard two nearest are merged across ranks)
+    sample_idx_h = asb.heuristics.sample_indices(n_global, 500, 129)
+    sample_idx = torch.from_numpy(sample_idx_h).to(dev)
     d1 = torch.empty(500, dtype=torch.float64, device=dev)
     d2 = torch.empty(500, dtype=torch.float64, device=dev)
     lib = ctx.lib
@@ -310,11 +319,16 @@ def run_b200(args):
     kernel_acc = {"twonn_kernel": [], "cluster_kernel": [], "taumode_kernel": [], "search_kernel": [],
                   "search_pf_kernel": [], "search_pf_prep": [], "search_pf_finish": []}
     pf_diag = {}
+    shard_diag = {}
     stage_acc = {"twonn": [], "cluster": [], "laplacian": [], "taumode": [], "search": []}
 
     def twonn():
-        ctx.check(lib.asb_twonn_distances(ctx.handle, rows_d.data_ptr(), n, f, sample_idx.data_ptr(), 500,
-                                          d1.data_ptr(), d2.data_ptr()))
+        if world == 1:
+            ctx.check(lib.asb_twonn_distances(ctx.handle, rows_d.data_ptr(), n, f, sample_idx.data_ptr(), 500,
+                                              d1.data_ptr(), d2.data_ptr()))
+        else:
+            ctx.check(lib.asb_twonn_distances_sharded(ctx.handle, comm.handle, rows_d.data_ptr(), n, f, lo,
+                                                      sample_idx.data_ptr(), 500, d1.data_ptr(), d2.data_ptr()))
 
     def step_resident(record: bool):
         """One step with every input already resident in HBM.  Returns (build_ms, search_ms)."""
@@ -342,14 +356,21 @@ def run_b200(args):
             result = (idx, score, info)
             lib.asb_index_destroy(h)
         else:
-            index = asb.parallel.build_sharded(compute, dist, rows_d, lo, n_global, gp, tm, maxk, radius,
-                                               comm_device=dev, rank=rank, world=world)
+            bp = asb.host.BuildParamsC(gp.to_c(), tm.mode, tm.value, maxk, radius, 0)
+            index = asb.host.ShardedIndex(ctx, comm, rows_d, lo, n_global, bp)
             e[1].record()
-            idx, score, count = asb.parallel.search_sharded(compute, dist, index, queries_d, TOPK, ALPHA,
-                                                            comm_device=dev, world=world)
+            idx, score, count, _ = index.search(queries_d, TOPK, ALPHA)
             e[2].record()
             torch.cuda.synchronize()
-            result = (idx, score, index)
+            info = index.info()
+            if record:
+                stage_acc["cluster"].append(info.ms_cluster)
+                stage_acc["laplacian"].append(info.ms_laplacian)
+                stage_acc["taumode"].append(info.ms_taumode)
+                shard_diag["speculative"] = ctx.kernel_ms("cluster_shard_speculative")
+                shard_diag["fallback"] = ctx.kernel_ms("cluster_shard_fallback")
+            result = (idx, score, info)
+            index.close()
         if record:
             pf_used = ctx.kernel_ms("search_pf_used") == 1.0
             for kname in kernel_acc:
@@ -426,20 +447,16 @@ def run_b200(args):
                        idx.nbytes + score.nbytes + count.nbytes + lq.nbytes)
                 aspace._release()
             else:
-                rd = rows_h.to(dev, non_blocking=True)
-                qd = queries_h.to(dev, non_blocking=True)
-                index = asb.parallel.build_sharded(compute, dist, rd, lo, n_global, gp, tm, maxk, radius,
-                                                   comm_device=dev, rank=rank, world=world)
-                lam_h = index.lambdas.cpu()
+                bp = asb.host.BuildParamsC(gp.to_c(), tm.mode, tm.value, maxk, radius, 0)
+                index = asb.host.ShardedIndex(ctx, comm, rows_h.numpy(), lo, n_global, bp)   # host rows: H2D inside
+                lam_h = index.lambdas()
                 torch.cuda.synchronize()
                 t1 = time.perf_counter()
-                idx, score, count = asb.parallel.search_sharded(compute, dist, index, qd, TOPK, ALPHA,
-                                                                comm_device=dev, world=world)
-                idx_h, score_h = idx.cpu(), score.cpu()
+                idx_h, score_h, count_h, _ = index.search(queries_h.numpy(), TOPK, ALPHA)     # host in, host out
                 torch.cuda.synchronize()
                 t2 = time.perf_counter()
-                d2h = lam_h.numel() * 8 + idx_h.numel() * 8 + score_h.numel() * 8
-                del rd, qd, index
+                d2h = lam_h.size * 8 + idx_h.size * 8 + score_h.size * 8 + count_h.size * 8
+                index.close()
             if it > 0:
                 e2e_build.append(max_over_ranks((t1 - t0) * 1e3))
                 e2e_search.append(max_over_ranks((t2 - t1) * 1e3))
@@ -457,9 +474,7 @@ def run_b200(args):
     hbm_peak, peak_src = measured_peaks()
     dmma_peak, dfma_peak = fp64_peak()
     kms = {k: float(np.mean(v)) if v else 0.0 for k, v in kernel_acc.items()}
-    info_nnz = None
-    if world == 1:
-        info_nnz = int(last[2].nnz)
+    info_nnz = int(last[2].nnz)
     kernels = {}
     if kms["taumode_kernel"] > 0:
         by = n * (8 * f + 16)        # read the item once, write lambda + norm  (8F + 8 per item)
@@ -543,6 +558,9 @@ def run_b200(args):
                             "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
                             "note": "kernels.cluster_kernel.ms is the LAST sequential launch only when the replay is on"}
                            if not args.no_cluster_replay else None),
+        "sharded": ({"collectives": "inside the C ABI (asb_comm_*: dlopen'd NCCL): Two-NN sample all-reduce + 2-min all-gather, "
+                                    "centroid-state broadcast / send / recv, CSR broadcast, lambda-stat all-reduce, top-k "
+                                    "all-gather + merge", "rank0": shard_diag} if world > 1 else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
 

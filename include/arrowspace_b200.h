@@ -15,6 +15,9 @@
  *    device inside the call, host outputs are copied back before the call returns; device
  *    pointers are used in place (zero copy).
  *  - calls are synchronous on return; one context per host thread; no global state.
+ *  - stream contract: all work runs on the context's stream (the one given to asb_ctx_create, or a private non-blocking
+ *    stream).  DEVICE buffers passed in must be complete when the call is made -- or produced on that same stream; the
+ *    library inserts no cross-stream dependencies.  Outputs are complete when the call returns.
  *  - return value: 0 = ASB_OK, otherwise one of the ASB_ERR_* codes; asb_last_error(ctx)
  *    gives the text.  The library never aborts and has NO CPU fallback.
  */
@@ -31,7 +34,7 @@ extern "C" {
 #define ASB_OK 0
 #define ASB_ERR_INVALID 1         /* bad argument                                         */
 #define ASB_ERR_CUDA 2            /* CUDA runtime error / no device                        */
-#define ASB_ERR_NCCL 3            /* reserved                                              */
+#define ASB_ERR_NCCL 3            /* NCCL error / libnccl.so.2 not loadable (row-sharded entry points only) */
 #define ASB_ERR_NONFINITE_QUERY 4 /* src/core.rs:534-537 assert                            */
 #define ASB_ERR_ZERO_LAMBDA 5     /* src/core.rs:773-776 assert_ne!(query.lambda, 0.0)     */
 #define ASB_ERR_SHAPE 6           /* src/laplacian.rs:129-134 (needs >= 2x2)               */
@@ -52,6 +55,7 @@ extern "C" {
 
 typedef struct asb_ctx asb_ctx;
 typedef struct asb_index asb_index;
+typedef struct asb_comm asb_comm; /* one rank of a row-sharded job (wraps an ncclComm_t) */
 
 /* GraphParams, src/graph.rs:94-102, as passed by with_lambda_graph (src/builder.rs:109-137) */
 typedef struct {
@@ -284,6 +288,44 @@ int asb_index_search(asb_ctx *ctx, const asb_index *index, const double *queries
 int asb_index_search_lambda_aware(asb_ctx *ctx, const asb_index *index, const double *queries,
                                   const double *lambda_q, int64_t nq, int64_t k, double alpha,
                                   int64_t *idx, double *score, int64_t *count);
+
+/* ---- row-sharded multi-GPU variants: one process per GPU, NCCL over NVLink ---------------------------
+ * Items (and their lambdas) are sharded by row in rank order: rank g holds global rows [offset_g, offset_g + n_g);
+ * centroids, the feature Laplacian and the queries are replicated.  No collective touches the N x F items.  The library
+ * opens libnccl.so.2 at run time, so a process that already loaded NCCL shares that copy.
+ *   - either wrap the host's communicator:        asb_comm_from_nccl(ctx, ncclComm_t, &comm)
+ *   - or let the library create one: rank 0 calls asb_comm_unique_id (128 bytes = ncclUniqueId), ships the bytes to the
+ *     other ranks by any means, every rank calls asb_comm_init_rank.
+ * Every sharded call is collective: all ranks must make it, with the same replicated arguments. */
+int asb_comm_unique_id(asb_ctx *ctx, void *id_out_128_bytes);
+int asb_comm_init_rank(asb_ctx *ctx, const void *unique_id_128_bytes, int nranks, int rank, asb_comm **out);
+int asb_comm_from_nccl(asb_ctx *ctx, void *nccl_comm, asb_comm **out); /* borrowed: not destroyed with the handle */
+void asb_comm_destroy(asb_comm *comm);
+int asb_comm_rank(const asb_comm *comm);
+int asb_comm_size(const asb_comm *comm);
+
+/* asb_twonn_distances over the shards (src/clustering.rs:118-145): sample_idx holds GLOBAL row indices, identical on every
+ * rank.  Sample rows are assembled with one all-reduce (s x f doubles), each rank scans its own shard, the per-shard two
+ * nearest distances are all-gathered (2 s doubles per rank) and merged.  d1 / d2: f64[s] on every rank. */
+int asb_twonn_distances_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_local, int64_t n_local, int64_t f,
+                                int64_t shard_offset, const int64_t *sample_idx, int64_t s, double *d1, double *d2);
+
+/* asb_index_build over the shards.  Stage 1 is the order-preserving walk: rank 0 walks the head of its shard and
+ * broadcasts that state as the common snapshot; the other ranks rank their rows against it while the ranks before them
+ * are still walking; the K x F state (<= 6.1 MB) then travels rank to rank (ncclSend / ncclRecv) and each shard's chains are
+ * certified against it exactly as on one GPU (a shard that cannot be certified is re-ranked from the fresh state: same
+ * bits).  Stage 2 runs on rank 0, the CSR is broadcast.  Stage 3 is local; lambda min / max / sum are all-reduced
+ * (src/eigenmaps.rs:372-382), so asb_index_info reports GLOBAL statistics; n_items stays the local row count.  The
+ * accessors (lambdas, assignments) return the local shard; centroids / sizes / Laplacian are the global ones. */
+int asb_index_build_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_local, int64_t n_local, int64_t f,
+                            int64_t shard_offset, int64_t n_global, const asb_build_params *params, asb_index **out);
+int64_t asb_index_shard_offset(const asb_index *index);
+
+/* asb_index_search over the shards: local top-k with GLOBAL indices, ncclAllGather of the lists (Q x k x 16 B per rank),
+ * k-way merge by (score desc, index asc) = the reference's stable sort (src/core.rs:785).  Merged result on every rank;
+ * an error on any rank (non-finite query, lambda_q == 0, NaN score) is returned by all of them. */
+int asb_index_search_sharded(asb_ctx *ctx, asb_comm *comm, const asb_index *index, const double *queries, int64_t nq,
+                             int64_t k, double alpha, int64_t *idx, double *score, int64_t *count, double *lambda_q_out);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,10 @@ pub struct asb_ctx {
     _private: [u8; 0],
 }
 #[repr(C)]
+pub struct asb_comm {
+    _private: [u8; 0],
+}
+#[repr(C)]
 pub struct asb_index {
     _private: [u8; 0],
 }
@@ -161,6 +165,23 @@ extern "C" {
         alpha: f64, idx: *mut i64, score: *mut f64, count: *mut i64, lambda_q_out: *mut f64) -> c_int;
     pub fn asb_index_search_lambda_aware(ctx: *mut asb_ctx, index: *const asb_index, queries: *const f64,
         lambda_q: *const f64, nq: i64, k: i64, alpha: f64, idx: *mut i64, score: *mut f64, count: *mut i64) -> c_int;
+
+    // ---- row-sharded multi-GPU variants (one process per GPU, NCCL) ----
+    pub fn asb_comm_unique_id(ctx: *mut asb_ctx, id_out_128_bytes: *mut c_void) -> c_int;
+    pub fn asb_comm_init_rank(ctx: *mut asb_ctx, unique_id_128_bytes: *const c_void, nranks: c_int, rank: c_int,
+        out: *mut *mut asb_comm) -> c_int;
+    pub fn asb_comm_from_nccl(ctx: *mut asb_ctx, nccl_comm: *mut c_void, out: *mut *mut asb_comm) -> c_int;
+    pub fn asb_comm_destroy(comm: *mut asb_comm);
+    pub fn asb_comm_rank(comm: *const asb_comm) -> c_int;
+    pub fn asb_comm_size(comm: *const asb_comm) -> c_int;
+    pub fn asb_twonn_distances_sharded(ctx: *mut asb_ctx, comm: *mut asb_comm, rows_local: *const f64, n_local: i64,
+        f: i64, shard_offset: i64, sample_idx: *const i64, s: i64, d1: *mut f64, d2: *mut f64) -> c_int;
+    pub fn asb_index_build_sharded(ctx: *mut asb_ctx, comm: *mut asb_comm, rows_local: *const f64, n_local: i64, f: i64,
+        shard_offset: i64, n_global: i64, params: *const asb_build_params, out: *mut *mut asb_index) -> c_int;
+    pub fn asb_index_shard_offset(index: *const asb_index) -> i64;
+    pub fn asb_index_search_sharded(ctx: *mut asb_ctx, comm: *mut asb_comm, index: *const asb_index,
+        queries: *const f64, nq: i64, k: i64, alpha: f64, idx: *mut i64, score: *mut f64, count: *mut i64,
+        lambda_q_out: *mut f64) -> c_int;
 }
 
 /// `Err(status)` unless `rc == ASB_OK` -- the shim turns it into the reference's panic.

@@ -2,6 +2,7 @@
     python tools/profile_driver.py taumode|search|search_exact|cluster|twonn|laplacian [n] [f] [nq]
 `search` runs the default path (certified TF32 prefilter + exact rescoring, search_pf_kernel), `search_exact` the
 FP64 DMMA kernel (search_prefilter = 0)."""
+import os
 import sys
 from pathlib import Path
 
@@ -17,6 +18,9 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
 f = int(sys.argv[3]) if len(sys.argv) > 3 else 384
 nq = int(sys.argv[4]) if len(sys.argv) > 4 else 2048
 ctx = asb.Context(0)
+for kv in filter(None, os.environ.get("ASB_OPTS", "").split(",")):      # e.g. ASB_OPTS=search_umma_kc=32,search_umma=0
+    key, val = kv.split("=")
+    ctx.set_option(key, float(val))
 x = asb.synth.protein_like(n, f, seed=42)
 xd = torch.from_numpy(x).cuda()
 _, kmax = asb.heuristics.step1_bounds(1_000_000, f, f)
