@@ -720,13 +720,56 @@ static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, in
         ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); }
     } evg{e0, e1, e2, e3};
 
+    // Rows in host memory travel on a second stream in chunks while stage 1 already works on the head of the matrix
+    // (the replay's chunks double in size, the upload runs ahead of them): a build from host memory costs about the
+    // copy itself instead of copy + build.  Pinned host memory makes the copies truly asynchronous.
+    RowsInFlight upload;
+    struct UploadGuard {
+        asb_ctx *ctx;
+        RowsInFlight *u;
+        cudaStream_t s = nullptr;
+        cudaEvent_t ready = nullptr;
+        ~UploadGuard() {
+            ctx->rows_in_flight = nullptr;
+            if (s) cudaStreamSynchronize(s);
+            for (cudaEvent_t e : u->events) cudaEventDestroy(e);
+            if (ready) cudaEventDestroy(ready);
+            if (s) cudaStreamDestroy(s);
+        }
+    } upg{ctx, &upload};
     if (asb_is_device_ptr(rows)) {
         ix->items = rows;
     } else {
         ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->items_owned, (size_t)n * f * sizeof(double), ctx->stream));
-        ASB_CUDA(ctx, cudaMemcpyAsync(ix->items_owned, rows, (size_t)n * f * sizeof(double), cudaMemcpyHostToDevice,
-                                      ctx->stream));
         ix->items = ix->items_owned;
+        const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)((16u << 20) / ((size_t)f * sizeof(double))));
+        bool overlap = false;
+        {
+            auto it = ctx->options.find("build_overlap_upload");
+            overlap = (it == ctx->options.end() || it->second != 0.0) && n > 4 * rows_per_chunk;
+        }
+        if (overlap && cudaStreamCreateWithFlags(&upg.s, cudaStreamNonBlocking) == cudaSuccess) {
+            // the allocation above is stream-ordered on the context's stream: the copies wait for it
+            ASB_CUDA(ctx, cudaEventCreateWithFlags(&upg.ready, cudaEventDisableTiming));
+            ASB_CUDA(ctx, cudaEventRecord(upg.ready, ctx->stream));
+            ASB_CUDA(ctx, cudaStreamWaitEvent(upg.s, upg.ready, 0));
+            upload.base = ix->items_owned;
+            upload.f = f;
+            upload.rows_per_event = rows_per_chunk;
+            for (int64_t r0 = 0; r0 < n; r0 += rows_per_chunk) {
+                const int64_t cnt = std::min<int64_t>(rows_per_chunk, n - r0);
+                ASB_CUDA(ctx, cudaMemcpyAsync(ix->items_owned + r0 * f, rows + r0 * f, (size_t)cnt * f * sizeof(double),
+                                              cudaMemcpyHostToDevice, upg.s));
+                cudaEvent_t ev;
+                ASB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ASB_CUDA(ctx, cudaEventRecord(ev, upg.s));
+                upload.events.push_back(ev);
+            }
+            ctx->rows_in_flight = &upload;
+        } else {
+            ASB_CUDA(ctx, cudaMemcpyAsync(ix->items_owned, rows, (size_t)n * f * sizeof(double), cudaMemcpyHostToDevice,
+                                          ctx->stream));
+        }
     }
     const int64_t cap = asb_laplacian_max_nnz(f, gp.topk);
     ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->lambdas, (size_t)n * sizeof(double), ctx->stream));
@@ -750,6 +793,7 @@ static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, in
     else
         ASB_TRY(asb_dev_cluster(ctx, ix->items, n, f, bp->max_clusters, bp->radius, ix->centroids, ix->assign, ix->sizes, &x));
     ix->x = x;
+    asb_wait_rows(ctx, ix->items + n * f);   // stage 3 reads every row
     cudaEventRecord(e1, ctx->stream);
     // stage 2: feature Laplacian (src/eigenmaps.rs:313-323); assert clustered.shape().0 <= n_items holds.  Row-sharded:
     // rank 0 builds it once, the CSR is broadcast (a few hundred kB) -- every rank ends with the same bytes

@@ -406,6 +406,7 @@ int asb_dev_cluster_seq(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f
                  (long long)max_clusters);
     if (f > 16384 || max_clusters > (1 << 20)) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "cluster: f or max_clusters too large");
     if (init_k < 0 || init_k > max_clusters) ASB_FAIL(ctx, ASB_ERR_INVALID, "cluster: init_k=%lld", (long long)init_k);
+    asb_wait_rows(ctx, rows_d + n * f);   // (a build from host memory may still be uploading the tail of the matrix)
     const size_t smem_cap = 227 * 1024;
     ClusterArgs A{};
     A.rows = rows_d;

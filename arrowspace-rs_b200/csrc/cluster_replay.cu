@@ -592,6 +592,7 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
 // Everything of a chunk that depends only on the SNAPSHOT the rows are ranked against: nearest / runner-up centroid of
 // every row, the rows sorted by nearest centroid, the per-position metadata.
 int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, const double *snap_d) {
+    asb_wait_rows(ctx, rows_d + (size_t)m * f);
     ASB_CUDA(ctx, cudaMemsetAsync(w.flags.ptr, 0, 2 * sizeof(int), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
     ASB_TRY(asb_dev_norms2(ctx, rows_d, m, f, w.qn2.ptr));
@@ -700,6 +701,7 @@ static int growth_run(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, 
     int64_t p = n < max_clusters ? n : max_clusters;
     if (p > 2048) p = 2048;
     if (p < 8 || !(radius == radius)) return ASB_OK;
+    asb_wait_rows(ctx, rows_d + p * f);
     DevTmp<int> first;
     ASB_TRY(first.init(ctx, 1));
     const int big = (int)p;

@@ -17,7 +17,17 @@ struct KTimerEvents {
     cudaEvent_t a = nullptr, b = nullptr;
 };
 
+// Rows still travelling host -> device on a second stream while the build already works on the head of the matrix
+// (asb_index_build from host memory): events recorded after every copied chunk, in row order.
+struct RowsInFlight {
+    const double *base = nullptr;   // device address of row 0
+    int64_t f = 0, rows_per_event = 0;
+    std::vector<cudaEvent_t> events;
+    int waited = -1;                // the compute stream already waits for events[0 .. waited]
+};
+
 struct asb_ctx {
+    RowsInFlight *rows_in_flight = nullptr;
     std::map<std::string, KTimerEvents> ktimers;  // per-kernel device timers (see KernelTimer)
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -150,6 +160,20 @@ struct DevTmp {
         if (ptr) cudaFreeAsync(ptr, stream);
     }
 };
+
+// Make the context's stream wait until the rows before `end` (a device address inside the matrix being uploaded) have
+// landed.  No-op unless an upload is in flight.
+static inline void asb_wait_rows(asb_ctx *ctx, const double *end) {
+    RowsInFlight *r = ctx->rows_in_flight;
+    if (!r || r->events.empty() || end <= r->base) return;
+    const int64_t rows = (int64_t)((end - r->base) + r->f - 1) / r->f;
+    int idx = (int)((rows + r->rows_per_event - 1) / r->rows_per_event) - 1;
+    if (idx >= (int)r->events.size()) idx = (int)r->events.size() - 1;
+    if (idx > r->waited) {
+        cudaStreamWaitEvent(ctx->stream, r->events[idx], 0);
+        r->waited = idx;
+    }
+}
 
 static inline int asb_sync(asb_ctx *ctx) {
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

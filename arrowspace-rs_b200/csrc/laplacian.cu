@@ -22,6 +22,27 @@ namespace {
 
 constexpr int kMaxT1 = 64;  // topk + 1 upper bound held in registers/local arrays
 
+// one thread per centroid: sequential, separately rounded sums over its F values (the oracle's order)
+__global__ void __launch_bounds__(128) standardise_rows_kernel(const double *__restrict__ cent, int x, int f, int ddof,
+                                                               double *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= x) return;
+    const double *row = cent + (size_t)c * f;
+    double s = 0.0, s2 = 0.0;
+    for (int j = 0; j < f; ++j) {
+        const double v = row[j];
+        s = __dadd_rn(s, v);
+        s2 = __dadd_rn(s2, __dmul_rn(v, v));
+    }
+    const double n = (double)f;
+    const double mean = __ddiv_rn(s, n);
+    double var = __dsub_rn(__ddiv_rn(s2, n), __dmul_rn(mean, mean));
+    if (ddof) var = __dmul_rn(var, __ddiv_rn(n, n - 1.0));
+    double sd = sqrt(var);
+    if (!(sd > 0.0)) sd = 1.0;
+    for (int j = 0; j < f; ++j) out[(size_t)c * f + j] = __ddiv_rn(__dsub_rn(row[j], mean), sd);
+}
+
 __global__ void feat_norms_kernel(const double *__restrict__ cent, int x, int f, double *__restrict__ mag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= f) return;
@@ -270,8 +291,6 @@ int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_
     if (x < 2 || f < 2)
         ASB_FAIL(ctx, ASB_ERR_SHAPE, "items should be at least of shape (2,2): (%lld,%lld)", (long long)f,
                  (long long)x);  // src/laplacian.rs:129-134
-    if (gp.normalise)
-        ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "normalise=true (smartcore StandardScaler) is a host-side step");
     if (gp.topk < 0 || gp.topk + 1 > kMaxT1)
         ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "topk=%lld outside 0..%d", (long long)gp.topk, kMaxT1 - 1);
     if (f > 32768) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "feature graph with %lld nodes", (long long)f);
@@ -296,6 +315,19 @@ int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_
     ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, 2 * sizeof(int), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(bitmap.ptr, 0, (size_t)f * wpr * sizeof(unsigned), ctx->stream));
 
+    // normalise (src/laplacian.rs:146-151): StandardScaler over the F x X matrix handed to build_laplacian_matrix, i.e.
+    // every COLUMN of it -- every centroid, across its F feature values -- is shifted to mean 0 and scaled to unit
+    // standard deviation.  smartcore 0.4.5 is not in the mount: mean = sum / F (features ascending), variance =
+    // sum(x^2) / F - mean^2 (normalise = 1, population form) or the same times F / (F - 1) (normalise = 2), a zero
+    // deviation leaves the column unscaled -- the oracle restates exactly this, the convention itself is "unpinned".
+    DevTmp<double> scaled;
+    if (gp.normalise) {
+        ASB_TRY(scaled.init(ctx, (size_t)x * f));
+        standardise_rows_kernel<<<(xi + 127) / 128, 128, 0, ctx->stream>>>(centroids_d, xi, fi, gp.normalise == 2 ? 1 : 0,
+                                                                          scaled.ptr);
+        ASB_TRY(asb_check_launch(ctx, "standardise_rows_kernel"));
+        centroids_d = scaled.ptr;
+    }
     feat_norms_kernel<<<(fi + 127) / 128, 128, 0, ctx->stream>>>(centroids_d, xi, fi, mag.ptr);
     ASB_TRY(asb_check_launch(ctx, "feat_norms_kernel"));
     feat_dist_kernel<<<dim3((fi + 127) / 128, fi), 128, 0, ctx->stream>>>(centroids_d, xi, fi, mag.ptr,

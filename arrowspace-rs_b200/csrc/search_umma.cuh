@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         double fdelta;
         if constexpr (MODE == PF_COSINE) fdelta = 1.0e-7 * (2.0 * fabs(A.alpha) + fabs(beta) * (3.0 * fabs(lq) + 8.0)) + 1e-30;
         else fdelta = 1.0e-6 * (lq + __longlong_as_double((long long)*A.xn2max_bits)) + 1e-300;
+        if (!(fdelta < 1e25)) fdelta = INFINITY;   // beyond FP32's range (or NaN): no pre-test
         for (int t = 0; t < ntile; ++t) {
             const int b = t & 1;
             const long long i0 = (t_begin + t) * UM_TN;
@@ -336,16 +337,39 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (!okq || c0 >= nvalid) continue;
+                // branch-free over the 32 columns: a bit per column whose FP32 score reaches the threshold
+                unsigned hot = 0u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = c0 + j;
-                    const float cosf = __uint_as_float(v[j]);
-                    float sf;
-                    if constexpr (MODE == PF_COSINE) sf = fmaf(alf, cosf, bef * (1.0f - fminf(fabsf(lqf - f0[c]), 1.0f)));
-                    else sf = fmaf(qnf2 * f1[c], cosf, -(lqf + f0[c]));
-                    if (sf < thr_f) continue;   // (a NaN falls through)
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(f0 + c0 + j4);
+                    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (MODE == PF_L2) a1 = *reinterpret_cast<const float4 *>(f1 + c0 + j4);
+                    const float x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float cosf = __uint_as_float(v[j4 + u]);
+                        float sf;
+                        if constexpr (MODE == PF_COSINE) sf = fmaf(alf, cosf, bef * (1.0f - fminf(fabsf(lqf - x0[u]), 1.0f)));
+                        else sf = fmaf(qnf2 * x1[u], cosf, -(lqf + x0[u]));
+                        hot |= (sf < thr_f) ? 0u : (1u << (j4 + u));   // (a NaN sets its bit)
+                    }
+                }
+                while (hot) {
+                    const int j = __ffs(hot) - 1;
+                    hot &= hot - 1;
+                    unsigned vj = 0u;
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) vj = (j == t) ? v[t] : vj;   // v stays in registers
+                    {   // the threshold may have risen since the bit was set
+                        const float cosf = __uint_as_float(vj);
+                        float sf;
+                        if constexpr (MODE == PF_COSINE) sf = fmaf(alf, cosf, bef * (1.0f - fminf(fabsf(lqf - f0[c0 + j]), 1.0f)));
+                        else sf = fmaf(qnf2 * f1[c0 + j], cosf, -(lqf + f0[c0 + j]));
+                        if (sf < thr_f) continue;
+                    }
                     // ---- rare: the exact FP64 evaluation and tests of search_pf.cuh
-                    const double cosv = (double)cosf;
+                    const int c = c0 + j;
+                    const double cosv = (double)__uint_as_float(vj);
                     double s;
                     bool valid = c < nvalid;
                     if constexpr (MODE == PF_COSINE) {

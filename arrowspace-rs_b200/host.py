@@ -765,6 +765,7 @@ class ArrowSpace:
         builder.cluster_radius = radius        # :217
         cent, asg, sizes = builder.ctx.cluster_incremental(rows, k_opt, radius)
         aspace.n_clusters = cent.shape[0]      # :242-245
+        aspace.is_standin = bool(getattr(builder, "is_standin", False))
         aspace.cluster_assignments = asg
         aspace.cluster_sizes = sizes
         aspace.cluster_radius = radius
@@ -1000,10 +1001,24 @@ class ArrowSpaceBuilder:
                            self.normalise, self.sparsity_check, self.self_included, self.rectified)
 
     def resolve_cluster_params(self, rows) -> Tuple[int, float]:
+        """(k_opt, radius).  The reference derives them with ``compute_optimal_k`` (src/clustering.rs:36-72: a
+        Calinski-Harabasz search over smartcore KMeans seeded through rand::StdRng) -- third-party code that cannot be
+        reproduced outside Rust, so a Rust host keeps calling the reference's own function and passes the pair in
+        (``with_cluster_params``).  Without them this Python mirror falls back to the documented STAND-IN
+        (heuristics.compute_optimal_k_standin): the build is then self-consistent but NOT the reference's build of the
+        same rows; ``is_standin`` is set on the returned space and a warning is emitted once per builder."""
         if self._explicit_cluster_params:
+            self.is_standin = False
             return int(self.cluster_max_clusters), float(self.cluster_radius)
+        import warnings
         from .heuristics import compute_optimal_k_standin
         k_opt, radius, _ = compute_optimal_k_standin(self.ctx, rows, self.clustering_seed)
+        if not getattr(self, "is_standin", False):
+            warnings.warn("ArrowSpaceBuilder: (max_clusters, radius) come from the stand-in heuristic, not from the "
+                          "reference's compute_optimal_k (smartcore KMeans + StdRng): results differ from arrowspace-rs on "
+                          "the same rows; pass with_cluster_params(k_opt, radius) for a drop-in build", RuntimeWarning,
+                          stacklevel=3)
+        self.is_standin = True
         return k_opt, radius
 
     def build(self, rows) -> Tuple[ArrowSpace, GraphLaplacian]:
@@ -1049,6 +1064,7 @@ class ArrowSpaceBuilder:
         aspace.cluster_assignments = asg
         aspace.cluster_sizes = sizes
         aspace.cluster_radius = radius
+        aspace.is_standin = bool(getattr(self, "is_standin", False))   # cluster parameters from the stand-in heuristic
         aspace.lambda_stats = (info.lambda_min, info.lambda_max, info.lambda_sum / n)
         gl = GraphLaplacian(indptr, indices, data, n, gp, cent)
         if self.prebuilt_spectral:

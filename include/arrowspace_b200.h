@@ -65,7 +65,8 @@ typedef struct {
     double p;
     int32_t has_sigma; /* sigma: Option<f64>; None -> 1.0 (src/laplacian.rs:254) */
     double sigma;
-    int32_t normalise;      /* must be 0 (StandardScaler path is host-side, unsupported) */
+    int32_t normalise;      /* src/laplacian.rs:146-151 StandardScaler over the F x X matrix: 0 off, 1 population variance
+                             * (sum x^2 / F - mean^2), 2 sample variance; smartcore's own convention is unpinned */
     int32_t sparsity_check; /* src/graph.rs:185-193 */
     int32_t self_included;  /* smartcore kNN switch, default 0 (see DESIGN.md "unpinned") */
     int32_t rectified;      /* 0: 1-cos (default) ; 1: 1-max(0,cos) */

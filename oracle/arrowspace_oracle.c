@@ -358,10 +358,34 @@ int aso_feature_laplacian(const double *centroids, int64_t x, int64_t f,
                           const aso_lap_params *P, int64_t *indptr, int64_t *indices,
                           double *data, int64_t *nnz_out) {
     if (x < 2 || f < 2) return ASO_ERR_SHAPE; /* laplacian.rs:129-134 */
-    if (P->normalise) return ASO_ERR_INVALID;  /* StandardScaler is third-party */
     int64_t t1 = P->topk + 1;                   /* :211 */
     double sigma = P->has_sigma ? P->sigma : 1.0; /* :254 */
     int rc = ASO_OK;
+    /* normalise (laplacian.rs:146-151): StandardScaler::fit(&transposed).transform -- per COLUMN of the F x X matrix =
+     * per centroid over its F values.  smartcore 0.4.5 is absent from the mount (PARITY UNPINNED for this branch):
+     * restated as mean = sum / F, var = sum(x^2) / F - mean^2 (normalise == 1) or x F / (F - 1) (normalise == 2),
+     * zero deviation -> divisor 1. */
+    double *scaled = NULL;
+    if (P->normalise) {
+        scaled = (double *)malloc((size_t)x * (size_t)f * sizeof(double));
+        if (!scaled) return ASO_ERR_INVALID;
+        for (int64_t c = 0; c < x; ++c) {
+            const double *row = centroids + c * f;
+            double s = 0.0, s2 = 0.0;
+            for (int64_t j = 0; j < f; ++j) {
+                s += row[j];
+                s2 += row[j] * row[j];
+            }
+            const double n = (double)f;
+            const double mean = s / n;
+            double var = s2 / n - mean * mean;
+            if (P->normalise == 2) var = var * (n / (n - 1.0));
+            double sd = sqrt(var);
+            if (!(sd > 0.0)) sd = 1.0;
+            for (int64_t j = 0; j < f; ++j) scaled[c * f + j] = (row[j] - mean) / sd;
+        }
+        centroids = scaled;
+    }
 
     /* node i = feature column i of the centroid matrix (graph.rs:172 transpose) */
     double *mag = (double *)malloc((size_t)f * sizeof(double));
@@ -479,6 +503,7 @@ int aso_feature_laplacian(const double *centroids, int64_t x, int64_t f,
     free(W);
     free(A);
     free(vn);
+    free(scaled);
     return rc;
 }
 

@@ -99,7 +99,7 @@ typedef struct {
     double p;
     int has_sigma;
     double sigma;
-    int normalise;      /* must be 0: StandardScaler is third-party (unpinned) */
+    int normalise;      /* 0 off; 1: StandardScaler, population variance; 2: sample variance (third-party: unpinned) */
     int sparsity_check; /* src/graph.rs:185-193 */
     int self_included;  /* 0 (default): kNN result never contains the query row */
     int rectified;      /* 0 (default): dist = 1 - cos ; 1: 1 - max(0,cos) */

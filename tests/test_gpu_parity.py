@@ -168,6 +168,60 @@ def test_taumode_heavy_duplicates_and_extremes(ctx, asb, oracle):
         assert np.allclose(lam, want, rtol=1e-14, atol=0, equal_nan=True), (mode, value, lam, want)
 
 
+def test_taumode_near_constant_rows_return_the_well_conditioned_value(ctx, asb, oracle):
+    """Near-constant rows (x = c + tiny ripple): the reference sums x_i L_ij x_j (src/taumode.rs:565-588), which cancels
+    catastrophically -- num is the small difference of O(c^2) terms and keeps only ~16 - 2 log10(c / ripple) digits; the
+    kernel sums w_ij (x_i - x_j)^2 over the undirected edges (taumode_sym.cuh), which does not cancel.  The two agree
+    to 1e-9 wherever the reference's own form is accurate to 1e-9, and where it is not the kernel returns the
+    WELL-CONDITIONED value: it matches an exact (fraction arithmetic) evaluation, the oracle does not."""
+    from fractions import Fraction
+    rng = np.random.default_rng(3)
+    f = 48
+    cent = asb.synth.protein_like(40, f, seed=9)
+    csr = _graph(oracle, cent)
+    ip, ii, dd = csr
+    rows = []
+    for ripple in (1e-2, 1e-5, 1e-7):
+        rows.append(3.0 + ripple * rng.standard_normal(f))
+    x = np.ascontiguousarray(np.vstack(rows))
+    # tau = 1 removes the (1 - tau) G term, which otherwise dominates lambda on such rows and hides the Rayleigh
+    # quotient's error (with tau < 1 both forms agree to ~1e-13 even here: lambda >= (1 - tau) / #edges)
+    tau = 1.0
+    want = oracle.compute_taumode(x, csr, TAU_FIXED, tau)
+    got, _, _ = ctx.compute_taumode(x, csr, _tm(asb, TAU_FIXED, tau))
+
+    def exact_lambda(row, tau):
+        xs = [Fraction(float(v)) for v in row]
+        num, edge = Fraction(0), Fraction(0)
+        shares = []
+        for r in range(f):
+            for e in range(ip[r], ip[r + 1]):
+                c, lij = int(ii[e]), Fraction(float(dd[e]))
+                num += xs[r] * lij * xs[c]
+                if c != r and lij < 0:
+                    t = -lij * (xs[r] - xs[c]) ** 2
+                    edge += t
+                    shares.append(t)
+        den = sum(v * v for v in xs)
+        energy = num / den if den > Fraction(1, 10 ** 12) else Fraction(0)
+        g = sum((t / edge) ** 2 for t in shares) if edge > 0 else Fraction(0)
+        g = min(max(g, Fraction(0)), Fraction(1))
+        t = Fraction(tau)
+        return float(t * (energy / (energy + t)) + (1 - t) * g)
+
+    exact = np.array([exact_lambda(r, tau) for r in x])
+    rel_gpu = np.abs(np.asarray(got) - exact) / np.abs(exact)
+    rel_ref = np.abs(want - exact) / np.abs(exact)
+    assert rel_gpu.max() < 1e-9, rel_gpu                 # the kernel is accurate on every row
+    assert rel_ref[0] < 1e-9                              # mild ripple: the reference's form is fine, both agree
+    assert abs(got[0] - want[0]) <= 1e-9 * abs(want[0])
+    assert rel_ref[2] > 1e-4                              # ripple 1e-7 on a base of 3: the reference's own sum has lost it
+    # same rows, tau = 0.3: the dispersion term carries lambda and the two forms agree to the parity bar
+    want3 = oracle.compute_taumode(x, csr, TAU_FIXED, 0.3)
+    got3, _, _ = ctx.compute_taumode(x, csr, _tm(asb, TAU_FIXED, 0.3))
+    _assert_lambda_close(got3, want3)
+
+
 def test_prepare_query_item(ctx, asb, oracle, golden):
     db = golden["proteins"]
     csr = _graph(oracle, db[:20])
@@ -364,9 +418,25 @@ def test_laplacian_errors(ctx, asb, golden):
     with pytest.raises(asb.ArrowSpaceError) as ei:               # zero-magnitude feature column
         ctx.build_feature_laplacian(z, gp)
     assert ei.value.status == 10
-    with pytest.raises(asb.ArrowSpaceError) as ei:               # StandardScaler path stays on the host
-        ctx.build_feature_laplacian(golden["proteins"][:10], asb.GraphParams(0.5, 6, 3, 2.0, None, normalise=True))
-    assert ei.value.status == 14
+
+
+@pytest.mark.parametrize("normalise", [1, 2])
+@pytest.mark.parametrize("x,f,eps", [(20, 24, 1.5), (100, 128, 1.2), (316, 384, 1.0)])
+def test_laplacian_with_normalisation(ctx, asb, oracle, golden, normalise, x, f, eps):
+    """normalise = true (src/laplacian.rs:146-151): column standardisation of the F x X matrix before the kNN.  Centred
+    columns make cosine distances spread over [0, 2], so eps is wider than in the other tests.  normalise = 1 / 2 selects
+    the variance convention (population / sample); smartcore's StandardScaler itself is unpinned."""
+    cent = golden["proteins"][:x] if (x, f) == (20, 24) else asb.synth.protein_like(x, f, seed=12)
+    gp = dict(eps=eps, k=12, topk=4, p=2.0, sigma=0.5)
+    want = oracle.feature_laplacian(cent, normalise=normalise, **gp)
+    got = ctx.build_feature_laplacian(cent, asb.GraphParams(eps, 12, 4, 2.0, 0.5, normalise=normalise))
+    _assert_csr_equal(got, want)
+    plain = oracle.feature_laplacian(cent, **gp)
+    assert want[0][-1] != plain[0][-1] or not np.array_equal(want[1], plain[1])      # it really changes the graph
+    d = np.zeros((f, f))
+    for r in range(f):
+        d[r, want[1][want[0][r]:want[0][r + 1]]] = want[2][want[0][r]:want[0][r + 1]]
+    assert np.allclose(d.sum(1), 0.0, atol=1e-12) and np.allclose(d, d.T)             # still a Laplacian
 
 
 # ================================================================================ clustering (K2)
