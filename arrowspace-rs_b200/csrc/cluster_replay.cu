@@ -24,15 +24,17 @@
 // 184k-row chunk (tests/replay_proto.py: min margin 0.14 against a net displacement of 0.066).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "comm.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) replay_keys_kernel(const int64_t *__restrict__ top2_idx, int m, int K,
+__global__ void __launch_bounds__(256) replay_keys_kernel(const int64_t *__restrict__ top2_idx, int stride, int m, int K,
                                                           int *__restrict__ keys, int *__restrict__ vals) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < m) {
-        const int64_t b = top2_idx[2 * (size_t)r];
+        const int64_t b = top2_idx[(size_t)stride * r];
         keys[r] = (b >= 0 && b < K) ? (int)b : K;   // a row without a nearest centroid (NaN row) goes to bucket K: no chain
         vals[r] = r;                                 // touches it, the certification fails on its missing candidates
     }
@@ -420,17 +422,24 @@ __global__ void __launch_bounds__(256) replay_bounds_kernel(const int *__restric
                                                             const long long *__restrict__ top2_cnt,
                                                             const double *__restrict__ qn2,
                                                             const unsigned long long *cn2max_bits,
+                                                            const double *__restrict__ near_b,
                                                             SegMeta *__restrict__ meta) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int r = rows_sorted[i];
-    const double cn2max = __longlong_as_double((long long)*cn2max_bits);
-    const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
-    const double d0 = top2_dist[2 * (size_t)r], d1 = top2_dist[2 * (size_t)r + 1];
     SegMeta mt;
-    mt.dlo = sqrt(fmax(d0 * d0 - e2, 0.0)) * (1.0 - 1e-15);
-    mt.dhi = sqrt(d0 * d0 + e2) * (1.0 + 1e-15);
-    mt.slo = top2_cnt[r] >= 2 ? sqrt(fmax(d1 * d1 - e2, 0.0)) * (1.0 - 1e-15) : 0.0;
+    if (near_b) {   // certified bounds straight from the tcgen05 ranking pass (search_umma.cuh, PF_NEAR)
+        mt.dlo = near_b[3 * (size_t)r];
+        mt.dhi = near_b[3 * (size_t)r + 1];
+        mt.slo = near_b[3 * (size_t)r + 2];
+    } else {
+        const double cn2max = __longlong_as_double((long long)*cn2max_bits);
+        const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
+        const double d0 = top2_dist[2 * (size_t)r], d1 = top2_dist[2 * (size_t)r + 1];
+        mt.dlo = sqrt(fmax(d0 * d0 - e2, 0.0)) * (1.0 - 1e-15);
+        mt.dhi = sqrt(d0 * d0 + e2) * (1.0 + 1e-15);
+        mt.slo = top2_cnt[r] >= 2 ? sqrt(fmax(d1 * d1 - e2, 0.0)) * (1.0 - 1e-15) : 0.0;
+    }
     if (!(mt.dhi == mt.dhi) || !(mt.dlo == mt.dlo) || !(mt.slo == mt.slo)) {   // no usable distance: exact steps only
         mt.dlo = 0.0;
         mt.dhi = 1e300;
@@ -446,11 +455,18 @@ __global__ void __launch_bounds__(256) replay_certify_kernel(const double *__res
                                                              const double *__restrict__ qn2, const unsigned long long *cn2max_bits,
                                                              const unsigned long long *maxdisp_bits,
                                                              const long long *__restrict__ assign, double radius, int f,
-                                                             int m, int *fail) {
+                                                             int m, const double *__restrict__ near_b, int *fail) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
-    const double cn2max = __longlong_as_double((long long)*cn2max_bits);
     const double maxdisp = __longlong_as_double((long long)*maxdisp_bits);
+    if (near_b) {   // bounds from the tcgen05 ranking pass: slo / dlo are already certified lower bounds
+        const double lower_n = near_b[3 * (size_t)r + 2] - maxdisp;
+        const double lb_n = fmax(near_b[3 * (size_t)r] - maxdisp, 0.0);
+        const bool dropped_n = lb_n * lb_n > 1.5 * radius * (1.0 + 1e-9) && assign[r] == -1;
+        if (!(dcur[r] < lower_n || dropped_n)) atomicOr(fail, 2);
+        return;
+    }
+    const double cn2max = __longlong_as_double((long long)*cn2max_bits);
     // GEMM-form squared distance |q|^2 + |c|^2 - 2 q.c from the FP64 tensor pipe: absolute error below e2
     const double e2 = 1e-15 * (double)(f + 32) * (qn2[r] + cn2max);
     const double s = top2_dist[2 * (size_t)r + 1];
@@ -555,9 +571,13 @@ struct ReplayWs {
     DevTmp<unsigned long long> sizes_tmp, scal;   // scal[0] = max |c|^2 bits, scal[1] = max displacement bits
     DevTmp<unsigned char> cub_tmp;
     DevTmp<SegMeta> meta;
+    DevTmp<int64_t> near_idx;
+    DevTmp<double> near_b;
+    bool use_near = false;   // the current preparation ranked with the tcgen05 tile (certified bounds, no exact top-2)
     size_t cub_bytes = 0;
     int cap_m = 0, cap_k = 0;
     double last_disp = INFINITY;   // largest centroid displacement of the previous (proven) chunk
+    int last_flags = 0;            // fail flags of the last run (bit 1: a row missed its certificate, bit 0: not replayable)
 };
 
 int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
@@ -578,6 +598,8 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     ASB_TRY(w.vals_s.init(ctx, (size_t)m));
     ASB_TRY(w.seg_off.init(ctx, (size_t)K + 1));
     ASB_TRY(w.meta.init(ctx, (size_t)m));
+    ASB_TRY(w.near_idx.init(ctx, (size_t)m));
+    ASB_TRY(w.near_b.init(ctx, (size_t)3 * m));
     ASB_TRY(w.flags.init(ctx, 2));
     ASB_TRY(w.sizes_tmp.init(ctx, (size_t)K));
     ASB_TRY(w.scal.init(ctx, 2));
@@ -591,7 +613,8 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
 
 // Everything of a chunk that depends only on the SNAPSHOT the rows are ranked against: nearest / runner-up centroid of
 // every row, the rows sorted by nearest centroid, the per-position metadata.
-int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, const double *snap_d) {
+int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, int K, const double *snap_d,
+                   bool allow_near = true) {
     asb_wait_rows(ctx, rows_d + (size_t)m * f);
     ASB_CUDA(ctx, cudaMemsetAsync(w.flags.ptr, 0, 2 * sizeof(int), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -599,9 +622,19 @@ int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f
     ASB_TRY(asb_dev_norms2(ctx, snap_d, K, f, w.xn2.ptr));
     replay_max_kernel<<<1, 256, 0, ctx->stream>>>(w.xn2.ptr, K, w.scal.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_max_kernel"));
-    ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, snap_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
-                            w.cnt.ptr, w.flags.ptr + 1));
-    replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.idx.ptr, m, K, w.keys.ptr, w.vals.ptr);
+    // ranking: the tcgen05 tile with certified distance bounds (option "cluster_replay_near", default 1), else -- and
+    // again whenever its bounds turn out too wide to certify a chunk -- the FP64 tensor kernel's exact top-2
+    w.use_near = false;
+    if (allow_near && opt_or(ctx, "cluster_replay_near", 1.0) != 0.0 && m >= 4096) {
+        bool done = false;
+        ASB_TRY(asb_dev_near_tf32(ctx, rows_d, m, f, snap_d, K, w.qn2.ptr, w.xn2.ptr, w.near_idx.ptr, w.near_b.ptr, &done));
+        w.use_near = done;
+    }
+    if (!w.use_near)
+        ASB_TRY(asb_dev_top2_l2(ctx, rows_d, m, f, snap_d, K, w.qn2.ptr, w.xn2.ptr, w.minus1.ptr, w.idx.ptr, w.dist.ptr,
+                                w.cnt.ptr, w.flags.ptr + 1));
+    replay_keys_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.use_near ? w.near_idx.ptr : w.idx.ptr, w.use_near ? 1 : 2, m,
+                                                                 K, w.keys.ptr, w.vals.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_keys_kernel"));
     int bits = 1;
     while ((1ll << bits) < (long long)K + 1) ++bits;
@@ -611,7 +644,8 @@ int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f
     replay_offsets_kernel<<<(K + 1 + 255) / 256, 256, 0, ctx->stream>>>(w.keys_s.ptr, m, K, w.seg_off.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_offsets_kernel"));
     replay_bounds_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.vals_s.ptr, m, f, w.dist.ptr, (const long long *)w.cnt.ptr,
-                                                                   w.qn2.ptr, w.scal.ptr, w.meta.ptr);
+                                                                   w.qn2.ptr, w.scal.ptr, w.use_near ? w.near_b.ptr : nullptr,
+                                                                   w.meta.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_bounds_kernel"));
     return ASB_OK;
 }
@@ -672,13 +706,15 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
     ASB_TRY(asb_check_launch(ctx, "replay_chain_kernel"));
     replay_certify_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.dcur.ptr, w.dist.ptr, (const long long *)w.cnt.ptr,
                                                                     w.qn2.ptr, w.scal.ptr, w.scal.ptr + 1,
-                                                                    (const long long *)assign_d, radius, f, m, w.flags.ptr);
+                                                                    (const long long *)assign_d, radius, f, m,
+                                                                    w.use_near ? w.near_b.ptr : nullptr, w.flags.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_certify_kernel"));
     int hflags[2] = {0, 0};
     unsigned long long hdisp = 0;
     ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(&hdisp, w.scal.ptr + 1, sizeof(hdisp), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    w.last_flags = hflags[0] | (hflags[1] << 8);
     if (hflags[0] != 0 || hflags[1] != 0) {
         w.last_disp = INFINITY;   // the next attempt follows a sequential stretch: no estimate
         return ASB_OK;
@@ -757,7 +793,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     }
     ReplayWs w;
     bool ws_ready = false;
-    int fails = 0, tried = 0, proven = 0;
+    int fails = 0, tried = 0, proven = 0, near_retries = 0;
     int64_t rows_replayed = 0;
     int64_t cur = chunk;   // rows per attempt: doubles after every proven chunk (one snapshot holds for longer and
                            // longer stretches as the centroids settle), back to `chunk` after a failure
@@ -774,6 +810,12 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, centroids_d));
             ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
                                centroids_d, centroids_d, assign_d + lo, sizes_d, &ok));
+            if (!ok && w.use_near && w.last_flags == 2) {   // only certificates missed: the tile's bounds may be too wide
+                ++near_retries;
+                ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, centroids_d, false));
+                ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
+                                   centroids_d, centroids_d, assign_d + lo, sizes_d, &ok));
+            }
             ms_top2 += ktimer_ms(ctx, "cluster_top2_kernel");
             ms_chain += ktimer_ms(ctx, "cluster_chain_kernel");
         }
@@ -803,6 +845,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ctx->kernel_ms["cluster_replay_seq_ms"] = ms_seq;
     ctx->kernel_ms["cluster_replay_top2_ms"] = ms_top2;
     ctx->kernel_ms["cluster_replay_chain_ms"] = ms_chain;
+    ctx->kernel_ms["cluster_replay_near_retries"] = (double)near_retries;
     return ASB_OK;
 }
 
@@ -851,8 +894,8 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
     DevTmp<double> snap;
     ASB_TRY(pack.init(ctx, sb));
     ASB_TRY(snap.init(ctx, (size_t)max_clusters * f));
-    ctx->kernel_ms["cluster_shard_speculative"] = 0.0;   // 1: this shard's rows were proven against the common snapshot
-    ctx->kernel_ms["cluster_shard_fallback"] = 0.0;      // 1: ... were not, and the shard was re-ranked from the fresh state
+    ctx->kernel_ms["cluster_shard_speculative"] = 0.0;   // pieces of this shard proven against the common snapshot
+    ctx->kernel_ms["cluster_shard_fallback"] = 0.0;      // pieces that were not, and were re-ranked from the fresh state
     int64_t x = 0;
     if (r == 0) {
         int64_t head = (int64_t)opt_or(ctx, "cluster_shard_snapshot_rows", 262144.0);
@@ -870,29 +913,55 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
         ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, 0));
         int64_t x_snap = 0;
         ASB_TRY(shard_unpack(ctx, pack.ptr, &x_snap, snap.ptr, nullptr, max_clusters, f));
-        // speculative ranking against the common snapshot, in parallel with the ranks still walking
-        ReplayWs w;
+        // speculative ranking against the common snapshot, in parallel with the ranks still walking.  The shard is cut
+        // into pieces that are certified one by one, so a piece with an uncertifiable row (two centroids sharing a blob
+        // leave rows on their bisector) costs a walk of that piece, not of the shard.
         const bool speculate = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && opt_or(ctx, "cluster_shard_speculate", 1.0) != 0.0 &&
-                               x_snap == max_clusters && x_snap >= 2 && n_local >= 1024 && n_local <= (1 << 24) &&
-                               max_clusters * f <= (1ll << 27);
-        if (speculate) {
-            ASB_TRY(replay_ws_init(ctx, w, (int)n_local, (int)max_clusters, (int)f));
-            ASB_TRY(replay_prepare(ctx, w, rows_d, (int)n_local, (int)f, (int)x_snap, snap.ptr));
+                               x_snap == max_clusters && x_snap >= 2 && n_local >= 1024 && max_clusters * f <= (1ll << 27);
+        int64_t piece = (int64_t)opt_or(ctx, "cluster_shard_piece", 131072.0);
+        if (piece < 4096) piece = 4096;
+        if (piece > (1 << 24)) piece = 1 << 24;
+        const int64_t npieces = speculate ? (n_local + piece - 1) / piece : 0;
+        std::vector<ReplayWs> ws((size_t)npieces);
+        for (int64_t i = 0; i < npieces; ++i) {
+            const int64_t lo = i * piece, m = std::min<int64_t>(piece, n_local - lo);
+            ASB_TRY(replay_ws_init(ctx, ws[(size_t)i], (int)m, (int)max_clusters, (int)f));
+            ASB_TRY(replay_prepare(ctx, ws[(size_t)i], rows_d + lo * f, (int)m, (int)f, (int)x_snap, snap.ptr));
         }
         ASB_TRY(asb_comm_recv_bytes(ctx, comm, pack.ptr, sb, r - 1));
         ASB_TRY(shard_unpack(ctx, pack.ptr, &x, centroids_d, sizes_d, max_clusters, f));
-        int ok = 0;
-        if (speculate && x == x_snap) {
-            w.last_disp = INFINITY;   // no hint: rows with thin margins take the exact step
-            ASB_TRY(replay_run(ctx, w, rows_d, (int)n_local, (int)f, (int)x, 1, radius, snap.ptr, centroids_d, assign_d,
-                               sizes_d, &ok));
-            ctx->kernel_ms["cluster_shard_speculative"] = ok ? 1.0 : 0.0;
-            ctx->kernel_ms["cluster_shard_fallback"] = ok ? 0.0 : 1.0;
-        }
-        if (!ok && n_local > 0) {
+        int64_t proven = 0, walked = 0;
+        if (npieces == 0 && n_local > 0) {
             const int64_t x_before = x;
             ASB_TRY(asb_dev_cluster(ctx, rows_d, n_local, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, x_before));
+            walked = 1;
         }
+        for (int64_t i = 0; i < npieces; ++i) {
+            const int64_t lo = i * piece, m = std::min<int64_t>(piece, n_local - lo);
+            ReplayWs &w = ws[(size_t)i];
+            int ok = 0;
+            if (x == x_snap) {
+                w.last_disp = INFINITY;   // no hint: rows with thin margins take the exact step
+                ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x, 1, radius, snap.ptr, centroids_d,
+                                   assign_d + lo, sizes_d, &ok));
+                if (!ok && w.use_near && w.last_flags == 2) {   // the tile's bounds were too wide: exact top-2 of the snapshot
+                    ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x_snap, snap.ptr, false));
+                    w.last_disp = INFINITY;
+                    ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x, 1, radius, snap.ptr, centroids_d,
+                                       assign_d + lo, sizes_d, &ok));
+                }
+            }
+            if (ok) {
+                ++proven;
+            } else {
+                const int64_t x_before = x;
+                ASB_TRY(asb_dev_cluster(ctx, rows_d + lo * f, m, f, max_clusters, radius, centroids_d, assign_d + lo, sizes_d,
+                                        &x, x_before));
+                ++walked;
+            }
+        }
+        ctx->kernel_ms["cluster_shard_speculative"] = (double)proven;
+        ctx->kernel_ms["cluster_shard_fallback"] = (double)walked;
     }
     ASB_TRY(shard_pack(ctx, pack.ptr, x, centroids_d, sizes_d, max_clusters, f));
     if (r < R - 1) ASB_TRY(asb_comm_send_bytes(ctx, comm, pack.ptr, sb, r + 1));

@@ -296,6 +296,10 @@ int asb_dev_cluster_seq(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f
 int asb_dev_top2_l2(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const double *items_d, int64_t k_items,
                     const double *qn2_d, const double *xn2_d, const int64_t *minus1_d, int64_t *idx_d, double *dist_d,
                     int64_t *cnt_d, int *status_d);
+// the same question answered by the tcgen05 tile with certified bounds instead of exact distances (search_umma.cuh,
+// PF_NEAR): near_idx_d int64[m], near_b_d f64[m x 3] = {dlo, dhi, slo}; *done = false -> use asb_dev_top2_l2
+int asb_dev_near_tf32(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const double *items_d, int64_t k_items,
+                      const double *qn2_d, const double *xn2_d, int64_t *near_idx_d, double *near_b_d, bool *done);
 int asb_dev_laplacian(asb_ctx *ctx, const double *centroids_d, int64_t x, int64_t f,
                       const asb_graph_params &gp, int64_t *indptr_d, int64_t *indices_d, double *data_d,
                       int64_t capacity, int64_t *nnz_host);

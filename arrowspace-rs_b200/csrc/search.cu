@@ -787,6 +787,11 @@ int asb_dev_top2_l2(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const
     return run_search(ctx, MODE_L2, A, 0, idx_d, dist_d, cnt_d, "cluster_top2_kernel");
 }
 
+int asb_dev_near_tf32(asb_ctx *ctx, const double *q_d, int64_t m, int64_t f, const double *items_d, int64_t k_items,
+                      const double *qn2_d, const double *xn2_d, int64_t *near_idx_d, double *near_b_d, bool *done) {
+    return run_near_umma(ctx, items_d, k_items, (int)f, q_d, m, xn2_d, qn2_d, near_idx_d, near_b_d, done);
+}
+
 int asb_dev_topk_merge(asb_ctx *ctx, const double *in_score_d, const int64_t *in_idx_d, int64_t parts, int64_t nq,
                        int64_t k, double *out_score_d, int64_t *out_idx_d, int64_t *out_count_d) {
     if (parts < 1 || nq < 1 || k < 1) ASB_FAIL(ctx, ASB_ERR_INVALID, "topk_merge: bad sizes");

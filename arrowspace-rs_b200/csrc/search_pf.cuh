@@ -46,6 +46,7 @@ constexpr int PF_FLAG_FALLBACK = 1, PF_FLAG_OVERFLOW = 2;
 constexpr int PF_MAXSEL = 1024;            // rescored candidates per query
 constexpr int PF_COSINE = 0;               // score = alpha cos + (1 - alpha) lambda proximity (search_lambda_aware)
 constexpr int PF_L2 = 1;                   // score = -|q - x|^2 (nearest neighbours: Two-NN scan, replay top-2); opt-in
+constexpr int PF_NEAR = 2;                 // tcgen05 tile only: nearest item + certified distance bounds (the replay)
 
 struct PfArgs {
     const float *xf, *qf;   // n x fp, nq x fp unit rows
@@ -70,6 +71,11 @@ struct PfArgs {
     const long long *self_idx;               // per query: item index to leave out (clustering.rs:123), or null
     const unsigned long long *xn2max_bits;   // device scalar: bits of max |x|^2
     double band_rel, band_abs;               // band(q) = band_rel |q| max|x| + band_abs (|q|^2 + max|x|^2)
+    // PF_NEAR only: per query the nearest item by the approximate score and certified bounds {dlo, dhi} of its
+    // distance and slo, a lower bound of the distance to every OTHER item
+    double e_cos;
+    long long *near_idx;
+    double *near_b;                          // nq x 3
 };
 
 __device__ __forceinline__ unsigned long long pf_enc(double d) {
@@ -776,6 +782,69 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->kernel_ms["l2_pf_flags"] = (double)hflags;
     if (hflags != 0) return ASB_OK;
+    *done = true;
+    return ASB_OK;
+}
+
+// Nearest item and certified distance bounds for every query, straight from the tcgen05 tile (PF_NEAR): the replay of the
+// clustering walk needs, per row, a candidate centroid b, bounds dlo <= |x - c_b| <= dhi and a lower bound slo of the
+// distance to every OTHER centroid -- not the exact top-2.  One pass, no candidate lists, no rescoring.  near_idx int64[nq],
+// near_b f64[nq x 3] = {dlo, dhi, slo}.  *done = false: not applicable (the caller uses the FP64 kernel).
+static int run_near_umma(asb_ctx *ctx, const double *items_d, long long n, int f, const double *queries_d, long long nq,
+                         const double *xn2_d, const double *qn2_d, int64_t *near_idx_d, double *near_b_d, bool *done) {
+    *done = false;
+    if (n < 2 || n > 65536 || nq < 1 || nq > 0x7fffff00ll || !um_wanted(ctx)) return ASB_OK;
+    const int fp = (f + 31) & ~31;
+    if (um_smem_bytes(0, PF_NEAR) > 227 * 1024) return ASB_OK;
+    const double chain = 3.0 * fp / 8.0;
+    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+    DevTmp<float> xf, qf, xlo, qlo;
+    DevTmp<double> xnrm, qnrm;
+    DevTmp<int> flags;
+    DevTmp<unsigned long long> xmax;
+    if (xf.init(ctx, (size_t)n * fp) != ASB_OK || qf.init(ctx, (size_t)nq * fp) != ASB_OK ||
+        xlo.init(ctx, (size_t)n * fp) != ASB_OK || qlo.init(ctx, (size_t)nq * fp) != ASB_OK) {
+        cudaGetLastError();
+        return ASB_OK;
+    }
+    ASB_TRY(xnrm.init(ctx, (size_t)n));
+    ASB_TRY(qnrm.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 1));
+    ASB_TRY(xmax.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(xmax.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    UmMaps maps;
+    if (!um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp)) return ASB_OK;
+    pf_max_kernel<<<64, 256, 0, ctx->stream>>>(xn2_d, n, xmax.ptr);
+    ASB_TRY(asb_check_launch(ctx, "pf_max_kernel"));
+    um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr,
+                                                                          xnrm.ptr);
+    um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr,
+                                                                           flags.ptr, qnrm.ptr);
+    ASB_TRY(asb_check_launch(ctx, "um_split_rows_kernel"));
+    ctx->launches++;
+    PfArgs A{};
+    A.fp = fp;
+    A.n = n;
+    A.nq = nq;
+    A.k = 0;
+    A.nslabs = 1;
+    A.tiles_per_slab = (n + UM_TN - 1) / UM_TN;
+    A.flags = flags.ptr;
+    A.qn2 = qn2_d;
+    A.xn2 = xn2_d;
+    A.qnrm = qnrm.ptr;
+    A.xnrm = xnrm.ptr;
+    A.xn2max_bits = xmax.ptr;
+    A.e_cos = e_cos;
+    A.near_idx = (long long *)near_idx_d;
+    A.near_b = near_b_d;
+    ASB_TRY(um_launch<PF_NEAR>(ctx, maps, A, 1, "cluster_top2_kernel"));
+    ASB_TRY(asb_check_launch(ctx, "search_umma_kernel<NEAR>"));
+    int hflags = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&hflags, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // (the planes die with this scope)
+    if (hflags != 0) return ASB_OK;   // a row outside the certified range: the FP64 kernel decides
     *done = true;
     return ASB_OK;
 }

@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     // the swizzled boxes need 1024-byte alignment; the launch reserves the slack (um_smem_bytes)
     unsigned char *stages = um_smem + ((1024u - (um_smem_u32(um_smem) & 1023u)) & 1023u);
     double *ep_x0 = reinterpret_cast<double *>(stages + (size_t)UM_STAGES * UM_STAGE_BYTES);   // [2][UM_TN]: lambda / |x|^2
-    double *ep_x1 = ep_x0 + 2 * UM_TN;                                                           // [2][UM_TN]: |x| (PF_L2)
-    float *ep_f0 = reinterpret_cast<float *>(ep_x1 + (MODE == PF_L2 ? 2 * UM_TN : 0));           // FP32 copies of both
+    double *ep_x1 = ep_x0 + 2 * UM_TN;                                                           // [2][UM_TN]: |x| (PF_L2 / PF_NEAR)
+    float *ep_f0 = reinterpret_cast<float *>(ep_x1 + (MODE != PF_COSINE ? 2 * UM_TN : 0));       // FP32 copies of both
     float *ep_f1 = ep_f0 + 2 * UM_TN;
-    float *lists = ep_f1 + (MODE == PF_L2 ? 2 * UM_TN : 0);                                      // [UM_TQ][k]
+    float *lists = ep_f1 + (MODE != PF_COSINE ? 2 * UM_TN : 0);                                  // [UM_TQ][k]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = A.k, fp = A.fp;
@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         int len = 0;
         double kth = -INFINITY;
         bool saw_nan = false;
+        float near1 = -INFINITY, near2 = -INFINITY;   // PF_NEAR: largest and second largest FP32 score, column of the largest
+        int near_i = -1;
         const double beta = 1.0 - A.alpha;
         // The hot loop is FP32: sf approximates the FP64 score s~ of search_pf.cuh to within fdelta (operands rounded to
         // FP32, five FP32 operations on magnitudes bounded by smag), and only an element with sf >= thr_f = (bound - band
@@ -307,12 +309,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     const double v0 = gi < A.n ? A.xn2[gi] : 0.0, v1 = gi < A.n ? A.xnrm[gi] : 0.0;
                     ep_x0[b * UM_TN + c] = v0;
                     ep_x1[b * UM_TN + c] = v1;
-                    ep_f0[b * UM_TN + c] = (float)v0;
+                    ep_f0[b * UM_TN + c] = (MODE == PF_NEAR && gi >= A.n) ? INFINITY : (float)v0;   // padding never wins
                     ep_f1[b * UM_TN + c] = (float)v1;
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const double gb = okq ? pf_dec(__ldcg(&A.gthr[gq])) : -INFINITY;   // bound published by any slab
+            double gb = -INFINITY;                                             // bound published by any slab
+            if constexpr (MODE != PF_NEAR) gb = okq ? pf_dec(__ldcg(&A.gthr[gq])) : -INFINITY;
             um_mbar_wait(&bars.tfull[b], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long nvalid_ll = A.n - i0;   // columns below this index are real items
@@ -337,6 +340,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (!okq || c0 >= nvalid) continue;
+                if constexpr (MODE == PF_NEAR) {
+                    // the two largest FP32 scores -|q - x|^2 and the column of the largest, branch-free
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 a0 = *reinterpret_cast<const float4 *>(f0 + c0 + j4);
+                        const float4 a1 = *reinterpret_cast<const float4 *>(f1 + c0 + j4);
+                        const float x0[4] = {a0.x, a0.y, a0.z, a0.w}, x1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float sf = fmaf(qnf2 * x1[u], __uint_as_float(v[j4 + u]), -(lqf + x0[u]));
+                            near2 = fmaxf(near2, fminf(near1, sf));
+                            near_i = sf > near1 ? (int)(i0 + c0 + j4 + u) : near_i;
+                            near1 = fmaxf(near1, sf);
+                        }
+                    }
+                    continue;
+                }
                 // branch-free over the 32 columns: a bit per column whose FP32 score reaches the threshold
                 unsigned hot = 0u;
 #pragma unroll
@@ -412,6 +432,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
             if (changed && okq) atomicMax(&A.gthr[gq], pf_enc(kth));
         }
         if (saw_nan) atomicOr(A.flags, PF_FLAG_FALLBACK);
+        if constexpr (MODE == PF_NEAR) {
+            if (okq) {
+                // true d^2 = |q|^2 + |x|^2 - 2 |q| |x| cos: the tile's cos~ is within e_cos of cos (search_pf.cuh), the FP32
+                // evaluation of the score within fdelta of the FP64 one, the norms are FP64 sums (1e-13 covers them)
+                const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
+                const double etot = 2.0 * qn * sqrt(xmax2) * A.e_cos * (1.0 + 1e-6) + fdelta + 1e-13 * (lq + xmax2);
+                double dlo = sqrt(fmax(-(double)near1 - etot, 0.0)) * (1.0 - 1e-15);
+                double dhi = sqrt(fmax(-(double)near1 + etot, 0.0)) * (1.0 + 1e-15);
+                double slo = near2 > -INFINITY ? sqrt(fmax(-(double)near2 - etot, 0.0)) * (1.0 - 1e-15) : 0.0;
+                if (near_i < 0 || !(dhi == dhi) || !(dlo == dlo) || !(slo == slo) || !(etot < 1e300)) {
+                    dlo = 0.0;      // no usable bounds: the chain takes exact steps, the certification fails the row
+                    dhi = 1e300;
+                    slo = 0.0;
+                }
+                A.near_idx[gq] = near_i;
+                A.near_b[3 * gq] = dlo;
+                A.near_b[3 * gq + 1] = dhi;
+                A.near_b[3 * gq + 2] = slo;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -420,7 +460,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
 }
 
 size_t um_smem_bytes(int k, int mode) {
-    return (size_t)UM_RING_BYTES + (size_t)(mode == PF_L2 ? 4 : 2) * UM_TN * 12 + (size_t)UM_TQ * k * 4 + 1024;
+    return (size_t)UM_RING_BYTES + (size_t)(mode != PF_COSINE ? 4 : 2) * UM_TN * 12 + (size_t)UM_TQ * k * 4 + 1024;
 }
 
 typedef CUresult (*um_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

@@ -432,8 +432,18 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
             }
         return false;
     };
+    // error-free accumulation (TwoSum cascade): the residual r_i = L_ii + sum_{j != i} L_ij of a STORED Laplacian row is
+    // not zero -- the stored diagonal is the rounded degree -- and x^T L x of the stored matrix contains sum r_i x_i^2.
+    // Computing r_i in plain floating point would return the rounding noise of the subtraction instead of the value.
+    auto two_sum = [](double a, double b, double &err) {
+        const double s = a + b;
+        const double bb = s - a;
+        err = (a - (s - bb)) + (b - bb);
+        return s;
+    };
     for (int64_t i = 0; i < f && is_sym; ++i) {
         double diag = 0.0, wsum = 0.0;
+        double rs = 0.0, rc = 0.0;   // residual: running sum and its accumulated rounding error
         int64_t last_col = -1;
         for (int64_t e = indptr[i]; e < indptr[i + 1]; ++e) {
             const int64_t j = indices[e];
@@ -450,6 +460,11 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
             }
             const double w = -data[e];
             wsum += w;  // ascending j, like the degree sum of src/laplacian.rs:369
+            {
+                double e1;
+                rs = two_sum(rs, data[e], e1);
+                rc += e1;
+            }
             if (!(w > 0.0)) all_pos = false;
             if (j > i) {
                 SymEdge se;
@@ -459,7 +474,13 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
                 sym.push_back(se);
             }
         }
-        resid[i] = diag - wsum;
+        {
+            double e1;
+            rs = two_sum(rs, diag, e1);
+            rc += e1;
+        }
+        (void)wsum;
+        resid[i] = rs + rc;   // exact to ~1e-32 of the row's magnitude
     }
     plan->is_sym = is_sym;
     plan->all_pos = is_sym && all_pos;

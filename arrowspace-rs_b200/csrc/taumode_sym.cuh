@@ -12,7 +12,7 @@
 //     lane's own elements with warp-wide integer reductions (__reduce_add_sync) -- no barriers at all;
 //   * each undirected edge {i,j} is visited once, 32 edges per step (one per lane).  For a symmetric L
 //       x^T L x = sum_i (L_ii - sum_j w_ij) x_i^2 + sum_{i<j} w_ij (x_i - x_j)^2          (exact algebra;
-//     the residual is computed on the host in the reference's summation order, 0 for a Laplacian), and the
+//     the residual of the STORED row is accumulated error-free on the host: ~1e-16, not 0, for a Laplacian), and the
 //     dispersion sums of :577-583,:621-631 count every edge twice: edge = 2 S1, G = S2 / (2 S1^2);
 //   * the random x[i], x[j] reads would bank-conflict ~3-way, so the host packs the edge list into steps
 //     whose 16-lane halves touch 16 distinct bank pairs (greedy colouring; the graph is fixed for millions

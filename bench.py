@@ -50,6 +50,14 @@ def parse_args():
     ap.add_argument("--no-cluster-replay", action="store_true",
                     help="walk every row on the sequential clustering kernel (option cluster_replay = 0; the default is "
                          "the certified parallel replay, same bits)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --items is the GLOBAL row count, split evenly over the GPUs (BASELINE configs[3]: "
+                         "--items 10000000 --features 768 --strong --device-data)")
+    ap.add_argument("--device-data", action="store_true",
+                    help="draw the synthetic rows on the GPU (same blob model, torch generator) instead of on the host: for "
+                         "configurations whose host generation would take minutes; implies --no-e2e --no-cpu-baseline")
+    ap.add_argument("--no-unfriendly", action="store_true",
+                    help="skip the second, unfriendly clustering workload (512 blobs on K = 128, reported beside the main line)")
     ap.add_argument("--ref-full", action="store_true",
                     help="with --impl reference: run the WHOLE workload once on the host cores instead of a bounded sample")
     ap.add_argument("--exact-search", action="store_true",
@@ -63,6 +71,37 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def umma_tf32_peak():
+    p = ROOT / "profiles" / "r02_umma_tf32_peak.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text().splitlines()[0])
+            return float(d["tflops"]), "tcgen05 TF32 micro-benchmark on this pool (tools/umma_peak.cu, profiles/r02_umma_tf32_peak.json)"
+        except Exception:
+            pass
+    return 1116.3, "tcgen05 TF32 micro-benchmark on this pool (tools/umma_peak.cu): 1116 TFLOP/s"
+
+
+def ncu_traffic(kernel_substr, n, f, nq):
+    """DRAM bytes per launch of a kernel from the committed ncu launch list of THIS workload (profiles/r02_traffic.json,
+    written by tools/ncu_launches.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum ... bench.py`); None
+    when the capture is of another configuration."""
+    p = ROOT / "profiles" / "r02_traffic.json"
+    if not p.exists():
+        return None
+    try:
+        d = json.loads(p.read_text())
+        cfg = d.get("_config", {})
+        if (cfg.get("n"), cfg.get("f"), cfg.get("nq")) != (n, f, nq):
+            return None
+        for name, v in d.items():
+            if name != "_config" and kernel_substr in name:
+                return float(v["dram_bytes_per_launch"])
+    except Exception:
+        return None
+    return None
 
 
 def fp64_peak():
@@ -277,20 +316,51 @@ def run_b200(args):
         dist.broadcast_object_list(box, src=0)
         comm = asb.host.Comm(ctx, world, rank, box[0])
 
-    n, f, nq = args.n, args.f, args.nq
-    n_global = n * world
-    lo = rank * n
+    f, nq = args.f, args.nq
+    if args.strong:      # --items is the global row count; every rank takes an equal slice (the last one the remainder)
+        n_global = args.n
+        per = (n_global + world - 1) // world
+        lo = min(n_global, rank * per)
+        n = min(n_global, lo + per) - lo
+    else:                # weak scaling: --items rows per GPU
+        n = args.n
+        n_global = n * world
+        lo = rank * n
+    if args.device_data:
+        args.no_e2e = True
+        args.no_cpu_baseline = True
     t_gen = time.perf_counter()
-    rows_h = torch.empty((n, f), dtype=torch.float64).pin_memory()
-    asb.synth.protein_like(n, f, seed=DATA_SEED, out=rows_h.numpy(), row0=lo)
-    q_idx = asb.synth.query_indices(n_global, nq, QUERY_SEED)
-    queries_h = torch.from_numpy(asb.synth.rows_at(q_idx, f, DATA_SEED) * 1.02).pin_memory()
-    t_gen = time.perf_counter() - t_gen
-    rows_d = rows_h.to(dev, non_blocking=True)
-    queries_d = queries_h.to(dev, non_blocking=True)
+    if args.device_data:
+        # the same model (64 non-negative blobs + 0.05 noise), drawn on the GPU: centres from one seed on every rank, rows
+        # from a per-rank stream -- the global dataset is the concatenation of the shards
+        g0 = torch.Generator(device=dev).manual_seed(DATA_SEED)
+        centres = torch.rand((64, f), dtype=torch.float64, device=dev, generator=g0)
+        g1 = torch.Generator(device=dev).manual_seed(DATA_SEED * 1000 + rank)
+        rows_d = torch.empty((n, f), dtype=torch.float64, device=dev)
+        for r0 in range(0, n, 262144):
+            r1 = min(n, r0 + 262144)
+            lab = torch.randint(0, 64, (r1 - r0,), device=dev, generator=g1)
+            blk = centres[lab]
+            blk += 0.05 * torch.randn((r1 - r0, f), dtype=torch.float64, device=dev, generator=g1)
+            rows_d[r0:r1] = blk.clamp_(min=0.0)
+        # queries = the first rows of rank 0's shard x 1.02, broadcast
+        queries_d = (rows_d[:nq] * 1.02).contiguous() if rank == 0 else torch.empty((nq, f), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(queries_d, src=0)
+        rows_h = queries_h = None
+        head = rows_d[: min(n, 50_000)].cpu().numpy()
+    else:
+        rows_h = torch.empty((n, f), dtype=torch.float64).pin_memory()
+        asb.synth.protein_like(n, f, seed=DATA_SEED, out=rows_h.numpy(), row0=lo)
+        q_idx = asb.synth.query_indices(n_global, nq, QUERY_SEED)
+        queries_h = torch.from_numpy(asb.synth.rows_at(q_idx, f, DATA_SEED) * 1.02).pin_memory()
+        rows_d = rows_h.to(dev, non_blocking=True)
+        queries_d = queries_h.to(dev, non_blocking=True)
+        head = rows_h.numpy()[: min(n, 50_000)]
     torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
 
-    maxk, radius = cluster_inputs(n_global, f, rows_h.numpy()[: min(n, 50_000)])
+    maxk, radius = cluster_inputs(n_global, f, head)
     if world > 1:
         t = torch.tensor([radius], dtype=torch.float64, device=dev)
         dist.broadcast(t, src=0)
@@ -494,13 +564,22 @@ def run_b200(args):
         # tools/mma_peak.cu (0.5 m16n8k8 MMA / clk / SM at the boost clock the clocks line reports)
         fl = 2.0 * nq * n * f
         ach = fl / (kms["search_pf_kernel"] * 1e-3) / 1e12
-        tf32_peak = 148 * 0.5 * 2048 * 1.965e9 / 1e12
-        kernels["search_pf_kernel"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                                       "frac": ach / tf32_peak, "ms": kms["search_pf_kernel"], "traffic": None,
-                                       "executed_frac": 3.0 * ach / tf32_peak,
-                                       "peak_source": "mma.sync TF32 m16n8k8 micro-benchmark on this pool (tools/mma_peak.cu, "
-                                                      "DESIGN.md section 4): 0.5 MMA/clk/SM = 298 TFLOP/s; the kernel issues 3 "
-                                                      "MMAs per algorithmic product (3xTF32), executed_frac counts those",
+        umma = ctx.kernel_ms("search_pf_umma") == 1.0
+        if umma:
+            # the tile runs on tcgen05.mma kind::tf32 (csrc/search_umma.cuh); peak = the tcgen05 TF32 issue rate measured
+            # on this pool by tools/umma_peak.cu (M128 N256 K8 at 128 cycles per instruction on every SM)
+            tf32_peak, peak_src_pf = umma_tf32_peak()
+        else:
+            tf32_peak = 148 * 0.5 * 2048 * 1.965e9 / 1e12
+            peak_src_pf = ("mma.sync TF32 m16n8k8 micro-benchmark on this pool (tools/mma_peak.cu): 0.5 MMA/clk/SM = 298 "
+                           "TFLOP/s (search_umma = 0: the mma.sync tile)")
+        kernels["search_pf_kernel"] = {"bound": "tensor", "achieved": 3.0 * ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                                       "frac": 3.0 * ach / tf32_peak, "ms": kms["search_pf_kernel"], "traffic": None,
+                                       "algorithmic_tflops": ach, "algorithmic_frac": ach / tf32_peak,
+                                       "peak_source": peak_src_pf + "; `achieved` counts the 3 TF32 MMAs the kernel executes per "
+                                                      "algorithmic product (3xTF32: hi*lo + lo*hi + hi*hi), algorithmic_tflops "
+                                                      "= 2 Q N F / time",
+                                       "tile": "tcgen05.mma kind::tf32 + TMA + TMEM" if umma else "mma.sync + cp.async",
                                        "vs_fp64_dmma_peak": ach / dmma_peak,
                                        "prep_ms": kms["search_pf_prep"], "finish_ms": kms["search_pf_finish"],
                                        "candidates_per_query": pf_diag.get("search_pf_candidates", 0.0) / max(nq, 1),
@@ -521,30 +600,28 @@ def run_b200(args):
                                              "rows/s = %.0f" % (n / (kms["cluster_kernel"] * 1e-3)),
                                      "variant": ctx.kernel_ms("cluster_variant"),
                                      "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
-    # DRAM traffic per launch from `ncu --set full` captures (profiles/r01_final_ncu_summary.csv,
-    # profiles/r01_v1_*): only quoted for the configuration they were captured on.
-    if n == 1_000_000 and f == 384 and world == 1:
-        if "cluster_kernel" in kernels:
-            kernels["cluster_kernel"]["traffic"] = 4.67e9   # ncu (profiles/r01_v6_launches.md): 2.32 GB read + 10.5 MB written per 500k rows
-        if "taumode_kernel" in kernels:
-            kernels["taumode_kernel"]["traffic"] = 3.11e9   # 5 x (614.5 MB read + 7.1 MB written) measured on 200k items
-        if "search_kernel" in kernels:
-            kernels["search_kernel"]["traffic_note"] = ("ncu on 200k items x 2048 queries: 670 MB read for a 614 MB "
-                                                        "item set (L2 serves the per-query-tile re-reads)")
+    # DRAM traffic per launch: from the committed ncu launch list of this very command (profiles/r02_traffic.json)
+    if world == 1:
+        for kname, sub in (("taumode_kernel", "taumode_warp_kernel"), ("search_pf_kernel", "search_umma_kernel"),
+                           ("search_kernel", "search_kernel"), ("twonn_kernel", "search_kernel"),
+                           ("cluster_kernel", "cluster_f32p_kernel")):
+            if kname in kernels:
+                kernels[kname]["traffic"] = ncu_traffic(sub, n, f, nq)
     dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roofline = dict(kernels[dominant], kernel=dominant) if dominant else None
     if roofline is not None:
         # HBM peaks come from MEASURED_PEAKS.json (or the profiling guide's fallback); that file has no FP64 entry,
         # so FP64 tensor-bound kernels are held against the DMMA rate measured on this pool by tools/fp64_peak.cu
         roofline["peak_kind"] = peak_src if roofline["bound"] == "hbm" else (
-            "mma.sync TF32 rate measured on this pool by tools/mma_peak.cu; MEASURED_PEAKS.json's bf16 figure is a "
-            "tcgen05 cuBLAS number, not the ceiling of an mma.sync kernel" if dominant == "search_pf_kernel" else
+            "tcgen05 TF32 rate measured on this pool by tools/umma_peak.cu (MEASURED_PEAKS.json holds a bf16 cuBLAS figure, "
+            "1692 TFLOP/s burst: TF32 runs at half the bf16 rate, nominal 1.1 PFLOP/s)" if dominant == "search_pf_kernel" else
             "measured on this pool by tools/fp64_peak.cu (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure")
 
     line = {
         "metric": "lambda_tau_build_items_per_s", "value": items_per_s, "unit": "items/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (drawn on the GPU)" if args.device_data else "synthetic",
         "config": {"workload": f"{n_global}x{f} lambda-tau build ({n} rows/GPU) + {nq}-query lambda-aware search k={TOPK}",
                    "build": "Two-NN scan + incremental clustering + feature Laplacian + taumode (ArrowSpaceBuilder::build)",
                    "max_clusters": maxk, "radius": radius, "graph": GRAPH, "taumode": "Median", "alpha": ALPHA,
@@ -563,6 +640,35 @@ def run_b200(args):
                                     "all-gather + merge", "rank0": shard_diag} if world > 1 else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
+
+    # ---- a second, UNFRIENDLY clustering workload (outside the timed region): far more natural clusters than centroids
+    # (512 blobs on K = 128), so every centroid averages several blobs, keeps drifting and rows sit between centroids --
+    # the certified replay proves little here and the sequential kernel carries the walk
+    if world == 1 and not args.no_unfriendly:
+        nu, fu, ku = 200_000, f, 128
+        gu = torch.Generator(device=dev).manual_seed(7)
+        cu = torch.rand((512, fu), dtype=torch.float64, device=dev, generator=gu)
+        xu = cu[torch.randint(0, 512, (nu,), device=dev, generator=gu)]
+        xu += 0.05 * torch.randn((nu, fu), dtype=torch.float64, device=dev, generator=gu)
+        xu.clamp_(min=0.0)
+        ru = asb.heuristics.pilot_radius(xu[:50_000].cpu().numpy(), ku, asb.heuristics.CLUSTERING_SEED)
+        res_u = {}
+        for name, opt in (("replay", 1), ("sequential", 0)):
+            ctx.set_option("cluster_replay", opt)
+            for _ in range(2):
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                cent_u, asg_u, sizes_u = ctx.cluster_incremental(xu, ku, ru)
+                ev1.record()
+                torch.cuda.synchronize()
+            res_u[name] = {"ms": ev0.elapsed_time(ev1), "us_per_row": ev0.elapsed_time(ev1) * 1e3 / nu,
+                           "chunks": ctx.kernel_ms("cluster_replay_chunks"), "proven": ctx.kernel_ms("cluster_replay_chunks_ok"),
+                           "rows_replayed": ctx.kernel_ms("cluster_replay_rows"), "exact_rows": ctx.kernel_ms("cluster_exact_rows"),
+                           "clusters": int(len(cent_u))}
+        ctx.set_option("cluster_replay", 0 if args.no_cluster_replay else 1)
+        line["cluster_unfriendly"] = dict(res_u, workload=f"{nu}x{fu}, 512 blobs, max_clusters {ku}, radius {ru:.4f} (device-drawn)")
+        del xu
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:

@@ -149,15 +149,20 @@ def _check_abi_outputs(asb, tmp_path, world, n, f, maxk, radius, nq, k, expect_s
         assert spec_seen >= 1, "no shard was proven against the common snapshot (every shard fell back)"
 
 
-@pytest.mark.parametrize("n,f,maxk,rscale,expect_spec", [(600_000, 128, 100, 1.0, True),      # settles: shards proven
-                                                          (60_001, 128, 100, 1.0, False),      # snapshot = whole shard 0
-                                                          (40_000, 64, 500, 0.2, False)])      # never saturates: fallback
+@pytest.mark.parametrize("n,f,maxk,rscale,expect_spec", [
+    (600_000, 384, 384, None, True),     # the bench's shape and radius rule: pieces of shard 1 proven against the snapshot
+    (600_000, 128, 100, 1.0, False),     # two centroids share some blobs: rows on their bisector, pieces fall back
+    (60_001, 128, 100, 1.0, False),      # snapshot = whole shard 0
+    (40_000, 64, 500, 0.2, False)])      # never saturates: no speculation at all
 def test_two_gpu_c_abi_sharded_equals_single_gpu(tmp_path, asb, n, f, maxk, rscale, expect_spec):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     nq, k, world = 257, 10, 2
-    radius = rscale * 1.5 * f * 0.0025 * 2
+    if rscale is None:
+        radius = asb.heuristics.pilot_radius(asb.synth.protein_like(50_000, f, seed=42), maxk, asb.heuristics.CLUSTERING_SEED)
+    else:
+        radius = rscale * 1.5 * f * 0.0025 * 2
     mp.spawn(_worker_abi, args=(world, _free_port(), n, f, maxk, radius, nq, k, str(tmp_path), False), nprocs=world, join=True)
     _check_abi_outputs(asb, tmp_path, world, n, f, maxk, radius, nq, k, expect_spec)

@@ -60,4 +60,10 @@ elif stage == "twonn":
     si = torch.from_numpy(asb.heuristics.sample_indices(n, 500, 129)).cuda()
     for _ in range(3):
         ctx.twonn_distances(xd, si.cpu().numpy())
-    print("twonn_ms", ctx.kernel_ms("twonn_kernel"))
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.twonn_distances(xd, si.cpu().numpy())
+    torch.cuda.synchronize()
+    print("twonn_call_ms", (time.perf_counter() - t0) * 1e3, "twonn_kernel_ms", ctx.kernel_ms("twonn_kernel"), "l2_pf_kernel_ms",
+          ctx.kernel_ms("l2_pf_kernel"), "pf_used", ctx.kernel_ms("twonn_pf_used"))

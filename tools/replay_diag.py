@@ -50,7 +50,8 @@ def main():
                      "chunks": ctx.kernel_ms("cluster_replay_chunks"), "chunks_ok": ctx.kernel_ms("cluster_replay_chunks_ok"),
                      "rows_replayed": ctx.kernel_ms("cluster_replay_rows"),
                      "sequential_ms": ctx.kernel_ms("cluster_replay_seq_ms") if opt else ctx.kernel_ms("cluster_kernel"),
-                     "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms")}
+                     "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
+                     "near_retries": ctx.kernel_ms("cluster_replay_near_retries"), "growth_rows": ctx.kernel_ms("cluster_growth_rows")}
     s, r = res["sequential"], res["replay"]
     out["centroids_bit_identical"] = bool(s[0].shape == r[0].shape and np.array_equal(
         np.ascontiguousarray(s[0]).view(np.uint64), np.ascontiguousarray(r[0]).view(np.uint64)))
