@@ -148,6 +148,9 @@ template <typename T>
 struct DevTmp {
     T *ptr = nullptr;
     cudaStream_t stream = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp &) = delete;   // owns its buffer
+    DevTmp &operator=(const DevTmp &) = delete;
     int init(asb_ctx *ctx, size_t count) {
         if (ptr) cudaFreeAsync(ptr, stream);  // re-init: release the previous buffer (stream-ordered)
         ptr = nullptr;

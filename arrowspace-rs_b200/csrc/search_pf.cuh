@@ -589,7 +589,7 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     if (umma) umma = um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp);
     if (umma) {
         const long long utiles = (n + UM_TN - 1) / UM_TN;
-        pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, utiles, 64, &nslabs, &tps);
+        um_pick_slabs(ctx, (nq + UM_TQ - 1) / UM_TQ, utiles, fp, &nslabs, &tps);
     }
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
     ASB_TRY(flags.init(ctx, 1));
@@ -711,7 +711,7 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
         umma = false;
     }
     if (umma) umma = um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp);
-    if (umma) pick_slabs(ctx->sm_count, (nq + UM_TQ - 1) / UM_TQ, (n + UM_TN - 1) / UM_TN, 64, &nslabs, &tps);
+    if (umma) um_pick_slabs(ctx, (nq + UM_TQ - 1) / UM_TQ, (n + UM_TN - 1) / UM_TN, fp, &nslabs, &tps);
     ASB_TRY(xnrm.init(ctx, (size_t)n));
     ASB_TRY(qnrm.init(ctx, (size_t)nq));
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));

@@ -525,6 +525,42 @@ bool um_make_maps(asb_ctx *ctx, UmMaps *maps, const float *qhi, const float *qlo
            um_make_map(&maps->xhi, xhi, n, fp, xbox, kc) && um_make_map(&maps->xlo, xlo, n, fp, xbox, kc);
 }
 
+// Slabs of the tcgen05 tile: the CTAs of one slab (all query tiles) stream the same item tiles but start at different
+// times, so they only share those tiles through L2 if a whole slab's planes fit there: with 601-tile slabs the 3 GB of
+// planes were fetched from HBM 14 times over (profiles/r02_launches_c3.md: 42.6 GB per launch).  Slabs are capped at
+// "search_umma_slab_mb" (default 48 MB of hi + lo planes, under half of the 126 MB L2), wave balance permitting.
+void um_pick_slabs(asb_ctx *ctx, long long qtiles, long long ntiles, int fp, int *nslabs, long long *tps) {
+    double mb = 48.0;
+    auto it = ctx->options.find("search_umma_slab_mb");
+    if (it != ctx->options.end() && it->second > 0.0) mb = it->second;
+    const double tile_bytes = (double)UM_TN * fp * 8.0;
+    long long cap = (long long)(mb * 1048576.0 / tile_bytes);
+    if (cap < 4) cap = 4;
+    long long min_slabs = (ntiles + cap - 1) / cap;
+    if (min_slabs < 1) min_slabs = 1;
+    // the wave-balancing choice among splits with at least min_slabs slabs (and at most 4x that, 4096 at most)
+    long long limit = min_slabs * 4 < 4096 ? min_slabs * 4 : 4096;
+    if (limit < 64) limit = 64;
+    double best_cost = 0.0;
+    long long best_tps = ntiles > 0 ? ntiles : 1;
+    int best_ns = 1;
+    bool have = false;
+    for (long long ns = min_slabs; ns <= limit && ns <= (ntiles > 0 ? ntiles : 1); ++ns) {
+        const long long t = (ntiles + ns - 1) / ns;
+        const long long real_ns = (ntiles + t - 1) / t;
+        const long long waves = (qtiles * real_ns + ctx->sm_count - 1) / ctx->sm_count;
+        const double cost = (double)waves * (double)(t + 2) * (1.0 + 5e-4 * (double)real_ns);
+        if (!have || cost < best_cost) {
+            have = true;
+            best_cost = cost;
+            best_tps = t;
+            best_ns = (int)real_ns;
+        }
+    }
+    *nslabs = best_ns;
+    *tps = best_tps;
+}
+
 template <int MODE, int KC, int CL>
 int um_launch_one(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, size_t usmem) {
     ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<MODE, KC, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));

@@ -134,11 +134,24 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 kernel that keeps the centroid in memory instead of registers).  Same bits either
  *                                 way (csrc/cluster_replay.cu,
  *                                 tests/replay_proto.py).
- *   "twonn_prefilter", "cluster_replay_tf32" (0|1)  experimental, not yet run on hardware: the Two-NN scan / the
- *                                 replay's nearest-and-runner-up pass ranked by the certified 3xTF32 score of the
- *                                 search prefilter (score -|q - x|^2) with the surviving distances evaluated in the
- *                                 reference's direct form (bit-identical to a sequential evaluation) instead of the
- *                                 FP64 tensor kernel.
+ *   "twonn_prefilter" (1|0)       1 (default): the Two-NN scan is ranked by the certified 3xTF32 score of the search
+ *                                 prefilter (score -|q - x|^2, tcgen05 tile) and the surviving distances are evaluated in
+ *                                 the reference's direct form (bit-identical to a sequential evaluation); 0: the FP64
+ *                                 tensor kernel (distances to 1e-9).
+ *   "cluster_replay_near" (1|0)   1 (default): the replay ranks a chunk's rows against the snapshot on the tcgen05 tile
+ *                                 and works with certified distance BOUNDS (a chunk whose bounds are too wide is ranked
+ *                                 again by the FP64 kernel); 0: always the FP64 kernel's exact top-2.
+ *   "cluster_replay_tf32" (0|1)   the exact top-2 through the certified prefilter + direct-form distances (slower than
+ *                                 either of the above; kept for cross-checks).
+ *   "search_umma" (1|0), "search_umma_kc" (16|32), "search_umma_cluster" (2|1|4), "search_umma_slab_mb" (48)
+ *                                 the prefilter tile: tcgen05.mma + TMA + TMEM (1) or mma.sync + cp.async (0); features per
+ *                                 pipeline stage; CTAs sharing one multicast item stream; bytes of item planes per slab.
+ *   "build_overlap_upload" (1|0)  asb_index_build from HOST rows: upload in 16 MB chunks on a second stream while stage 1
+ *                                 already works on the head of the matrix.
+ *   "cluster_growth_run" (1|0), "cluster_shard_snapshot_rows", "cluster_shard_piece", "cluster_shard_speculate"
+ *                                 the creator run at the start of a walk; rows rank 0 walks before it broadcasts the
+ *                                 common snapshot (262144); rows per certified piece of a later shard (131072); 0 turns
+ *                                 the speculative ranking off (plain hand-off).
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
  * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
  * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */

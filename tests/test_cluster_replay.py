@@ -18,7 +18,7 @@ def rctx(ctx):
     finally:
         for key, val in (("cluster_replay", 1), ("cluster_replay_prefix", 2048), ("cluster_replay_chunk", 1024),
                          ("cluster_replay_chunk_max", 262144), ("cluster_replay_generic_chain", 0),
-                         ("cluster_replay_tf32", 0), ("twonn_prefilter", 0)):
+                         ("cluster_replay_tf32", 0), ("twonn_prefilter", 1)):
             ctx.set_option(key, val)
 
 

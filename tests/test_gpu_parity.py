@@ -593,16 +593,27 @@ def test_cluster_nan_rows_and_duplicates(ctx, asb, oracle):
 
 
 # ==================================================================================== Two-NN (K1)
-@pytest.mark.parametrize("n,f,s", [(5_000, 64, 100), (2_000, 384, 500), (300, 25, 300)])
-def test_twonn_parity(ctx, asb, oracle, n, f, s):
+@pytest.mark.parametrize("prefilter", [1, 0], ids=["tcgen05_prefilter", "fp64_kernel"])
+@pytest.mark.parametrize("n,f,s", [(5_000, 64, 100), (2_000, 384, 500), (300, 25, 300), (70_000, 128, 500)])
+def test_twonn_parity(ctx, asb, oracle, n, f, s, prefilter):
+    """prefilter = 1 (default): certified TF32 ranking + direct-form distances, bit-identical to the oracle;
+    0: the FP64 tensor kernel with exact rescoring of 4 candidates, distances to 1e-9."""
     x = asb.synth.protein_like(n, f, seed=31)
     x[17] = x[5]                      # exact duplicate -> d1 == 0 for both
     si = asb.heuristics.sample_indices(n, s, 129)
     si[0], si[1] = 5, 17
     w1, w2 = oracle.twonn_distances(x, si)
-    g1, g2 = ctx.twonn_distances(x, si)
+    ctx.set_option("twonn_prefilter", prefilter)
+    try:
+        g1, g2 = ctx.twonn_distances(x, si)
+        used = ctx.kernel_ms("twonn_pf_used")
+    finally:
+        ctx.set_option("twonn_prefilter", 1)
+    assert used == float(prefilter)
     assert g1[0] == 0.0 and g1[1] == 0.0
     assert np.allclose(g1, w1, rtol=1e-9, atol=0) and np.allclose(g2, w2, rtol=1e-9, atol=0)
+    if prefilter:
+        assert np.array_equal(np.asarray(g1), w1) and np.array_equal(np.asarray(g2), w2)
     assert asb.heuristics.intrinsic_dim_from_distances(n, f, g1, g2) == oracle.intrinsic_dim(n, f, w1, w2)
 
 
