@@ -1,6 +1,7 @@
 // api.cu -- the C ABI (include/arrowspace_b200.h): context, host/device staging, the stage
 // entry points and the device-resident index (ArrowSpaceBuilder::build, src/builder.rs:249-455).
 #include <algorithm>
+#include <chrono>
 
 #include "comm.cuh"
 
@@ -28,6 +29,11 @@ struct asb_index {
     double h_stats[3] = {0, 0, 0};
     double ms_cluster = 0, ms_laplacian = 0, ms_taumode = 0, ms_total = 0;
     int64_t shard_offset = 0, n_global = 0;   // row-sharded build: global index of the first local row, global row count
+    // with_dims_reduction: the materialised F x r projection, r, and (lazily, for the energy search) the projected items
+    double *proj = nullptr, *items_proj = nullptr;
+    int64_t r = 0;
+    // lazily built for the energy search with spectral signals: S (x'_i) for every item
+    double *items_sig = nullptr;
 };
 
 // {min, max, sum} <-> {min, -max, sum}: one MIN all-reduce covers the first two
@@ -673,6 +679,9 @@ void asb_index_destroy(asb_index *ix) {
     cudaFree(ix->sig_indptr);
     cudaFree(ix->sig_indices);
     cudaFree(ix->sig_data);
+    cudaFree(ix->proj);
+    cudaFree(ix->items_proj);
+    cudaFree(ix->items_sig);
     cudaGetLastError();
     delete ix;
 }
@@ -798,8 +807,23 @@ static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, in
     // stage 2: feature Laplacian (src/eigenmaps.rs:313-323); assert clustered.shape().0 <= n_items holds.  Row-sharded:
     // rank 0 builds it once, the CSR is broadcast (a few hundred kB) -- every rank ends with the same bytes
     int64_t nnz = 0;
+    // with_dims_reduction (src/eigenmaps.rs:248-269): the graph is built on the projected centroids, X x r -> r x r
+    const int64_t fg = (bp->projection && bp->reduced_dim > 0) ? bp->reduced_dim : f;   // nodes of the feature graph
+    DevTmp<double> cent_proj;
+    const double *lap_in = ix->centroids;
+    if (fg != f) {
+        if (fg < 2 || fg > f) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_build: reduced_dim=%lld outside 2..F", (long long)fg);
+        ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->proj, (size_t)f * fg * sizeof(double), ctx->stream));
+        ASB_CUDA(ctx, cudaMemcpyAsync(ix->proj, bp->projection, (size_t)f * fg * sizeof(double),
+                                      asb_is_device_ptr(bp->projection) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        ix->r = fg;
+        ASB_TRY(cent_proj.init(ctx, (size_t)x * fg));
+        ASB_TRY(asb_dev_project(ctx, ix->centroids, x, f, ix->proj, fg, cent_proj.ptr));
+        lap_in = cent_proj.ptr;
+    }
     if (!sharded || comm->rank == 0) {
-        int rc_lap = asb_dev_laplacian(ctx, ix->centroids, x, f, gp, ix->indptr, ix->indices, ix->data, cap, &nnz);
+        int rc_lap = asb_dev_laplacian(ctx, lap_in, x, fg, gp, ix->indptr, ix->indices, ix->data, cap, &nnz);
         if (!sharded) ASB_TRY(rc_lap);
         else if (rc_lap != ASB_OK) nnz = -(int64_t)rc_lap;   // the status travels with the broadcast: no rank hangs
     }
@@ -816,7 +840,7 @@ static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, in
             return (int)(-h_nnz);
         }
         nnz = h_nnz;
-        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->indptr, (size_t)(f + 1) * sizeof(int64_t), 0));
+        ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->indptr, (size_t)(fg + 1) * sizeof(int64_t), 0));
         ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->indices, (size_t)nnz * sizeof(int64_t), 0));
         ASB_TRY(asb_comm_bcast_bytes(ctx, comm, ix->data, (size_t)nnz * sizeof(double), 0));
     }
@@ -824,9 +848,10 @@ static int index_build_impl(asb_ctx *ctx, asb_comm *comm, const double *rows, in
     {
         std::vector<int64_t> hp, hi;
         std::vector<double> hd;
-        ASB_TRY(csr_to_host(ctx, ix->indptr, ix->indices, ix->data, f, hp, hi, hd));
-        ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), f, &ix->plan));
+        ASB_TRY(csr_to_host(ctx, ix->indptr, ix->indices, ix->data, fg, hp, hi, hd));
+        ASB_TRY(asb_graph_plan_from_host(ctx, hp.data(), hi.data(), hd.data(), fg, &ix->plan));
         if (bp->spectral) {
+            const int64_t f = fg;   // (the signals graph lives on the feature graph's nodes)
             // optional stage (src/eigenmaps.rs:325-345 -> src/graph.rs:211-231): signals = the same Laplacian
             // construction run on dense(L)^T, i.e. with the F rows of L as the "items" and its F columns as nodes
             std::vector<double> dense((size_t)f * f, 0.0);
@@ -943,7 +968,7 @@ int asb_index_cluster_sizes(asb_ctx *ctx, const asb_index *ix, uint64_t *dst) {
 int asb_index_laplacian(asb_ctx *ctx, const asb_index *ix, int64_t *indptr, int64_t *indices, double *data) {
     ASB_TRY(set_device(ctx));
     if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
-    ASB_TRY(copy_out(ctx, indptr, ix->indptr, (size_t)(ix->f + 1) * sizeof(int64_t)));
+    ASB_TRY(copy_out(ctx, indptr, ix->indptr, (size_t)((ix->r ? ix->r : ix->f) + 1) * sizeof(int64_t)));
     ASB_TRY(copy_out(ctx, indices, ix->indices, (size_t)ix->nnz * sizeof(int64_t)));
     return copy_out(ctx, data, ix->data, (size_t)ix->nnz * sizeof(double));
 }
@@ -952,7 +977,7 @@ int asb_index_signals(asb_ctx *ctx, const asb_index *ix, int64_t *indptr, int64_
     ASB_TRY(set_device(ctx));
     if (!ix) ASB_FAIL(ctx, ASB_ERR_INVALID, "null index");
     if (!ix->sig_indptr) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_signals: the index was built without spectral signals");
-    ASB_TRY(copy_out(ctx, indptr, ix->sig_indptr, (size_t)(ix->f + 1) * sizeof(int64_t)));
+    ASB_TRY(copy_out(ctx, indptr, ix->sig_indptr, (size_t)((ix->r ? ix->r : ix->f) + 1) * sizeof(int64_t)));
     ASB_TRY(copy_out(ctx, indices, ix->sig_indices, (size_t)ix->sig_nnz * sizeof(int64_t)));
     return copy_out(ctx, data, ix->sig_data, (size_t)ix->sig_nnz * sizeof(double));
 }
@@ -962,6 +987,8 @@ int asb_index_search(asb_ctx *ctx, const asb_index *ix, const double *queries, i
     ASB_TRY(set_device(ctx));
     if (!ix || !queries || !idx || !score) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search: null pointer");
     if (nq <= 0 || k < 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search: bad sizes");
+    if (ix->r)   // EigenMaps::search hands the PROJECTED query to lambda_similarity against raw items: src/core.rs:157-161
+        ASB_FAIL(ctx, ASB_ERR_DIM, "items should be of the same length");
     const int64_t f = ix->f;
     DevIn<double> q;
     DevTmp<double> lq;
@@ -1045,6 +1072,10 @@ int asb_index_search_sharded(asb_ctx *ctx, asb_comm *comm, const asb_index *ix, 
     ASB_TRY(gi.init(ctx, (size_t)R * nq * k));
     ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
     ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, 2 * sizeof(int), ctx->stream));
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     ASB_TRY(asb_dev_taumode(ctx, q.ptr, nq, f, ix->plan, ix->tau_mode, ix->tau_value, lq.ptr, nullptr, nullptr, flags.ptr));
     // every collective is reached by every rank: an error on one rank is agreed on first
     DevTmp<long long> agree;
@@ -1064,6 +1095,8 @@ int asb_index_search_sharded(asb_ctx *ctx, asb_comm *comm, const asb_index *ix, 
         }
         bad = rc;
     }
+    ctx->kernel_ms["sharded_search_local_ms"] = ms_since(t_begin);
+    const auto t_x = std::chrono::steady_clock::now();
     ASB_CUDA(ctx, cudaMemcpyAsync(agree.ptr, &bad, 8, cudaMemcpyHostToDevice, ctx->stream));
     ASB_TRY(asb_comm_allreduce_i64(ctx, comm, agree.ptr, 1, ASB_RED_MAX));
     long long worst = 0;
@@ -1087,7 +1120,9 @@ int asb_index_search_sharded(asb_ctx *ctx, asb_comm *comm, const asb_index *ix, 
     ASB_TRY(oi.finish(ctx));
     ASB_TRY(os.finish(ctx));
     ASB_TRY(oc.finish(ctx));
-    return asb_sync(ctx);
+    ASB_TRY(asb_sync(ctx));
+    ctx->kernel_ms["sharded_search_exchange_ms"] = ms_since(t_x);   // includes waiting for the slowest rank
+    return ASB_OK;
 }
 
 /* The Two-NN scan over a row-sharded dataset (src/clustering.rs:118-145): sample_idx are GLOBAL row
@@ -1126,5 +1161,118 @@ int asb_twonn_distances_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows
 }
 
 int64_t asb_index_shard_offset(const asb_index *ix) { return ix ? ix->shard_offset : 0; }
+
+}  // extern "C"
+
+// queries -> (projected queries when the index carries a projection) and their lambdas (src/core.rs:533-549)
+static int index_query_prep(asb_ctx *ctx, const asb_index *ix, const double *q_d, int64_t nq, DevTmp<double> &qp,
+                            const double **q_used, double *lq_d, int *flag_d) {
+    const int64_t f = ix->f;
+    // the finiteness assert looks at the RAW query (:534-537): a throw-away lambda pass over it sets the flag
+    *q_used = q_d;
+    int64_t fq = f;
+    if (ix->r) {
+        DevTmp<double> scratch;
+        ASB_TRY(scratch.init(ctx, (size_t)nq));
+        ASB_TRY(asb_dev_nonfinite_rows(ctx, q_d, nq, f, flag_d));
+        ASB_TRY(qp.init(ctx, (size_t)nq * ix->r));
+        ASB_TRY(asb_dev_project(ctx, q_d, nq, f, ix->proj, ix->r, qp.ptr));
+        *q_used = qp.ptr;
+        fq = ix->r;
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return asb_dev_taumode(ctx, *q_used, nq, fq, ix->plan, ix->tau_mode, ix->tau_value, lq_d, nullptr, nullptr, flag_d);
+}
+
+extern "C" {
+
+int asb_index_prepare_query(asb_ctx *ctx, const asb_index *ix, const double *queries, int64_t nq, double *lambda_q) {
+    ASB_TRY(set_device(ctx));
+    if (!ix || !queries || !lambda_q || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_prepare_query: bad argument");
+    DevIn<double> q;
+    DevTmp<double> qp;
+    DevOut<double> lq;
+    DevTmp<int> flag;
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * ix->f));
+    ASB_TRY(lq.init(ctx, lambda_q, (size_t)nq));
+    ASB_TRY(flag.init(ctx, 1));
+    ASB_CUDA(ctx, cudaMemsetAsync(flag.ptr, 0, sizeof(int), ctx->stream));
+    const double *qu = nullptr;
+    ASB_TRY(index_query_prep(ctx, ix, q.ptr, nq, qp, &qu, lq.ptr, flag.ptr));
+    int h = 0;
+    ASB_CUDA(ctx, cudaMemcpyAsync(&h, flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h)
+        ASB_FAIL(ctx, ASB_ERR_NONFINITE_QUERY,
+                 "Query item contains invalid values (NaN or infinity). All values must be finite.");
+    ASB_TRY(lq.finish(ctx));
+    return asb_sync(ctx);
+}
+
+int asb_index_search_energy(asb_ctx *ctx, asb_index *ix, const double *queries, int64_t nq, int64_t k, double w_lambda,
+                            double w_dirichlet, int64_t *idx, double *score, int64_t *count) {
+    ASB_TRY(set_device(ctx));
+    if (!ix || !queries || !idx || !score || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "index_search_energy: bad argument");
+    if (k < 1 || k > 56) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "index_search_energy: k=%lld outside 1..56", (long long)k);
+    const int64_t f = ix->f, n = ix->n, d = ix->r ? ix->r : f;   // d: dimension the differences live in
+    DevIn<double> q;
+    DevTmp<double> qp, lq, qs;
+    DevTmp<int> flags;
+    DevTmp<int64_t> cnt_tmp;
+    DevOut<int64_t> oi, oc;
+    DevOut<double> os;
+    ASB_TRY(q.init(ctx, queries, (size_t)nq * f));
+    ASB_TRY(lq.init(ctx, (size_t)nq));
+    ASB_TRY(flags.init(ctx, 2));
+    ASB_TRY(cnt_tmp.init(ctx, (size_t)nq));
+    ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, 2 * sizeof(int), ctx->stream));
+    const double *qu = nullptr;
+    ASB_TRY(index_query_prep(ctx, ix, q.ptr, nq, qp, &qu, lq.ptr, flags.ptr));   // lambda_q (:885) and project_vec(query)
+    int h[2] = {0, 0};
+    ASB_CUDA(ctx, cudaMemcpyAsync(h, flags.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[0])
+        ASB_FAIL(ctx, ASB_ERR_NONFINITE_QUERY,
+                 "Query item contains invalid values (NaN or infinity). All values must be finite.");
+    // project_vec(item) for every item, once per index (the reference redoes it per query and item, :889-891)
+    const double *xu = ix->items;
+    if (ix->r) {
+        if (!ix->items_proj) {
+            ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->items_proj, (size_t)n * d * sizeof(double), ctx->stream));
+            ASB_TRY(asb_dev_project(ctx, ix->items, n, f, ix->proj, d, ix->items_proj));
+        }
+        xu = ix->items_proj;
+    }
+    // projected_dirichlet (:866-882): through the signals when they exist and their column count is the difference's
+    // length (they are built on the feature graph's nodes, so this holds whenever they exist)
+    const bool use_sig = ix->sig_indptr != nullptr;
+    const double *xr = xu, *qr = qu;   // what the ranking pass measures distances between
+    if (use_sig) {
+        if (!ix->items_sig) {
+            ASB_CUDA(ctx, cudaMallocAsync((void **)&ix->items_sig, (size_t)n * d * sizeof(double), ctx->stream));
+            ASB_TRY(asb_dev_csr_apply_rows(ctx, ix->sig_indptr, ix->sig_indices, ix->sig_data, d, xu, n, ix->items_sig));
+        }
+        ASB_TRY(qs.init(ctx, (size_t)nq * d));
+        ASB_TRY(asb_dev_csr_apply_rows(ctx, ix->sig_indptr, ix->sig_indices, ix->sig_data, d, qu, nq, qs.ptr));
+        xr = ix->items_sig;   // |S q' - S x'| = |S (q' - x')|: the ranking pass works on the transformed rows
+        qr = qs.ptr;
+    }
+    ASB_TRY(oi.init(ctx, idx, (size_t)nq * k));
+    ASB_TRY(os.init(ctx, score, (size_t)nq * k));
+    ASB_TRY(oc.init(ctx, count, count ? (size_t)nq : 0));
+    StageTimer ts(ctx, "search_energy");
+    int rc = asb_dev_search_energy_ex(ctx, xr, xu, ix->lambdas, n, d, qr, qu, lq.ptr, nq, k, w_lambda, w_dirichlet,
+                                      use_sig ? ix->sig_indptr : nullptr, ix->sig_indices, ix->sig_data, oi.ptr, os.ptr,
+                                      count ? oc.ptr : cnt_tmp.ptr, flags.ptr + 1);
+    ts.stop();
+    ASB_TRY(rc);
+    ASB_CUDA(ctx, cudaMemcpyAsync(h + 1, flags.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASB_TRY(search_status_to_rc(ctx, h[1]));
+    ASB_TRY(oi.finish(ctx));
+    ASB_TRY(os.finish(ctx));
+    ASB_TRY(oc.finish(ctx));
+    return asb_sync(ctx);
+}
 
 }  // extern "C"

@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 
 #include "comm.cuh"
 
@@ -897,6 +898,12 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
     ctx->kernel_ms["cluster_shard_speculative"] = 0.0;   // pieces of this shard proven against the common snapshot
     ctx->kernel_ms["cluster_shard_fallback"] = 0.0;      // pieces that were not, and were re-ranked from the fresh state
     int64_t x = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *key) {   // host wall time since the call began (the phases below end in stream syncs)
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->kernel_ms[key] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return (int)ASB_OK;
+    };
     if (r == 0) {
         int64_t head = (int64_t)opt_or(ctx, "cluster_shard_snapshot_rows", 262144.0);
         if (head > n_local) head = n_local;
@@ -904,6 +911,7 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
             ASB_TRY(asb_dev_cluster(ctx, rows_d, head, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &x, 0));
         ASB_TRY(shard_pack(ctx, pack.ptr, x, centroids_d, sizes_d, max_clusters, f));
         ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, 0));
+        ASB_TRY(lap("shard_t_snapshot_ms"));
         if (n_local > head) {
             const int64_t x_before = x;
             ASB_TRY(asb_dev_cluster(ctx, rows_d + head * f, n_local - head, f, max_clusters, radius, centroids_d,
@@ -928,8 +936,10 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
             ASB_TRY(replay_ws_init(ctx, ws[(size_t)i], (int)m, (int)max_clusters, (int)f));
             ASB_TRY(replay_prepare(ctx, ws[(size_t)i], rows_d + lo * f, (int)m, (int)f, (int)x_snap, snap.ptr));
         }
+        ASB_TRY(lap("shard_t_ranked_ms"));
         ASB_TRY(asb_comm_recv_bytes(ctx, comm, pack.ptr, sb, r - 1));
         ASB_TRY(shard_unpack(ctx, pack.ptr, &x, centroids_d, sizes_d, max_clusters, f));
+        ASB_TRY(lap("shard_t_state_in_ms"));
         int64_t proven = 0, walked = 0;
         if (npieces == 0 && n_local > 0) {
             const int64_t x_before = x;
@@ -963,10 +973,12 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
         ctx->kernel_ms["cluster_shard_speculative"] = (double)proven;
         ctx->kernel_ms["cluster_shard_fallback"] = (double)walked;
     }
+    ASB_TRY(lap("shard_t_walked_ms"));
     ASB_TRY(shard_pack(ctx, pack.ptr, x, centroids_d, sizes_d, max_clusters, f));
     if (r < R - 1) ASB_TRY(asb_comm_send_bytes(ctx, comm, pack.ptr, sb, r + 1));
     ASB_TRY(asb_comm_bcast_bytes(ctx, comm, pack.ptr, sb, R - 1));
     ASB_TRY(shard_unpack(ctx, pack.ptr, &x, centroids_d, sizes_d, max_clusters, f));
+    ASB_TRY(lap("shard_t_done_ms"));
     *x_out_host = x;
     return ASB_OK;
 }

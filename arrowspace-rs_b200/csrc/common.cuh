@@ -315,3 +315,11 @@ int asb_dev_mark_tail(asb_ctx *ctx, int64_t *idx_d, const int64_t *cnt_d, int64_
 int asb_dev_twonn_gather(asb_ctx *ctx, const double *rows_d, int64_t n_local, int64_t f, int64_t offset,
                          const int64_t *sample_d, int64_t s, double *q_d, int64_t *self_d);
 int asb_dev_twonn_merge(asb_ctx *ctx, const double *all_d, int parts, int64_t s, double *d1_d, double *d2_d);
+int asb_dev_nonfinite_rows(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int *flag_d);
+int asb_dev_csr_apply_rows(asb_ctx *ctx, const int64_t *indptr_d, const int64_t *indices_d, const double *data_d, int64_t d,
+                           const double *rows_d, int64_t n, double *out_d);
+int asb_dev_search_energy_ex(asb_ctx *ctx, const double *rank_items_d, const double *items_d, const double *lambdas_d,
+                             int64_t n, int64_t d, const double *rank_queries_d, const double *queries_d,
+                             const double *lambda_q_d, int64_t nq, int64_t k, double w_lambda, double w_dirichlet,
+                             const int64_t *sig_indptr_d, const int64_t *sig_indices_d, const double *sig_data_d,
+                             int64_t *idx_d, double *score_d, int64_t *count_d, int *status_d);

@@ -216,3 +216,146 @@ int asb_dev_twonn_merge(asb_ctx *ctx, const double *all_d, int parts, int64_t s,
     twonn_merge_kernel<<<(unsigned)((s + 255) / 256), 256, 0, ctx->stream>>>(all_d, parts, (long long)s, d1_d, d2_d);
     return asb_check_launch(ctx, "twonn_merge_kernel");
 }
+
+// ---- energy search through a projection / the spectral signals (api.cu: asb_index_search_energy) ------------------------
+namespace {
+__global__ void __launch_bounds__(256) nonfinite_rows_kernel(const double *__restrict__ rows, long long total, int *flag) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) bad |= !(fabs(rows[i]) < INFINITY);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+// out[i] = S x_i for every row x_i (S: d x d CSR); one warp per row, the row staged in shared memory, lanes over the
+// rows of S, each summing val * x[col] in stored order (the order of projected_dirichlet, src/energymaps.rs:869-876)
+__global__ void __launch_bounds__(128) csr_apply_rows_kernel(const long long *__restrict__ indptr,
+                                                             const long long *__restrict__ indices,
+                                                             const double *__restrict__ data, int d,
+                                                             const double *__restrict__ rows, long long n,
+                                                             double *__restrict__ out) {
+    extern __shared__ double xs_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *xs = xs_all + (size_t)warp * d;
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (i >= n) return;
+    for (int j = lane; j < d; j += 32) xs[j] = rows[i * d + j];
+    __syncwarp();
+    for (int r = lane; r < d; r += 32) {
+        double sum = 0.0;
+        for (long long e = indptr[r]; e < indptr[r + 1]; ++e) sum = __dadd_rn(sum, __dmul_rn(data[e], xs[indices[e]]));
+        out[i * d + r] = sum;
+    }
+}
+// second pass of the energy search: exact scores of the kc candidates from the DIFFERENCE vector (ProjectedEnergy::score,
+// src/energymaps.rs:884-894): diff = q' - x' element-wise, then |S diff| (signals) or |diff|, bounded, blended with
+// |lambda_q - lambda_i|; best k by (score desc, index asc).  One warp per query, kc <= 64.
+__global__ void __launch_bounds__(128) energy_rescore_ex_kernel(
+    const double *__restrict__ items, const double *__restrict__ lambdas, int d, const double *__restrict__ queries,
+    const double *__restrict__ lambda_q, long long nq, int kc, int k, double w_lambda, double w_dir,
+    const long long *__restrict__ sig_indptr, const long long *__restrict__ sig_indices, const double *__restrict__ sig_data,
+    const long long *__restrict__ cand_idx, const long long *__restrict__ cand_cnt, long long *__restrict__ idx_out,
+    double *__restrict__ score_out, long long *__restrict__ count_out) {
+    extern __shared__ double diff_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *diff = diff_all + (size_t)warp * d;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= nq) return;
+    const int cnt = (int)cand_cnt[w];
+    const double *q = queries + w * (long long)d;
+    const double lq = lambda_q[w];
+    double sc[2] = {-INFINITY, -INFINITY};
+    long long id[2] = {-1, -1};
+    for (int c = 0; c < cnt; ++c) {
+        const long long gi = cand_idx[w * kc + c];
+        const double *x = items + gi * (long long)d;
+        __syncwarp();
+        double acc = 0.0;
+        for (int t = lane; t < d; t += 32) {
+            const double df = q[t] - x[t];
+            diff[t] = df;
+            acc = fma(df, df, acc);
+        }
+        __syncwarp();
+        if (sig_indptr) {
+            acc = 0.0;
+            for (int r = lane; r < d; r += 32) {
+                double sum = 0.0;
+                for (long long e = sig_indptr[r]; e < sig_indptr[r + 1]; ++e)
+                    sum = __dadd_rn(sum, __dmul_rn(sig_data[e], diff[sig_indices[e]]));
+                acc = fma(sum, sum, acc);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const double dn = sqrt(acc);
+        const double s = -(w_lambda * fabs(lq - lambdas[gi]) + w_dir * fmin(dn / (1.0 + dn), 1.0));
+        if ((c & 31) == lane) {
+            sc[c >> 5] = s;
+            id[c >> 5] = gi;
+        }
+    }
+    const int kout = k < cnt ? k : cnt;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = h * 32 + lane;
+        int rank = 0;
+        for (int o = 0; o < cnt; ++o) {
+            const double os = __shfl_sync(0xffffffffu, sc[o >> 5], o & 31);
+            const long long oi = __shfl_sync(0xffffffffu, id[o >> 5], o & 31);
+            if (c < cnt && (os > sc[h] || (os == sc[h] && oi < id[h]))) rank++;
+        }
+        if (c < cnt && rank < kout) {
+            idx_out[w * k + rank] = id[h];
+            score_out[w * k + rank] = sc[h];
+        }
+    }
+    for (int r = kout + lane; r < k; r += 32) {
+        idx_out[w * k + r] = -1;
+        score_out[w * k + r] = 0.0;
+    }
+    if (lane == 0 && count_out) count_out[w] = kout;
+}
+}  // namespace
+
+int asb_dev_nonfinite_rows(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, int *flag_d) {
+    nonfinite_rows_kernel<<<256, 256, 0, ctx->stream>>>(rows_d, (long long)n * f, flag_d);
+    return asb_check_launch(ctx, "nonfinite_rows_kernel");
+}
+
+int asb_dev_csr_apply_rows(asb_ctx *ctx, const int64_t *indptr_d, const int64_t *indices_d, const double *data_d, int64_t d,
+                           const double *rows_d, int64_t n, double *out_d) {
+    if (d * 8 * 4 > 200 * 1024) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "csr_apply_rows: dimension %lld too large", (long long)d);
+    const size_t smem = (size_t)4 * d * sizeof(double);
+    ASB_CUDA(ctx, cudaFuncSetAttribute(csr_apply_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    csr_apply_rows_kernel<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>((const long long *)indptr_d,
+                                                                               (const long long *)indices_d, data_d, (int)d,
+                                                                               rows_d, (long long)n, out_d);
+    return asb_check_launch(ctx, "csr_apply_rows_kernel");
+}
+
+// rank_items / rank_queries: the rows the fused pass measures distances between (S x' / S q' with signals, else x' / q');
+// items / queries: the (projected) vectors themselves, for the exact second pass
+int asb_dev_search_energy_ex(asb_ctx *ctx, const double *rank_items_d, const double *items_d, const double *lambdas_d,
+                             int64_t n, int64_t d, const double *rank_queries_d, const double *queries_d,
+                             const double *lambda_q_d, int64_t nq, int64_t k, double w_lambda, double w_dirichlet,
+                             const int64_t *sig_indptr_d, const int64_t *sig_indices_d, const double *sig_data_d,
+                             int64_t *idx_d, double *score_d, int64_t *count_d, int *status_d) {
+    if (n <= 0 || d <= 0 || nq <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "search_energy: empty input");
+    if (k < 1 || k > 56) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search_energy: k=%lld outside 1..56", (long long)k);
+    if (d * 8 * 4 > 200 * 1024) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "search_energy: dimension %lld too large", (long long)d);
+    int64_t kc = k + 4;
+    if (kc > n) kc = n;
+    DevTmp<int64_t> ci, cc;
+    DevTmp<double> cs;
+    ASB_TRY(ci.init(ctx, (size_t)nq * kc));
+    ASB_TRY(cs.init(ctx, (size_t)nq * kc));
+    ASB_TRY(cc.init(ctx, (size_t)nq));
+    // first pass: kc candidates by the fused kernel's own (GEMM-form) energy on the ranking rows
+    ASB_TRY(asb_dev_search_energy(ctx, rank_items_d, lambdas_d, nullptr, n, d, rank_queries_d, lambda_q_d, nq, kc, w_lambda,
+                                  w_dirichlet, 0, ci.ptr, cs.ptr, cc.ptr, status_d));
+    const size_t smem = (size_t)4 * d * sizeof(double);
+    ASB_CUDA(ctx, cudaFuncSetAttribute(energy_rescore_ex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    energy_rescore_ex_kernel<<<(unsigned)((nq + 3) / 4), 128, smem, ctx->stream>>>(
+        items_d, lambdas_d, (int)d, queries_d, lambda_q_d, (long long)nq, (int)kc, (int)k, w_lambda, w_dirichlet,
+        (const long long *)sig_indptr_d, (const long long *)sig_indices_d, sig_data_d, (const long long *)ci.ptr,
+        (const long long *)cc.ptr, (long long *)idx_d, score_d, (long long *)count_d);
+    return asb_check_launch(ctx, "energy_rescore_ex_kernel");
+}

@@ -504,7 +504,7 @@ int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, c
                     int tau_mode, double tau_value, double *lambdas_d, double *norms2_d, double *stats_d,
                     int *nonfinite_flag_d) {
     if (n <= 0 || f <= 0) ASB_FAIL(ctx, ASB_ERR_INVALID, "taumode: n=%lld f=%lld", (long long)n, (long long)f);
-    if (plan.f != f)
+    if (plan.f > f)
         ASB_FAIL(ctx, ASB_ERR_DIM, "taumode: graph is %lldx%lld but items have %lld features", (long long)plan.f,
                  (long long)plan.f, (long long)f);
     if (tau_mode < ASB_TAU_FIXED || tau_mode > ASB_TAU_PERCENTILE)
@@ -514,6 +514,8 @@ int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, c
         auto it = ctx->options.find("taumode_generic");
         if (it != ctx->options.end() && it->second != 0.0) generic = true;
     }
+    if (plan.f < f && (generic || (size_t)f * sizeof(double) > 200 * 1024))
+        ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "taumode: a graph smaller than the items (JL-projected build) needs the symmetric kernel");
     if (!generic && (size_t)f * sizeof(double) <= 200 * 1024) {
         // one warp per item; as many warps per CTA as the private shared-memory copies allow
         int wpc = kTauWarps;
@@ -534,11 +536,11 @@ int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, c
             if (plan.all_pos)
                 taumode_warp_kernel<true><<<(unsigned)grid, kTauWarps * 32, smem, ctx->stream>>>(
                     items_d, (long long)n, (int)f, (const SymEdge *)plan.sym_edges, nsteps, plan.resid, tau_mode,
-                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc);
+                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc, (int)plan.f);
             else
                 taumode_warp_kernel<false><<<(unsigned)grid, kTauWarps * 32, smem, ctx->stream>>>(
                     items_d, (long long)n, (int)f, (const SymEdge *)plan.sym_edges, nsteps, plan.resid, tau_mode,
-                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc);
+                    tau_value, lambdas_d, norms2_d, nonfinite_flag_d, wpc, (int)plan.f);
         }
         ASB_TRY(asb_check_launch(ctx, "taumode_warp_kernel"));
         if (stats_d) {

@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(kTauWarps * 32)
 taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const SymEdge *__restrict__ sched,
                     int nsteps, const double *__restrict__ resid, int tau_mode, double tau_value,
                     double *__restrict__ lambdas, double *__restrict__ norms2, int *__restrict__ nonfinite_flag,
-                    int warps_per_cta) {
+                    int warps_per_cta, int rg) {
+    // rg = nodes of the graph, <= f: after a JL-projected build the graph is r x r while the items keep their F
+    // values -- the reference then reads item[0 .. r) in the Rayleigh sums and ALL F values for tau and the
+    // denominator (src/taumode.rs:233-245,596 with src/eigenmaps.rs:248-269)
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp >= warps_per_cta) return;  // no block-level barrier anywhere below
@@ -64,7 +67,7 @@ taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const 
             xs[j] = x;
             const double x2 = x * x;
             den += x2;
-            num = fma(__ldg(resid + j), x2, num);
+            if (j < rg) num = fma(__ldg(resid + j), x2, num);
             if (fabs(x) < INFINITY) {
                 cnt++;
                 vsum += x;

@@ -60,7 +60,7 @@ class BuildParamsC(C.Structure):
     _fields_ = [
         ("graph", GraphParamsC), ("tau_mode", C.c_int32), ("tau_value", C.c_double),
         ("max_clusters", C.c_int64), ("radius", C.c_double), ("apply_define_result_k", C.c_int32),
-        ("spectral", C.c_int32),
+        ("spectral", C.c_int32), ("projection", C.c_void_p), ("reduced_dim", C.c_int64),
     ]
 
 
@@ -115,6 +115,8 @@ ABI_SYMBOLS = {
     "asb_index_signals": (C.c_int, [_P, _P, _P, _P, _P]),
     "asb_index_search": (C.c_int, [_P, _P, _P, _I64, _I64, _D, _P, _P, _P, _P]),
     "asb_index_search_lambda_aware": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _D, _P, _P, _P]),
+    "asb_index_prepare_query": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "asb_index_search_energy": (C.c_int, [_P, _P, _P, _I64, _I64, _D, _D, _P, _P, _P]),
     "asb_comm_unique_id": (C.c_int, [_P, _P]),
     "asb_comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "asb_comm_from_nccl": (C.c_int, [_P, _P, C.POINTER(_P)]),
@@ -803,6 +805,11 @@ class ArrowSpace:
         if q.shape[1] != self.nfeatures:
             raise ArrowSpaceError(ASB_ERR_DIM, f"Query dimension {q.shape[1]} doesn't match index original dimension "
                                                f"{self.nfeatures}")
+        if self.projection_matrix is not None:      # :540-545: the query is projected first
+            if not np.all(np.isfinite(q)):           # :534-537 looks at the raw query
+                raise ArrowSpaceError(ASB_ERR_NONFINITE_QUERY, "Query item contains invalid values (NaN or infinity). "
+                                                               "All values must be finite.")
+            q = np.ascontiguousarray(self.projection_matrix.project(q[0]).reshape(1, -1))
         return float(self.ctx.prepare_query_lambdas(q, gl.csr, self.taumode)[0])
 
     def prepare_query_items(self, queries, gl: GraphLaplacian):
@@ -860,13 +867,47 @@ class ArrowSpace:
         """``EnergyMaps::search_energy`` (src/energymaps.rs:368-407): lambda_q from ``prepare_query_item`` on
         ``gl_energy`` (:885), then (index, -energy) for the k items of least projected energy.  Spaces with a JL
         projection or spectral signals take other branches of the reference's score (:858-882) -- unsupported."""
-        if self.projection_matrix is not None or self.signals is not None:
-            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "search_energy: projection / signals branches are not built")
         q = np.ascontiguousarray(query.item if isinstance(query, ArrowItem) else query, dtype=np.float64)
+        if self.projection_matrix is not None or self.signals is not None:
+            # project_vec through the projection, projected_dirichlet through the signals (:858-882): both live in the
+            # native index (the space must come from ArrowSpaceBuilder.build)
+            if self._index is None:
+                raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "search_energy with a projection / signals needs the native "
+                                                           "index of ArrowSpaceBuilder.build")
+            idx, score, count = self.search_energy_batch(q.reshape(1, -1), k, w_lambda, w_dirichlet)
+            return [(int(idx[0, r]), float(score[0, r])) for r in range(int(count[0]))]
         lq = self.prepare_query_item(q, gl_energy)
         idx, score, count = self.ctx.search_energy_batch(self.data, self.lambdas, q.reshape(1, -1), np.array([lq]), k,
                                                          w_lambda, w_dirichlet)
         return [(int(idx[0, r]), float(score[0, r])) for r in range(int(count[0]))]
+
+    def search_energy_batch(self, queries, k: int, w_lambda: float, w_dirichlet: float):
+        """Batched ``search_energy`` against the native index, every branch of ``ProjectedEnergy::score``."""
+        if self._index is None:
+            raise ArrowSpaceError(ASB_ERR_INVALID, "no native index: call ArrowSpaceBuilder.build first")
+        queries = _as_f64_matrix(queries)
+        nq, fq = _shape2(queries)
+        if fq != self.nfeatures:
+            raise ArrowSpaceError(ASB_ERR_DIM, f"Query dimension {fq} doesn't match index original dimension "
+                                               f"{self.nfeatures}")
+        idx = np.full((nq, k), -1, dtype=np.int64)
+        score = np.zeros((nq, k), dtype=np.float64)
+        count = np.zeros(nq, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.asb_index_search_energy(self.ctx.handle, self._index, _ptr(queries), nq, int(k),
+                                                            float(w_lambda), float(w_dirichlet), _ptr(idx), _ptr(score),
+                                                            _ptr(count)))
+        return idx, score, count
+
+    def prepare_query_items_index(self, queries):
+        """``prepare_query_item`` for a batch against the native index (queries are projected first when the build
+        used a JL projection, src/core.rs:540-545)."""
+        if self._index is None:
+            raise ArrowSpaceError(ASB_ERR_INVALID, "no native index: call ArrowSpaceBuilder.build first")
+        queries = _as_f64_matrix(queries)
+        nq = _shape2(queries)[0]
+        lq = np.empty(nq, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.asb_index_prepare_query(self.ctx.handle, self._index, _ptr(queries), nq, _ptr(lq)))
+        return lq
 
     def range_search(self, query: ArrowItem, gl: GraphLaplacian, eps: float) -> List[Tuple[int, float]]:
         """``ArrowSpace::range_search`` (src/core.rs:944-976): the query lambda is re-prepared when it is
@@ -933,6 +974,7 @@ class ArrowSpaceBuilder:
         self.deterministic_clustering = False
         self.use_dims_reduction = False
         self.rp_eps = 0.3
+        self.projection = None
         self._explicit_cluster_params = False
         self.self_included = False
         self.rectified = False
@@ -970,6 +1012,16 @@ class ArrowSpaceBuilder:
     def with_dims_reduction(self, enable: bool, eps: Optional[float]):  # :181-185
         self.use_dims_reduction = bool(enable)
         self.rp_eps = 0.5 if eps is None else float(eps)
+        return self
+
+    def with_projection(self, projection):
+        """The materialised Gaussian matrix of the build's ``ImplicitProjection`` (F x r, feature-major: row j holds the
+        r samples drawn for feature j).  The reference keeps an 8-byte seed and redraws the matrix with ChaCha8 +
+        StandardNormal (src/reduction.rs:176-199) -- third-party generators -- so a Rust host draws it once and hands it
+        over; without Rust any matrix gives a self-consistent JL build.  Either an :class:`ImplicitProjection`, an array,
+        or a callable ``(F, r) -> array`` evaluated once r is known (r = min(compute_jl_dimension(n_clusters, eps), F / 2),
+        src/eigenmaps.rs:249-250)."""
+        self.projection = projection
         return self
 
     def with_seed(self, seed: int):  # :190-195 -> deterministic (sequential) clustering
@@ -1032,26 +1084,51 @@ class ArrowSpaceBuilder:
             raise ArrowSpaceError(ASB_ERR_UNSUPPORTED,
                                   "inline sampling uses an OS-seeded RNG in the reference (src/sampling.rs:123,184); "
                                   "use with_inline_sampling(None)")
-        if self.use_dims_reduction:
-            raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "JL projection is a 'next' row (SURVEY 8f)")
         n, f = _shape2(rows)
         aspace = ArrowSpace(rows, self.synthesis, self.ctx)
         k_opt, radius = self.resolve_cluster_params(rows)
         self.cluster_max_clusters, self.cluster_radius = k_opt, radius
         gp = self.graph_params()
+        proj_mat, r = None, 0
+        if self.use_dims_reduction and f > 64:                      # src/eigenmaps.rs:248
+            if not self._explicit_cluster_params:
+                raise ArrowSpaceError(ASB_ERR_UNSUPPORTED, "with_dims_reduction needs with_cluster_params: the target "
+                                                           "dimension follows the cluster count (src/eigenmaps.rs:249)")
+            if self.projection is None:
+                raise ArrowSpaceError(ASB_ERR_UNSUPPORTED,
+                                      "with_dims_reduction(true, eps) needs the materialised projection matrix "
+                                      "(with_projection): the reference's seed-driven generators are third-party")
+            # the reference sizes the projection by the number of clusters actually formed; the walk is deterministic,
+            # so one clustering call tells it (the build below repeats the walk: same bits)
+            cent0, _, _ = self.ctx.cluster_incremental(rows, int(k_opt), float(radius))
+            target = min(compute_jl_dimension(int(cent0.shape[0]), self.rp_eps), f // 2)   # :249-250
+            if target < f:                                           # :252
+                pm = self.projection
+                if callable(pm):
+                    pm = pm(f, target)
+                if isinstance(pm, ImplicitProjection):
+                    pm = pm.matrix
+                proj_mat = np.ascontiguousarray(pm, dtype=np.float64)
+                if proj_mat.shape != (f, target):
+                    raise ArrowSpaceError(ASB_ERR_DIM, f"projection matrix must be {f} x {target}, got {proj_mat.shape}")
+                r = target
         bp = BuildParamsC(gp.to_c(), self.synthesis.mode, self.synthesis.value, int(k_opt), float(radius), 0,
-                          1 if self.prebuilt_spectral else 0)
+                          1 if self.prebuilt_spectral else 0, _ptr(proj_mat) if proj_mat is not None else None, int(r))
         h = _P()
         lib = self.ctx.lib
         self.ctx.check(lib.asb_index_build(self.ctx.handle, _ptr(rows), n, f, C.byref(bp), C.byref(h)))
         aspace._index = h
+        if r:
+            aspace.projection_matrix = ImplicitProjection(proj_mat, self.ctx)   # eigenmaps.rs:260-261
+            aspace.reduced_dim = r
         info = aspace.index_info()
         x, nnz = int(info.n_clusters), int(info.nnz)
+        fg = r if r else f                                           # nodes of the feature graph
         lam = np.empty(n, dtype=np.float64)
         cent = np.empty((x, f), dtype=np.float64)
         asg = np.empty(n, dtype=np.int64)
         sizes = np.empty(x, dtype=np.uint64)
-        indptr = np.empty(f + 1, dtype=np.int64)
+        indptr = np.empty(fg + 1, dtype=np.int64)
         indices = np.empty(nnz, dtype=np.int64)
         data = np.empty(nnz, dtype=np.float64)
         self.ctx.check(lib.asb_index_lambdas(self.ctx.handle, h, _ptr(lam)))
@@ -1069,7 +1146,7 @@ class ArrowSpaceBuilder:
         gl = GraphLaplacian(indptr, indices, data, n, gp, cent)
         if self.prebuilt_spectral:
             snnz = int(info.nnz_signals)
-            sp, si, sd = np.empty(f + 1, dtype=np.int64), np.empty(snnz, dtype=np.int64), np.empty(snnz, dtype=np.float64)
+            sp, si, sd = np.empty(fg + 1, dtype=np.int64), np.empty(snnz, dtype=np.int64), np.empty(snnz, dtype=np.float64)
             self.ctx.check(lib.asb_index_signals(self.ctx.handle, h, _ptr(sp), _ptr(si), _ptr(sd)))
             aspace.signals = (sp, si, sd)
         return aspace, gl

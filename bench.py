@@ -434,11 +434,15 @@ def run_b200(args):
             torch.cuda.synchronize()
             info = index.info()
             if record:
+                shard_diag["search_local_ms"] = ctx.kernel_ms("sharded_search_local_ms")
+                shard_diag["search_exchange_ms"] = ctx.kernel_ms("sharded_search_exchange_ms")
+            if record:
                 stage_acc["cluster"].append(info.ms_cluster)
                 stage_acc["laplacian"].append(info.ms_laplacian)
                 stage_acc["taumode"].append(info.ms_taumode)
-                shard_diag["speculative"] = ctx.kernel_ms("cluster_shard_speculative")
-                shard_diag["fallback"] = ctx.kernel_ms("cluster_shard_fallback")
+                for key in ("cluster_shard_speculative", "cluster_shard_fallback", "shard_t_snapshot_ms", "shard_t_ranked_ms",
+                            "shard_t_state_in_ms", "shard_t_walked_ms", "shard_t_done_ms"):
+                    shard_diag[key] = ctx.kernel_ms(key)
             result = (idx, score, info)
             index.close()
         if record:
@@ -535,6 +539,10 @@ def run_b200(args):
                "search_qps": nq / (float(np.mean(e2e_search)) * 1e-3),
                "build_ms": float(np.mean(e2e_build)), "search_ms": float(np.mean(e2e_search))}
 
+    if world > 1:
+        all_diag = [None] * world
+        dist.all_gather_object(all_diag, shard_diag)
+        shard_diag = {f"rank{i}": d for i, d in enumerate(all_diag)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -637,7 +645,7 @@ def run_b200(args):
                            if not args.no_cluster_replay else None),
         "sharded": ({"collectives": "inside the C ABI (asb_comm_*: dlopen'd NCCL): Two-NN sample all-reduce + 2-min all-gather, "
                                     "centroid-state broadcast / send / recv, CSR broadcast, lambda-stat all-reduce, top-k "
-                                    "all-gather + merge", "rank0": shard_diag} if world > 1 else None),
+                                    "all-gather + merge", "per_rank": shard_diag} if world > 1 else None),
         "kernels": kernels, "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
 

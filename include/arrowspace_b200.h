@@ -84,6 +84,17 @@ typedef struct {
     int32_t spectral; /* with_spectral (src/builder.rs:157-162): also build the Laplacian-of-Laplacian "signals"
                        * (src/graph.rs:211-231) and synthesise the ITEM lambdas from it (src/taumode.rs:195-200);
                        * query lambdas keep using the feature Laplacian (src/core.rs:548) */
+    /* with_dims_reduction (src/builder.rs:181-185, src/eigenmaps.rs:248-269): the F x r Gaussian matrix of the
+     * ImplicitProjection, MATERIALISED by the host (projection[j * r + k] = the sample for feature j, output k; the
+     * reference redraws it from an 8-byte seed with ChaCha8 + StandardNormal, third-party generators), host or device
+     * pointer; NULL / 0 = no projection.  The host decides r = min(compute_jl_dimension(n_clusters, eps), F / 2) and
+     * whether to project at all (F > 64).  Effects, as in the reference: the centroids are projected before the feature
+     * Laplacian (r x r graph); item lambdas read item[0 .. r) against that graph with tau and the denominator over all F
+     * values; query lambdas and the energy search work on projected vectors; the lambda-aware search
+     * of a projected index fails with ASB_ERR_DIM exactly where the reference panics ("items should be of the same
+     * length", src/core.rs:157-161). */
+    const double *projection;
+    int64_t reduced_dim;
 } asb_build_params;
 
 typedef struct {
@@ -296,6 +307,18 @@ int asb_index_signals(asb_ctx *ctx, const asb_index *idx, int64_t *indptr, int64
 int asb_index_search(asb_ctx *ctx, const asb_index *index, const double *queries, int64_t nq,
                      int64_t k, double alpha, int64_t *idx, double *score, int64_t *count,
                      double *lambda_q_out);
+
+/* ArrowSpace::prepare_query_item (src/core.rs:533-549) against the resident index for a batch: the queries are projected
+ * first when the index carries a projection (:540-545), tau comes from the (projected) query, lambda from gl.matrix. */
+int asb_index_prepare_query(asb_ctx *ctx, const asb_index *index, const double *queries, int64_t nq, double *lambda_q);
+
+/* EnergyMaps::search_energy with ProjectedEnergy::score (src/energymaps.rs:368-407,838-895) against the resident index,
+ * every branch: project_vec through the index's projection (if any), projected_dirichlet through the spectral signals
+ * when they exist and match the (projected) dimension -- y = S (q' - x'), |y| / (1 + |y|) -- else bounded L2.  A fused
+ * pass ranks k + 4 candidates per query in the transformed space, a second pass rescoring them from the difference
+ * vector.  Results (index, -energy), best first, ties -> lower index, k <= 56. */
+int asb_index_search_energy(asb_ctx *ctx, asb_index *index, const double *queries, int64_t nq, int64_t k, double w_lambda,
+                            double w_dirichlet, int64_t *idx, double *score, int64_t *count);
 
 /* ArrowSpace::search_lambda_aware (src/core.rs:760-798) against the resident index with
  * caller-prepared query lambdas (the reference's two-step prepare_query_item + search). */

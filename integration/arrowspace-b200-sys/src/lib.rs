@@ -71,6 +71,8 @@ pub struct asb_build_params {
     pub radius: f64,
     pub apply_define_result_k: i32,
     pub spectral: i32,
+    pub projection: *const f64,
+    pub reduced_dim: i64,
 }
 
 #[repr(C)]
@@ -165,6 +167,11 @@ extern "C" {
         alpha: f64, idx: *mut i64, score: *mut f64, count: *mut i64, lambda_q_out: *mut f64) -> c_int;
     pub fn asb_index_search_lambda_aware(ctx: *mut asb_ctx, index: *const asb_index, queries: *const f64,
         lambda_q: *const f64, nq: i64, k: i64, alpha: f64, idx: *mut i64, score: *mut f64, count: *mut i64) -> c_int;
+
+    pub fn asb_index_prepare_query(ctx: *mut asb_ctx, index: *const asb_index, queries: *const f64, nq: i64,
+        lambda_q: *mut f64) -> c_int;
+    pub fn asb_index_search_energy(ctx: *mut asb_ctx, index: *mut asb_index, queries: *const f64, nq: i64, k: i64,
+        w_lambda: f64, w_dirichlet: f64, idx: *mut i64, score: *mut f64, count: *mut i64) -> c_int;
 
     // ---- row-sharded multi-GPU variants (one process per GPU, NCCL) ----
     pub fn asb_comm_unique_id(ctx: *mut asb_ctx, id_out_128_bytes: *mut c_void) -> c_int;

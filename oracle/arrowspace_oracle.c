@@ -101,11 +101,22 @@ double aso_select_tau(const double *x, size_t n, int mode, double value) {
     return r;
 }
 
+double aso_synthetic_lambda_g(const double *x, int64_t f_item, int64_t f, const int64_t *indptr,
+                              const int64_t *indices, const double *data, double tau);
+
 /* src/taumode.rs:552-660.  Rows are visited in order and their partial sums are
  * added in row order (the reference reduces them in a nondeterministic rayon
  * order, :565-588 -- any order is "the reference"). */
 double aso_synthetic_lambda(const double *x, int64_t f, const int64_t *indptr,
                             const int64_t *indices, const double *data, double tau) {
+    return aso_synthetic_lambda_g(x, f, f, indptr, indices, data, tau);
+}
+
+/* The same with a graph of rg <= f nodes: graph.outer_iterator() runs over the graph's rows (:565,:611) and indexes
+ * item_vector[i], item_vector[j] with i, j < rg, while the denominator (:596) runs over the WHOLE item -- the shape a
+ * JL-projected build produces (r x r graph, F-long items: src/eigenmaps.rs:248-269). */
+double aso_synthetic_lambda_g(const double *x, int64_t f_item, int64_t f, const int64_t *indptr,
+                              const int64_t *indices, const double *data, double tau) {
     double numerator = 0.0, edge_energy_sum = 0.0;
     for (int64_t i = 0; i < f; ++i) {
         double xi = x[i];
@@ -126,7 +137,7 @@ double aso_synthetic_lambda(const double *x, int64_t f, const int64_t *indptr,
         edge_energy_sum += local_edge;
     }
     double denominator = 0.0; /* :596 */
-    for (int64_t i = 0; i < f; ++i) denominator += x[i] * x[i];
+    for (int64_t i = 0; i < f_item; ++i) denominator += x[i] * x[i];
     double e_raw = denominator > 1e-12 ? numerator / denominator : 0.0;
 
     double g_sq_sum = 0.0; /* :611-639 */
@@ -752,6 +763,72 @@ int aso_search_energy(const double *items, const double *lambdas, int64_t n, int
     }
     free(res);
     free(tmp);
+    return rc;
+}
+
+int aso_project_matrix(const double *rows, int64_t n, int64_t f, const double *projection, int64_t r, double *out);
+
+/* ProjectedEnergy::score, every branch (src/energymaps.rs:856-895): project_vec through a materialised projection (f x r,
+ * or NULL), projected_dirichlet through the signals CSR (d x d, or NULL; used when its column count equals the
+ * difference's length, :868) else bounded L2.  lambda_q is an input (prepare_query_item of the PROJECTED query,
+ * src/core.rs:540-548, computed by the caller with aso_compute_taumode on the projected query).  Same ordering rules as
+ * aso_search_energy. */
+int aso_search_energy_ex(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
+                         double lambda_q, int64_t k, double w_lambda, double w_dirichlet, const double *projection,
+                         int64_t r, const int64_t *sig_indptr, const int64_t *sig_indices, const double *sig_data,
+                         int64_t sig_n, int64_t *idx_out, double *score_out, int64_t *count_out) {
+    if (n <= 0 || f <= 0 || k < 0) return ASO_ERR_INVALID;
+    const int64_t d = projection ? r : f;
+    sc_t *res = (sc_t *)malloc((size_t)n * sizeof(sc_t));
+    sc_t *tmp = (sc_t *)malloc((size_t)n * sizeof(sc_t));
+    double *qp = (double *)malloc((size_t)d * sizeof(double));
+    double *xp = (double *)malloc((size_t)d * sizeof(double));
+    double *diff = (double *)malloc((size_t)d * sizeof(double));
+    double *y = (double *)malloc((size_t)(sig_n > 0 ? sig_n : 1) * sizeof(double));
+    if (projection) aso_project_matrix(q, 1, f, projection, r, qp);      /* project_vec(query), :889 */
+    else memcpy(qp, q, (size_t)f * sizeof(double));
+    int has_nan = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double d_lambda = fabs(lambda_q - lambdas[i]);               /* :887 */
+        if (projection) aso_project_matrix(items + i * f, 1, f, projection, r, xp);   /* project_vec(item), :891 */
+        else memcpy(xp, items + i * f, (size_t)f * sizeof(double));
+        for (int64_t j = 0; j < d; ++j) diff[j] = qp[j] - xp[j];            /* vec_diff, :499-501,:892 */
+        double ss = 0.0;
+        if (sig_indptr && sig_n > 0 && sig_n == d) {                        /* :868: signals.cols() == diff.len() */
+            for (int64_t row = 0; row < sig_n; ++row) {                     /* :869-876 */
+                double sum = 0.0;
+                for (int64_t e = sig_indptr[row]; e < sig_indptr[row + 1]; ++e) sum += sig_data[e] * diff[sig_indices[e]];
+                y[row] = sum;
+            }
+            for (int64_t row = 0; row < sig_n; ++row) ss += y[row] * y[row];
+        } else {
+            for (int64_t j = 0; j < d; ++j) ss += diff[j] * diff[j];
+        }
+        const double num = sqrt(ss);
+        const double d_dir = fmin(num / (1.0 + num), 1.0);                  /* :878 / :847-850 */
+        const double e = w_lambda * d_lambda + w_dirichlet * d_dir;         /* :894 */
+        if (e != e) has_nan = 1;
+        res[i].s = -e;
+        res[i].i = i;
+    }
+    int rc = ASO_OK;
+    if (has_nan) {
+        rc = ASO_ERR_NAN_SCORE;
+    } else {
+        merge_sort_desc(res, tmp, n);
+        int64_t cnt = k < n ? k : n;
+        for (int64_t t = 0; t < cnt; ++t) {
+            idx_out[t] = res[t].i;
+            score_out[t] = res[t].s;
+        }
+        *count_out = cnt;
+    }
+    free(res);
+    free(tmp);
+    free(qp);
+    free(xp);
+    free(diff);
+    free(y);
     return rc;
 }
 

@@ -55,6 +55,8 @@ extern "C" {
 double aso_select_tau(const double *x, size_t n, int mode, double value);
 
 /* src/taumode.rs:552-660 (== :381-519) */
+double aso_synthetic_lambda_g(const double *x, int64_t f_item, int64_t f_graph, const int64_t *indptr,
+                              const int64_t *indices, const double *data, double tau);
 double aso_synthetic_lambda(const double *x, int64_t f, const int64_t *indptr,
                             const int64_t *indices, const double *data, double tau);
 
@@ -139,6 +141,12 @@ int aso_search_lambda_aware_hybrid(const double *items, const double *lambdas, i
 int aso_search_energy(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
                       double lambda_q, int64_t k, double w_lambda, double w_dirichlet, int64_t *idx_out,
                       double *score_out, int64_t *count_out);
+/* every branch of ProjectedEnergy::score (src/energymaps.rs:856-895): projection f x r (or NULL), signals CSR sig_n x
+ * sig_n (or NULL) */
+int aso_search_energy_ex(const double *items, const double *lambdas, int64_t n, int64_t f, const double *q,
+                         double lambda_q, int64_t k, double w_lambda, double w_dirichlet, const double *projection,
+                         int64_t r, const int64_t *sig_indptr, const int64_t *sig_indices, const double *sig_data,
+                         int64_t sig_n, int64_t *idx_out, double *score_out, int64_t *count_out);
 /* src/reduction.rs:127-141 and :143-199 with the Gaussian matrix materialised by the caller
  * (projection[j * r + k] = the sample drawn for feature j, output k) */
 int64_t aso_jl_dimension(int64_t n_points, double epsilon);

@@ -60,7 +60,11 @@ class Oracle:
         lib.aso_jl_dimension.argtypes = [_I64, _D]
         lib.aso_project_matrix.argtypes = [_P, _I64, _I64, _P, _I64, _P]
         lib.aso_search_energy.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _D, _P, _P, C.POINTER(_I64)]
+        lib.aso_search_energy_ex.argtypes = [_P, _P, _I64, _I64, _P, _D, _I64, _D, _D, _P, _I64, _P, _P, _P, _I64, _P, _P,
+                                             C.POINTER(_I64)]
         lib.aso_num_threads.restype = C.c_int
+        lib.aso_synthetic_lambda_g.restype = _D
+        lib.aso_synthetic_lambda_g.argtypes = [_P, _I64, _I64, _P, _P, _P, _D]
         lib.aso_set_num_threads.restype = C.c_int
         lib.aso_set_num_threads.argtypes = [C.c_int]
         self.lib = lib
@@ -85,6 +89,13 @@ class Oracle:
         x = np.ascontiguousarray(x, dtype=np.float64)
         ip, ii, dd = csr
         return float(self.lib.aso_synthetic_lambda(_p(x), len(x), _p(ip), _p(ii), _p(dd), tau))
+
+    def synthetic_lambda_prefix(self, x, csr, tau, rg) -> float:
+        """lambda of an F-long item against a graph of rg <= F nodes (JL-projected build): the Rayleigh sums read
+        x[0 .. rg), the denominator the whole item."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ip, ii, dd = csr
+        return float(self.lib.aso_synthetic_lambda_g(_p(x), len(x), int(rg), _p(ip), _p(ii), _p(dd), tau))
 
     def compute_taumode(self, items, csr, mode, value=0.0, threads=0) -> np.ndarray:
         items = np.ascontiguousarray(items, dtype=np.float64)
@@ -193,6 +204,30 @@ class Oracle:
         self._chk(self.lib.aso_search_energy(_p(items), _p(lambdas), n, f, _p(q), lambda_q, k, w_lambda, w_dirichlet,
                                              _p(idx), _p(sc), C.byref(cnt)))
         return [(int(idx[r]), float(sc[r])) for r in range(cnt.value)]
+
+    def search_energy_ex(self, items, lambdas, q, lambda_q, k, w_lambda, w_dirichlet, projection=None, signals=None):
+        """Every branch of ProjectedEnergy::score: ``projection`` F x r (or None), ``signals`` CSR triple (or None)."""
+        items = np.ascontiguousarray(items, dtype=np.float64)
+        lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        n, f = items.shape
+        idx = np.full(max(k, 1), -1, dtype=np.int64)
+        sc = np.zeros(max(k, 1), dtype=np.float64)
+        cnt = _I64(0)
+        pj = np.ascontiguousarray(projection, dtype=np.float64) if projection is not None else None
+        r = pj.shape[1] if pj is not None else 0
+        if signals is not None:
+            sp, si, sd = (np.ascontiguousarray(signals[0], dtype=np.int64), np.ascontiguousarray(signals[1], dtype=np.int64),
+                          np.ascontiguousarray(signals[2], dtype=np.float64))
+            sn = len(sp) - 1
+        else:
+            sp = si = sd = None
+            sn = 0
+        self._chk(self.lib.aso_search_energy_ex(_p(items), _p(lambdas), n, f, _p(q), lambda_q, k, w_lambda, w_dirichlet,
+                                                _p(pj) if pj is not None else None, r,
+                                                _p(sp) if sp is not None else None, _p(si) if si is not None else None,
+                                                _p(sd) if sd is not None else None, sn, _p(idx), _p(sc), C.byref(cnt)))
+        return [(int(idx[r_]), float(sc[r_])) for r_ in range(cnt.value)]
 
     def search_lambda_aware(self, items, lambdas, q, lambda_q, k, alpha):
         items = np.ascontiguousarray(items, dtype=np.float64)

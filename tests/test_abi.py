@@ -30,7 +30,7 @@ def test_python_binding_covers_header(asb):
 def test_struct_layouts(asb):
     # POD structs must match the C layout (8-byte aligned doubles / int64)
     assert ctypes.sizeof(asb.host.GraphParamsC) == 64
-    assert ctypes.sizeof(asb.host.BuildParamsC) == 64 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(asb.host.BuildParamsC) == 64 + 8 + 8 + 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(asb.host.IndexInfoC) == 14 * 8
     assert asb.host.BuildParamsC.spectral.offset == asb.host.BuildParamsC.apply_define_result_k.offset + 4
 
@@ -129,8 +129,8 @@ def test_rust_sys_crate_covers_header():
     c_structs = {name: b for b, name in re.findall(r"typedef struct \{([^}]*)\} (\w+);", body)}
     for struct in ("asb_graph_params", "asb_build_params", "asb_index_info"):
         c_body = c_structs[struct]
-        c_fields = [f.strip() for decl in c_body.split(";") if decl.strip()
-                    for f in re.sub(r"^\s*[a-z_0-9]+\s+", "", decl.strip()).split(",")]
+        c_fields = [re.search(r"(\w+)\s*$", f).group(1) for decl in c_body.split(";") if decl.strip()
+                    for f in decl.strip().split(",")]          # the declared name = the last identifier of a declarator
         r_body = re.search(r"pub struct " + struct + r" \{(.*?)\n\}", lib_rs, flags=re.S).group(1)
         r_fields = re.findall(r"pub ([a-z_0-9]+):", r_body)
         assert r_fields == c_fields, (struct, r_fields, c_fields)

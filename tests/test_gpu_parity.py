@@ -873,3 +873,77 @@ def test_range_search_parity(ctx, asb, oracle, golden):
     got = aspace.range_search(asb.ArrowItem.new(q, 0.0), gl, 0.01)            # lambda 0 -> re-prepared (:953-957)
     assert [i for i, _ in got] == want[0].tolist()
     assert np.allclose([d for _, d in got], want[1], rtol=0, atol=1e-12)
+
+
+# ============================================ SURVEY 8f rank 2 + 4: JL-projected build, every branch of the energy score
+def _oracle_projected_build(oracle, x, maxk, radius, gp, proj):
+    """The reference's with_dims_reduction flow (src/eigenmaps.rs:248-269, src/taumode.rs:233-245): centroids projected
+    before the Laplacian (r x r graph); item lambdas read item[0 .. r) against it, tau and the denominator over all F."""
+    cent, asg, sizes = oracle.cluster_incremental(x, maxk, radius)
+    centp = oracle.project_matrix(cent, proj)
+    csr = oracle.feature_laplacian(centp, **gp)
+    r = proj.shape[1]
+    lam = np.array([oracle.synthetic_lambda_prefix(row, csr, oracle.select_tau(row, TAU_MEDIAN), r) for row in x])
+    return cent, asg, csr, lam
+
+
+@pytest.mark.parametrize("spectral", [False, True])
+def test_projected_build_and_energy_search(ctx, asb, oracle, spectral):
+    n, f, maxk = 3_000, 96, 40
+    x = asb.synth.protein_like(n, f, seed=42)
+    radius = 1.5 * f * 0.0025 * 2
+    gp = dict(eps=1.6, k=12, topk=4, p=2.0, sigma=0.5)           # projected centroids are signed: wide eps
+    rng = np.random.default_rng(17)
+    cent0, _, _ = oracle.cluster_incremental(x, maxk, radius)
+    r = min(asb.host.compute_jl_dimension(cent0.shape[0], 0.5), f // 2)
+    proj = rng.normal(size=(f, r))                                  # the host materialises the Gaussian matrix
+    cent, asg, csr, lam = _oracle_projected_build(oracle, x, maxk, radius, gp, proj)
+    b = (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(gp["eps"], gp["k"], gp["topk"], gp["p"], gp["sigma"])
+         .with_synthesis(asb.TauMode.Median).with_seed(42).with_inline_sampling(None)
+         .with_dims_reduction(True, 0.5).with_projection(proj).with_cluster_params(maxk, radius).with_spectral(spectral))
+    aspace, gl = b.build(x)
+    assert aspace.reduced_dim == r and gl.indptr.shape[0] == r + 1
+    assert np.array_equal(gl.init_data.view(np.uint64), cent.view(np.uint64))     # clustering is untouched by the projection
+    _assert_csr_equal(gl.csr, csr)
+    sig = oracle.spectral_signals(csr, **gp) if spectral else None
+    if spectral:
+        _assert_csr_equal(aspace.signals, sig)
+        lam = np.array([oracle.synthetic_lambda_prefix(row, sig, oracle.select_tau(row, TAU_MEDIAN), r) for row in x])
+    _assert_lambda_close(aspace.lambdas, lam)
+    # prepare_query_item projects the query first (src/core.rs:540-545)
+    queries, _ = asb.synth.queries_from_items(x, 9, seed=43)
+    qp = oracle.project_matrix(queries, proj)
+    lq_want = oracle.compute_taumode(qp, csr, TAU_MEDIAN)
+    _assert_lambda_close(aspace.prepare_query_items_index(queries), lq_want)
+    assert abs(aspace.prepare_query_item(queries[0], gl) - lq_want[0]) <= 1e-9 * abs(lq_want[0])
+    # the lambda-aware search of a projected index panics in the reference (lengths differ, src/core.rs:157-161)
+    with pytest.raises(asb.ArrowSpaceError) as ei:
+        aspace.search_batch(queries, 5, 0.7)
+    assert ei.value.status == 12
+    # energy search: project_vec on both sides, projected_dirichlet through the signals when they exist
+    idx, score, count = aspace.search_energy_batch(queries, 10, 1.0, 0.5)
+    for qi in range(len(queries)):
+        want = oracle.search_energy_ex(x, lam, queries[qi], float(lq_want[qi]), 10, 1.0, 0.5, projection=proj, signals=sig)
+        assert [int(i) for i in idx[qi, :len(want)]] == [i for i, _ in want], qi
+        assert np.allclose(score[qi, :len(want)], [s for _, s in want], rtol=0, atol=1e-12)
+    one = aspace.search_energy(queries[2], gl, 7, 0.25, 2.0)
+    want = oracle.search_energy_ex(x, lam, queries[2], float(lq_want[2]), 7, 0.25, 2.0, projection=proj, signals=sig)
+    assert [i for i, _ in one] == [i for i, _ in want]
+
+
+def test_energy_search_through_signals_without_projection(ctx, asb, oracle):
+    """with_spectral(true) without a projection: projected_dirichlet runs through the F x F signals."""
+    n, f, maxk = 4_000, 64, 40
+    x = asb.synth.protein_like(n, f, seed=42)
+    radius = 1.5 * f * 0.0025 * 2
+    gp = dict(eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    aspace, gl = (asb.ArrowSpaceBuilder.new(ctx).with_lambda_graph(0.5, 12, 4, 2.0, 0.25).with_seed(42)
+                  .with_inline_sampling(None).with_cluster_params(maxk, radius).with_spectral(True).build(x))
+    sig = aspace.signals
+    queries, _ = asb.synth.queries_from_items(x, 6, seed=43)
+    lq = oracle.compute_taumode(queries, gl.csr, TAU_MEDIAN)
+    idx, score, count = aspace.search_energy_batch(queries, 12, 1.0, 0.5)
+    for qi in range(len(queries)):
+        want = oracle.search_energy_ex(x, aspace.lambdas, queries[qi], float(lq[qi]), 12, 1.0, 0.5, signals=sig)
+        assert [int(i) for i in idx[qi, :len(want)]] == [i for i, _ in want], qi
+        assert np.allclose(score[qi, :len(want)], [s for _, s in want], rtol=0, atol=1e-12)
