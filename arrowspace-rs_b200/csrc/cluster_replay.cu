@@ -393,12 +393,92 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                 for (int u = 0; u < NPW; ++u) X[t][u] = (u < NPW - 1 || last_valid) ? src[128 * u] : 0.0;
                 mt[t] = metas[slot * RG + t];
             }
+            // ---- the group path: all RG rows of the slot are certain updates (by far the common case once the counts
+            // are large) -> the scalar bookkeeping of the RG steps is done up front, with instruction-level parallelism
+            // across the rows, and the element chains c += (x - c) / k run back to back: a step then costs about its
+            // own dependent latency (sub, mul, 4 FMA, add) instead of ~110 serial instructions.  The exponent-range
+            // test of the division is voted on once per group; a hit restores the centroid and replays the slot row
+            // by row.  Needs `interval` >= RG so that the bound B is refreshed on a group boundary.
+            bool grouped = false;
+            {
+                const int interval = kd < 512.0 ? 1 : (kd < 4096.0 ? (int)(kd * (1.0 / 256.0)) : 16);
+                if (nr == RG && interval >= RG && since + RG <= interval) {
+                    double hi[RG], yk[RG + 1], kk[RG];
+                    double Bt = B;
+                    bool allfast = true;
+                    yk[0] = y_next;
 #pragma unroll
-            for (int t = 0; t < RG; ++t)
-                if (t < nr && go) {
-                    step(X[t], mt[t]);
-                    if (go) ++done;
+                    for (int t = 0; t < RG; ++t) {
+                        kk[t] = kd + (double)(t + 1);
+                        yk[t + 1] = __drcp_rn(kd + (double)(t + 2));   // RG independent reciprocals (the last one: next y)
+                    }
+#pragma unroll
+                    for (int t = 0; t < RG; ++t) {
+                        hi[t] = mt[t].dhi + Bt;
+                        allfast = allfast && (hi[t] * hi[t] < thr_upd) && (hi[t] + disp_hint < mt[t].slo);
+                        Bt = fma(hi[t] * yk[t], 1.0 + 1e-9, Bt);
+                    }
+                    if (allfast) {
+                        double save[NPW];
+                        bool slow = false;
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) save[u] = cr[u];
+#pragma unroll
+                        for (int t = 0; t < RG; ++t) {
+#pragma unroll
+                            for (int u = 0; u < NPW; ++u) {
+                                const double a = __dsub_rn(X[t][u], cr[u]);
+                                const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
+                                const bool out = h - 0x05d00000u > 0x74200000u;
+                                slow |= (u < NPW - 1) ? out : (out && last_valid);
+                                const double q0 = __dmul_rn(a, yk[t]);
+                                const double q1 = __fma_rn(__fma_rn(-q0, kk[t], a), yk[t], q0);
+                                cr[u] = __dadd_rn(cr[u], __fma_rn(__fma_rn(-q1, kk[t], a), yk[t], q1));
+                            }
+                        }
+                        if (!__any_sync(0xffffffffu, slow)) {
+                            grouped = true;
+                            kd += (double)RG;
+                            y_next = yk[RG];
+                            B = Bt;
+                            dmax = fmax(dmax, B);
+                            since += RG;
+                            done += RG;
+                            if (threadIdx.x == 0) {
+#pragma unroll
+                                for (int t = 0; t < RG; ++t) {
+                                    assign[mt[t].row] = (long long)c;
+                                    dub[mt[t].row] = hi[t];
+                                }
+                            }
+                            if (since >= interval) {   // B back to the exact displacement
+                                double p = 0.0;
+#pragma unroll
+                                for (int u = 0; u < NPW; ++u) {
+                                    const double e = cr[u] - s0[u];
+                                    p = fma(e, e, p);
+                                }
+                                const double tt = block_sum(p, true);
+                                const double nb = sqrt(tt) * (1.0 + 1e-12);
+                                if (!(nb == nb) || !(nb <= 1e300)) bad = true;
+                                else B = fmin(B, nb);
+                                since = 0;
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < NPW; ++u) cr[u] = save[u];   // an element needs the careful division
+                        }
+                    }
                 }
+            }
+            if (!grouped) {
+#pragma unroll
+                for (int t = 0; t < RG; ++t)
+                    if (t < nr && go) {
+                        step(X[t], mt[t]);
+                        if (go) ++done;
+                    }
+            }
         }
         __syncwarp();
         if (lane == 0) rp_mbar_arrive(&sh.empty[slot]);   // (a lost chain keeps draining its ring: the producer must finish)
@@ -926,7 +1006,7 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
         // leave rows on their bisector) costs a walk of that piece, not of the shard.
         const bool speculate = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && opt_or(ctx, "cluster_shard_speculate", 1.0) != 0.0 &&
                                x_snap == max_clusters && x_snap >= 2 && n_local >= 1024 && max_clusters * f <= (1ll << 27);
-        int64_t piece = (int64_t)opt_or(ctx, "cluster_shard_piece", 131072.0);
+        int64_t piece = (int64_t)opt_or(ctx, "cluster_shard_piece", 262144.0);
         if (piece < 4096) piece = 4096;
         if (piece > (1 << 24)) piece = 1 << 24;
         const int64_t npieces = speculate ? (n_local + piece - 1) / piece : 0;

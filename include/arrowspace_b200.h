@@ -161,7 +161,7 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 already works on the head of the matrix.
  *   "cluster_growth_run" (1|0), "cluster_shard_snapshot_rows", "cluster_shard_piece", "cluster_shard_speculate"
  *                                 the creator run at the start of a walk; rows rank 0 walks before it broadcasts the
- *                                 common snapshot (262144); rows per certified piece of a later shard (131072); 0 turns
+ *                                 common snapshot (262144); rows per certified piece of a later shard (262144); 0 turns
  *                                 the speculative ranking off (plain hand-off).
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
  * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
