@@ -54,6 +54,20 @@ __global__ void __launch_bounds__(256) replay_offsets_kernel(const int *__restri
     seg_off[c] = lo;
 }
 
+// order[b] = the centroid block b of the chain kernel walks: longest chain first, so that the critical path of the chunk
+// starts at once and the short chains fill the SMs behind it (K may exceed the CTAs that fit the device at a time)
+__global__ void __launch_bounds__(1024) replay_order_kernel(const int *__restrict__ seg_off, int K, int *__restrict__ order) {
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const int len = seg_off[c + 1] - seg_off[c];
+        int rank = 0;
+        for (int o = 0; o < K; ++o) {
+            const int lo = seg_off[o + 1] - seg_off[o];
+            rank += (lo > len || (lo == len && o < c)) ? 1 : 0;
+        }
+        order[rank] = c;
+    }
+}
+
 __global__ void __launch_bounds__(256) replay_max_kernel(const double *__restrict__ v, int n, unsigned long long *__restrict__ out_bits) {
     double mx = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mx = fmax(mx, v[i]);
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
 //     chunk saw (`disp_hint`) -- takes the exact step: |x - c|^2 reduced across lanes and warps (shared memory, one
 //     named barrier), classified with the guard band;
 //   * keeps B rigorous and cheap: every update moves the centroid by |x - c| / k <= (dhi + B) / k, which is added to B;
-//     every `interval` steps (1 while the count is small, k / 256 up to 16 later: the bound may grow by about 0.5 %
+//     every `interval` steps (1 while the count is small, k / 256 up to 64 later: the bound may grow by about 0.4 %
 //     of the row distance between two exact values) B is reset to the exact |c - S0| (one reduction + one barrier);
 //   * divides branch-free: reciprocal + two FMA corrections for every element (Markstein; div_by_count of the
 //     sequential kernel, correctly rounded for an integer divisor), an exponent-field test on the integer pipe sends the
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
 // The certification kernel receives an UPPER BOUND of the row's distance to its centroid at the row's own time
 // (dhi + B, or the exact value from the exact step).
 constexpr int kChainWarps = 4;    // consumer warps; warp kChainWarps is the producer
-constexpr int kRingSlots = 4;
+constexpr int kRingSlots = 8;   // at most
 
 struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
     double dlo, dhi;              // certified bounds of the row's distance to the snapshot of its nearest centroid
@@ -181,8 +195,30 @@ struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
 struct ChainShared {
     double part[2][kChainWarps];
     int stop[2];
+    int drops;                    // rows the consumers classified "dropped" so far (the producer's count prediction)
     unsigned long long full[kRingSlots], empty[kRingSlots];
 };
+
+// per ring slot, written by the PRODUCER warp (it has nothing else to do between two bulk copies): everything of a
+// group's bookkeeping that follows from the metadata and the predicted count alone
+template <int RG>
+struct __align__(16) GroupDesc {
+    double yk[RG + 2];            // 1 / (kd_pred + 1 + t), t = 0 .. RG  (yk[RG]: the next group's first)
+    double hmax;                  // max dhi of the group
+    double minslack;              // min (slo - dhi)
+    double kd_pred;               // the count the reciprocals assume
+    double pad;
+};
+
+// ring depth: about 100 kB of rows in flight per chain (two chains per SM; bulk copies from DRAM take ~2 us, a row ~0.1)
+__host__ __device__ constexpr int chain_ring_slots(int npw, int rg) {
+    return 96 / (npw * rg) < 2 ? 2 : (96 / (npw * rg) > kRingSlots ? kRingSlots : 96 / (npw * rg));
+}
+__device__ __forceinline__ int chain_interval(double kd) {
+    // steps between two exact values of the displacement bound: 1 while the count is small, then count / 256 (the
+    // bound may grow by about 0.4 % of the row distance in between), at most 64
+    return kd < 512.0 ? 1 : (kd < 16384.0 ? (int)(kd * (1.0 / 256.0)) : 64);
+}
 
 __device__ __forceinline__ unsigned rp_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void rp_mbar_init(unsigned long long *bar, int count) {
@@ -215,7 +251,8 @@ __device__ __forceinline__ void rp_bulk_g2s(void *dst, const void *src, unsigned
 // shared memory: ring[kRingSlots][RG][fpad] doubles, then meta[kRingSlots][RG]; fpad = 128 NPW
 template <int NPW, int RG>
 __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kernel(
-    const double *__restrict__ rows, int f, const int *__restrict__ seg_off, const SegMeta *__restrict__ seg_meta, int K,
+    const double *__restrict__ rows, int f, const int *__restrict__ seg_off, const int *__restrict__ order,
+    const SegMeta *__restrict__ seg_meta, int K,
     int saturated, double radius, double disp_hint, double *__restrict__ cent, const double *__restrict__ cent0,
     const double *__restrict__ disp0, unsigned long long *sizes, long long *__restrict__ assign, double *__restrict__ dub,
     unsigned long long *maxdisp_bits, int *fail) {
@@ -224,35 +261,76 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     extern __shared__ __align__(128) unsigned char rp_smem[];
     __shared__ ChainShared sh;
     constexpr int FP = 128 * NPW;
+    constexpr int NS = chain_ring_slots(NPW, RG);
+    static_assert(NS <= kRingSlots && RG <= 8 && RG >= 2, "ring geometry");
     double *ring = reinterpret_cast<double *>(rp_smem);
-    SegMeta *metas = reinterpret_cast<SegMeta *>(rp_smem + (size_t)kRingSlots * RG * FP * sizeof(double));
-    const int c = blockIdx.x;
+    SegMeta *metas = reinterpret_cast<SegMeta *>(rp_smem + (size_t)NS * RG * FP * sizeof(double));
+    GroupDesc<RG> *descs = reinterpret_cast<GroupDesc<RG> *>(metas + NS * RG);
+    const int c = order[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int beg = seg_off[c], end = seg_off[c + 1];
     if (beg == end) return;
     const int ngroups = (end - beg + RG - 1) / RG;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRingSlots; ++s) {
+        for (int s = 0; s < NS; ++s) {
             rp_mbar_init(&sh.full[s], 1);
             rp_mbar_init(&sh.empty[s], kChainWarps);
         }
+        sh.drops = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == kChainWarps) {
-        // ---- producer: one slot = RG rows + their metadata
+        // ---- producer: one slot = RG rows + their metadata + the group descriptor.  The count a group starts from is
+        // predictable: every row of the chain adds one unless it is dropped (rare; the consumers publish their tally,
+        // a descriptor built from a stale tally is recognised by its kd_pred and ignored)
+        const double kd0 = (double)sizes[c];
+        // the metadata of 32 rows (32 / RG groups) per coalesced load, one batch ahead of the groups being issued: the
+        // producer's own global-memory latency stays off the ring's critical path
+        constexpr int GPB = 32 / RG;   // groups per batch
+        SegMeta cur, nxt;
+        cur.dlo = cur.dhi = cur.slo = 0.0;
+        cur.row = cur.pad = 0;
+        nxt = cur;
+        if (beg + lane < end) cur = seg_meta[beg + lane];
         for (int g = 0; g < ngroups; ++g) {
-            const int slot = g % kRingSlots;
-            if (g >= kRingSlots) rp_mbar_wait(&sh.empty[slot], ((g / kRingSlots) - 1) & 1);
+            const int gi = g % GPB;
+            if (gi == 0) {
+                if (g > 0) cur = nxt;
+                const int np = beg + (g + GPB) * RG + lane;
+                if (np < end) nxt = seg_meta[np];
+            }
+            const int slot = g % NS;
+            if (g >= NS) rp_mbar_wait(&sh.empty[slot], ((g / NS) - 1) & 1);
             const int pos = beg + g * RG;
             const int nr = end - pos < RG ? end - pos : RG;
-            if (lane == 0) rp_mbar_expect_tx(&sh.full[slot], (unsigned)(nr * (f * 8 + (int)sizeof(SegMeta))));
-            __syncwarp();
-            if (lane < nr) {
-                const int r = seg_meta[pos + lane].row;
-                rp_bulk_g2s(ring + ((size_t)slot * RG + lane) * FP, rows + (size_t)r * f, (unsigned)(f * 8), &sh.full[slot]);
+            const int drops = atomicAdd(&sh.drops, 0);   // (an atomic read: the tally may be stale, never torn)
+            const double kdp = kd0 + (double)(g * RG - drops);
+            const int src = gi * RG + (lane < RG ? lane : 0);
+            const int r = __shfl_sync(0xffffffffu, cur.row, src);
+            double dh = __shfl_sync(0xffffffffu, cur.dhi, src);
+            double sl = __shfl_sync(0xffffffffu, cur.slo, src) - dh;
+            if (lane >= nr) {
+                dh = -INFINITY;
+                sl = INFINITY;
             }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {   // RG <= 8
+                dh = fmax(dh, __shfl_xor_sync(0xffffffffu, dh, o));
+                sl = fmin(sl, __shfl_xor_sync(0xffffffffu, sl, o));
+            }
+            if (lane <= RG) descs[slot].yk[lane] = __drcp_rn(kdp + (double)(lane + 1));
+            if (lane == 0) {
+                descs[slot].hmax = dh;
+                descs[slot].minslack = sl;
+                descs[slot].kd_pred = kdp;
+            }
+            __syncwarp();
+            if (lane == 0) rp_mbar_expect_tx(&sh.full[slot], (unsigned)(nr * (f * 8 + (int)sizeof(SegMeta))));   // (release)
+            __syncwarp();
+            if (lane < nr)
+                rp_bulk_g2s(ring + ((size_t)slot * RG + lane) * FP, rows + (size_t)r * f, (unsigned)(f * 8), &sh.full[slot]);
             if (lane == 0) rp_bulk_g2s(metas + slot * RG, seg_meta + pos, (unsigned)(nr * sizeof(SegMeta)), &sh.full[slot]);
         }
         return;
@@ -273,6 +351,10 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     double B = disp0 ? disp0[c] : 0.0, dmax = B;
     int since = 0, par = 0;
     bool bad = false, go = true;
+    if (disp_hint < 0.0) {   // (CTAs that start later may see a larger value: more exact steps, same bits)
+        const double md0 = __longlong_as_double((long long)*(volatile unsigned long long *)maxdisp_bits);
+        disp_hint = (md0 == md0) ? 2.0 * md0 : INFINITY;
+    }
     const double guard = 1e-9 * radius;
     const double thr_upd = (saturated ? radius : 0.5 * radius) * (1.0 - 1e-9);   // (dhi + B)^2 below: an update for sure
     const double thr_drop = 1.5 * radius * (1.0 + 1e-9);                         // (dlo - B)^2 above: dropped for sure
@@ -354,8 +436,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
             dmax = fmax(dmax, B);
             y_next = __drcp_rn(kd + 1.0);
             ++since;
-            const int interval = kd < 512.0 ? 1 : (kd < 4096.0 ? (int)(kd * (1.0 / 256.0)) : 16);
-            if (since >= interval) {   // B back to the exact displacement
+            if (since >= chain_interval(kd)) {   // B back to the exact displacement
                 double p = 0.0;
 #pragma unroll
                 for (int u = 0; u < NPW; ++u) {
@@ -375,109 +456,96 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
         if (threadIdx.x == 0) {
             assign[mt.row] = cls == 2 ? -1ll : (long long)c;
             dub[mt.row] = d_up;
+            if (cls == 2) atomicAdd(&sh.drops, 1);   // the producer's count prediction
         }
     };
 
     int done = 0;   // rows applied
     for (int g = 0; g < ngroups; ++g) {
-        const int slot = g % kRingSlots;
-        rp_mbar_wait(&sh.full[slot], (g / kRingSlots) & 1);
+        const int slot = g % NS;
+        rp_mbar_wait(&sh.full[slot], (g / NS) & 1);
         const int nr = end - (beg + g * RG) < RG ? end - (beg + g * RG) : RG;
         if (go) {
-            double X[RG][NPW];
-            SegMeta mt[RG];
-#pragma unroll
-            for (int t = 0; t < RG; ++t) {
-                const double *src = ring + ((size_t)slot * RG + t) * FP + j0;
-#pragma unroll
-                for (int u = 0; u < NPW; ++u) X[t][u] = (u < NPW - 1 || last_valid) ? src[128 * u] : 0.0;
-                mt[t] = metas[slot * RG + t];
-            }
+            const double *xrow = ring + (size_t)slot * RG * FP + j0;
+            const SegMeta *mrow = metas + slot * RG;
             // ---- the group path: all RG rows of the slot are certain updates (by far the common case once the counts
-            // are large) -> the scalar bookkeeping of the RG steps is done up front, with instruction-level parallelism
-            // across the rows, and the element chains c += (x - c) / k run back to back: a step then costs about its
-            // own dependent latency (sub, mul, 4 FMA, add) instead of ~110 serial instructions.  The exponent-range
-            // test of the division is voted on once per group; a hit restores the centroid and replays the slot row
-            // by row.  Needs `interval` >= RG so that the bound B is refreshed on a group boundary.
+            // are large).  Everything scalar comes from the producer's descriptor (reciprocals of the next RG + 1 counts,
+            // the largest dhi and the thinnest margin of the group); the displacement bound of the whole group follows
+            // from one product:  with u = 1.01 (hmax + B) / (k + 1)  every step t of the group keeps B_t <= B + t u
+            // (induction: the increment (dhi_t + B_{t-1}) / (k + t) (1 + 1e-9) is at most
+            // (hmax + B + (t - 1) u) / (k + 1) (1 + 1e-9) <= u (1 + 7 * 1.01 / 1024) (1 + 1e-9) / 1.01 < u  for
+            // k >= 1024, RG <= 8 -- `interval >= RG` implies k >= 256 RG), so the element chains c += (x - c) / k run back
+            // to back: a row costs about its own dependent latency (sub, mul, 4 FMA, add).  The exponent-range test of
+            // the division is voted on once per group; a hit restores the centroid and replays the slot row by row.
             bool grouped = false;
-            {
-                const int interval = kd < 512.0 ? 1 : (kd < 4096.0 ? (int)(kd * (1.0 / 256.0)) : 16);
-                if (nr == RG && interval >= RG && since + RG <= interval) {
-                    double hi[RG], yk[RG + 1], kk[RG];
-                    double Bt = B;
-                    bool allfast = true;
-                    yk[0] = y_next;
+            const GroupDesc<RG> &gd = descs[slot];
+            const int interval = chain_interval(kd);
+            if (nr == RG && interval >= RG && gd.kd_pred == kd) {
+                if (since + RG > interval) {   // B back to the exact displacement before the group, not in the middle
+                    double p = 0.0;
+#pragma unroll
+                    for (int u = 0; u < NPW; ++u) {
+                        const double e = cr[u] - s0[u];
+                        p = fma(e, e, p);
+                    }
+                    const double tt = block_sum(p, true);
+                    const double nb = sqrt(tt) * (1.0 + 1e-12);
+                    if (!(nb == nb) || !(nb <= 1e300)) bad = true;
+                    else B = fmin(B, nb);
+                    since = 0;
+                }
+                const double uinc = (gd.hmax + B) * gd.yk[0] * 1.01;
+                const double Bend = fma((double)RG, uinc, B);
+                const double himax = gd.hmax + Bend;
+                if (himax * himax < thr_upd && Bend + disp_hint < gd.minslack) {
+                    double save[NPW];
+                    bool slow = false;
+#pragma unroll
+                    for (int u = 0; u < NPW; ++u) save[u] = cr[u];
 #pragma unroll
                     for (int t = 0; t < RG; ++t) {
-                        kk[t] = kd + (double)(t + 1);
-                        yk[t + 1] = __drcp_rn(kd + (double)(t + 2));   // RG independent reciprocals (the last one: next y)
-                    }
+                        const double y = gd.yk[t], kk = kd + (double)(t + 1);
 #pragma unroll
-                    for (int t = 0; t < RG; ++t) {
-                        hi[t] = mt[t].dhi + Bt;
-                        allfast = allfast && (hi[t] * hi[t] < thr_upd) && (hi[t] + disp_hint < mt[t].slo);
-                        Bt = fma(hi[t] * yk[t], 1.0 + 1e-9, Bt);
-                    }
-                    if (allfast) {
-                        double save[NPW];
-                        bool slow = false;
-#pragma unroll
-                        for (int u = 0; u < NPW; ++u) save[u] = cr[u];
-#pragma unroll
-                        for (int t = 0; t < RG; ++t) {
-#pragma unroll
-                            for (int u = 0; u < NPW; ++u) {
-                                const double a = __dsub_rn(X[t][u], cr[u]);
-                                const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
-                                const bool out = h - 0x05d00000u > 0x74200000u;
-                                slow |= (u < NPW - 1) ? out : (out && last_valid);
-                                const double q0 = __dmul_rn(a, yk[t]);
-                                const double q1 = __fma_rn(__fma_rn(-q0, kk[t], a), yk[t], q0);
-                                cr[u] = __dadd_rn(cr[u], __fma_rn(__fma_rn(-q1, kk[t], a), yk[t], q1));
-                            }
+                        for (int u = 0; u < NPW; ++u) {
+                            const double xv = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + 128 * u] : 0.0;
+                            const double a = __dsub_rn(xv, cr[u]);
+                            const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
+                            const bool out = h - 0x05d00000u > 0x74200000u;
+                            slow |= (u < NPW - 1) ? out : (out && last_valid);
+                            const double q0 = __dmul_rn(a, y);
+                            const double q1 = __fma_rn(__fma_rn(-q0, kk, a), y, q0);
+                            cr[u] = __dadd_rn(cr[u], __fma_rn(__fma_rn(-q1, kk, a), y, q1));
                         }
-                        if (!__any_sync(0xffffffffu, slow)) {
-                            grouped = true;
-                            kd += (double)RG;
-                            y_next = yk[RG];
-                            B = Bt;
-                            dmax = fmax(dmax, B);
-                            since += RG;
-                            done += RG;
-                            if (threadIdx.x == 0) {
-#pragma unroll
-                                for (int t = 0; t < RG; ++t) {
-                                    assign[mt[t].row] = (long long)c;
-                                    dub[mt[t].row] = hi[t];
-                                }
-                            }
-                            if (since >= interval) {   // B back to the exact displacement
-                                double p = 0.0;
-#pragma unroll
-                                for (int u = 0; u < NPW; ++u) {
-                                    const double e = cr[u] - s0[u];
-                                    p = fma(e, e, p);
-                                }
-                                const double tt = block_sum(p, true);
-                                const double nb = sqrt(tt) * (1.0 + 1e-12);
-                                if (!(nb == nb) || !(nb <= 1e300)) bad = true;
-                                else B = fmin(B, nb);
-                                since = 0;
-                            }
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < NPW; ++u) cr[u] = save[u];   // an element needs the careful division
+                    }
+                    if (!__any_sync(0xffffffffu, slow)) {
+                        grouped = true;
+                        kd += (double)RG;
+                        y_next = gd.yk[RG];
+                        B = Bend;
+                        dmax = fmax(dmax, B);
+                        since += RG;
+                        done += RG;
+                        if (warp == 0 && lane < RG) {
+                            const SegMeta m = mrow[lane];
+                            assign[m.row] = (long long)c;
+                            dub[m.row] = m.dhi + Bend;   // an upper bound of the row's distance at its own time
                         }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) cr[u] = save[u];   // an element needs the careful division
                     }
                 }
             }
             if (!grouped) {
+#pragma unroll 1
+                for (int t = 0; t < nr && go; ++t) {
+                    double X[NPW];
 #pragma unroll
-                for (int t = 0; t < RG; ++t)
-                    if (t < nr && go) {
-                        step(X[t], mt[t]);
-                        if (go) ++done;
-                    }
+                    for (int u = 0; u < NPW; ++u) X[u] = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + 128 * u] : 0.0;
+                    const SegMeta mt = mrow[t];
+                    step(X, mt);
+                    if (go) ++done;
+                }
             }
         }
         __syncwarp();
@@ -648,7 +716,7 @@ double ktimer_ms(asb_ctx *ctx, const char *name) {
 struct ReplayWs {
     DevTmp<double> qn2, xn2, dist, dcur, cent_tmp, disp0;
     DevTmp<int64_t> idx, cnt, minus1;
-    DevTmp<int> keys, vals, keys_s, vals_s, seg_off, flags;
+    DevTmp<int> keys, vals, keys_s, vals_s, seg_off, order, flags;
     DevTmp<unsigned long long> sizes_tmp, scal;   // scal[0] = max |c|^2 bits, scal[1] = max displacement bits
     DevTmp<unsigned char> cub_tmp;
     DevTmp<SegMeta> meta;
@@ -678,6 +746,7 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     ASB_TRY(w.keys_s.init(ctx, (size_t)m));
     ASB_TRY(w.vals_s.init(ctx, (size_t)m));
     ASB_TRY(w.seg_off.init(ctx, (size_t)K + 1));
+    ASB_TRY(w.order.init(ctx, (size_t)K));
     ASB_TRY(w.meta.init(ctx, (size_t)m));
     ASB_TRY(w.near_idx.init(ctx, (size_t)m));
     ASB_TRY(w.near_b.init(ctx, (size_t)3 * m));
@@ -724,6 +793,8 @@ int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f
     ctx->launches++;
     replay_offsets_kernel<<<(K + 1 + 255) / 256, 256, 0, ctx->stream>>>(w.keys_s.ptr, m, K, w.seg_off.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_offsets_kernel"));
+    replay_order_kernel<<<1, 1024, 0, ctx->stream>>>(w.seg_off.ptr, K, w.order.ptr);
+    ASB_TRY(asb_check_launch(ctx, "replay_order_kernel"));
     replay_bounds_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(w.vals_s.ptr, m, f, w.dist.ptr, (const long long *)w.cnt.ptr,
                                                                    w.qn2.ptr, w.scal.ptr, w.use_near ? w.near_b.ptr : nullptr,
                                                                    w.meta.ptr);
@@ -754,17 +825,20 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
         // the ring kernel needs 16-byte aligned rows of a multiple of 16 bytes (bulk copies) and f <= 1024
         const bool generic = f > 1024 || (f & 1) || (((uintptr_t)rows_d) & 15) ||
                              opt_or(ctx, "cluster_replay_generic_chain", 0.0) != 0.0;
-        const double hint = 2.0 * w.last_disp;   // the displacement the previous chunk saw, doubled (inf at first)
+        // the displacement the previous chunk saw, doubled (inf at first); negative: the kernel takes twice the largest
+        // |start - snapshot| instead (row-sharded build: the drift since the common snapshot dominates)
+        const double hint = w.last_disp < 0.0 ? -1.0 : 2.0 * w.last_disp;
 #define ASB_CHAIN_ARGS                                                                                                  \
     K, saturated, radius, w.cent_tmp.ptr, snap_d, disp0, w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr,           \
         w.scal.ptr + 1, w.flags.ptr
 #define ASB_CHAIN_TMA(NPW, RG)                                                                                         \
     {                                                                                                                   \
-        const size_t smem = (size_t)kRingSlots * RG * (128 * NPW * sizeof(double) + sizeof(SegMeta));                   \
+        const size_t smem = (size_t)chain_ring_slots(NPW, RG) * (RG * (128 * NPW * sizeof(double) + sizeof(SegMeta)) + \
+                                                                   sizeof(GroupDesc<RG>));                            \
         ASB_CUDA(ctx, cudaFuncSetAttribute(replay_chain_tma_kernel<NPW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem));                                                                 \
         replay_chain_tma_kernel<NPW, RG><<<(unsigned)K, (kChainWarps + 1) * 32, smem, ctx->stream>>>(                   \
-            rows_d, f, w.seg_off.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, snap_d, disp0,           \
+            rows_d, f, w.seg_off.ptr, w.order.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, snap_d, disp0, \
             w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);                          \
     }
         if (generic)
@@ -772,14 +846,14 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
                                                                                   ASB_CHAIN_ARGS);
         else
             switch ((f + 127) / 128) {
-                case 1: ASB_CHAIN_TMA(1, 4) break;
-                case 2: ASB_CHAIN_TMA(2, 4) break;
-                case 3: ASB_CHAIN_TMA(3, 4) break;
+                case 1: ASB_CHAIN_TMA(1, 8) break;
+                case 2: ASB_CHAIN_TMA(2, 8) break;
+                case 3: ASB_CHAIN_TMA(3, 8) break;
                 case 4: ASB_CHAIN_TMA(4, 4) break;
-                case 5: ASB_CHAIN_TMA(5, 2) break;
-                case 6: ASB_CHAIN_TMA(6, 2) break;
-                case 7: ASB_CHAIN_TMA(7, 2) break;
-                default: ASB_CHAIN_TMA(8, 2) break;
+                case 5: ASB_CHAIN_TMA(5, 4) break;
+                case 6: ASB_CHAIN_TMA(6, 4) break;
+                case 7: ASB_CHAIN_TMA(7, 4) break;
+                default: ASB_CHAIN_TMA(8, 4) break;
             }
 #undef ASB_CHAIN_TMA
 #undef ASB_CHAIN_ARGS
@@ -1031,12 +1105,15 @@ int asb_dev_cluster_sharded(asb_ctx *ctx, asb_comm *comm, const double *rows_d, 
             ReplayWs &w = ws[(size_t)i];
             int ok = 0;
             if (x == x_snap) {
-                w.last_disp = INFINITY;   // no hint: rows with thin margins take the exact step
+                // hint for the thin-margin test: what the piece before measured (drift since the snapshot included), or
+                // the drift at the start of this one
+                w.last_disp = (i > 0 && ws[(size_t)i - 1].last_disp < INFINITY && ws[(size_t)i - 1].last_disp >= 0.0)
+                                  ? ws[(size_t)i - 1].last_disp : -1.0;
                 ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x, 1, radius, snap.ptr, centroids_d,
                                    assign_d + lo, sizes_d, &ok));
                 if (!ok && w.use_near && w.last_flags == 2) {   // the tile's bounds were too wide: exact top-2 of the snapshot
                     ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x_snap, snap.ptr, false));
-                    w.last_disp = INFINITY;
+                    w.last_disp = -1.0;
                     ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)m, (int)f, (int)x, 1, radius, snap.ptr, centroids_d,
                                        assign_d + lo, sizes_d, &ok));
                 }

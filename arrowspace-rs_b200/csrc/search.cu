@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_kernel(SearchArgs A) {
                         }
                     }
                 }
+                __syncwarp();   // every lane has read list_len[q]
                 if (lane == 0) list_len[q] = len;
             }
             __syncthreads();
@@ -576,6 +577,72 @@ static int run_search(asb_ctx *ctx, int mode, SearchArgs &A, long long index_off
     return ASB_OK;
 }
 
+// The exact kernel ranks with DMMA-order dot products (1e-15 relative): ids are right except inside near-ties, but
+// the scores are not the reference's bits and the order inside a near-tie may differ from the prefilter path, which
+// rescoring in the reference's arithmetic.  This kernel gives both paths the same output: the exact kernel keeps a few
+// spare candidates (kx >= k), every one is scored as src/core.rs:214-236,:135-165 does (sequential sums, products and
+// sums rounded separately -- the same statements as pf_finish_kernel), and the best k by (score desc, index asc)
+// are written; unused slots hold -inf / -1.  One warp per query, two candidates per lane (kx <= 64).
+__global__ void __launch_bounds__(128) exact_rescore_kernel(const double *__restrict__ items, const double *__restrict__ lambdas,
+                                                            const double *__restrict__ queries,
+                                                            const double *__restrict__ lambda_q, long long nq, int f,
+                                                            double alpha, long long index_offset,
+                                                            const long long *__restrict__ in_idx, int kx, int k,
+                                                            long long *__restrict__ idx_out, double *__restrict__ score_out,
+                                                            long long *__restrict__ count_out, int *status) {
+    const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const double *qr = queries + q * (long long)f;
+    const double lq = lambda_q[q];
+    double sc[2];
+    long long id[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        id[h] = c < kx ? in_idx[q * kx + c] : -1;
+        sc[h] = -INFINITY;
+        if (id[h] >= 0) {
+            const double *x = items + id[h] * (long long)f;
+            double nq2 = 0.0, nx2 = 0.0, dot = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < f; ++j) {
+                const double qv = qr[j], xv = x[j];
+                nq2 = __dadd_rn(nq2, __dmul_rn(qv, qv));
+                nx2 = __dadd_rn(nx2, __dmul_rn(xv, xv));
+                dot = __dadd_rn(dot, __dmul_rn(qv, xv));
+            }
+            const double denom = __dmul_rn(sqrt(nq2), sqrt(nx2));
+            const double cosv = denom > 0.0 ? dot / denom : 0.0;
+            const double lam = 1.0 - fmin(fabs(lq - lambdas[id[h]]), 1.0);
+            const double s = __dadd_rn(__dmul_rn(alpha, cosv), __dmul_rn(1.0 - alpha, lam));
+            if (s != s) atomicOr(status, STATUS_NAN);
+            sc[h] = (s == s) ? s : -INFINITY;
+        }
+    }
+    int rank[2] = {0, 0}, valid = 0;
+    for (int src = 0; src < 64; ++src) {
+        const double os = __shfl_sync(0xffffffffu, src < 32 ? sc[0] : sc[1], src & 31);
+        const long long oi = __shfl_sync(0xffffffffu, src < 32 ? id[0] : id[1], src & 31);
+        if (oi < 0) continue;   // warp-uniform
+        ++valid;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) rank[h] += (os > sc[h] || (os == sc[h] && oi < id[h])) ? 1 : 0;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (id[h] >= 0 && rank[h] < k) {
+            score_out[q * k + rank[h]] = sc[h];
+            idx_out[q * k + rank[h]] = id[h] + index_offset;
+        }
+    const int taken = valid < k ? valid : k;
+    for (int r = taken + lane; r < k; r += 32) {
+        score_out[q * k + r] = -INFINITY;
+        idx_out[q * k + r] = -1;
+    }
+    if (lane == 0 && count_out) count_out[q] = taken;
+}
+
 #include "search_pf.cuh"
 
 int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,
@@ -606,31 +673,30 @@ int asb_dev_search(asb_ctx *ctx, const double *items_d, const double *lambdas_d,
     A.k = (int)(k < n ? k : n);
     A.alpha = alpha;
     A.status = status_d;
-    // lists are k_eff wide; outputs are k wide: merge writes k_eff columns, pad the rest
-    if (A.k != k) {
-        // k > n: run with k_eff = n into temporaries, then scatter into the k-wide outputs
-        DevTmp<double> ts;
-        DevTmp<int64_t> ti;
-        ASB_TRY(ts.init(ctx, (size_t)nq * A.k));
-        ASB_TRY(ti.init(ctx, (size_t)nq * A.k));
-        ASB_TRY(run_search(ctx, MODE_COSINE, A, index_offset, ti.ptr, ts.ptr, count_d));
-        ASB_CUDA(ctx, cudaMemsetAsync(idx_d, 0xff, (size_t)nq * k * sizeof(int64_t), ctx->stream));
-        ASB_CUDA(ctx, cudaMemsetAsync(score_d, 0, (size_t)nq * k * sizeof(double), ctx->stream));
-        ASB_CUDA(ctx, cudaMemcpy2DAsync(idx_d, k * sizeof(int64_t), ti.ptr, A.k * sizeof(int64_t),
-                                        A.k * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, ctx->stream));
-        ASB_CUDA(ctx, cudaMemcpy2DAsync(score_d, k * sizeof(double), ts.ptr, A.k * sizeof(double),
-                                        A.k * sizeof(double), nq, cudaMemcpyDeviceToDevice, ctx->stream));
-        return ASB_OK;
-    }
     {
         auto it = ctx->options.find("search_prefilter");  // default on; 0 = always the exact FP64 kernel
-        if (it == ctx->options.end() || it->second != 0.0) {
+        if (A.k == k && (it == ctx->options.end() || it->second != 0.0)) {
             bool done = false;
             ASB_TRY(run_search_pf(ctx, A, index_offset, idx_d, score_d, count_d, &done));
             if (done) return ASB_OK;
         }
     }
-    return run_search(ctx, MODE_COSINE, A, index_offset, idx_d, score_d, count_d);
+    // exact FP64 kernel with a few spare candidates, then the reference-order rescoring both paths share; the lists are
+    // kx wide, the outputs k wide (k > n: the rest is padded with -inf / -1, count = n)
+    const int k_eff = A.k;
+    int kx = k_eff + 4;
+    if (kx > 64) kx = k_eff > 64 ? k_eff : 64;
+    if (kx > n) kx = (int)n;
+    A.k = kx;
+    DevTmp<double> ts;
+    DevTmp<int64_t> ti;
+    ASB_TRY(ts.init(ctx, (size_t)nq * kx));
+    ASB_TRY(ti.init(ctx, (size_t)nq * kx));
+    ASB_TRY(run_search(ctx, MODE_COSINE, A, 0, ti.ptr, ts.ptr, nullptr));
+    exact_rescore_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, ctx->stream>>>(
+        items_d, lambdas_d, queries_d, lambda_q_d, (long long)nq, (int)f, alpha, (long long)index_offset,
+        (const long long *)ti.ptr, kx, (int)k, (long long *)idx_d, score_d, (long long *)count_d, status_d);
+    return asb_check_launch(ctx, "exact_rescore_kernel");
 }
 
 int asb_dev_search_energy(asb_ctx *ctx, const double *items_d, const double *lambdas_d, const double *norms2_d,

@@ -31,8 +31,9 @@
 //                                cluster_check_tile option (worst observed error 0.05 of that bound);
 // times 1.1.  The exact kernel is the fallback for everything the bound does not cover: non-finite rows or norms
 // outside [1e-145, 1e145], a NaN score (the reference panics there: status from the exact kernel), k > 32, a
-// candidate list that overflows.  Results are therefore identical to the exact path by construction, and the
-// rescored values are bit-identical to the oracle's.
+// candidate list that overflows.  The exact path ends in the same reference-order rescoring (exact_rescore_kernel
+// over its top k + 4), so scores and tie order do not depend on which path ran; the rescored values are
+// bit-identical to the oracle's.
 #pragma once
 
 namespace {
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
                     }
                 }
             }
+            __syncwarp();   // every lane has read list_len[q]
             if (lane == 0) {
                 list_len[q] = len;
                 if (changed && len == k) atomicMax(&A.gthr[gq], pf_enc(kth));
@@ -364,28 +366,52 @@ __global__ void __launch_bounds__(kThreads, 1) search_pf_kernel(PfArgs A) {
 // One block per query: drop the candidates below the final bound, score the rest in the reference's arithmetic
 // (src/core.rs:214-236, :135-165 -- sequential sums, products and sums rounded separately), select the best k by
 // (score desc, index asc) = the reference's stable descending sort (:785-786).
+//
+// v2 (ncu of v1, profiles/r02_pf_finish_*: 3.5 ms at C3 for 0.3 ms of DRAM time -- a third of the samples in the 64
+// block barriers of a 32-step bisection, a quarter in row reads at one 8-byte word per 32-byte sector, the rest in the
+// k selection rounds with two barriers each):
+//   * A_k by a radix select over the order-preserving keys, three 8-bit digits = 9 barriers; the low 8 bits of the
+//     key are left at zero: a lower bound of A_k 2^-15 relative below it (the band is ~2^-12), which only admits a
+//     few more candidates;
+//   * the survivors' rows are read by the warp TOGETHER -- 16 features of two candidates per load instruction, two
+//     full 128-byte lines -- into a padded shared-memory tile that every lane then walks for its own candidate in
+//     feature order: same statements, same order, same bits, an eighth of the sectors;
+//   * the best k by counting ranks (one pass over the m <= 1024 survivors per thread), one barrier.
+constexpr int PF_FT = 16;                  // features per staged chunk
+constexpr int PF_FTP = PF_FT + 1;          // tile pitch (doubles): lane c walks row c conflict-free
+
+__device__ __forceinline__ unsigned pf_fkey(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+
+// dynamic shared memory: q row (f doubles, padded to PF_FT) | 4 tiles of 32 x PF_FTP doubles
 template <int MODE>
 __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *__restrict__ items,
                                                         const double *__restrict__ queries, int f, long long index_offset,
                                                         double band_f, long long *__restrict__ idx_out,
                                                         double *__restrict__ score_out, long long *__restrict__ count_out) {
+    extern __shared__ double pf_dyn[];
     __shared__ int sel_idx[PF_MAXSEL];
     __shared__ double sel_s[PF_MAXSEL];
-    __shared__ int nsel;
-    __shared__ double red_s[4];
-    __shared__ int red_i[4];
+    __shared__ int hist[256];
+    __shared__ int nsel, pick_digit, pick_rem;
     const long long q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = A.k;
+    const int fq = (f + PF_FT - 1) / PF_FT * PF_FT;
+    double *qs = pf_dyn;
+    double *tile = pf_dyn + fq + (size_t)warp * 32 * PF_FTP;
     if (tid == 0) nsel = 0;
-    __syncthreads();
     const int cnt = A.cand_cnt[q];
     if (cnt > A.cap) {
         if (tid == 0) atomicOr(A.flags, PF_FLAG_OVERFLOW);
         return;
     }
+    const double *qr = queries + q * (long long)f;
+    for (int j = tid; j < fq; j += 128) qs[j] = j < f ? qr[j] : 0.0;
     // Every item of the approximate top-k passed the emission test (its s~ >= A_k >= any bound), so the k-th largest
-    // s~ of the list IS A_k: a bisection over the order-preserving key of the stored floats finds it by counting.
+    // s~ of the list IS A_k.
     const float *cs = A.cand_s + (size_t)q * A.cap;
     if constexpr (MODE == PF_L2) {   // per-query band; the stored floats round |s~| <= 2 (|q|^2 + max|x|^2)
         const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
@@ -394,26 +420,52 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     }
     double thr = pf_dec(A.gthr[q]) - band_f;
     if (cnt >= k) {
-        unsigned key = 0;
-        for (int bit = 31; bit >= 0; --bit) {
-            const unsigned probe = key | (1u << bit);
-            int local = 0;
+        unsigned prefix = 0;   // the digits fixed so far (high bits of the key)
+        int rem = k;           // rank still to be found inside the prefix bucket
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = tid; b < 256; b += 128) hist[b] = 0;
+            __syncthreads();
             for (int c = tid; c < cnt; c += 128) {
-                const unsigned b = __float_as_uint(cs[c]);
-                local += (((b >> 31) ? ~b : (b | 0x80000000u)) >= probe) ? 1 : 0;
+                const unsigned key = pf_fkey(cs[c]);
+                if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1);
             }
-            for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-            if (lane == 0) red_i[warp] = local;
             __syncthreads();
-            const int total = red_i[0] + red_i[1] + red_i[2] + red_i[3];
+            if (warp == 0) {   // largest digit d with #(digit >= d) >= rem; lane l owns digits 8 l .. 8 l + 7
+                int loc[8], tot = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    loc[i] = hist[8 * lane + i];
+                    tot += loc[i];
+                }
+                int suf = tot;   // suffix sum over the lanes: items in this lane's digits and all higher ones
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + o < 32) suf += v;
+                }
+                const int above = suf - tot;
+                const bool mine = above < rem && suf >= rem;   // exactly one lane
+                if (mine) {
+                    int acc = above, d = 7;
+                    for (; d > 0; --d) {
+                        if (acc + loc[d] >= rem) break;
+                        acc += loc[d];
+                    }
+                    pick_digit = 8 * lane + d;
+                    pick_rem = rem - acc;
+                }
+            }
             __syncthreads();
-            if (total >= k) key = probe;
+            prefix |= (unsigned)pick_digit << shift;
+            rem = pick_rem;
         }
-        const float akf = __uint_as_float((key >> 31) ? (key & 0x7fffffffu) : ~key);
+        const float akf = __uint_as_float((prefix >> 31) ? (prefix & 0x7fffffffu) : ~prefix);   // <= A_k, within 2^-15
         thr = fmax(thr, (double)akf - band_f);
     }
+    __syncthreads();
     for (int c = tid; c < cnt; c += 128)
-        if ((double)A.cand_s[(size_t)q * A.cap + c] >= thr) {
+        if ((double)cs[c] >= thr) {
             const int p = atomicAdd(&nsel, 1);
             if (p < PF_MAXSEL) sel_idx[p] = A.cand_idx[(size_t)q * A.cap + c];
         }
@@ -427,98 +479,104 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
         atomicAdd(&A.diag[0], (unsigned long long)cnt);
         atomicAdd(&A.diag[1], (unsigned long long)m);
     }
-    const double *qr = queries + q * (long long)f;
-    if constexpr (MODE == PF_L2) {
-        // reference arithmetic of the distance scan (src/clustering.rs:125-130): df = a - b, acc += df * df in feature
-        // order, products and sums rounded separately; ranked by -acc, reported as sqrt(acc)
-        for (int c = tid; c < m; c += 128) {
-            const double *x = items + (long long)sel_idx[c] * f;
-            double acc = 0.0;
-#pragma unroll 4
-            for (int j = 0; j < f; ++j) {
-                const double df = __dsub_rn(qr[j], x[j]);
-                acc = __dadd_rn(acc, __dmul_rn(df, df));
+    const double lq = MODE == PF_L2 ? 0.0 : A.lambda_q[q];
+    // ---- exact scores: warp w takes candidates 32 (w + 4 r) .. + 31, lane = candidate
+    const int half = lane >> 4, l16 = lane & 15;
+    for (int base = 32 * warp; base < m; base += 128) {
+        const int nc = m - base < 32 ? m - base : 32;
+        const int li = lane < nc ? sel_idx[base + lane] : 0;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;   // L2: acc0 = sum (q - x)^2;  cosine: |q|^2, |x|^2, q.x
+        for (int j0 = 0; j0 < f; j0 += PF_FT) {
+            __syncwarp();
+            {   // all 16 loads of the chunk in flight before the first store
+                double v[16];
+                const int fj = j0 + l16;
+#pragma unroll
+                for (int ii = 0; ii < 16; ++ii) {
+                    const int i = 2 * ii + half;
+                    v[ii] = (i < nc && fj < f) ? __ldg(items + (long long)sel_idx[base + i] * f + fj) : 0.0;
+                }
+#pragma unroll
+                for (int ii = 0; ii < 16; ++ii) {
+                    const int i = 2 * ii + half;
+                    if (i < nc) tile[i * PF_FTP + l16] = v[ii];
+                }
             }
-            sel_s[c] = (acc == acc) ? -acc : -INFINITY;
+            __syncwarp();
+            if (lane < nc) {
+                const double *tr = tile + lane * PF_FTP;
+                const int jn = f - j0 < PF_FT ? f - j0 : PF_FT;
+                if (jn == PF_FT) {
+#pragma unroll
+                    for (int jj = 0; jj < PF_FT; ++jj) {
+                        const double qv = qs[j0 + jj], xv = tr[jj];
+                        if constexpr (MODE == PF_L2) {
+                            const double df = __dsub_rn(qv, xv);                 // src/clustering.rs:125-130
+                            acc0 = __dadd_rn(acc0, __dmul_rn(df, df));
+                        } else {
+                            acc0 = __dadd_rn(acc0, __dmul_rn(qv, qv));
+                            acc1 = __dadd_rn(acc1, __dmul_rn(xv, xv));
+                            acc2 = __dadd_rn(acc2, __dmul_rn(qv, xv));
+                        }
+                    }
+                } else {
+                    for (int jj = 0; jj < jn; ++jj) {
+                        const double qv = qs[j0 + jj], xv = tr[jj];
+                        if constexpr (MODE == PF_L2) {
+                            const double df = __dsub_rn(qv, xv);
+                            acc0 = __dadd_rn(acc0, __dmul_rn(df, df));
+                        } else {
+                            acc0 = __dadd_rn(acc0, __dmul_rn(qv, qv));
+                            acc1 = __dadd_rn(acc1, __dmul_rn(xv, xv));
+                            acc2 = __dadd_rn(acc2, __dmul_rn(qv, xv));
+                        }
+                    }
+                }
+            }
         }
-    } else {
-    const double lq = A.lambda_q[q];
-    for (int c = tid; c < m; c += 128) {
-        const int li = sel_idx[c];
-        const double *x = items + (long long)li * f;
-        double nq2 = 0.0, nx2 = 0.0, dot = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < f; ++j) {
-            const double qv = qr[j], xv = x[j];
-            nq2 = __dadd_rn(nq2, __dmul_rn(qv, qv));
-            nx2 = __dadd_rn(nx2, __dmul_rn(xv, xv));
-            dot = __dadd_rn(dot, __dmul_rn(qv, xv));
+        if (lane < nc) {
+            double sres;
+            if constexpr (MODE == PF_L2) {
+                sres = (acc0 == acc0) ? -acc0 : -INFINITY;
+            } else {
+                const double denom = __dmul_rn(sqrt(acc0), sqrt(acc1));       // core.rs:230
+                const double cosv = denom > 0.0 ? acc2 / denom : 0.0;        // :231-236
+                const double lam = 1.0 - fmin(fabs(lq - A.lambdas[li]), 1.0);  // :136-137
+                sres = __dadd_rn(__dmul_rn(A.alpha, cosv), __dmul_rn(1.0 - A.alpha, lam));  // :165
+                if (sres != sres) {
+                    atomicOr(A.status, STATUS_NAN);
+                    sres = -INFINITY;
+                }
+            }
+            sel_s[base + lane] = sres;
         }
-        const double denom = __dmul_rn(sqrt(nq2), sqrt(nx2));       // core.rs:230
-        const double cosv = denom > 0.0 ? dot / denom : 0.0;        // :231-236
-        const double lam = 1.0 - fmin(fabs(lq - A.lambdas[li]), 1.0);  // :136-137
-        const double s = __dadd_rn(__dmul_rn(A.alpha, cosv), __dmul_rn(1.0 - A.alpha, lam));  // :165
-        if (s != s) atomicOr(A.status, STATUS_NAN);
-        sel_s[c] = s;
-    }
     }
     __syncthreads();
-    double last_s = INFINITY;
-    int last_i = -1, taken = 0;
-    for (int r = 0; r < k; ++r) {
-        double bs = -INFINITY;
-        int bi = -1;
-        for (int c = tid; c < m; c += 128) {
-            const double s = sel_s[c];
-            const int ii = sel_idx[c];
-            const bool after = (s < last_s) || (s == last_s && ii > last_i);
-            if (!after) continue;
-            if (bi < 0 || s > bs || (s == bs && ii < bi)) {
-                bs = s;
-                bi = ii;
-            }
+    // ---- rank by (score desc, index asc): position = number of survivors that come first
+    for (int c = tid; c < m; c += 128) {
+        const double sc = sel_s[c];
+        const int ic = sel_idx[c];
+        int rank = 0;
+        for (int o = 0; o < m; ++o) {
+            const double so = sel_s[o];
+            rank += (so > sc || (so == sc && sel_idx[o] < ic)) ? 1 : 0;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
-                bs = os;
-                bi = oi;
-            }
+        if (rank < k) {
+            score_out[q * k + rank] = MODE == PF_L2 ? sqrt(fmax(-sc, 0.0)) : sc;
+            idx_out[q * k + rank] = (long long)ic + index_offset;
         }
-        if (lane == 0) {
-            red_s[warp] = bs;
-            red_i[warp] = bi;
-        }
-        __syncthreads();
-        bs = red_s[0];
-        bi = red_i[0];
-#pragma unroll
-        for (int w = 1; w < 4; ++w) {
-            const double os = red_s[w];
-            const int oi = red_i[w];
-            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) {
-                bs = os;
-                bi = oi;
-            }
-        }
-        __syncthreads();
-        if (bi < 0) break;
-        if (tid == 0) {
-            score_out[q * k + r] = MODE == PF_L2 ? sqrt(fmax(-bs, 0.0)) : bs;
-            idx_out[q * k + r] = (long long)bi + index_offset;
-        }
-        last_s = bs;
-        last_i = bi;
-        ++taken;
     }
-    if (tid == 0) {
-        for (int r = taken; r < k; ++r) {
-            score_out[q * k + r] = MODE == PF_L2 ? INFINITY : -INFINITY;
-            idx_out[q * k + r] = -1;
-        }
-        if (count_out) count_out[q] = taken;
+    const int taken = m < k ? m : k;
+    for (int r = taken + tid; r < k; r += 128) {
+        score_out[q * k + r] = MODE == PF_L2 ? INFINITY : -INFINITY;
+        idx_out[q * k + r] = -1;
     }
+    if (tid == 0 && count_out) count_out[q] = taken;
+}
+
+static size_t pf_finish_smem(int f) {
+    const int fq = (f + PF_FT - 1) / PF_FT * PF_FT;
+    return ((size_t)fq + 4 * 32 * PF_FTP) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(256) pf_max_kernel(const double *__restrict__ v, long long n, unsigned long long *__restrict__ out_bits) {
@@ -646,7 +704,9 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     ASB_TRY(asb_check_launch(ctx, "search_pf_kernel"));
     {
         KernelTimer kt(ctx, "search_pf_finish");
-        pf_finish_kernel<PF_COSINE><<<(unsigned)nq, 128, 0, ctx->stream>>>(A, SA.items, SA.queries, f, index_offset, band_f,
+        ASB_CUDA(ctx, cudaFuncSetAttribute(pf_finish_kernel<PF_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)pf_finish_smem(f)));
+        pf_finish_kernel<PF_COSINE><<<(unsigned)nq, 128, pf_finish_smem(f), ctx->stream>>>(A, SA.items, SA.queries, f, index_offset, band_f,
                                                                 (long long *)idx_d, score_d, (long long *)count_d);
     }
     ASB_TRY(asb_check_launch(ctx, "pf_finish_kernel"));
@@ -774,7 +834,9 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
         search_pf_kernel<PF_L2><<<dim3((unsigned)qtiles, (unsigned)nslabs), kThreads, smem, ctx->stream>>>(A);
     }
     ASB_TRY(asb_check_launch(ctx, "search_pf_kernel<L2>"));
-    pf_finish_kernel<PF_L2><<<(unsigned)nq, 128, 0, ctx->stream>>>(A, items_d, queries_d, f, 0, 0.0, (long long *)idx_d, dist_d,
+    ASB_CUDA(ctx, cudaFuncSetAttribute(pf_finish_kernel<PF_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pf_finish_smem((int)f)));
+    pf_finish_kernel<PF_L2><<<(unsigned)nq, 128, pf_finish_smem((int)f), ctx->stream>>>(A, items_d, queries_d, f, 0, 0.0, (long long *)idx_d, dist_d,
                                                                   (long long *)count_d);
     ASB_TRY(asb_check_launch(ctx, "pf_finish_kernel<L2>"));
     int hflags = 0;

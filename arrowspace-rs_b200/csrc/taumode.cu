@@ -500,6 +500,30 @@ int asb_graph_plan_from_host(asb_ctx *ctx, const int64_t *indptr, const int64_t 
     return ASB_OK;
 }
 
+// v4 (taumode_sym.cuh): item in registers + shared memory, IPP items per warp pass; f <= 32 NPL <= 1024
+template <bool ALLPOS, int NPL, int IPP>
+static int launch_taumode_reg(asb_ctx *ctx, const char *tname, const double *items_d, int64_t n, int f,
+                              const GraphPlan &plan, int tau_mode, double tau_value, double *lambdas_d, double *norms2_d,
+                              int *nonfinite_flag_d) {
+    auto kern = taumode_reg_kernel<ALLPOS, NPL, IPP>;
+    const size_t smem = (size_t)kTauWarps * (IPP * f + kSelCap) * sizeof(double);   // items + the selection scratch
+    ASB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    ASB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTauWarps * 32, smem));
+    if (per_sm < 1) ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "taumode: item does not fit shared memory (f=%d)", f);
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long need = ((n + IPP - 1) / IPP + kTauWarps - 1) / kTauWarps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    {
+        KernelTimer kt(ctx, tname);
+        kern<<<(unsigned)grid, kTauWarps * 32, smem, ctx->stream>>>(items_d, (long long)n, f, (const SymEdge *)plan.sym_edges,
+                                                                    (int)(plan.nedges / 32), plan.resid, tau_mode, tau_value,
+                                                                    lambdas_d, norms2_d, nonfinite_flag_d, (int)plan.f);
+    }
+    return asb_check_launch(ctx, "taumode_reg_kernel");
+}
+
 int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, const GraphPlan &plan,
                     int tau_mode, double tau_value, double *lambdas_d, double *norms2_d, double *stats_d,
                     int *nonfinite_flag_d) {
@@ -516,6 +540,38 @@ int asb_dev_taumode(asb_ctx *ctx, const double *items_d, int64_t n, int64_t f, c
     }
     if (plan.f < f && (generic || (size_t)f * sizeof(double) > 200 * 1024))
         ASB_FAIL(ctx, ASB_ERR_UNSUPPORTED, "taumode: a graph smaller than the items (JL-projected build) needs the symmetric kernel");
+    bool regs = !generic && f <= 1024;
+    {
+        auto it = ctx->options.find("taumode_regs");
+        if (it != ctx->options.end() && it->second == 0.0) regs = false;
+    }
+    if (regs) {
+        int rc = ASB_OK;
+        const char *tname = nonfinite_flag_d ? "query_taumode_kernel" : "taumode_kernel";
+#define ASB_TAU_REG(NPL_, IPP_)                                                                                       \
+    rc = plan.all_pos ? launch_taumode_reg<true, NPL_, IPP_>(ctx, tname, items_d, n, (int)f, plan, tau_mode, tau_value,  \
+                                                             lambdas_d, norms2_d, nonfinite_flag_d)                  \
+                      : launch_taumode_reg<false, NPL_, IPP_>(ctx, tname, items_d, n, (int)f, plan, tau_mode, tau_value, \
+                                                              lambdas_d, norms2_d, nonfinite_flag_d)
+        int ipp = 2;  // items per warp pass (f <= 512; wider items take one)
+        {
+            auto it = ctx->options.find("taumode_ipp");
+            if (it != ctx->options.end() && it->second == 1.0) ipp = 1;
+        }
+        if (f <= 128) { if (ipp == 2) ASB_TAU_REG(4, 2); else ASB_TAU_REG(4, 1); }
+        else if (f <= 256) { if (ipp == 2) ASB_TAU_REG(8, 2); else ASB_TAU_REG(8, 1); }
+        else if (f <= 384) { if (ipp == 2) ASB_TAU_REG(12, 2); else ASB_TAU_REG(12, 1); }
+        else if (f <= 512) { if (ipp == 2) ASB_TAU_REG(16, 2); else ASB_TAU_REG(16, 1); }
+        else if (f <= 768) ASB_TAU_REG(24, 1);
+        else ASB_TAU_REG(32, 1);
+#undef ASB_TAU_REG
+        ASB_TRY(rc);
+        if (stats_d) {
+            lambda_stats_kernel<<<1, 1024, 0, ctx->stream>>>(lambdas_d, (long long)n, stats_d);
+            ASB_TRY(asb_check_launch(ctx, "lambda_stats_kernel"));
+        }
+        return ASB_OK;
+    }
     if (!generic && (size_t)f * sizeof(double) <= 200 * 1024) {
         // one warp per item; as many warps per CTA as the private shared-memory copies allow
         int wpc = kTauWarps;

@@ -251,6 +251,252 @@ taumode_warp_kernel(const double *__restrict__ items, long long n, int f, const 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// v4: the item lives in REGISTERS as well (lane l holds features l, l+32, ...: NPL of them, compile time), two
+// items per warp pass.  ncu of v3 (profiles/r02_taumode_v3_*): the kernel is bound by the L1 / shared-memory data path
+// (570 wavefront cycles per item and SM: 188 for the two x reads per edge, 188 for the 16-byte schedule entry per
+// edge, 144 for the selection's re-reads of the item, 48 for the copy-in), not by HBM or the FP64 pipe.  v4 keeps only
+// the random x[i], x[j] reads in shared memory: the statistics, the counting passes of the tau selection and the
+// extraction run on the lane's registers, and one schedule entry serves IPP items (330 cycles per item at IPP = 2).
+// Lanes' missing elements (f < 32 NPL) are NaN: every comparison is false, every statistic is predicated on j < f.
+template <int NPL>
+struct TauItem {
+    double xv[NPL];
+    double den, num, vsum, vmin, vmax;
+    int cnt, nneg;
+};
+
+template <int NPL>
+__device__ __forceinline__ double tau_select_regs(const double (&xv)[NPL], int lane, int tau_mode, double tau_value, int nf,
+                                                  int nneg_all, double vmin, double vmax, double *scratch) {
+    // scratch: kSelCap doubles of this warp's shared memory (the gathered bracket)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    int rb;
+    bool need_pair = false;
+    if (tau_mode == ASB_TAU_PERCENTILE) {
+        double pp = tau_value;
+        pp = pp < 0.0 ? 0.0 : (pp > 1.0 ? 1.0 : pp);
+        const double fi = round((double)(nf - 1) * pp);  // half away from zero
+        rb = (fi != fi || fi < 0.0) ? 0 : (int)fi;
+        if (rb > nf - 1) rb = nf - 1;
+    } else {
+        rb = nf / 2;
+        need_pair = (nf % 2 == 0);
+    }
+    double lo = vmin, hi = INFINITY;
+    int c_lo = 0, c_hi = nf;
+    for (int iter = 0; iter < 200; ++iter) {  // every quantity below is warp-uniform
+        const bool dup = (lo == vmax) || (hi < INFINITY && ord_key(hi) == ord_key(lo) + 1ull);
+        if (c_hi - c_lo <= kSelCap || dup) break;
+        const double hi_f = (hi == INFINITY) ? vmax : hi;
+        // (any value inside (lo, hi) is a valid pivot -- only the exact counts decide -- so the interpolation weight
+        // may be a fast FP32 quotient)
+        const float fracf = __fdividef((float)(rb - c_lo) + 0.5f, (float)(c_hi - c_lo));
+        double pv = fma(hi_f - lo, (double)fracf, lo);
+        if (iter >= 6 || !(fabs(pv) < INFINITY)) {
+            const unsigned long long kl = ord_key(lo), kh = ord_key(hi_f);
+            pv = ord_val(kl + ((kh - kl) >> 1) + ((kh - kl) & 1ull));
+        }
+        if (hi < INFINITY) {
+            if (!(pv < hi)) pv = ord_val(ord_key(hi) - 1ull);
+        } else if (pv > vmax) {
+            pv = vmax;
+        }
+        if (!(pv > lo)) pv = ord_val(ord_key(lo) + 1ull);
+        int c = 0;
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) c += (xv[t] < pv) ? 1 : 0;  // NaN / +inf compare false
+        const int c_p = __reduce_add_sync(0xffffffffu, c) - nneg_all;
+        if (c_p <= rb) {
+            lo = pv;
+            c_lo = c_p;
+        } else {
+            hi = pv;
+            c_hi = c_p;
+        }
+    }
+    const bool small = (c_hi - c_lo <= kSelCap);
+    // ---- extraction: the <= kSelCap finite values inside [lo, hi) go to the warp's scratch (lane-major order: any
+    //      order will do, they are ranked below); also the largest finite value below lo
+    int mycnt = 0;
+    double below = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NPL; ++t) {
+        const double x = xv[t];
+        mycnt += (x >= lo && x < hi) ? 1 : 0;                      // NaN compares false; +-inf fall outside
+        if (x < lo && x > -INFINITY) below = x > below ? x : below;
+    }
+    int pos = mycnt;   // inclusive scan over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += v;
+    }
+    const int nv = small ? __shfl_sync(0xffffffffu, pos, 31) : 0;
+    pos -= mycnt;
+    __syncwarp();
+    if (small && mycnt > 0) {
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) {
+            const double x = xv[t];
+            if (x >= lo && x < hi) scratch[pos++] = x;
+        }
+    }
+    __syncwarp();
+    const double mine = (small && lane < nv) ? scratch[lane] : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, below, o);
+        below = ob > below ? ob : below;
+    }
+    double v_rb, v_ra;
+    if (small) {
+        int rank = 0;
+#pragma unroll
+        for (int q = 0; q < kSelCap; ++q) {
+            const double o = __shfl_sync(0xffffffffu, mine, q);
+            rank += (q < nv && (o < mine || (o == mine && q < lane))) ? 1 : 0;
+        }
+        const int k = rb - c_lo;
+        const unsigned has_k = __ballot_sync(0xffffffffu, lane < nv && rank == k);
+        const unsigned has_km1 = __ballot_sync(0xffffffffu, lane < nv && rank == k - 1);
+        v_rb = __shfl_sync(0xffffffffu, mine, has_k ? __ffs(has_k) - 1 : 0);
+        v_ra = has_km1 ? __shfl_sync(0xffffffffu, mine, __ffs(has_km1) - 1) : below;
+    } else {
+        v_rb = lo;
+        v_ra = (rb - 1 >= c_lo) ? lo : below;
+    }
+    return fmax(need_pair ? 0.5 * (v_ra + v_rb) : v_rb, kTauFloor);
+}
+
+template <bool ALLPOS, int NPL, int IPP>
+__global__ void __launch_bounds__(kTauWarps * 32)
+taumode_reg_kernel(const double *__restrict__ items, long long n, int f, const SymEdge *__restrict__ sched, int nsteps,
+                   const double *__restrict__ resid, int tau_mode, double tau_value, double *__restrict__ lambdas,
+                   double *__restrict__ norms2, int *__restrict__ nonfinite_flag, int rg) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xs = smem + (size_t)warp * IPP * f;
+    double *scratch = smem + (size_t)kTauWarps * IPP * f + warp * kSelCap;
+    const long long npass = (n + IPP - 1) / IPP;
+    const long long wstride = (long long)gridDim.x * kTauWarps;
+    for (long long pass = (long long)blockIdx.x * kTauWarps + warp; pass < npass; pass += wstride) {
+        TauItem<NPL> it[IPP];
+        long long idx[IPP];
+        __syncwarp();  // the previous pass's readers are done with xs
+        // ---- all loads of the pass first (IPP * NPL independent 256-byte requests per warp)
+#pragma unroll
+        for (int p = 0; p < IPP; ++p) {
+            const long long item = pass * IPP + p;
+            idx[p] = item < n ? item : -1;
+            const double *src = items + (item < n ? item : pass * IPP) * (long long)f;  // a missing item repeats item 0
+#pragma unroll
+            for (int t = 0; t < NPL; ++t) {
+                const int j = 32 * t + lane;
+                it[p].xv[t] = j < f ? __ldg(src + j) : __longlong_as_double(0x7ff8000000000000ll);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < IPP; ++p) {
+            it[p].den = 0.0, it[p].num = 0.0, it[p].vsum = 0.0, it[p].vmin = INFINITY, it[p].vmax = -INFINITY;
+            it[p].cnt = 0, it[p].nneg = 0;
+        }
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) {
+            const int j = 32 * t + lane;
+            if (j < f) {
+                const double r = j < rg ? __ldg(resid + j) : 0.0;
+#pragma unroll
+                for (int p = 0; p < IPP; ++p) {
+                    const double x = it[p].xv[t];
+                    xs[p * f + j] = x;
+                    const double x2 = x * x;
+                    it[p].den += x2;
+                    if (j < rg) it[p].num = fma(r, x2, it[p].num);
+                    if (fabs(x) < INFINITY) {
+                        it[p].cnt++;
+                        it[p].vsum += x;
+                        it[p].vmin = x < it[p].vmin ? x : it[p].vmin;   // (x is finite: no NaN semantics needed)
+                        it[p].vmax = x > it[p].vmax ? x : it[p].vmax;
+                    }
+                    it[p].nneg += (x == -INFINITY) ? 1 : 0;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- edges: one schedule entry per lane and step, applied to every item of the pass
+        double s1[IPP], s2[IPP];
+#pragma unroll
+        for (int p = 0; p < IPP; ++p) s1[p] = 0.0, s2[p] = 0.0;
+        {
+            const SymEdge *sp = sched + lane;
+#pragma unroll 4
+            for (int s = 0; s < nsteps; ++s) {
+                const SymEdge e = ld_edge(sp + (size_t)s * 32);
+#pragma unroll
+                for (int p = 0; p < IPP; ++p) {
+                    const double d = xs[p * f + e.i] - xs[p * f + e.j];
+                    const double c = e.w * (d * d);
+                    if (ALLPOS) {
+                        s1[p] += c;
+                        s2[p] = fma(c, c, s2[p]);
+                    } else {
+                        it[p].num += c;
+                        if (e.w > 0.0) {
+                            s1[p] += c;
+                            s2[p] = fma(c, c, s2[p]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < IPP; ++p) {
+            double den = it[p].den, num = it[p].num, a1 = s1[p], a2 = s2[p];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                den += __shfl_xor_sync(0xffffffffu, den, o);
+                num += __shfl_xor_sync(0xffffffffu, num, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (ALLPOS) num += a1;
+            const int nf = __reduce_add_sync(0xffffffffu, it[p].cnt);
+            const int nneg_all = __reduce_add_sync(0xffffffffu, it[p].nneg);
+            double tau;
+            if (tau_mode == ASB_TAU_FIXED) {
+                tau = (fabs(tau_value) < INFINITY && tau_value > 0.0) ? tau_value : kTauFloor;
+            } else if (tau_mode == ASB_TAU_MEAN) {
+                double vsum = it[p].vsum;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+                tau = fmax(nf > 0 ? vsum / (double)nf : 0.0, kTauFloor);
+            } else if (nf == 0) {
+                tau = kTauFloor;
+            } else {
+                tau = tau_select_regs<NPL>(it[p].xv, lane, tau_mode, tau_value, nf, nneg_all, it[p].vmin, it[p].vmax, scratch);
+            }
+            if (lane == 0 && idx[p] >= 0) {
+                const double e_raw = den > 1e-12 ? num / den : 0.0;
+                double g = 0.0;
+                if (a1 > 0.0) {
+                    g = a2 / (2.0 * a1 * a1);
+                    g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+                }
+                const double e_bounded = e_raw / (e_raw + tau);
+                lambdas[idx[p]] = tau * e_bounded + (1.0 - tau) * g;
+                if (norms2) norms2[idx[p]] = den;
+                if (nonfinite_flag && nf < f) atomicOr(nonfinite_flag, 1);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // Host side: pack the undirected edges into steps of 32 such that, inside each half-warp (16 lanes), the

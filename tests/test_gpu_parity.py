@@ -108,6 +108,32 @@ def test_taumode_synthetic(ctx, asb, oracle, n, f):
     assert np.all(np.isfinite(want)) and want.std() > 0
 
 
+@pytest.mark.parametrize("variant", ["regs_ipp2", "regs_ipp1", "smem_v3"])
+@pytest.mark.parametrize("n,f", [(2_001, 24), (1_500, 100), (3_333, 384), (901, 500), (700, 770), (333, 1000), (100, 1100)])
+def test_taumode_symmetric_kernel_variants(ctx, asb, oracle, n, f, variant):
+    """The three one-warp-per-item kernels (item in registers with one / two items per pass, item in shared memory
+    only) against the oracle: every register width NPL, widths that are not multiples of 32, an odd item count (the
+    last pass is half empty), non-finite values, Median / Percentile / Mean."""
+    x = asb.synth.protein_like(n, f, seed=7)
+    cent, _, _ = oracle.cluster_incremental(x[:1500], 40, 1.5 * f * 0.0025 * 2)
+    csr = _graph(oracle, cent)
+    x[3, f // 2] = np.nan
+    x[n - 1, 0] = -np.inf
+    x[n // 2, f - 1] = np.inf
+    ctx.set_option("taumode_regs", 0 if variant == "smem_v3" else 1)
+    ctx.set_option("taumode_ipp", 1 if variant == "regs_ipp1" else 2)
+    try:
+        for mode, value in [(TAU_MEDIAN, 0.0), (TAU_PERCENTILE, 0.9), (TAU_MEAN, 0.0)]:
+            want = oracle.compute_taumode(x, csr, mode, value)
+            lam, n2, _ = ctx.compute_taumode(x, csr, _tm(asb, mode, value), want_norms=True)
+            _assert_lambda_close(lam, want)
+            fin = np.isfinite(x).all(axis=1)
+            assert np.allclose(n2[fin], (x[fin] ** 2).sum(axis=1), rtol=1e-13)
+    finally:
+        ctx.set_option("taumode_regs", 1)
+        ctx.set_option("taumode_ipp", 2)
+
+
 def test_taumode_generic_and_symmetric_kernels_agree(ctx, asb, oracle, golden):
     """Symmetric graphs take the edge-once kernel, anything else the generic CSR kernel; both must
     match the oracle (non-symmetric, positive off-diagonal and diagonal-free matrices included)."""
