@@ -933,16 +933,25 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
 
     int64_t x = init_k;
     double ms_seq = 0.0, ms_top2 = 0.0, ms_chain = 0.0;   // device time per part, summed over the chunks
+    double wall_growth = 0.0, wall_prefix = 0.0, wall_prepare = 0.0, wall_run = 0.0, wall_seq = 0.0;   // host wall, ms
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     int64_t lo = 0;
     if (init_k == 0 && opt_or(ctx, "cluster_growth_run", 1.0) != 0.0) {
+        const auto t = now();
         ASB_TRY(growth_run(ctx, rows_d, n, f, max_clusters, radius, centroids_d, assign_d, sizes_d, &lo));
+        wall_growth = since(t);
         x = lo;
         ctx->kernel_ms["cluster_growth_rows"] = (double)lo;
     }
     if (lo < prefix) {
         const int64_t x_before = x;
+        const auto t = now();
         ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, prefix - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
                                     sizes_d, &x, x_before));
+        wall_prefix = since(t);
         ms_seq += ktimer_ms(ctx, "cluster_kernel");
         lo = prefix;
     }
@@ -962,9 +971,13 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
                 ws_ready = true;
             }
             ++tried;
+            auto t = now();
             ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, centroids_d));
+            wall_prepare += since(t);
+            t = now();
             ASB_TRY(replay_run(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, x >= max_clusters ? 1 : 0, radius,
                                centroids_d, centroids_d, assign_d + lo, sizes_d, &ok));
+            wall_run += since(t);
             if (!ok && w.use_near && w.last_flags == 2) {   // only certificates missed: the tile's bounds may be too wide
                 ++near_retries;
                 ASB_TRY(replay_prepare(ctx, w, rows_d + lo * f, (int)(hi - lo), (int)f, (int)x, centroids_d, false));
@@ -987,8 +1000,10 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             hi = lo + span < n ? lo + span : n;
             cur = chunk;
             const int64_t x_before = x;
+            const auto t = now();
             ASB_TRY(asb_dev_cluster_seq(ctx, rows_d + lo * f, hi - lo, f, max_clusters, radius, centroids_d, assign_d + lo,
                                         sizes_d, &x, x_before));
+            wall_seq += since(t);
             ms_seq += ktimer_ms(ctx, "cluster_kernel");
         }
         lo = hi;
@@ -998,6 +1013,12 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     ctx->kernel_ms["cluster_replay_chunks_ok"] = (double)proven;
     ctx->kernel_ms["cluster_replay_rows"] = (double)rows_replayed;
     ctx->kernel_ms["cluster_replay_seq_ms"] = ms_seq;
+    // host wall time per phase (prepare returns before its kernels end; run ends in a stream synchronisation)
+    ctx->kernel_ms["cluster_wall_growth_ms"] = wall_growth;
+    ctx->kernel_ms["cluster_wall_prefix_ms"] = wall_prefix;
+    ctx->kernel_ms["cluster_wall_prepare_ms"] = wall_prepare;
+    ctx->kernel_ms["cluster_wall_run_ms"] = wall_run;
+    ctx->kernel_ms["cluster_wall_fallback_ms"] = wall_seq;
     ctx->kernel_ms["cluster_replay_top2_ms"] = ms_top2;
     ctx->kernel_ms["cluster_replay_chain_ms"] = ms_chain;
     ctx->kernel_ms["cluster_replay_near_retries"] = (double)near_retries;

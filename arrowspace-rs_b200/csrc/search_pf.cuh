@@ -595,6 +595,17 @@ size_t pf_smem_bytes(int k, int mode = PF_COSINE) {
 
 #include "search_umma.cuh"   // the same tile on tcgen05 / TMA / TMEM (needs PfArgs and the helpers above)
 
+// hi / lo planes for the tcgen05 tile: TF32 planes (fp32 words) or BF16 planes in the same buffers (half used)
+#define UM_SPLIT_LAUNCH(grid, rows, norms2, n_, f_, fp_, hi_, lo_, flags_, nout_)                                          \
+    do {                                                                                                                 \
+        if (bf16)                                                                                                        \
+            um_split_rows_bf16_kernel<<<(grid), 256, 0, ctx->stream>>>(rows, norms2, n_, f_, fp_,                        \
+                                                                       reinterpret_cast<__nv_bfloat16 *>(hi_),          \
+                                                                       reinterpret_cast<__nv_bfloat16 *>(lo_), flags_, nout_); \
+        else                                                                                                             \
+            um_split_rows_kernel<<<(grid), 256, 0, ctx->stream>>>(rows, norms2, n_, f_, fp_, hi_, lo_, flags_, nout_);   \
+    } while (0)
+
 // Tries the prefilter path; *done = true when idx/score/count hold the final answer.  *done = false (with ASB_OK)
 // means "not applicable / not certain": the caller runs the exact kernel, which then decides everything.
 static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_offset, int64_t *idx_d, double *score_d,
@@ -621,8 +632,8 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     const size_t smem = pf_smem_bytes(k);
     if (smem > 227 * 1024) return ASB_OK;
 
-    const double chain = 3.0 * fp / 8.0;
-    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+    const bool bf16 = um_wanted(ctx) && um_bf16(ctx);   // BF16x3 planes on the tcgen05 tile (the bound covers both tiles)
+    const double e_cos = um_e_cos(fp, bf16);
     const double E = fabs(SA.alpha) * e_cos + 1e-10;
     const double band = 2.0 * E;
     const double band_f = band + 1.1920928955078125e-7 * (fabs(SA.alpha) + fabs(1.0 - SA.alpha) + 1.0);  // cand_s is a float
@@ -660,10 +671,8 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     {
         KernelTimer kt(ctx, "search_pf_prep");
         if (umma) {
-            um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, xlo.ptr,
-                                                                                  flags.ptr, nullptr);
-            um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr,
-                                                                                   qlo.ptr, flags.ptr, nullptr);
+            UM_SPLIT_LAUNCH((unsigned)((n + 7) / 8), SA.items, SA.norms2, n, f, fp, xf.ptr, xlo.ptr, flags.ptr, nullptr);
+            UM_SPLIT_LAUNCH((unsigned)((nq + 7) / 8), SA.queries, SA.qnorms2, nq, f, fp, qf.ptr, qlo.ptr, flags.ptr, nullptr);
         } else {
             pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(SA.items, SA.norms2, n, f, fp, xf.ptr, flags.ptr);
             pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(SA.queries, SA.qnorms2, nq, f, fp, qf.ptr, flags.ptr);
@@ -752,8 +761,8 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     if ((double)nq * cap * 8.0 > 2e9) return ASB_OK;
     const size_t smem = pf_smem_bytes(k, PF_L2);
     if (smem > 227 * 1024) return ASB_OK;
-    const double chain = 3.0 * fp / 8.0;
-    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+    const bool bf16 = um_wanted(ctx) && um_bf16(ctx);   // BF16x3 planes on the tcgen05 tile (the bound covers both tiles)
+    const double e_cos = um_e_cos(fp, bf16);
 
     DevTmp<float> xf, qf, xlo, qlo, cand_s;
     DevTmp<double> xnrm, qnrm;
@@ -789,10 +798,8 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     pf_max_kernel<<<64, 256, 0, ctx->stream>>>(xn2_d, n, xmax.ptr);
     ASB_TRY(asb_check_launch(ctx, "pf_max_kernel"));
     if (umma) {
-        um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr,
-                                                                              xnrm.ptr);
-        um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr,
-                                                                               flags.ptr, qnrm.ptr);
+        UM_SPLIT_LAUNCH((unsigned)((n + 7) / 8), items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr, xnrm.ptr);
+        UM_SPLIT_LAUNCH((unsigned)((nq + 7) / 8), queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr, flags.ptr, qnrm.ptr);
     } else {
         pf_unit_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, flags.ptr, xnrm.ptr);
         pf_unit_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, flags.ptr, qnrm.ptr);
@@ -858,8 +865,8 @@ static int run_near_umma(asb_ctx *ctx, const double *items_d, long long n, int f
     if (n < 2 || n > 65536 || nq < 1 || nq > 0x7fffff00ll || !um_wanted(ctx)) return ASB_OK;
     const int fp = (f + 31) & ~31;
     if (um_smem_bytes(0, PF_NEAR) > 227 * 1024) return ASB_OK;
-    const double chain = 3.0 * fp / 8.0;
-    const double e_cos = 1.1 * (2.384185791015625e-7 + 3.0 * 9.5367431640625e-7 + (9.0 * chain + 16.0) * 1.1920928955078125e-7);
+    const bool bf16 = um_wanted(ctx) && um_bf16(ctx);   // BF16x3 planes on the tcgen05 tile (the bound covers both tiles)
+    const double e_cos = um_e_cos(fp, bf16);
     DevTmp<float> xf, qf, xlo, qlo;
     DevTmp<double> xnrm, qnrm;
     DevTmp<int> flags;
@@ -879,10 +886,8 @@ static int run_near_umma(asb_ctx *ctx, const double *items_d, long long n, int f
     if (!um_make_maps(ctx, &maps, qf.ptr, qlo.ptr, nq, xf.ptr, xlo.ptr, n, fp)) return ASB_OK;
     pf_max_kernel<<<64, 256, 0, ctx->stream>>>(xn2_d, n, xmax.ptr);
     ASB_TRY(asb_check_launch(ctx, "pf_max_kernel"));
-    um_split_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr,
-                                                                          xnrm.ptr);
-    um_split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, ctx->stream>>>(queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr,
-                                                                           flags.ptr, qnrm.ptr);
+    UM_SPLIT_LAUNCH((unsigned)((n + 7) / 8), items_d, xn2_d, n, f, fp, xf.ptr, xlo.ptr, flags.ptr, xnrm.ptr);
+    UM_SPLIT_LAUNCH((unsigned)((nq + 7) / 8), queries_d, qn2_d, nq, f, fp, qf.ptr, qlo.ptr, flags.ptr, qnrm.ptr);
     ASB_TRY(asb_check_launch(ctx, "um_split_rows_kernel"));
     ctx->launches++;
     PfArgs A{};

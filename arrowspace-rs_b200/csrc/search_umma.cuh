@@ -19,6 +19,7 @@
 #pragma once
 
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -92,6 +93,15 @@ __device__ __forceinline__ void um_mma_tf32(unsigned tmem_c, unsigned long long 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
+// kind::f16 with BF16 operands: K = 16 per instruction (32 bytes per row, the same descriptor step as TF32's K = 8)
+__device__ __forceinline__ void um_mma_bf16(unsigned tmem_c, unsigned long long da, unsigned long long db, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
 // the same box delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in mask
 __device__ __forceinline__ void um_tma_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar,
                                              unsigned short mask) {
@@ -141,6 +151,36 @@ __global__ void __launch_bounds__(256) um_split_rows_kernel(const double *__rest
     }
 }
 
+// BF16x3 planes: hi = bf16(v) (round to nearest), lo = bf16(v - hi): |v - hi - lo| <= 2^-18 |v|.  Half the operand bytes
+// and twice the tensor rate of the TF32 planes for the same certificate (search_pf.cuh: the accumulation term dominates
+// E_cos, not the representation term).
+__global__ void __launch_bounds__(256) um_split_rows_bf16_kernel(const double *__restrict__ rows, const double *__restrict__ norms2,
+                                                                 long long n, int f, int fp, __nv_bfloat16 *__restrict__ hi,
+                                                                 __nv_bfloat16 *__restrict__ lo, int *__restrict__ flags,
+                                                                 double *__restrict__ norm_out) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double n2 = norms2[r];
+    const bool ok = (n2 == 0.0) || (n2 >= 1e-290 && n2 <= 1e290);   // false for NaN / inf as well
+    if (!ok && lane == 0) atomicOr(flags, PF_FLAG_FALLBACK);
+    const double inv = (ok && n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+    if (norm_out && lane == 0) norm_out[r] = ok ? sqrt(n2) : 0.0;
+    const double *src = rows + r * (long long)f;
+    for (int j = 2 * lane; j < fp; j += 64) {   // two features per lane: 4-byte stores
+        float v[2];
+        __nv_bfloat16 h[2], l[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            v[u] = (ok && j + u < f) ? (float)(src[j + u] * inv) : 0.0f;
+            h[u] = __float2bfloat16_rn(v[u]);
+            l[u] = __float2bfloat16_rn(v[u] - __bfloat162float(h[u]));
+        }
+        *reinterpret_cast<__nv_bfloat162 *>(hi + r * (long long)fp + j) = __nv_bfloat162(h[0], h[1]);
+        *reinterpret_cast<__nv_bfloat162 *>(lo + r * (long long)fp + j) = __nv_bfloat162(l[0], l[1]);
+    }
+}
+
 struct UmMaps {
     CUtensorMap qhi, qlo, xhi, xlo;
 };
@@ -151,8 +191,10 @@ struct UmMaps {
 // every item box is fetched from L2 ONCE per cluster and multicast into all CL shared memories -- rank c fetches piece c
 // of the 2 planes x 256 rows (CL = 2: one plane each; CL = 4: half a plane each).  A stage may only be refilled when
 // every CTA of the cluster has multiplied it: the MMA threads commit their "stage free" signal to all CL empty barriers.
-template <int MODE, int UM_KC, int CL>
+// BF: BF16x3 planes (kind::f16, K = 16 per instruction): a stage row of 4 UM_KC bytes then holds 2 UM_KC features.
+template <int MODE, int UM_KC, int CL, bool BF>
 __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid_constant__ UmMaps maps, PfArgs A) {
+    constexpr int FPC = BF ? 2 * UM_KC : UM_KC;   // features per pipeline stage
     constexpr int UM_A_BYTES = UmCfg<UM_KC>::A_BYTES, UM_B_BYTES = UmCfg<UM_KC>::B_BYTES;
     constexpr int UM_STAGE_BYTES = UmCfg<UM_KC>::STAGE_BYTES, UM_STAGES = UmCfg<UM_KC>::STAGES;
     extern __shared__ __align__(1024) unsigned char um_smem[];
@@ -173,7 +215,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     long long t_end = t_begin + A.tiles_per_slab;
     if (t_end > ntiles_total) t_end = ntiles_total;
     const int ntile = (int)(t_end > t_begin ? t_end - t_begin : 0);
-    const int nchunks = fp / UM_KC;
+    const int nchunks = fp / FPC;
     if (ntile == 0) return;
 
     const unsigned crank = CL > 1 ? um_cluster_ctarank() : 0u;
@@ -210,17 +252,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     if (it >= UM_STAGES) um_mbar_wait(&bars.empty[s], ((it / UM_STAGES) - 1) & 1);
                     unsigned char *st = stages + (size_t)s * UM_STAGE_BYTES;
                     um_mbar_expect_tx(&bars.full[s], UM_STAGE_BYTES);
-                    um_tma_2d(st, &maps.qhi, c * UM_KC, (int)q0, &bars.full[s]);
-                    um_tma_2d(st + UM_A_BYTES, &maps.qlo, c * UM_KC, (int)q0, &bars.full[s]);
+                    um_tma_2d(st, &maps.qhi, c * FPC, (int)q0, &bars.full[s]);
+                    um_tma_2d(st + UM_A_BYTES, &maps.qlo, c * FPC, (int)q0, &bars.full[s]);
                     if constexpr (CL == 1) {
-                        um_tma_2d(st + 2 * UM_A_BYTES, &maps.xhi, c * UM_KC, row_x, &bars.full[s]);
-                        um_tma_2d(st + 2 * UM_A_BYTES + UM_B_BYTES, &maps.xlo, c * UM_KC, row_x, &bars.full[s]);
+                        um_tma_2d(st + 2 * UM_A_BYTES, &maps.xhi, c * FPC, row_x, &bars.full[s]);
+                        um_tma_2d(st + 2 * UM_A_BYTES + UM_B_BYTES, &maps.xlo, c * FPC, row_x, &bars.full[s]);
                     } else if constexpr (CL == 2) {   // rank 0: the hi plane, rank 1: the lo plane
-                        um_tma_2d_mc(st + 2 * UM_A_BYTES + crank * UM_B_BYTES, crank == 0 ? &maps.xhi : &maps.xlo, c * UM_KC,
+                        um_tma_2d_mc(st + 2 * UM_A_BYTES + crank * UM_B_BYTES, crank == 0 ? &maps.xhi : &maps.xlo, c * FPC,
                                      row_x, &bars.full[s], kAllCtas);
                     } else {                          // rank 0 / 1: halves of the hi plane, rank 2 / 3: of the lo plane
                         um_tma_2d_mc(st + 2 * UM_A_BYTES + (crank >> 1) * UM_B_BYTES + (crank & 1) * (UM_B_BYTES / 2),
-                                     (crank >> 1) == 0 ? &maps.xhi : &maps.xlo, c * UM_KC, row_x + (int)(crank & 1) * (UM_TN / 2),
+                                     (crank >> 1) == 0 ? &maps.xhi : &maps.xlo, c * FPC, row_x + (int)(crank & 1) * (UM_TN / 2),
                                      &bars.full[s], kAllCtas);
                     }
                 }
@@ -230,7 +272,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         // ---- MMA issuer: D[128 x 256] (+)= A[128 x 8] B[256 x 8]^T, three instructions per K-step
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(UM_TN >> 3) << 17) | ((unsigned)(UM_TQ >> 4) << 24);
+            // (formats: TF32 = 2 with kind::tf32, BF16 = 1 with kind::f16)
+            const unsigned fmt = BF ? 1u : 2u;
+            const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(UM_TN >> 3) << 17) | ((unsigned)(UM_TQ >> 4) << 24);
             int it = 0;
             for (int t = 0; t < ntile; ++t) {
                 const int b = t & 1;
@@ -247,9 +291,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                         const unsigned long long dah = um_desc<UM_KC>(sa + 32 * j), dal = um_desc<UM_KC>(sa + UM_A_BYTES + 32 * j);
                         const unsigned long long dbh = um_desc<UM_KC>(sa + 2 * UM_A_BYTES + 32 * j);
                         const unsigned long long dbl = um_desc<UM_KC>(sa + 2 * UM_A_BYTES + UM_B_BYTES + 32 * j);
-                        um_mma_tf32(tmem_c, dah, dbl, idesc, (c | j) ? 1u : 0u);
-                        um_mma_tf32(tmem_c, dal, dbh, idesc, 1u);
-                        um_mma_tf32(tmem_c, dah, dbh, idesc, 1u);
+                        if constexpr (BF) {
+                            um_mma_bf16(tmem_c, dah, dbl, idesc, (c | j) ? 1u : 0u);
+                            um_mma_bf16(tmem_c, dal, dbh, idesc, 1u);
+                            um_mma_bf16(tmem_c, dah, dbh, idesc, 1u);
+                        } else {
+                            um_mma_tf32(tmem_c, dah, dbl, idesc, (c | j) ? 1u : 0u);
+                            um_mma_tf32(tmem_c, dal, dbh, idesc, 1u);
+                            um_mma_tf32(tmem_c, dah, dbh, idesc, 1u);
+                        }
                     }
                     // the stage is free once these instructions have read it -- in every CTA that feeds it
                     if constexpr (CL == 1) um_commit(&bars.empty[s]);
@@ -484,14 +534,16 @@ um_encode_fn um_encoder() {
 }
 
 // rows x fp fp32 plane, boxes of kc features x box_rows rows, swizzle span = box row, out-of-range rows read as zeros
-bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, int box_rows, int kc) {
+// (bf: the plane holds BF16 values, a box row of 4 kc bytes = 2 kc features)
+bool um_make_map(CUtensorMap *map, const float *plane, long long rows, int fp, int box_rows, int kc, bool bf) {
     um_encode_fn enc = um_encoder();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)fp, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)fp * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)fp * (bf ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(bf ? 2 * kc : kc), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims, strides, box, estr,
+    return enc(map, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims,
+               strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -502,10 +554,25 @@ bool um_wanted(asb_ctx *ctx) {
     auto it = ctx->options.find("search_umma");
     return it == ctx->options.end() || it->second != 0.0;
 }
-// option "search_umma_kc": features per pipeline stage, 16 (default) or 32
+// option "search_umma_bf16" (default 1): BF16x3 planes on kind::f16 instead of 3xTF32 (0)
+bool um_bf16(asb_ctx *ctx) {
+    auto it = ctx->options.find("search_umma_bf16");
+    return it == ctx->options.end() || it->second != 0.0;
+}
+// option "search_umma_kc": 32-bit words per stage row, 16 (default: 64-byte rows) or 32 (TF32 planes only)
 int um_kc(asb_ctx *ctx) {
     auto it = ctx->options.find("search_umma_kc");
-    return (it != ctx->options.end() && it->second == 32.0) ? 32 : 16;
+    return (it != ctx->options.end() && it->second == 32.0 && !um_bf16(ctx)) ? 32 : 16;
+}
+// the cosine error bound of the tile (search_pf.cuh, "E_cos"): FP32 rounding of the unit rows, the split's residual and
+// dropped lo * lo term, and the accumulation chain -- 3 fp / K instructions into one FP32 accumulator, each within
+// (K + 1) 2^-23 of exact (K products and the accumulator through truncating aligned adders: measured by
+// tools/umma_probe.cu for both operand types) -- times 1.1.  The BF16 bound is never below the TF32 one.
+double um_e_cos(int fp, bool bf) {
+    const double u23 = 1.1920928955078125e-7;
+    const double tf = 2.0 * u23 + 3.0 * 9.5367431640625e-7 + (9.0 * (3.0 * fp / 8.0) + 16.0) * u23;
+    const double b16 = 2.0 * u23 + 3.0 * 3.814697265625e-6 + (17.0 * (3.0 * fp / 16.0) + 16.0) * u23;
+    return 1.1 * (bf ? (b16 > tf ? b16 : tf) : tf);
 }
 
 // option "search_umma_cluster": CTAs that share one multicast item stream, 1, 2 (default) or 4
@@ -520,9 +587,10 @@ int um_cluster(asb_ctx *ctx, long long nq) {
 bool um_make_maps(asb_ctx *ctx, UmMaps *maps, const float *qhi, const float *qlo, long long nq, const float *xhi,
                   const float *xlo, long long n, int fp) {
     const int kc = um_kc(ctx);
+    const bool bf = um_bf16(ctx);
     const int xbox = um_cluster(ctx, nq) == 4 ? UM_TN / 2 : UM_TN;   // rows per item box (a CTA of 4 fetches half a plane)
-    return um_make_map(&maps->qhi, qhi, nq, fp, UM_TQ, kc) && um_make_map(&maps->qlo, qlo, nq, fp, UM_TQ, kc) &&
-           um_make_map(&maps->xhi, xhi, n, fp, xbox, kc) && um_make_map(&maps->xlo, xlo, n, fp, xbox, kc);
+    return um_make_map(&maps->qhi, qhi, nq, fp, UM_TQ, kc, bf) && um_make_map(&maps->qlo, qlo, nq, fp, UM_TQ, kc, bf) &&
+           um_make_map(&maps->xhi, xhi, n, fp, xbox, kc, bf) && um_make_map(&maps->xlo, xlo, n, fp, xbox, kc, bf);
 }
 
 // Slabs of the tcgen05 tile: the CTAs of one slab (all query tiles) stream the same item tiles but start at different
@@ -561,9 +629,9 @@ void um_pick_slabs(asb_ctx *ctx, long long qtiles, long long ntiles, int fp, int
     *tps = best_tps;
 }
 
-template <int MODE, int KC, int CL>
+template <int MODE, int KC, int CL, bool BF>
 int um_launch_one(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, size_t usmem) {
-    ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<MODE, KC, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+    ASB_CUDA(ctx, cudaFuncSetAttribute(search_umma_kernel<MODE, KC, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
     const unsigned qtiles = (unsigned)((A.nq + UM_TQ - 1) / UM_TQ);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((qtiles + CL - 1) / CL * CL, (unsigned)nslabs);   // a padding CTA sees no query in range
@@ -577,7 +645,7 @@ int um_launch_one(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs,
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ASB_CUDA(ctx, cudaLaunchKernelEx(&cfg, search_umma_kernel<MODE, KC, CL>, maps, A));
+    ASB_CUDA(ctx, cudaLaunchKernelEx(&cfg, search_umma_kernel<MODE, KC, CL, BF>, maps, A));
     return ASB_OK;
 }
 
@@ -587,7 +655,14 @@ int um_launch(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, con
     const int kc = um_kc(ctx), cl = um_cluster(ctx, A.nq);
     ctx->kernel_ms["search_umma_cluster"] = (double)cl;
     KernelTimer kt(ctx, timer);
-#define ASB_UM_GO(KC, CL) return um_launch_one<MODE, KC, CL>(ctx, maps, A, nslabs, usmem)
+#define ASB_UM_GO(KC, CL) return um_launch_one<MODE, KC, CL, false>(ctx, maps, A, nslabs, usmem)
+    if (um_bf16(ctx)) {
+        ctx->kernel_ms["search_umma_bf16"] = 1.0;
+        if (cl == 4) return um_launch_one<MODE, 16, 4, true>(ctx, maps, A, nslabs, usmem);
+        if (cl == 2) return um_launch_one<MODE, 16, 2, true>(ctx, maps, A, nslabs, usmem);
+        return um_launch_one<MODE, 16, 1, true>(ctx, maps, A, nslabs, usmem);
+    }
+    ctx->kernel_ms["search_umma_bf16"] = 0.0;
     if (kc == 32) {
         if (cl == 4) ASB_UM_GO(32, 4);
         if (cl == 2) ASB_UM_GO(32, 2);

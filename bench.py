@@ -73,6 +73,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bf16_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["bf16_tflops"]), ("dense bf16 measured on this pool (MEASURED_PEAKS.json: %.0f TFLOP/s burst, %.0f sustained)"
+                                         % (d["bf16_tflops"], d.get("bf16_tflops_sustained", float("nan"))))
+    return 2250.0, "fallback: nominal dense bf16 (B200_PROFILING.md)"
+
+
 def umma_tf32_peak():
     p = ROOT / "profiles" / "r02_umma_tf32_peak.json"
     if p.exists():
@@ -573,7 +582,12 @@ def run_b200(args):
         fl = 2.0 * nq * n * f
         ach = fl / (kms["search_pf_kernel"] * 1e-3) / 1e12
         umma = ctx.kernel_ms("search_pf_umma") == 1.0
-        if umma:
+        bf16 = umma and ctx.kernel_ms("search_umma_bf16") == 1.0
+        if bf16:
+            # BF16x3 planes on tcgen05.mma kind::f16 (csrc/search_umma.cuh): peak = the dense bf16 throughput the driver
+            # measured on this pool (MEASURED_PEAKS.json, cuBLAS 8192^3: the burst figure -- the kernel is timed alone)
+            tf32_peak, peak_src_pf = bf16_peak()
+        elif umma:
             # the tile runs on tcgen05.mma kind::tf32 (csrc/search_umma.cuh); peak = the tcgen05 TF32 issue rate measured
             # on this pool by tools/umma_peak.cu (M128 N256 K8 at 128 cycles per instruction on every SM)
             tf32_peak, peak_src_pf = umma_tf32_peak()
@@ -584,10 +598,11 @@ def run_b200(args):
         kernels["search_pf_kernel"] = {"bound": "tensor", "achieved": 3.0 * ach, "peak": tf32_peak, "unit": "TFLOP/s",
                                        "frac": 3.0 * ach / tf32_peak, "ms": kms["search_pf_kernel"], "traffic": None,
                                        "algorithmic_tflops": ach, "algorithmic_frac": ach / tf32_peak,
-                                       "peak_source": peak_src_pf + "; `achieved` counts the 3 TF32 MMAs the kernel executes per "
-                                                      "algorithmic product (3xTF32: hi*lo + lo*hi + hi*hi), algorithmic_tflops "
-                                                      "= 2 Q N F / time",
-                                       "tile": "tcgen05.mma kind::tf32 + TMA + TMEM" if umma else "mma.sync + cp.async",
+                                       "peak_source": peak_src_pf + "; `achieved` counts the 3 MMAs the kernel executes per "
+                                                      "algorithmic product (split operands: hi*lo + lo*hi + hi*hi), "
+                                                      "algorithmic_tflops = 2 Q N F / time",
+                                       "tile": ("tcgen05.mma kind::f16 (BF16x3) + TMA + TMEM" if bf16 else
+                                                "tcgen05.mma kind::tf32 (3xTF32) + TMA + TMEM" if umma else "mma.sync + cp.async"),
                                        "vs_fp64_dmma_peak": ach / dmma_peak,
                                        "prep_ms": kms["search_pf_prep"], "finish_ms": kms["search_pf_finish"],
                                        "candidates_per_query": pf_diag.get("search_pf_candidates", 0.0) / max(nq, 1),

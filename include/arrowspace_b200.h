@@ -157,6 +157,7 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 again by the FP64 kernel); 0: always the FP64 kernel's exact top-2.
  *   "cluster_replay_tf32" (0|1)   the exact top-2 through the certified prefilter + direct-form distances (slower than
  *                                 either of the above; kept for cross-checks).
+ *   "search_umma_bf16" (1|0)      operand planes of the tcgen05 tile: BF16x3 on kind::f16 (default) or 3xTF32 on kind::tf32;
  *   "search_umma" (1|0), "search_umma_kc" (16|32), "search_umma_cluster" (2|1|4), "search_umma_slab_mb" (48)
  *                                 the prefilter tile: tcgen05.mma + TMA + TMEM (1) or mma.sync + cp.async (0); features per
  *                                 pipeline stage; CTAs sharing one multicast item stream; bytes of item planes per slab.

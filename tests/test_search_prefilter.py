@@ -15,17 +15,20 @@ from oracle_binding import TAU_MEDIAN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["tcgen05", "mma_sync"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["tcgen05_bf16x3", "tcgen05_3xtf32", "mma_sync"])
 def pctx(ctx, request):
-    """Both instantiations of the prefilter tile: search_umma = 1 (default: tcgen05.mma + TMA + TMEM, csrc/search_umma.cuh)
-    and 0 (mma.sync + cp.async, csrc/search_pf.cuh) -- same certificate, same candidate lists, same finishing kernel."""
+    """The instantiations of the prefilter tile: search_umma = 1 (default: tcgen05.mma + TMA + TMEM, csrc/search_umma.cuh)
+    with BF16x3 planes on kind::f16 (default) or 3xTF32 planes on kind::tf32, and search_umma = 0 (mma.sync + cp.async,
+    csrc/search_pf.cuh) -- same certificate, same candidate lists, same finishing kernel."""
     ctx.set_option("search_prefilter", 1)
-    ctx.set_option("search_umma", request.param)
+    ctx.set_option("search_umma", request.param[0])
+    ctx.set_option("search_umma_bf16", request.param[1])
     try:
         yield ctx
     finally:
         ctx.set_option("search_prefilter", 1)
         ctx.set_option("search_umma", 1)
+        ctx.set_option("search_umma_bf16", 1)
 
 
 def _case(asb, oracle, n, f, nq, seed=42):

@@ -6,6 +6,7 @@ Rows have the bench data's shape (drawn on the GPU), max_clusters / radius come 
 time of both paths (CUDA events around the C-ABI call), how many chunks were proven, and whether centroids,
 assignments and sizes are identical.  A timing / agreement probe; tests/test_cluster_replay.py is the parity test."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -38,6 +39,10 @@ def main():
         ctx.set_option("cluster_replay_tf32", tf32 if opt else 0)   # nearest / runner-up pass on the certified TF32 ranking
         ctx.set_option("cluster_replay_prefix", prefix)
         ctx.set_option("cluster_replay_chunk", chunk)
+        if opt:
+            for kv in filter(None, os.environ.get("ASB_OPTS", "").split(",")):   # e.g. ASB_OPTS=cluster_first_variant=0
+                key, val = kv.split("=")
+                ctx.set_option(key, float(val))
         for _ in range(2):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,7 +56,8 @@ def main():
                      "rows_replayed": ctx.kernel_ms("cluster_replay_rows"),
                      "sequential_ms": ctx.kernel_ms("cluster_replay_seq_ms") if opt else ctx.kernel_ms("cluster_kernel"),
                      "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
-                     "near_retries": ctx.kernel_ms("cluster_replay_near_retries"), "growth_rows": ctx.kernel_ms("cluster_growth_rows")}
+                     "near_retries": ctx.kernel_ms("cluster_replay_near_retries"), "growth_rows": ctx.kernel_ms("cluster_growth_rows"),
+                     "wall_ms": {k: round(ctx.kernel_ms("cluster_wall_%s_ms" % k), 3) for k in ("growth", "prefix", "prepare", "run", "fallback")}}
     s, r = res["sequential"], res["replay"]
     out["centroids_bit_identical"] = bool(s[0].shape == r[0].shape and np.array_equal(
         np.ascontiguousarray(s[0]).view(np.uint64), np.ascontiguousarray(r[0]).view(np.uint64)))
