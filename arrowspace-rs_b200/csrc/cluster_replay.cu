@@ -372,6 +372,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
         return t;
     };
 
+    unsigned n_exact = 0;
     auto step = [&](const double(&X)[NPW], const SegMeta &mt) {
         const double hi = mt.dhi + B, lo = mt.dlo - B;
         const double hi2 = hi * hi;
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
 #pragma unroll
             for (int u = 0; u < NPW; ++u) p = fma(a[u], a[u], p);
             const double d2 = block_sum(p, false);   // ~1e-15 relative, NOT the reference's summation order: guard band
+            ++n_exact;
             if (!(d2 == d2) || fabs(d2 - radius) <= guard || fabs(d2 - 1.5 * radius) <= guard ||
                 (!saturated && fabs(d2 - 0.5 * radius) <= guard))
                 bad = true;
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     };
 
     int done = 0;   // rows applied
+    unsigned n_grouped = 0, n_byrow = 0, n_ckpt = 0;   // diagnostics (thread 0 publishes them)
     for (int g = 0; g < ngroups; ++g) {
         const int slot = g % NS;
         rp_mbar_wait(&sh.full[slot], (g / NS) & 1);
@@ -493,6 +496,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                     if (!(nb == nb) || !(nb <= 1e300)) bad = true;
                     else B = fmin(B, nb);
                     since = 0;
+                    ++n_ckpt;
                 }
                 const double uinc = (gd.hmax + B) * gd.yk[0] * 1.01;
                 const double Bend = fma((double)RG, uinc, B);
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                     }
                     if (!__any_sync(0xffffffffu, slow)) {
                         grouped = true;
+                        n_grouped += RG;
                         kd += (double)RG;
                         y_next = gd.yk[RG];
                         B = Bend;
@@ -544,6 +549,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                     for (int u = 0; u < NPW; ++u) X[u] = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + 128 * u] : 0.0;
                     const SegMeta mt = mrow[t];
                     step(X, mt);
+                    ++n_byrow;
                     if (go) ++done;
                 }
             }
@@ -560,6 +566,10 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
         if (dm == dm) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(dm));
         else bad = true;
         if (bad || !go || done < end - beg) atomicOr(fail, 1);
+        atomicAdd(maxdisp_bits + 1, (unsigned long long)n_grouped);
+        atomicAdd(maxdisp_bits + 2, (unsigned long long)n_byrow);
+        atomicAdd(maxdisp_bits + 3, (unsigned long long)n_exact);
+        atomicAdd(maxdisp_bits + 4, (unsigned long long)n_ckpt);
     }
 }
 
@@ -752,7 +762,7 @@ int replay_ws_init(asb_ctx *ctx, ReplayWs &w, int m, int K, int f) {
     ASB_TRY(w.near_b.init(ctx, (size_t)3 * m));
     ASB_TRY(w.flags.init(ctx, 2));
     ASB_TRY(w.sizes_tmp.init(ctx, (size_t)K));
-    ASB_TRY(w.scal.init(ctx, 2));
+    ASB_TRY(w.scal.init(ctx, 6));   // + [2..5]: chain diagnostics (rows by group / by row, exact steps, checkpoints)
     ASB_CUDA(ctx, cudaMemsetAsync(w.minus1.ptr, 0xff, (size_t)m * sizeof(int64_t), ctx->stream));
     w.cub_bytes = 0;
     ASB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.keys.ptr, w.keys_s.ptr, w.vals.ptr, w.vals_s.ptr, m,
@@ -767,7 +777,7 @@ int replay_prepare(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f
                    bool allow_near = true) {
     asb_wait_rows(ctx, rows_d + (size_t)m * f);
     ASB_CUDA(ctx, cudaMemsetAsync(w.flags.ptr, 0, 2 * sizeof(int), ctx->stream));
-    ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(w.scal.ptr, 0, 6 * sizeof(unsigned long long), ctx->stream));
     ASB_TRY(asb_dev_norms2(ctx, rows_d, m, f, w.qn2.ptr));
     ASB_TRY(asb_dev_norms2(ctx, snap_d, K, f, w.xn2.ptr));
     replay_max_kernel<<<1, 256, 0, ctx->stream>>>(w.xn2.ptr, K, w.scal.ptr);
@@ -865,10 +875,15 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
                                                                     w.use_near ? w.near_b.ptr : nullptr, w.flags.ptr);
     ASB_TRY(asb_check_launch(ctx, "replay_certify_kernel"));
     int hflags[2] = {0, 0};
-    unsigned long long hdisp = 0;
+    unsigned long long hsc[5] = {0, 0, 0, 0, 0};
     ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
-    ASB_CUDA(ctx, cudaMemcpyAsync(&hdisp, w.scal.ptr + 1, sizeof(hdisp), cudaMemcpyDeviceToHost, ctx->stream));
+    ASB_CUDA(ctx, cudaMemcpyAsync(hsc, w.scal.ptr + 1, sizeof(hsc), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long hdisp = hsc[0];
+    ctx->kernel_ms["cluster_chain_rows_grouped"] += (double)hsc[1];   // (reset by asb_dev_cluster / the sharded entry)
+    ctx->kernel_ms["cluster_chain_rows_by_row"] += (double)hsc[2];
+    ctx->kernel_ms["cluster_chain_exact_steps"] += (double)hsc[3];
+    ctx->kernel_ms["cluster_chain_checkpoints"] += (double)hsc[4];
     w.last_flags = hflags[0] | (hflags[1] << 8);
     if (hflags[0] != 0 || hflags[1] != 0) {
         w.last_disp = INFINITY;   // the next attempt follows a sequential stretch: no estimate
@@ -924,6 +939,9 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     if (chunk_max < chunk) chunk_max = chunk;
     const bool replay = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
                         n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
+    for (const char *key : {"cluster_chain_rows_grouped", "cluster_chain_rows_by_row", "cluster_chain_exact_steps",
+                            "cluster_chain_checkpoints"})
+        ctx->kernel_ms[key] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;
     ctx->kernel_ms["cluster_replay_rows"] = 0.0;
