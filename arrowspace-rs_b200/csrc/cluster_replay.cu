@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <vector>
 
 #include "comm.cuh"
 
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
 //     huge or not finite; the reciprocal of the next count is computed while the current update is in flight.
 // The certification kernel receives an UPPER BOUND of the row's distance to its centroid at the row's own time
 // (dhi + B, or the exact value from the exact step).
-constexpr int kChainWarps = 4;    // consumer warps; warp kChainWarps is the producer
+constexpr int kChainWarpsMax = 16;   // consumer warps CW (template); warps CW .. CW + kChainProducers - 1 are producers
+constexpr int kChainProducers = 2;
 constexpr int kRingSlots = 8;   // at most
 
 struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
@@ -193,7 +195,7 @@ struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
 };
 
 struct ChainShared {
-    double part[2][kChainWarps];
+    double part[2][kChainWarpsMax];
     int stop[2];
     int drops;                    // rows the consumers classified "dropped" so far (the producer's count prediction)
     unsigned long long full[kRingSlots], empty[kRingSlots];
@@ -210,14 +212,43 @@ struct __align__(16) GroupDesc {
     double pad;
 };
 
-// ring depth: about 100 kB of rows in flight per chain (two chains per SM; bulk copies from DRAM take ~2 us, a row ~0.1)
-__host__ __device__ constexpr int chain_ring_slots(int npw, int rg) {
-    return 96 / (npw * rg) < 2 ? 2 : (96 / (npw * rg) > kRingSlots ? kRingSlots : 96 / (npw * rg));
+// ring depth: the chain kernel is bound by the round trip of its ring (consumer frees a slot -> producer wakes, issues the
+// bulk copies -> rows arrive from DRAM -> consumer wakes: ~4 us measured -- 16 rows in flight gave 241 ns per row, 24 gave
+// 180, 32 gave 130), so the ring takes what one CTA per SM can have: up to 192 kB of rows, at most kRingSlots slots;
+// row128 = the ring pitch of a row in units of 128 features (1 kB)
+__host__ __device__ constexpr int chain_ring_slots(int row128, int rg) {
+    return 192 / (row128 * rg) < 2 ? 2 : (192 / (row128 * rg) > kRingSlots ? kRingSlots : 192 / (row128 * rg));
 }
 __device__ __forceinline__ int chain_interval(double kd) {
     // steps between two exact values of the displacement bound: 1 while the count is small, then count / 256 (the
     // bound may grow by about 0.4 % of the row distance in between), at most 64
     return kd < 512.0 ? 1 : (kd < 16384.0 ? (int)(kd * (1.0 / 256.0)) : 64);
+}
+
+// FP64 operations the compiler may not reorder among themselves: the chain kernel issues the element chains of a row
+// LAYER BY LAYER (sub for every element, then mul for every element, ...) so that a warp always has NPW independent
+// instructions between two dependent ones (8 cycles of FP64 latency: profiles/r02_dp_latency.json).  Left to its own
+// scheduler ptxas emitted the rows of a group element after element -- one fully dependent chain of 7 operations after
+// the other, ~150 cycles per row instead of ~60 (profiles/r02_chain6_hotspots.txt).
+__device__ __forceinline__ double rp_vsub(double a, double b) {
+    double r;
+    asm volatile("sub.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double rp_vadd(double a, double b) {
+    double r;
+    asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double rp_vmul(double a, double b) {
+    double r;
+    asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double rp_vfma(double a, double b, double c) {
+    double r;
+    asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+    return r;
 }
 
 __device__ __forceinline__ unsigned rp_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -248,20 +279,30 @@ __device__ __forceinline__ void rp_bulk_g2s(void *dst, const void *src, unsigned
                  : "memory");
 }
 
+__device__ __forceinline__ void rp_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // shared memory: ring[kRingSlots][RG][fpad] doubles, then meta[kRingSlots][RG]; fpad = 128 NPW
-template <int NPW, int RG>
-__global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kernel(
+// CW consumer warps, NPW elements per lane: element u of a lane = feature 32 CW u + 32 warp + lane.  ONE element per lane
+// wherever the row allows it (f <= 512): the update of an element is a chain of 7 dependent FP64 operations (8 cycles
+// each, profiles/r02_dp_latency.json), and ptxas emits the chains of a lane's elements one AFTER the other rather than
+// interleaved (profiles/r02_chain6_hotspots.txt: ~150 cycles per row at 3 elements per lane) -- with one element per lane
+// the hardware interleaves the warps instead and a row costs its own latency.
+template <int CW, int NPW, int RG>
+__global__ void __launch_bounds__((CW + kChainProducers) * 32, 1) replay_chain_tma_kernel(
     const double *__restrict__ rows, int f, const int *__restrict__ seg_off, const int *__restrict__ order,
     const SegMeta *__restrict__ seg_meta, int K,
     int saturated, double radius, double disp_hint, double *__restrict__ cent, const double *__restrict__ cent0,
     const double *__restrict__ disp0, unsigned long long *sizes, long long *__restrict__ assign, double *__restrict__ dub,
-    unsigned long long *maxdisp_bits, int *fail) {
+    unsigned long long *maxdisp_bits, int *fail, unsigned long long *probe) {
+    // probe (or null): per block {centroid, rows, start ns, end ns} (option cluster_chain_probe)
     // cent: the state the chains start from (in) and leave behind (out); cent0: the snapshot the rows were ranked
     // against; disp0 (or null when the two coincide): |cent - cent0| per centroid on entry
     extern __shared__ __align__(128) unsigned char rp_smem[];
     __shared__ ChainShared sh;
-    constexpr int FP = 128 * NPW;
-    constexpr int NS = chain_ring_slots(NPW, RG);
+    constexpr int FP = 32 * CW * NPW;
+    constexpr int NS = chain_ring_slots((FP + 127) / 128, RG);
     static_assert(NS <= kRingSlots && RG <= 8 && RG >= 2, "ring geometry");
     double *ring = reinterpret_cast<double *>(rp_smem);
     SegMeta *metas = reinterpret_cast<SegMeta *>(rp_smem + (size_t)NS * RG * FP * sizeof(double));
@@ -271,17 +312,19 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     const int beg = seg_off[c], end = seg_off[c + 1];
     if (beg == end) return;
     const int ngroups = (end - beg + RG - 1) / RG;
+    unsigned long long t_start = 0;
+    if (probe && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
             rp_mbar_init(&sh.full[s], 1);
-            rp_mbar_init(&sh.empty[s], kChainWarps);
+            rp_mbar_init(&sh.empty[s], CW);
         }
         sh.drops = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == kChainWarps) {
+    if (warp >= CW) {
         // ---- producer: one slot = RG rows + their metadata + the group descriptor.  The count a group starts from is
         // predictable: every row of the chain adds one unless it is dropped (rare; the consumers publish their tally,
         // a descriptor built from a stale tally is recognised by its kd_pred and ignored)
@@ -289,62 +332,75 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
         // the metadata of 32 rows (32 / RG groups) per coalesced load, one batch ahead of the groups being issued: the
         // producer's own global-memory latency stays off the ring's critical path
         constexpr int GPB = 32 / RG;   // groups per batch
+        // kChainProducers producer warps take the batches in turn: one warp could not issue a group's descriptor and bulk
+        // copies in the time the consumers need for it (probe: the longest chain paid 138 ns per row whatever the ring
+        // depth or the consumers' instruction count)
+        const int pw = warp - CW;
+        const int nbatches = (ngroups + GPB - 1) / GPB;
         SegMeta cur, nxt;
         cur.dlo = cur.dhi = cur.slo = 0.0;
         cur.row = cur.pad = 0;
         nxt = cur;
-        if (beg + lane < end) cur = seg_meta[beg + lane];
-        for (int g = 0; g < ngroups; ++g) {
-            const int gi = g % GPB;
-            if (gi == 0) {
-                if (g > 0) cur = nxt;
-                const int np = beg + (g + GPB) * RG + lane;
-                if (np < end) nxt = seg_meta[np];
+        if (beg + pw * 32 + lane < end) nxt = seg_meta[beg + pw * 32 + lane];
+        for (int bt = pw; bt < nbatches; bt += kChainProducers) {
+            cur = nxt;
+            {
+                const int np = beg + (bt + kChainProducers) * 32 + lane;
+                if (np < end) {
+                    nxt = seg_meta[np];
+                    rp_prefetch_l2(rows + (size_t)nxt.row * f, (unsigned)(f * 8));   // the ring's copies then hit L2
+                }
             }
-            const int slot = g % NS;
-            if (g >= NS) rp_mbar_wait(&sh.empty[slot], ((g / NS) - 1) & 1);
-            const int pos = beg + g * RG;
-            const int nr = end - pos < RG ? end - pos : RG;
-            const int drops = atomicAdd(&sh.drops, 0);   // (an atomic read: the tally may be stale, never torn)
-            const double kdp = kd0 + (double)(g * RG - drops);
-            const int src = gi * RG + (lane < RG ? lane : 0);
-            const int r = __shfl_sync(0xffffffffu, cur.row, src);
-            double dh = __shfl_sync(0xffffffffu, cur.dhi, src);
-            double sl = __shfl_sync(0xffffffffu, cur.slo, src) - dh;
-            if (lane >= nr) {
-                dh = -INFINITY;
-                sl = INFINITY;
-            }
+#pragma unroll 1
+            for (int gi = 0; gi < GPB; ++gi) {
+                const int g = bt * GPB + gi;
+                if (g >= ngroups) break;
+                const int slot = g % NS;
+                if (g >= NS) rp_mbar_wait(&sh.empty[slot], ((g / NS) - 1) & 1);
+                const int pos = beg + g * RG;
+                const int nr = end - pos < RG ? end - pos : RG;
+                const int drops = atomicAdd(&sh.drops, 0);   // (an atomic read: the tally may be stale, never torn)
+                const double kdp = kd0 + (double)(g * RG - drops);
+                const int src = gi * RG + (lane < RG ? lane : 0);
+                const int r = __shfl_sync(0xffffffffu, cur.row, src);
+                double dh = __shfl_sync(0xffffffffu, cur.dhi, src);
+                double sl = __shfl_sync(0xffffffffu, cur.slo, src) - dh;
+                if (lane >= nr) {
+                    dh = -INFINITY;
+                    sl = INFINITY;
+                }
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {   // RG <= 8
-                dh = fmax(dh, __shfl_xor_sync(0xffffffffu, dh, o));
-                sl = fmin(sl, __shfl_xor_sync(0xffffffffu, sl, o));
+                for (int o = 4; o > 0; o >>= 1) {   // RG <= 8
+                    dh = fmax(dh, __shfl_xor_sync(0xffffffffu, dh, o));
+                    sl = fmin(sl, __shfl_xor_sync(0xffffffffu, sl, o));
+                }
+                if (lane <= RG) descs[slot].yk[lane] = __drcp_rn(kdp + (double)(lane + 1));
+                if (lane == 0) {
+                    descs[slot].hmax = dh;
+                    descs[slot].minslack = sl;
+                    descs[slot].kd_pred = kdp;
+                }
+                __syncwarp();
+                if (lane == 0) rp_mbar_expect_tx(&sh.full[slot], (unsigned)(nr * (f * 8 + (int)sizeof(SegMeta))));   // (release)
+                __syncwarp();
+                if (lane < nr)
+                    rp_bulk_g2s(ring + ((size_t)slot * RG + lane) * FP, rows + (size_t)r * f, (unsigned)(f * 8), &sh.full[slot]);
+                if (lane == 0) rp_bulk_g2s(metas + slot * RG, seg_meta + pos, (unsigned)(nr * sizeof(SegMeta)), &sh.full[slot]);
             }
-            if (lane <= RG) descs[slot].yk[lane] = __drcp_rn(kdp + (double)(lane + 1));
-            if (lane == 0) {
-                descs[slot].hmax = dh;
-                descs[slot].minslack = sl;
-                descs[slot].kd_pred = kdp;
-            }
-            __syncwarp();
-            if (lane == 0) rp_mbar_expect_tx(&sh.full[slot], (unsigned)(nr * (f * 8 + (int)sizeof(SegMeta))));   // (release)
-            __syncwarp();
-            if (lane < nr)
-                rp_bulk_g2s(ring + ((size_t)slot * RG + lane) * FP, rows + (size_t)r * f, (unsigned)(f * 8), &sh.full[slot]);
-            if (lane == 0) rp_bulk_g2s(metas + slot * RG, seg_meta + pos, (unsigned)(nr * sizeof(SegMeta)), &sh.full[slot]);
         }
         return;
     }
 
-    // ---- consumers.  Element u of this lane = feature 128 u + 32 warp + lane
+    // ---- consumers.  Element u of this lane = feature 32 CW u + 32 warp + lane
+    constexpr int EP = 32 * CW;   // features per element index
     const int j0 = 32 * warp + lane;
-    const bool last_valid = 128 * (NPW - 1) + j0 < f;   // NPW = ceil(f / 128): only the last element can be padding
+    const bool last_valid = EP * (NPW - 1) + j0 < f;   // NPW = ceil(f / EP): only the last element can be padding
     double cr[NPW], s0[NPW];
 #pragma unroll
     for (int u = 0; u < NPW; ++u) {
         const bool v = u < NPW - 1 || last_valid;
-        s0[u] = v ? cent0[(size_t)c * f + 128 * u + j0] : 0.0;   // padding holds zeros everywhere: no effect
-        cr[u] = v ? cent[(size_t)c * f + 128 * u + j0] : 0.0;
+        s0[u] = v ? cent0[(size_t)c * f + EP * u + j0] : 0.0;   // padding holds zeros everywhere: no effect
+        cr[u] = v ? cent[(size_t)c * f + EP * u + j0] : 0.0;
     }
     double kd = (double)sizes[c];
     double y_next = __drcp_rn(kd + 1.0);
@@ -359,14 +415,17 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     const double thr_upd = (saturated ? radius : 0.5 * radius) * (1.0 - 1e-9);   // (dhi + B)^2 below: an update for sure
     const double thr_drop = 1.5 * radius * (1.0 + 1e-9);                         // (dlo - B)^2 above: dropped for sure
 
-    // all four warps reduce `v` to the same bits: butterfly inside the warp, fixed-order sum of the four partials
+    // all consumer warps reduce `v` to the same bits: butterfly inside the warp, fixed-order sum of the CW partials
     auto block_sum = [&](double v, bool want_stop) -> double {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) sh.part[par][warp] = v;
         if (want_stop && threadIdx.x == 0) sh.stop[par] = *(volatile int *)fail;
-        asm volatile("bar.sync 1, %0;" ::"n"(kChainWarps * 32) : "memory");
-        const double t = (sh.part[par][0] + sh.part[par][1]) + (sh.part[par][2] + sh.part[par][3]);
+        asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < CW; i += 4)   // the same fixed order in every warp
+            t += (sh.part[par][i] + sh.part[par][i + 1]) + (sh.part[par][i + 2] + sh.part[par][i + 3]);
         if (want_stop && sh.stop[par] != 0) go = false;   // the chunk is lost already: stop early
         par ^= 1;
         return t;
@@ -477,13 +536,13 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
             // from one product:  with u = 1.01 (hmax + B) / (k + 1)  every step t of the group keeps B_t <= B + t u
             // (induction: the increment (dhi_t + B_{t-1}) / (k + t) (1 + 1e-9) is at most
             // (hmax + B + (t - 1) u) / (k + 1) (1 + 1e-9) <= u (1 + 7 * 1.01 / 1024) (1 + 1e-9) / 1.01 < u  for
-            // k >= 1024, RG <= 8 -- `interval >= RG` implies k >= 256 RG), so the element chains c += (x - c) / k run back
+            // k >= 1024, RG <= 8), so the element chains c += (x - c) / k run back
             // to back: a row costs about its own dependent latency (sub, mul, 4 FMA, add).  The exponent-range test of
             // the division is voted on once per group; a hit restores the centroid and replays the slot row by row.
             bool grouped = false;
             const GroupDesc<RG> &gd = descs[slot];
             const int interval = chain_interval(kd);
-            if (nr == RG && interval >= RG && gd.kd_pred == kd) {
+            if (nr == RG && kd >= 64.0 && gd.kd_pred == kd) {
                 if (since + RG > interval) {   // B back to the exact displacement before the group, not in the middle
                     double p = 0.0;
 #pragma unroll
@@ -498,7 +557,10 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                     since = 0;
                     ++n_ckpt;
                 }
-                const double uinc = (gd.hmax + B) * gd.yk[0] * 1.01;
+                // (k >= 1024: factor 1.01 as derived above; 64 <= k < 1024: 1.15 >= (1 + 7 * 1.15 / 65) (1 + 1e-9).  Small
+                // counts get an exact B before every group -- `interval` < RG -- and the margin test below decides
+                // whether 8 steps of growth are affordable)
+                const double uinc = (gd.hmax + B) * gd.yk[0] * (kd >= 1024.0 ? 1.01 : 1.15);
                 const double Bend = fma((double)RG, uinc, B);
                 const double himax = gd.hmax + Bend;
                 if (himax * himax < thr_upd && Bend + disp_hint < gd.minslack) {
@@ -508,17 +570,31 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                     for (int u = 0; u < NPW; ++u) save[u] = cr[u];
 #pragma unroll
                     for (int t = 0; t < RG; ++t) {
-                        const double y = gd.yk[t], kk = kd + (double)(t + 1);
+                        const double y = gd.yk[t], nkk = -(kd + (double)(t + 1));
+                        double a[NPW], q[NPW], r[NPW];
+                        // (fma(q, -k, a) = fma(-q, k, a) bit for bit: the product is exact either way)
 #pragma unroll
                         for (int u = 0; u < NPW; ++u) {
-                            const double xv = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + 128 * u] : 0.0;
-                            const double a = __dsub_rn(xv, cr[u]);
-                            const unsigned h = (unsigned)__double2hiint(a) & 0x7fffffffu;
+                            const double xv = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + EP * u] : 0.0;
+                            a[u] = rp_vsub(xv, cr[u]);                      // clustering.rs:749
+                        }
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) q[u] = rp_vmul(a[u], y);
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) r[u] = rp_vfma(q[u], nkk, a[u]);
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) q[u] = rp_vfma(r[u], y, q[u]);
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) r[u] = rp_vfma(q[u], nkk, a[u]);
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) q[u] = rp_vfma(r[u], y, q[u]);
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) cr[u] = rp_vadd(cr[u], q[u]);   // :747-751
+#pragma unroll
+                        for (int u = 0; u < NPW; ++u) {
+                            const unsigned h = (unsigned)__double2hiint(a[u]) & 0x7fffffffu;
                             const bool out = h - 0x05d00000u > 0x74200000u;
                             slow |= (u < NPW - 1) ? out : (out && last_valid);
-                            const double q0 = __dmul_rn(a, y);
-                            const double q1 = __fma_rn(__fma_rn(-q0, kk, a), y, q0);
-                            cr[u] = __dadd_rn(cr[u], __fma_rn(__fma_rn(-q1, kk, a), y, q1));
                         }
                     }
                     if (!__any_sync(0xffffffffu, slow)) {
@@ -546,7 +622,7 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
                 for (int t = 0; t < nr && go; ++t) {
                     double X[NPW];
 #pragma unroll
-                    for (int u = 0; u < NPW; ++u) X[u] = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + 128 * u] : 0.0;
+                    for (int u = 0; u < NPW; ++u) X[u] = (u < NPW - 1 || last_valid) ? xrow[(size_t)t * FP + EP * u] : 0.0;
                     const SegMeta mt = mrow[t];
                     step(X, mt);
                     ++n_byrow;
@@ -559,13 +635,21 @@ __global__ void __launch_bounds__((kChainWarps + 1) * 32) replay_chain_tma_kerne
     }
 #pragma unroll
     for (int u = 0; u < NPW; ++u)
-        if (u < NPW - 1 || last_valid) cent[(size_t)c * f + 128 * u + j0] = cr[u];
+        if (u < NPW - 1 || last_valid) cent[(size_t)c * f + EP * u + j0] = cr[u];
     if (threadIdx.x == 0) {
         sizes[c] = (unsigned long long)kd;
         const double dm = dmax * (1.0 + 1e-12);
         if (dm == dm) atomicMax(maxdisp_bits, (unsigned long long)__double_as_longlong(dm));
         else bad = true;
         if (bad || !go || done < end - beg) atomicOr(fail, 1);
+        if (probe) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            probe[4 * blockIdx.x] = (unsigned long long)c;
+            probe[4 * blockIdx.x + 1] = (unsigned long long)(end - beg);
+            probe[4 * blockIdx.x + 2] = t_start;
+            probe[4 * blockIdx.x + 3] = t_end;
+        }
         atomicAdd(maxdisp_bits + 1, (unsigned long long)n_grouped);
         atomicAdd(maxdisp_bits + 2, (unsigned long long)n_byrow);
         atomicAdd(maxdisp_bits + 3, (unsigned long long)n_exact);
@@ -830,6 +914,13 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
         ASB_TRY(asb_check_launch(ctx, "replay_disp0_kernel"));
         disp0 = w.disp0.ptr;
     }
+    unsigned long long *probe_d = nullptr;
+    DevTmp<unsigned long long> probe;
+    if (opt_or(ctx, "cluster_chain_probe", 0.0) != 0.0) {
+        ASB_TRY(probe.init(ctx, (size_t)K * 4));
+        ASB_CUDA(ctx, cudaMemsetAsync(probe.ptr, 0, (size_t)K * 4 * sizeof(unsigned long long), ctx->stream));
+        probe_d = probe.ptr;
+    }
     {
         KernelTimer kt(ctx, "cluster_chain_kernel");
         // the ring kernel needs 16-byte aligned rows of a multiple of 16 bytes (bulk copies) and f <= 1024
@@ -841,30 +932,26 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
 #define ASB_CHAIN_ARGS                                                                                                  \
     K, saturated, radius, w.cent_tmp.ptr, snap_d, disp0, w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr,           \
         w.scal.ptr + 1, w.flags.ptr
-#define ASB_CHAIN_TMA(NPW, RG)                                                                                         \
+#define ASB_CHAIN_TMA(CW, NPW, RG)                                                                                     \
     {                                                                                                                   \
-        const size_t smem = (size_t)chain_ring_slots(NPW, RG) * (RG * (128 * NPW * sizeof(double) + sizeof(SegMeta)) + \
-                                                                   sizeof(GroupDesc<RG>));                            \
-        ASB_CUDA(ctx, cudaFuncSetAttribute(replay_chain_tma_kernel<NPW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem));                                                                 \
-        replay_chain_tma_kernel<NPW, RG><<<(unsigned)K, (kChainWarps + 1) * 32, smem, ctx->stream>>>(                   \
+        constexpr int fp_ = 32 * CW * NPW;                                                                              \
+        const size_t smem = (size_t)chain_ring_slots((fp_ + 127) / 128, RG) *                                           \
+                            (RG * (fp_ * sizeof(double) + sizeof(SegMeta)) + sizeof(GroupDesc<RG>));                    \
+        ASB_CUDA(ctx, cudaFuncSetAttribute(replay_chain_tma_kernel<CW, NPW, RG>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        replay_chain_tma_kernel<CW, NPW, RG><<<(unsigned)K, (CW + kChainProducers) * 32, smem, ctx->stream>>>(         \
             rows_d, f, w.seg_off.ptr, w.order.ptr, w.meta.ptr, K, saturated, radius, hint, w.cent_tmp.ptr, snap_d, disp0, \
-            w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr);                          \
+            w.sizes_tmp.ptr, (long long *)assign_d, w.dcur.ptr, w.scal.ptr + 1, w.flags.ptr, probe_d);                 \
     }
         if (generic)
             replay_chain_kernel<<<(unsigned)((K + 3) / 4), 128, 0, ctx->stream>>>(rows_d, f, w.seg_off.ptr, w.vals_s.ptr,
                                                                                   ASB_CHAIN_ARGS);
-        else
-            switch ((f + 127) / 128) {
-                case 1: ASB_CHAIN_TMA(1, 8) break;
-                case 2: ASB_CHAIN_TMA(2, 8) break;
-                case 3: ASB_CHAIN_TMA(3, 8) break;
-                case 4: ASB_CHAIN_TMA(4, 4) break;
-                case 5: ASB_CHAIN_TMA(5, 4) break;
-                case 6: ASB_CHAIN_TMA(6, 4) break;
-                case 7: ASB_CHAIN_TMA(7, 4) break;
-                default: ASB_CHAIN_TMA(8, 4) break;
-            }
+        else if (f <= 128) ASB_CHAIN_TMA(4, 1, 8)
+        else if (f <= 256) ASB_CHAIN_TMA(8, 1, 8)
+        else if (f <= 384) ASB_CHAIN_TMA(12, 1, 8)
+        else if (f <= 512) ASB_CHAIN_TMA(16, 1, 8)
+        else if (f <= 768) ASB_CHAIN_TMA(12, 2, 4)
+        else ASB_CHAIN_TMA(16, 2, 4)
 #undef ASB_CHAIN_TMA
 #undef ASB_CHAIN_ARGS
     }
@@ -879,6 +966,30 @@ int replay_run(asb_ctx *ctx, ReplayWs &w, const double *rows_d, int m, int f, in
     ASB_CUDA(ctx, cudaMemcpyAsync(hflags, w.flags.ptr, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaMemcpyAsync(hsc, w.scal.ptr + 1, sizeof(hsc), cudaMemcpyDeviceToHost, ctx->stream));
     ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (probe_d) {   // the largest chunk so far: who was on the critical path?
+        std::vector<unsigned long long> hp((size_t)K * 4);
+        ASB_CUDA(ctx, cudaMemcpy(hp.data(), probe_d, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull, t1 = 0, longest_rows = 0, longest_ns = 0, last_rows = 0;
+        for (int b = 0; b < K; ++b) {
+            if (hp[4 * b + 3] == 0) continue;
+            if (hp[4 * b + 2] < t0) t0 = hp[4 * b + 2];
+            if (hp[4 * b + 3] > t1) {
+                t1 = hp[4 * b + 3];
+                last_rows = hp[4 * b + 1];
+            }
+            if (hp[4 * b + 1] > longest_rows) {
+                longest_rows = hp[4 * b + 1];
+                longest_ns = hp[4 * b + 3] - hp[4 * b + 2];
+            }
+        }
+        if (m >= ctx->kernel_ms["cluster_probe_rows"]) {
+            ctx->kernel_ms["cluster_probe_rows"] = (double)m;
+            ctx->kernel_ms["cluster_probe_span_us"] = (t1 > t0 ? (double)(t1 - t0) : 0.0) * 1e-3;
+            ctx->kernel_ms["cluster_probe_longest_rows"] = (double)longest_rows;
+            ctx->kernel_ms["cluster_probe_longest_us"] = (double)longest_ns * 1e-3;
+            ctx->kernel_ms["cluster_probe_last_block_rows"] = (double)last_rows;
+        }
+    }
     const unsigned long long hdisp = hsc[0];
     ctx->kernel_ms["cluster_chain_rows_grouped"] += (double)hsc[1];   // (reset by asb_dev_cluster / the sharded entry)
     ctx->kernel_ms["cluster_chain_rows_by_row"] += (double)hsc[2];
@@ -940,7 +1051,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     const bool replay = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
                         n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
     for (const char *key : {"cluster_chain_rows_grouped", "cluster_chain_rows_by_row", "cluster_chain_exact_steps",
-                            "cluster_chain_checkpoints"})
+                            "cluster_chain_checkpoints", "cluster_probe_rows"})
         ctx->kernel_ms[key] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks"] = 0.0;
     ctx->kernel_ms["cluster_replay_chunks_ok"] = 0.0;

@@ -75,6 +75,7 @@ struct PfArgs {
     // PF_NEAR only: per query the nearest item by the approximate score and certified bounds {dlo, dhi} of its
     // distance and slo, a lower bound of the distance to every OTHER item
     double e_cos;
+    int epi_groups;                          // tcgen05 tile: epilogue groups (search_umma.cuh)
     long long *near_idx;
     double *near_b;                          // nq x 3
 };

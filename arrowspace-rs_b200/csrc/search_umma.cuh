@@ -24,7 +24,8 @@
 namespace {
 
 constexpr int UM_TQ = 128, UM_TN = 256;
-constexpr int UM_THREADS = 256;                                    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..7 epilogue
+constexpr int UM_THREADS = 384;                                    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..7 / 8..11 epilogue
+constexpr int UM_EPI_GROUPS = 2;                                   // epilogue group g drains the tiles t = g (mod 2)
 constexpr int UM_RING_BYTES = 192 * 1024;                          // operand ring: UM_RING_BYTES / stage bytes stages
 constexpr int UM_MAX_STAGES = 4;
 // features per stage KC = 32 (128-byte rows, SWIZZLE_128B, 96 KB stages, 2 in the ring) or 16 (64-byte rows, SWIZZLE_64B,
@@ -309,8 +310,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
             }
         }
     } else if (warp >= 4) {
-        // ---- epilogue: thread e = query q0 + e = TMEM lane e
-        const int e = tid - 128, ew = warp - 4;
+        // ---- epilogue: thread e = query q0 + e = TMEM lane e.  TWO groups of four warps: group g owns accumulator buffer g,
+        // i.e. the tiles t = g (mod 2), with its own sorted list and bounds per query (like two interleaved slabs; the
+        // groups meet in gthr like slabs do).  ncu of the one-group version (profiles/r02_umma_bf16_*): tensor pipe 45 %
+        // active, the four epilogue warps -- one per scheduler, nothing to hide a tcgen05.ld or a dependent FP32 chain
+        // behind -- took two tiles' worth of MMA time per tile.
+        const int eg = (warp - 4) >> 2, ew = (warp - 4) & 3;   // group, TMEM lane quarter (= warp % 4)
+        const int e = ew * 32 + lane;
+        const int ngroups = A.epi_groups;   // 1 when the second group's lists do not fit shared memory (k > 20)
+        if (eg < ngroups) {
         const long long gq = q0 + e;
         const bool okq = gq < A.nq;
         double lq = 1.0, qn = 0.0, qband = A.band;
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
             qband = A.band_rel * qn * sqrt(xmax2) + A.band_abs * (lq + xmax2);
             self = (okq && A.self_idx) ? A.self_idx[gq] : -1ll;
         }
-        float *lst = lists + (size_t)e * k;
+        float *lst = lists + ((size_t)eg * UM_TQ + e) * k;
         int len = 0;
         double kth = -INFINITY;
         bool saw_nan = false;
@@ -345,10 +353,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         if constexpr (MODE == PF_COSINE) fdelta = 1.0e-7 * (2.0 * fabs(A.alpha) + fabs(beta) * (3.0 * fabs(lq) + 8.0)) + 1e-30;
         else fdelta = 1.0e-6 * (lq + __longlong_as_double((long long)*A.xn2max_bits)) + 1e-300;
         if (!(fdelta < 1e25)) fdelta = INFINITY;   // beyond FP32's range (or NaN): no pre-test
-        for (int t = 0; t < ntile; ++t) {
-            const int b = t & 1;
+        for (int t = eg; t < ntile; t += ngroups) {
+            const int b = t & 1;   // (= eg with two groups)
             const long long i0 = (t_begin + t) * UM_TN;
-            // item-side inputs of this tile (two items per thread); the buffer was last read two tiles ago
+            // item-side inputs of this tile (two items per thread) go to the group's buffer: every thread of the group
+            // must be done reading the previous tile's values first
+            if (t >= ngroups) {
+                if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
             for (int c = e; c < UM_TN; c += 128) {
                 const long long gi = i0 + c;
                 if constexpr (MODE == PF_COSINE) {
@@ -363,7 +376,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                     ep_f1[b * UM_TN + c] = (float)v1;
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
             double gb = -INFINITY;                                             // bound published by any slab
             if constexpr (MODE != PF_NEAR) gb = okq ? pf_dec(__ldcg(&A.gthr[gq])) : -INFINITY;
             um_mbar_wait(&bars.tfull[b], (t >> 1) & 1);
@@ -483,7 +497,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
         }
         if (saw_nan) atomicOr(A.flags, PF_FLAG_FALLBACK);
         if constexpr (MODE == PF_NEAR) {
-            if (okq) {
+            // the two groups of a query merge their (largest, second largest, column) through the list area (unused here)
+            float *mrg = lists;   // [UM_TQ][3]
+            if (eg == 1) {
+                mrg[3 * e] = near1;
+                mrg[3 * e + 1] = near2;
+                mrg[3 * e + 2] = __int_as_float(near_i);
+            }
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (eg == 0) {
+                const float o1 = mrg[3 * e], o2 = mrg[3 * e + 1];
+                const int oi = __float_as_int(mrg[3 * e + 2]);
+                const float hi1 = fmaxf(near1, o1);
+                near2 = fmaxf(fminf(near1, o1), fmaxf(near2, o2));
+                // equal scores: the lower column, as one group walking all tiles in order would have kept
+                near_i = (o1 > near1 || (o1 == near1 && oi >= 0 && (near_i < 0 || oi < near_i))) ? oi : near_i;
+                near1 = hi1;
+            }
+            if (okq && eg == 0) {
                 // true d^2 = |q|^2 + |x|^2 - 2 |q| |x| cos: the tile's cos~ is within e_cos of cos (search_pf.cuh), the FP32
                 // evaluation of the score within fdelta of the FP64 one, the norms are FP64 sums (1e-13 covers them)
                 const double xmax2 = __longlong_as_double((long long)*A.xn2max_bits);
@@ -502,6 +533,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
                 A.near_b[3 * gq + 2] = slo;
             }
         }
+        }   // eg < ngroups
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -509,8 +541,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) search_umma_kernel(const __grid
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-size_t um_smem_bytes(int k, int mode) {
-    return (size_t)UM_RING_BYTES + (size_t)(mode != PF_COSINE ? 4 : 2) * UM_TN * 12 + (size_t)UM_TQ * k * 4 + 1024;
+size_t um_smem_bytes(int k, int mode, int groups = 1) {
+    const size_t lists = (size_t)groups * UM_TQ * k * 4;
+    return (size_t)UM_RING_BYTES + (size_t)(mode != PF_COSINE ? 4 : 2) * UM_TN * 12 + (lists > 3 * UM_TQ * 4 ? lists : 3 * UM_TQ * 4) + 1024;
 }
 
 typedef CUresult (*um_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -650,8 +683,10 @@ int um_launch_one(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs,
 }
 
 template <int MODE>
-int um_launch(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A, int nslabs, const char *timer) {
-    const size_t usmem = um_smem_bytes(A.k, MODE);
+int um_launch(asb_ctx *ctx, const UmMaps &maps, const PfArgs &A_in, int nslabs, const char *timer) {
+    PfArgs A = A_in;
+    A.epi_groups = (MODE == PF_NEAR || um_smem_bytes(A.k, MODE, UM_EPI_GROUPS) <= 226 * 1024) ? UM_EPI_GROUPS : 1;
+    const size_t usmem = um_smem_bytes(A.k, MODE, A.epi_groups);
     const int kc = um_kc(ctx), cl = um_cluster(ctx, A.nq);
     ctx->kernel_ms["search_umma_cluster"] = (double)cl;
     KernelTimer kt(ctx, timer);

@@ -58,6 +58,7 @@ def main():
                      "top2_ms": ctx.kernel_ms("cluster_replay_top2_ms"), "chain_ms": ctx.kernel_ms("cluster_replay_chain_ms"),
                      "near_retries": ctx.kernel_ms("cluster_replay_near_retries"), "growth_rows": ctx.kernel_ms("cluster_growth_rows"),
                      "chain_rows": {k: ctx.kernel_ms("cluster_chain_%s" % k) for k in ("rows_grouped", "rows_by_row", "exact_steps", "checkpoints")},
+                     "probe": {k: ctx.kernel_ms("cluster_probe_%s" % k) for k in ("rows", "span_us", "longest_rows", "longest_us", "last_block_rows")},
                      "wall_ms": {k: round(ctx.kernel_ms("cluster_wall_%s_ms" % k), 3) for k in ("growth", "prefix", "prepare", "run", "fallback")}}
     s, r = res["sequential"], res["replay"]
     out["centroids_bit_identical"] = bool(s[0].shape == r[0].shape and np.array_equal(
