@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) replay_chain_kernel(const double *__restr
 // The certification kernel receives an UPPER BOUND of the row's distance to its centroid at the row's own time
 // (dhi + B, or the exact value from the exact step).
 constexpr int kChainWarpsMax = 16;   // consumer warps CW (template); warps CW .. CW + kChainProducers - 1 are producers
-constexpr int kChainProducers = 2;
+constexpr int kChainProducers = 4;
 constexpr int kRingSlots = 8;   // at most
 
 struct __align__(16) SegMeta {    // per sorted position (replay_bounds_kernel)
@@ -217,7 +217,7 @@ struct __align__(16) GroupDesc {
 // 180, 32 gave 130), so the ring takes what one CTA per SM can have: up to 192 kB of rows, at most kRingSlots slots;
 // row128 = the ring pitch of a row in units of 128 features (1 kB)
 __host__ __device__ constexpr int chain_ring_slots(int row128, int rg) {
-    return 192 / (row128 * rg) < 2 ? 2 : (192 / (row128 * rg) > kRingSlots ? kRingSlots : 192 / (row128 * rg));
+    return 192 / (row128 * rg) < 2 ? 2 : (192 / (row128 * rg) > kRingSlots ? kRingSlots : (192 / (row128 * rg)) & ~1);   // even
 }
 __device__ __forceinline__ int chain_interval(double kd) {
     // steps between two exact values of the displacement bound: 1 while the count is small, then count / 256 (the
@@ -303,6 +303,8 @@ __global__ void __launch_bounds__((CW + kChainProducers) * 32, 1) replay_chain_t
     __shared__ ChainShared sh;
     constexpr int FP = 32 * CW * NPW;
     constexpr int NS = chain_ring_slots((FP + 127) / 128, RG);
+    constexpr int NP = NS % 4 == 0 ? 4 : 2;   // producer warps in use (<= kChainProducers)
+    static_assert(NS % NP == 0 && NP <= kChainProducers, "slot ownership");
     static_assert(NS <= kRingSlots && RG <= 8 && RG >= 2, "ring geometry");
     double *ring = reinterpret_cast<double *>(rp_smem);
     SegMeta *metas = reinterpret_cast<SegMeta *>(rp_smem + (size_t)NS * RG * FP * sizeof(double));
@@ -332,20 +334,28 @@ __global__ void __launch_bounds__((CW + kChainProducers) * 32, 1) replay_chain_t
         // the metadata of 32 rows (32 / RG groups) per coalesced load, one batch ahead of the groups being issued: the
         // producer's own global-memory latency stays off the ring's critical path
         constexpr int GPB = 32 / RG;   // groups per batch
-        // kChainProducers producer warps take the batches in turn: one warp could not issue a group's descriptor and bulk
-        // copies in the time the consumers need for it (probe: the longest chain paid 138 ns per row whatever the ring
-        // depth or the consumers' instruction count)
+        // Several producer warps: one warp cannot issue a group's descriptor and bulk copies (a loop over the lanes: the
+        // copy instruction takes uniform operands) in the time the consumers need for the group -- with one producer the
+        // longest chain paid 138 ns per row whatever the ring depth or the consumers' instruction count, with two 103.
+        // Producer p owns the groups g = p (mod NP), hence the slots s = p (mod NP) (NS is a multiple of NP): every slot
+        // is refilled by the same warp each time round, so no waiter ever lags its mbarrier by more than one phase.
         const int pw = warp - CW;
-        const int nbatches = (ngroups + GPB - 1) / GPB;
+        if (pw >= NP) return;
+        const int my_groups = ngroups > pw ? (ngroups - pw + NP - 1) / NP : 0;   // groups pw, pw + NP, ...
+        const int nbatches = (my_groups + GPB - 1) / GPB;
+        auto batch_row = [&](int bt) {   // position of this lane's row in batch bt of this producer
+            const int g = pw + (bt * GPB + lane / RG) * NP;
+            return beg + g * RG + lane % RG;
+        };
         SegMeta cur, nxt;
         cur.dlo = cur.dhi = cur.slo = 0.0;
         cur.row = cur.pad = 0;
         nxt = cur;
-        if (beg + pw * 32 + lane < end) nxt = seg_meta[beg + pw * 32 + lane];
-        for (int bt = pw; bt < nbatches; bt += kChainProducers) {
+        if (nbatches > 0 && batch_row(0) < end) nxt = seg_meta[batch_row(0)];
+        for (int bt = 0; bt < nbatches; ++bt) {
             cur = nxt;
-            {
-                const int np = beg + (bt + kChainProducers) * 32 + lane;
+            if (bt + 1 < nbatches) {
+                const int np = batch_row(bt + 1);
                 if (np < end) {
                     nxt = seg_meta[np];
                     rp_prefetch_l2(rows + (size_t)nxt.row * f, (unsigned)(f * 8));   // the ring's copies then hit L2
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__((CW + kChainProducers) * 32, 1) replay_chain_t
             }
 #pragma unroll 1
             for (int gi = 0; gi < GPB; ++gi) {
-                const int g = bt * GPB + gi;
+                const int g = pw + (bt * GPB + gi) * NP;
                 if (g >= ngroups) break;
                 const int slot = g % NS;
                 if (g >= NS) rp_mbar_wait(&sh.empty[slot], ((g / NS) - 1) & 1);

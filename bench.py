@@ -636,8 +636,7 @@ def run_b200(args):
         # HBM peaks come from MEASURED_PEAKS.json (or the profiling guide's fallback); that file has no FP64 entry,
         # so FP64 tensor-bound kernels are held against the DMMA rate measured on this pool by tools/fp64_peak.cu
         roofline["peak_kind"] = peak_src if roofline["bound"] == "hbm" else (
-            "tcgen05 TF32 rate measured on this pool by tools/umma_peak.cu (MEASURED_PEAKS.json holds a bf16 cuBLAS figure, "
-            "1692 TFLOP/s burst: TF32 runs at half the bf16 rate, nominal 1.1 PFLOP/s)" if dominant == "search_pf_kernel" else
+            kernels[dominant].get("peak_source", "") if dominant == "search_pf_kernel" else
             "measured on this pool by tools/fp64_peak.cu (profiles/r01_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure")
 
     line = {
