@@ -220,9 +220,9 @@ __host__ __device__ constexpr int chain_ring_slots(int row128, int rg) {
     return 192 / (row128 * rg) < 2 ? 2 : (192 / (row128 * rg) > kRingSlots ? kRingSlots : (192 / (row128 * rg)) & ~1);   // even
 }
 __device__ __forceinline__ int chain_interval(double kd) {
-    // steps between two exact values of the displacement bound: 1 while the count is small, then count / 256 (the
-    // bound may grow by about 0.4 % of the row distance in between), at most 64
-    return kd < 512.0 ? 1 : (kd < 16384.0 ? (int)(kd * (1.0 / 256.0)) : 64);
+    // steps between two exact values of the displacement bound: 1 while the count is small, then count / 128 (the
+    // bound may grow by about 0.8 % of the row distance in between), at most 128
+    return kd < 256.0 ? 1 : (kd < 16384.0 ? (int)(kd * (1.0 / 128.0)) : 128);
 }
 
 // FP64 operations the compiler may not reorder among themselves: the chain kernel issues the element chains of a row
