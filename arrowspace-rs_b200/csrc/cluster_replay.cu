@@ -1058,6 +1058,9 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
     const int64_t chunk = (int64_t)opt_or(ctx, "cluster_replay_chunk", 1024.0);
     int64_t chunk_max = (int64_t)opt_or(ctx, "cluster_replay_chunk_max", 262144.0);
     if (chunk_max < chunk) chunk_max = chunk;
+    int64_t grow = (int64_t)opt_or(ctx, "cluster_replay_growth", 2.0);   // chunk size factor after a proven chunk
+    if (grow < 1) grow = 1;
+    if (grow > 16) grow = 16;
     const bool replay = opt_or(ctx, "cluster_replay", 1.0) != 0.0 && prefix >= 1 && chunk >= 256 && chunk_max <= (1 << 24) &&
                         n >= prefix + chunk / 4 && f <= 16384 && max_clusters * f <= (1ll << 27);
     for (const char *key : {"cluster_chain_rows_grouped", "cluster_chain_rows_by_row", "cluster_chain_exact_steps",
@@ -1130,7 +1133,7 @@ int asb_dev_cluster(asb_ctx *ctx, const double *rows_d, int64_t n, int64_t f, in
             fails = 0;
             ++proven;
             rows_replayed += hi - lo;
-            cur = cur * 2 < chunk_max ? cur * 2 : chunk_max;
+            cur = cur * grow < chunk_max ? cur * grow : chunk_max;
         } else {
             // not provable (yet): walk sequentially, and twice as far after every further failure in a row -- data that
             // never settles costs O(log(n / chunk)) wasted attempts, data that settles late is picked up when it does

@@ -44,7 +44,8 @@ constexpr int PF_STAGES = 3;
 constexpr int PF_STAGE_FLOATS = (TQ + TN) * PF_PITCH;
 constexpr int PF_SP = 136;                 // cos~ tile pitch (floats): conflict-free float2 stores and row scans
 constexpr int PF_FLAG_FALLBACK = 1, PF_FLAG_OVERFLOW = 2;
-constexpr int PF_MAXSEL = 1024;            // rescored candidates per query
+constexpr int PF_FLAG_OVERFLOW_SOME = 4;   // cosine mode: the queries marked in PfArgs::ovf go to the exact kernel, the rest stand
+constexpr int PF_MAXSEL = 2048;            // rescored candidates per query
 constexpr int PF_COSINE = 0;               // score = alpha cos + (1 - alpha) lambda proximity (search_lambda_aware)
 constexpr int PF_L2 = 1;                   // score = -|q - x|^2 (nearest neighbours: Two-NN scan, replay top-2); opt-in
 constexpr int PF_NEAR = 2;                 // tcgen05 tile only: nearest item + certified distance bounds (the replay)
@@ -76,6 +77,7 @@ struct PfArgs {
     // distance and slo, a lower bound of the distance to every OTHER item
     double e_cos;
     int epi_groups;                          // tcgen05 tile: epilogue groups (search_umma.cuh)
+    int *ovf;                                // per query (or null): 1 = list or survivor overflow, handled per query
     long long *near_idx;
     double *near_b;                          // nq x 3
 };
@@ -406,7 +408,14 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     if (tid == 0) nsel = 0;
     const int cnt = A.cand_cnt[q];
     if (cnt > A.cap) {
-        if (tid == 0) atomicOr(A.flags, PF_FLAG_OVERFLOW);
+        if (tid == 0) {
+            if (A.ovf) {
+                A.ovf[q] = 1;
+                atomicOr(A.flags, PF_FLAG_OVERFLOW_SOME);
+            } else {
+                atomicOr(A.flags, PF_FLAG_OVERFLOW);
+            }
+        }
         return;
     }
     const double *qr = queries + q * (long long)f;
@@ -483,7 +492,14 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     __syncthreads();
     const int m = nsel;
     if (m > PF_MAXSEL) {
-        if (tid == 0) atomicOr(A.flags, PF_FLAG_OVERFLOW);
+        if (tid == 0) {
+            if (A.ovf) {
+                A.ovf[q] = 1;
+                atomicOr(A.flags, PF_FLAG_OVERFLOW_SOME);
+            } else {
+                atomicOr(A.flags, PF_FLAG_OVERFLOW);
+            }
+        }
         return;
     }
     if (tid == 0) {
@@ -622,6 +638,29 @@ size_t pf_smem_bytes(int k, int mode = PF_COSINE) {
             um_split_rows_kernel<<<(grid), 256, 0, ctx->stream>>>(rows, norms2, n_, f_, fp_, hi_, lo_, flags_, nout_);   \
     } while (0)
 
+__global__ void __launch_bounds__(128) pf_gather_queries_kernel(const double *__restrict__ queries, const double *__restrict__ lambda_q,
+                                                                const double *__restrict__ qn2, int f,
+                                                                const long long *__restrict__ list, double *__restrict__ out_q,
+                                                                double *__restrict__ out_lq, double *__restrict__ out_qn) {
+    const long long s = blockIdx.x, q = list[s];
+    for (int j = threadIdx.x; j < f; j += 128) out_q[s * f + j] = queries[q * f + j];
+    if (threadIdx.x == 0) {
+        out_lq[s] = lambda_q[q];
+        out_qn[s] = qn2[q];
+    }
+}
+__global__ void __launch_bounds__(64) pf_scatter_results_kernel(const long long *__restrict__ list, int k,
+                                                                const long long *__restrict__ in_i, const double *__restrict__ in_s,
+                                                                const long long *__restrict__ in_c, long long *__restrict__ idx_out,
+                                                                double *__restrict__ score_out, long long *__restrict__ count_out) {
+    const long long s = blockIdx.x, q = list[s];
+    for (int r = threadIdx.x; r < k; r += 64) {
+        idx_out[q * k + r] = in_i[s * k + r];
+        score_out[q * k + r] = in_s[s * k + r];
+    }
+    if (threadIdx.x == 0 && count_out) count_out[q] = in_c[s];
+}
+
 // Tries the prefilter path; *done = true when idx/score/count hold the final answer.  *done = false (with ASB_OK)
 // means "not applicable / not certain": the caller runs the exact kernel, which then decides everything.
 static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_offset, int64_t *idx_d, double *score_d,
@@ -676,11 +715,14 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
         const long long utiles = (n + UM_TN - 1) / UM_TN;
         um_pick_slabs(ctx, (nq + UM_TQ - 1) / UM_TQ, utiles, fp, &nslabs, &tps);
     }
+    DevTmp<int> ovf;
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
+    ASB_TRY(ovf.init(ctx, (size_t)nq));
     ASB_TRY(flags.init(ctx, 1));
     ASB_TRY(gthr.init(ctx, (size_t)nq));
     ASB_TRY(diag.init(ctx, 2));
     ASB_CUDA(ctx, cudaMemsetAsync(flags.ptr, 0, sizeof(int), ctx->stream));
+    ASB_CUDA(ctx, cudaMemsetAsync(ovf.ptr, 0, (size_t)nq * sizeof(int), ctx->stream));
     ASB_CUDA(ctx, cudaMemsetAsync(diag.ptr, 0, 2 * sizeof(unsigned long long), ctx->stream));
     pf_init_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(gthr.ptr, cand_cnt.ptr, nq);
     ASB_TRY(asb_check_launch(ctx, "pf_init_kernel"));
@@ -718,6 +760,7 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     A.flags = flags.ptr;
     A.diag = diag.ptr;
     A.status = SA.status;
+    A.ovf = ovf.ptr;
     ctx->kernel_ms["search_pf_umma"] = umma ? 1.0 : 0.0;
     if (umma) {
         ASB_TRY(um_launch<PF_COSINE>(ctx, maps, A, nslabs, "search_pf_kernel"));
@@ -746,7 +789,52 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     ctx->kernel_ms["search_pf_band"] = band;
     ctx->kernel_ms["search_pf_candidates"] = (double)hdiag[0];
     ctx->kernel_ms["search_pf_rescored"] = (double)hdiag[1];
-    if (hflags != 0) return ASB_OK;  // the exact kernel decides (and reports NaN scores the way the reference does)
+    if ((hflags & ~PF_FLAG_OVERFLOW_SOME) != 0) return ASB_OK;  // the exact kernel decides (and reports NaN scores the way the reference does)
+    ctx->kernel_ms["search_pf_overflow_queries"] = 0.0;
+    if (hflags & PF_FLAG_OVERFLOW_SOME) {
+        // Some queries have more near-ties than the lists hold (tightly packed scores: every item of a blob within the
+        // band).  They alone go to the exact FP64 kernel + reference-order rescoring; the other queries' answers stand.
+        std::vector<int> hov((size_t)nq);
+        ASB_CUDA(ctx, cudaMemcpy(hov.data(), ovf.ptr, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<long long> list;
+        for (long long q = 0; q < nq; ++q)
+            if (hov[(size_t)q]) list.push_back(q);
+        ctx->kernel_ms["search_pf_overflow_queries"] = (double)list.size();
+        if ((long long)list.size() * 2 > nq) return ASB_OK;   // most of the batch: one exact pass for all of it
+        const long long ns = (long long)list.size();
+        DevTmp<long long> lidx, sub_i, out_i, sub_c;
+        DevTmp<double> sub_q, sub_lq, sub_qn, sub_s, out_s;
+        int kx = k + 4 > 64 ? 64 : k + 4;
+        if (kx > n) kx = (int)n;
+        ASB_TRY(lidx.init(ctx, (size_t)ns));
+        ASB_TRY(sub_q.init(ctx, (size_t)ns * f));
+        ASB_TRY(sub_lq.init(ctx, (size_t)ns));
+        ASB_TRY(sub_qn.init(ctx, (size_t)ns));
+        ASB_TRY(sub_i.init(ctx, (size_t)ns * kx));
+        ASB_TRY(sub_s.init(ctx, (size_t)ns * kx));
+        ASB_TRY(out_i.init(ctx, (size_t)ns * k));
+        ASB_TRY(out_s.init(ctx, (size_t)ns * k));
+        ASB_TRY(sub_c.init(ctx, (size_t)ns));
+        ASB_CUDA(ctx, cudaMemcpyAsync(lidx.ptr, list.data(), (size_t)ns * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        pf_gather_queries_kernel<<<(unsigned)ns, 128, 0, ctx->stream>>>(SA.queries, SA.lambda_q, SA.qnorms2, f, lidx.ptr, sub_q.ptr,
+                                                                       sub_lq.ptr, sub_qn.ptr);
+        ASB_TRY(asb_check_launch(ctx, "pf_gather_queries_kernel"));
+        SearchArgs S2 = SA;
+        S2.queries = sub_q.ptr;
+        S2.lambda_q = sub_lq.ptr;
+        S2.qnorms2 = sub_qn.ptr;
+        S2.nq = ns;
+        S2.k = kx;
+        ASB_TRY(run_search(ctx, MODE_COSINE, S2, 0, (int64_t *)sub_i.ptr, sub_s.ptr, nullptr, "search_pf_overflow_exact"));
+        exact_rescore_kernel<<<(unsigned)((ns + 3) / 4), 128, 0, ctx->stream>>>(SA.items, SA.lambdas, sub_q.ptr, sub_lq.ptr, ns, f,
+                                                                               SA.alpha, index_offset, sub_i.ptr, kx, k, out_i.ptr,
+                                                                               out_s.ptr, sub_c.ptr, SA.status);
+        ASB_TRY(asb_check_launch(ctx, "exact_rescore_kernel"));
+        pf_scatter_results_kernel<<<(unsigned)ns, 64, 0, ctx->stream>>>(lidx.ptr, k, out_i.ptr, out_s.ptr, sub_c.ptr, (long long *)idx_d,
+                                                                       score_d, (long long *)count_d);
+        ASB_TRY(asb_check_launch(ctx, "pf_scatter_results_kernel"));
+        ASB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `list` and the temporaries go out of scope
+    }
     ctx->kernel_ms["search_pf_used"] = 1.0;
     *done = true;
     return ASB_OK;

@@ -625,7 +625,7 @@ def run_b200(args):
                                      "exact_rows": ctx.kernel_ms("cluster_exact_rows")}
     # DRAM traffic per launch: from the committed ncu launch list of this very command (profiles/r02_traffic.json)
     if world == 1:
-        for kname, sub in (("taumode_kernel", "taumode_warp_kernel"), ("search_pf_kernel", "search_umma_kernel"),
+        for kname, sub in (("taumode_kernel", "taumode_reg_kernel"), ("search_pf_kernel", "search_umma_kernel"),
                            ("search_kernel", "search_kernel"), ("twonn_kernel", "search_kernel"),
                            ("cluster_kernel", "cluster_f32p_kernel")):
             if kname in kernels:

@@ -144,3 +144,29 @@ def test_prefilter_through_the_index_handle(pctx, asb, oracle):
     assert np.allclose(np.asarray(score), np.asarray(score0), rtol=0, atol=1e-12)
     want = oracle.search_lambda_aware_batch(x, np.asarray(aspace.lambdas), queries, np.asarray(lq), 10, 0.7)
     assert np.array_equal(np.asarray(idx), want[0])
+
+def test_prefilter_sends_only_the_overflowing_queries_to_the_exact_kernel(pctx, asb, oracle):
+    """A blob of near-identical items puts thousands of scores inside the band of the queries drawn from it: their
+    survivor lists overflow (PF_MAXSEL) and they alone take the exact FP64 kernel + reference-order rescoring, while the
+    other queries keep the prefilter's answer.  Either way the ids and scores are the oracle's."""
+    n, f, nq, k = 24_000, 64, 96, 10
+    x, lam, queries, lq = _case(asb, oracle, n, f, nq, seed=11)
+    rng = np.random.RandomState(5)
+    x[:6_000] = x[0] * (1.0 + 1e-7 * rng.randn(6_000, 1)) + 1e-7 * rng.rand(6_000, f)
+    x = np.ascontiguousarray(np.abs(x))
+    csr = oracle.feature_laplacian(oracle.cluster_incremental(x[6_000:8_000], 50, 1.5 * f * 0.0025 * 2)[0],
+                                   eps=0.5, k=12, topk=4, p=2.0, sigma=0.25)
+    lam = oracle.compute_taumode(x, csr, TAU_MEDIAN)
+    queries[:16] = x[:16] * 1.01
+    lq = oracle.compute_taumode(queries, csr, TAU_MEDIAN)
+    want = oracle.search_lambda_aware_batch(x, lam, queries, lq, k, 0.9)
+    got = pctx.search_lambda_aware_batch(x, lam, queries, lq, k, 0.9)
+    assert pctx.kernel_ms("search_pf_used") == 1.0
+    novf = pctx.kernel_ms("search_pf_overflow_queries")
+    assert 16 <= novf < nq // 2, novf
+    assert np.allclose(np.asarray(got[1]), want[1], rtol=0, atol=1e-12)
+    same = np.asarray(got[0]) == want[0]
+    gap_ok = np.abs(np.asarray(got[1]) - want[1]) < 1e-12          # ids may differ only inside exact score ties
+    assert (same | gap_ok).all()
+    assert np.array_equal(np.asarray(got[0])[16:], want[0][16:])   # the untouched queries: bit-identical as ever
+    assert np.array_equal(np.asarray(got[1])[16:].view(np.uint64), want[1][16:].view(np.uint64))
