@@ -128,9 +128,9 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *   "cluster_phase_times" (0|1), "cluster_tick_tid" (t)  per-block cycle probes, read back with
  *                                 asb_last_kernel_ms(ctx, "cluster_phaseN");
  *   "taumode_generic" (0|1)       use the generic CSR kernel even for a symmetric graph;
- *   "taumode_regs" (1|0), "taumode_ipp" (2|1)   symmetric graphs, f <= 1024: keep the item in registers as well as in
- *                                 shared memory and serve two items (f <= 512) per schedule entry; 0 = the
- *                                 shared-memory-only kernel of round 1;
+ *   "taumode_regs" (1|0), "taumode_ipp" (1|2)   symmetric graphs, f <= 1024: keep the item in registers as well as in
+ *                                 shared memory; ipp = 2 serves two items (f <= 512) per schedule entry;
+ *                                 taumode_regs = 0: the shared-memory-only kernel of round 1;
  *   "search_prefilter" (1|0)      1 (default): asb_search_lambda_aware_batch / asb_index_search rank all pairs with a
  *                                 certified 3xTF32 tensor-core score and compute only the pairs the error bound cannot
  *                                 exclude from the top-k in the reference's FP64 arithmetic (k <= 32, n >= 1024; any

@@ -131,7 +131,7 @@ def test_taumode_symmetric_kernel_variants(ctx, asb, oracle, n, f, variant):
             assert np.allclose(n2[fin], (x[fin] ** 2).sum(axis=1), rtol=1e-13)
     finally:
         ctx.set_option("taumode_regs", 1)
-        ctx.set_option("taumode_ipp", 2)
+        ctx.set_option("taumode_ipp", 1)
 
 
 def test_taumode_generic_and_symmetric_kernels_agree(ctx, asb, oracle, golden):

@@ -54,12 +54,12 @@ csr = ctx.build_feature_laplacian(cent, gp)
 csr_n = ctx.build_feature_laplacian(cent, asb.GraphParams(1.2, 12, 4, 2.0, 0.5, normalise=1))
 print("laplacian ok: nnz", csr[0][-1], "normalised nnz", csr_n[0][-1])
 lam, n2, st = ctx.compute_taumode(x, csr, asb.TauMode.Median, want_norms=True)
-for opts in (dict(taumode_ipp=1), dict(taumode_regs=0)):
+for opts in (dict(taumode_ipp=2), dict(taumode_regs=0)):
     for k_, v_ in opts.items():
         ctx.set_option(k_, v_)
     lam_v, _, _ = ctx.compute_taumode(x, csr, asb.TauMode.Median)
     assert np.allclose(lam, lam_v, rtol=1e-12)
-ctx.set_option("taumode_ipp", 2)
+ctx.set_option("taumode_ipp", 1)
 ctx.set_option("taumode_regs", 1)
 ctx.set_option("taumode_generic", 1)
 lam_g, _, _ = ctx.compute_taumode(x, csr, asb.TauMode.Median)
