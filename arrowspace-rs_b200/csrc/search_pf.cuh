@@ -45,7 +45,7 @@ constexpr int PF_STAGE_FLOATS = (TQ + TN) * PF_PITCH;
 constexpr int PF_SP = 136;                 // cos~ tile pitch (floats): conflict-free float2 stores and row scans
 constexpr int PF_FLAG_FALLBACK = 1, PF_FLAG_OVERFLOW = 2;
 constexpr int PF_FLAG_OVERFLOW_SOME = 4;   // cosine mode: the queries marked in PfArgs::ovf go to the exact kernel, the rest stand
-constexpr int PF_MAXSEL = 2048;            // rescored candidates per query
+constexpr int PF_MAXSEL = 2048;            // rescored candidates per query, at most (PfArgs::maxsel: what the scratch holds)
 constexpr int PF_COSINE = 0;               // score = alpha cos + (1 - alpha) lambda proximity (search_lambda_aware)
 constexpr int PF_L2 = 1;                   // score = -|q - x|^2 (nearest neighbours: Two-NN scan, replay top-2); opt-in
 constexpr int PF_NEAR = 2;                 // tcgen05 tile only: nearest item + certified distance bounds (the replay)
@@ -78,6 +78,11 @@ struct PfArgs {
     double e_cos;
     int epi_groups;                          // tcgen05 tile: epilogue groups (search_umma.cuh)
     int *ovf;                                // per query (or null): 1 = list or survivor overflow, handled per query
+    // survivors of the final bound, per query, in global scratch (L2-resident; in shared memory they cost the finishing
+    // kernel half its resident blocks)
+    int *sel_idx;                            // nq x maxsel
+    double *sel_s;                           // nq x maxsel
+    int maxsel;
     long long *near_idx;
     double *near_b;                          // nq x 3
 };
@@ -395,13 +400,14 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
                                                         double band_f, long long *__restrict__ idx_out,
                                                         double *__restrict__ score_out, long long *__restrict__ count_out) {
     extern __shared__ double pf_dyn[];
-    __shared__ int sel_idx[PF_MAXSEL];
-    __shared__ double sel_s[PF_MAXSEL];
     __shared__ int hist[256];
     __shared__ int nsel, pick_digit, pick_rem;
     const long long q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = A.k;
+    const int maxsel = A.maxsel;
+    int *sel_idx = A.sel_idx + (size_t)q * maxsel;
+    double *sel_s = A.sel_s + (size_t)q * maxsel;
     const int fq = (f + PF_FT - 1) / PF_FT * PF_FT;
     double *qs = pf_dyn;
     double *tile = pf_dyn + fq + (size_t)warp * 32 * PF_FTP;
@@ -487,11 +493,11 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
     for (int c = tid; c < cnt; c += 128)
         if ((double)cs[c] >= thr) {
             const int p = atomicAdd(&nsel, 1);
-            if (p < PF_MAXSEL) sel_idx[p] = A.cand_idx[(size_t)q * A.cap + c];
+            if (p < maxsel) sel_idx[p] = A.cand_idx[(size_t)q * A.cap + c];
         }
     __syncthreads();
     const int m = nsel;
-    if (m > PF_MAXSEL) {
+    if (m > maxsel) {
         if (tid == 0) {
             if (A.ovf) {
                 A.ovf[q] = 1;
@@ -526,7 +532,8 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
 #pragma unroll
                 for (int ii = 0; ii < 16; ++ii) {
                     const int i = 2 * ii + half;
-                    v[ii] = (i < nc && fj < f) ? __ldg(items + (long long)sel_idx[base + i] * f + fj) : 0.0;
+                    const int ri = __shfl_sync(0xffffffffu, li, i);   // candidate i's row (lane i holds it)
+                    v[ii] = (i < nc && fj < f) ? __ldg(items + (long long)ri * f + fj) : 0.0;
                 }
 #pragma unroll
                 for (int ii = 0; ii < 16; ++ii) {
@@ -604,6 +611,15 @@ __global__ void __launch_bounds__(128) pf_finish_kernel(PfArgs A, const double *
         idx_out[q * k + r] = -1;
     }
     if (tid == 0 && count_out) count_out[q] = taken;
+}
+
+// survivors the scratch holds per query: PF_MAXSEL, less when many queries share 512 MB (the replay's PF_L2 ranking of a
+// whole chunk: k = 2, a handful of survivors per row)
+static int pf_maxsel(long long nq) {
+    long long m = (512ll << 20) / (12 * (nq > 0 ? nq : 1));
+    if (m > PF_MAXSEL) m = PF_MAXSEL;
+    if (m < 64) m = 64;
+    return (int)m;
 }
 
 static size_t pf_finish_smem(int f) {
@@ -715,7 +731,8 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
         const long long utiles = (n + UM_TN - 1) / UM_TN;
         um_pick_slabs(ctx, (nq + UM_TQ - 1) / UM_TQ, utiles, fp, &nslabs, &tps);
     }
-    DevTmp<int> ovf;
+    DevTmp<int> ovf, sel_idx_g;
+    DevTmp<double> sel_s_g;
     ASB_TRY(cand_cnt.init(ctx, (size_t)nq));
     ASB_TRY(ovf.init(ctx, (size_t)nq));
     ASB_TRY(flags.init(ctx, 1));
@@ -761,6 +778,11 @@ static int run_search_pf(asb_ctx *ctx, const SearchArgs &SA, long long index_off
     A.diag = diag.ptr;
     A.status = SA.status;
     A.ovf = ovf.ptr;
+    A.maxsel = pf_maxsel(nq);
+    ASB_TRY(sel_idx_g.init(ctx, (size_t)nq * A.maxsel));
+    ASB_TRY(sel_s_g.init(ctx, (size_t)nq * A.maxsel));
+    A.sel_idx = sel_idx_g.ptr;
+    A.sel_s = sel_s_g.ptr;
     ctx->kernel_ms["search_pf_umma"] = umma ? 1.0 : 0.0;
     if (umma) {
         ASB_TRY(um_launch<PF_COSINE>(ctx, maps, A, nslabs, "search_pf_kernel"));
@@ -933,6 +955,13 @@ static int run_search_pf_l2(asb_ctx *ctx, const double *items_d, long long n, in
     A.qnrm = qnrm.ptr;
     A.xnrm = xnrm.ptr;
     A.self_idx = self_idx_d;
+    DevTmp<int> sel_idx_g;
+    DevTmp<double> sel_s_g;
+    A.maxsel = pf_maxsel(nq);
+    ASB_TRY(sel_idx_g.init(ctx, (size_t)nq * A.maxsel));
+    ASB_TRY(sel_s_g.init(ctx, (size_t)nq * A.maxsel));
+    A.sel_idx = sel_idx_g.ptr;
+    A.sel_s = sel_s_g.ptr;
     A.xn2max_bits = xmax.ptr;
     // |s~ - s| <= E(q) = 2 |q| max|x| E_cos + 1e-13 (|q|^2 + max|x|^2)  (norm rounding, the reference's own sum);  band = 2 E
     A.band_rel = 4.0 * e_cos * (1.0 + 1e-6);

@@ -629,12 +629,16 @@ bool um_make_maps(asb_ctx *ctx, UmMaps *maps, const float *qhi, const float *qlo
 // Slabs of the tcgen05 tile: the CTAs of one slab (all query tiles) stream the same item tiles but start at different
 // times, so they only share those tiles through L2 if a whole slab's planes fit there: with 601-tile slabs the 3 GB of
 // planes were fetched from HBM 14 times over (profiles/r02_launches_c3.md: 42.6 GB per launch).  Slabs are capped at
-// "search_umma_slab_mb" (default 48 MB of hi + lo planes, under half of the 126 MB L2), wave balance permitting.
+// "search_umma_slab_mb" (default 80 MB of BF16 hi + lo planes, 48 MB of TF32 planes: under the 126 MB L2), wave balance
+// permitting.
 void um_pick_slabs(asb_ctx *ctx, long long qtiles, long long ntiles, int fp, int *nslabs, long long *tps) {
-    double mb = 48.0;
+    // (measured at C3: 24 / 48 / 80 MB of BF16 planes per slab -> tile 19.2 / 19.1 / 18.5 ms, 1 624 / 1 309 / 1 095 candidates
+    // emitted per query: longer slabs share their bounds sooner and fill the pipeline less often)
+    const bool bf = um_bf16(ctx);
+    double mb = bf ? 80.0 : 48.0;
     auto it = ctx->options.find("search_umma_slab_mb");
     if (it != ctx->options.end() && it->second > 0.0) mb = it->second;
-    const double tile_bytes = (double)UM_TN * fp * 8.0;
+    const double tile_bytes = (double)UM_TN * fp * (bf ? 4.0 : 8.0);   // hi + lo planes of one item tile
     long long cap = (long long)(mb * 1048576.0 / tile_bytes);
     if (cap < 4) cap = 4;
     long long min_slabs = (ntiles + cap - 1) / cap;
