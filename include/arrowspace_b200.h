@@ -148,7 +148,7 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 kernel that keeps the centroid in memory instead of registers).  Same bits either
  *                                 way (csrc/cluster_replay.cu,
  *                                 tests/replay_proto.py).
- *   "twonn_prefilter" (1|0)       1 (default): the Two-NN scan is ranked by the certified 3xTF32 score of the search
+ *   "twonn_prefilter" (1|0)       1 (default): the Two-NN scan is ranked by the certified split-operand score of the search
  *                                 prefilter (score -|q - x|^2, tcgen05 tile) and the surviving distances are evaluated in
  *                                 the reference's direct form (bit-identical to a sequential evaluation); 0: the FP64
  *                                 tensor kernel (distances to 1e-9).
@@ -158,9 +158,12 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *   "cluster_replay_tf32" (0|1)   the exact top-2 through the certified prefilter + direct-form distances (slower than
  *                                 either of the above; kept for cross-checks).
  *   "search_umma_bf16" (1|0)      operand planes of the tcgen05 tile: BF16x3 on kind::f16 (default) or 3xTF32 on kind::tf32;
- *   "search_umma" (1|0), "search_umma_kc" (16|32), "search_umma_cluster" (2|1|4), "search_umma_slab_mb" (48)
- *                                 the prefilter tile: tcgen05.mma + TMA + TMEM (1) or mma.sync + cp.async (0); features per
- *                                 pipeline stage; CTAs sharing one multicast item stream; bytes of item planes per slab.
+ *   "search_umma" (1|0), "search_umma_kc" (16|32), "search_umma_cluster" (2|1|4), "search_umma_slab_mb" (80 | 48)
+ *                                 the prefilter tile: tcgen05.mma + TMA + TMEM (1) or mma.sync + cp.async (0); 32-bit words
+ *                                 per stage row (32: TF32 planes only); CTAs sharing one multicast item stream; MB of item
+ *                                 planes per slab (default 80 for BF16 planes, 48 for TF32 planes).
+ *   "cluster_replay_growth" (2)   chunk size factor after a proven chunk; "cluster_chain_probe" (0|1) records per chain
+ *                                 block {rows, start, end} of the largest chunk ("cluster_probe_*" diagnostics).
  *   "build_overlap_upload" (1|0)  asb_index_build from HOST rows: upload in 16 MB chunks on a second stream while stage 1
  *                                 already works on the head of the matrix.
  *   "cluster_growth_run" (1|0), "cluster_shard_snapshot_rows", "cluster_shard_piece", "cluster_shard_speculate"
@@ -168,8 +171,11 @@ double asb_last_kernel_ms(asb_ctx *ctx, const char *which);
  *                                 common snapshot (262144); rows per certified piece of a later shard (262144); 0 turns
  *                                 the speculative ranking off (plain hand-off).
  * Read-only diagnostics through asb_last_kernel_ms: "cluster_replay_chunks", "cluster_replay_chunks_ok",
- * "cluster_replay_rows", "search_pf_used", "search_pf_flags", "search_pf_candidates",
- * "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band". */
+ * "cluster_replay_rows", "cluster_replay_{seq,top2,chain}_ms", "cluster_wall_{growth,prefix,prepare,run,fallback}_ms",
+ * "cluster_chain_{rows_grouped,rows_by_row,exact_steps,checkpoints}", "search_pf_used", "search_pf_umma",
+ * "search_umma_bf16", "search_pf_flags", "search_pf_overflow_queries" (queries sent alone to the exact kernel),
+ * "search_pf_candidates", "search_pf_rescored", "search_pf_cap", "search_pf_slabs", "search_pf_band",
+ * "shard_t_{snapshot,ranked,state_in,walked,done}_ms", "cluster_shard_{speculative,fallback}". */
 int asb_ctx_set_option(asb_ctx *ctx, const char *key, double value);
 /* The slab split the search kernels use for nq queries x n items on a device with sm_count SMs (pure host
  * arithmetic, no device needed): a (128-query tile, slab) pair is one CTA and CTAs run in waves of sm_count, so the
